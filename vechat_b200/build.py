@@ -1,0 +1,81 @@
+"""In-tree builds (no JIT cache): the CUDA engine libvgc.so (sm_100a) and the host-only simulator.
+
+`python -m vechat_b200.build` builds everything; __graft_entry__.build() calls build_all().
+The built .so files are git-ignored but travel to the GPU box with the repo snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INC = os.path.join(ROOT, "include")
+LIB_DIR = os.path.join(HERE, "lib")
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+
+
+def engine_sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))
+            ] + [os.path.join(INC, "vgc.h")]
+
+
+def build_engine(force=False, verbose=False):
+    """libvgc.so: the C-ABI + hand-written sm_100a kernels."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, "libvgc.so")
+    srcs = [os.path.join(CSRC, "vgc_engine.cu")]
+    if force or _stale(out, engine_sources()):
+        cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", out] + srcs + ["-lcudart"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        _run(cmd)
+    return out
+
+
+def build_sim(force=False):
+    """libvgcsim.so: synthetic reads / ground-truth overlaps / windowizer (host only)."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, "libvgcsim.so")
+    src = os.path.join(CSRC, "sim.cpp")
+    if force or _stale(out, [src, os.path.join(INC, "vgc.h")]):
+        _run([CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", INC, "-o", out, src])
+    return out
+
+
+def build_oracle():
+    """The checkers under oracle/ (test infrastructure): our CPU restatement and, when the reference
+    tree is present, the compiled reference itself."""
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    if os.path.isdir("/root/reference/src"):
+        _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+
+
+def build_all(force=False):
+    build_sim(force)
+    build_engine(force)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
