@@ -1,0 +1,209 @@
+// TEST INFRASTRUCTURE — host instantiation of the engine's algorithm template (vechat_b200/csrc/poa_core.h)
+// with a one-lane executor and a scalar DP fill that writes the same H-matrix layout as the CUDA fill.
+// It exists so the serial graph logic that runs inside the kernel (AddAlignment, TopologicalSort, Subgraph,
+// PruneGraph, LargestSubgraph, traceback, ...) can be compared with the oracle on a machine without a GPU.
+// It is built only by tests/ (tests/test_host_model.py) and is never linked into libvgc.so.
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_prep.h"
+#include "poa_core.h"
+#include "vgc.h"
+
+namespace {
+
+using namespace vgc;
+
+struct HostEx {
+  std::vector<uint8_t> fl;
+  std::vector<uint16_t> off16, tail16, stk16;
+  std::vector<uint8_t> codes;
+  bool allow_fast = true;
+  uint32_t small_stack = 0;  // test hook: tiny fast stack to force the overflow path
+
+  int lane() const { return 0; }
+  int width() const { return 1; }
+  bool leader() const { return true; }
+  void sync() {}
+  uint32_t atomic_add(uint32_t* p, uint32_t v) {
+    uint32_t o = *p;
+    *p += v;
+    return o;
+  }
+  uint32_t excl_scan(uint32_t v, uint32_t* total) {
+    *total = v;
+    return 0;
+  }
+  bool stage_fast(uint32_t nV, uint32_t nE, uint8_t** f, uint16_t** o, uint16_t** t, uint16_t** s, uint32_t* cap) {
+    if (!allow_fast || nV >= 65535 || nE >= 65535) return false;
+    fl.assign(nV + 1, 0);
+    off16.assign(nV + 2, 0);
+    tail16.assign(nE + 1, 0);
+    uint32_t c = small_stack ? small_stack : 1024;
+    stk16.assign(c, 0);
+    *f = fl.data();
+    *o = off16.data();
+    *t = tail16.data();
+    *s = stk16.data();
+    *cap = c;
+    return true;
+  }
+  uint8_t* seq_codes() {
+    if (codes.size() < 70000) codes.assign(70000, 0);
+    return codes.data();
+  }
+
+  template <int K>
+  void fill(Slot& sl, WinState& ws, const uint8_t* codes_, uint32_t len, uint32_t mode, const Scores& sc,
+            uint32_t /*num_codes*/) {
+    using RM = RowMap<K>;
+    const uint32_t nR = ws.nR;
+    auto cell = [&](uint32_t row, uint32_t c) -> int16_t* {
+      int h, l, k;
+      RM::locate(c, &h, &l, &k);
+      return reinterpret_cast<int16_t*>(sl.H + static_cast<uint64_t>(row) * sl.row_words + RM::word(l, k)) + h;
+    };
+    auto H = [&](uint32_t row, uint32_t j) -> int32_t {  // j = DP column, 0 = first column
+      if (j == 0) return mode == kModeSW ? 0 : sl.fc[row];
+      return *cell(row, j - 1);
+    };
+    // virtual row 0
+    sl.fc[0] = 0;
+    for (uint32_t c = 0; c < len; ++c) *cell(0, c) = static_cast<int16_t>(mode == kModeSW ? 0 : (c + 1) * sc.g);
+    int32_t best = mode == kModeSW ? 0 : INT32_MIN;
+    uint32_t best_row = 0, best_col = 0;
+    std::vector<int32_t> row(len + 1);
+    for (uint32_t r = 0; r < nR; ++r) {
+      const uint32_t v = sl.rowprog[4 * r], meta = sl.rowprog[4 * r + 1];
+      const uint32_t code = meta_code(meta);
+      uint32_t np = meta_npred(meta);
+      const bool nopred = np == 0;
+      if (nopred) np = 1;
+      int32_t fcv = INT32_MIN;
+      for (uint32_t j = 1; j <= len; ++j) row[j] = INT32_MIN;
+      for (uint32_t p = 0; p < np; ++p) {
+        uint32_t pr;
+        if (nopred) pr = 0;
+        else if (p == 0) pr = sl.rowprog[4 * r + 2];
+        else if (meta_npred(meta) == 2) pr = sl.rowprog[4 * r + 3];
+        else pr = sl.ovf[sl.rowprog[4 * r + 3] + p - 1];
+        fcv = std::max(fcv, H(pr, 0));
+        for (uint32_t j = 1; j <= len; ++j) {
+          const int32_t s = codes_[j - 1] == code ? sc.m : sc.x;
+          row[j] = std::max(row[j], std::max(H(pr, j - 1) + s, H(pr, j) + sc.g));
+        }
+      }
+      row[0] = mode == kModeSW ? 0 : fcv + sc.g;
+      sl.fc[v + 1] = static_cast<int16_t>(row[0]);
+      for (uint32_t j = 1; j <= len; ++j) {
+        row[j] = std::max(row[j], row[j - 1] + sc.g);
+        if (mode == kModeSW) row[j] = std::max(row[j], 0);
+        *cell(v + 1, j - 1) = static_cast<int16_t>(row[j]);
+        if (mode == kModeSW) {
+          if (best < row[j]) {
+            best = row[j];
+            best_row = v + 1;
+            best_col = j;
+          }
+        } else if ((meta & kMetaSink) && j == len) {
+          if (best < row[j]) {
+            best = row[j];
+            best_row = v + 1;
+            best_col = j;
+          }
+        }
+      }
+    }
+    ws.best_row = best_row;
+    ws.best_col = best_col;
+    ws.best_score = best;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Same contract as ref_polish / oracle_polish.  flags: bit0 = disable the staged (16-bit) sort path,
+// bits 8.. = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).
+int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags, int k_regs, uint32_t* status_out) {
+  Prepared prep;
+  std::string err;
+  int rc = prepare_batch(b, p, &prep, &err);
+  if (rc != VGC_OK) return rc;
+  const int K = k_regs;
+  SlotDims d;
+  d.max_nodes = static_cast<uint32_t>(std::max<uint64_t>(prep.max_nodes_ub, 16));
+  d.max_edges = d.max_nodes;
+  d.max_len = std::max<uint32_t>(prep.max_len, 16);
+  d.row_words = 32 * K;
+  std::vector<uint8_t> buf(slot_bytes(d));
+  Slot sl;
+  slot_carve(d, buf.data(), &sl);
+  BatchView bv;
+  bv.bases = b->bases;
+  bv.quals = b->quals;
+  bv.seq_off = b->seq_off;
+  bv.has_qual = b->has_qual;
+  bv.begin = b->begin;
+  bv.end = b->end;
+  bv.win_first = b->win_first;
+  bv.win_flags = b->win_flags;
+  bv.layer_rank = prep.layer_rank.data();
+  bv.win_nseq = prep.win_nseq.data();
+  bv.win_avgw = prep.win_avgw.data();
+  bv.out_off = prep.out_off.data();
+  bv.out_cap = prep.out_cap.data();
+  bv.coder = prep.coder;
+  bv.decoder = prep.decoder;
+  bv.wlut = prep.wlut;
+  bv.num_codes = prep.num_codes;
+  std::vector<uint8_t> out(prep.out_total + 16);
+  std::vector<uint32_t> out_len(b->n_windows, 0);
+  HostEx ex;
+  ex.allow_fast = !(flags & 1);
+  ex.small_stack = static_cast<uint32_t>(flags) >> 8;
+  Scores nw{p->match, p->mismatch, p->gap};
+  for (uint32_t w = 0; w < b->n_windows; ++w) {
+    if (status_out) status_out[w] = 0;
+    if (prep.win_nseq[w] < 3) {
+      const uint32_t f = b->win_first[w];
+      const uint32_t blen = static_cast<uint32_t>(b->seq_off[f + 1] - b->seq_off[f]);
+      std::memcpy(out.data() + prep.out_off[w], b->bases + b->seq_off[f], blen);
+      out_len[w] = blen;
+      r->polished[w] = 0;
+      continue;
+    }
+    WinState ws;
+    std::memset(&ws, 0, sizeof(ws));
+    uint32_t n = 0;
+    if (K == 10) {
+      Poa<HostEx, 10> poa(ex, bv, sl, ws, nw);
+      poa.run_window(w, p->haplotype != 0, p->trim != 0, p->min_confidence, p->min_support, p->num_prune,
+                     out.data() + prep.out_off[w], &n);
+    } else {
+      Poa<HostEx, 16> poa(ex, bv, sl, ws, nw);
+      poa.run_window(w, p->haplotype != 0, p->trim != 0, p->min_confidence, p->min_support, p->num_prune,
+                     out.data() + prep.out_off[w], &n);
+    }
+    if (status_out) status_out[w] = ws.status;
+    if (ws.status != kStOk) n = 0;
+    out_len[w] = n;
+    r->polished[w] = 1;
+  }
+  uint64_t off = 0;
+  for (uint32_t w = 0; w < b->n_windows; ++w) {
+    r->cons_off[w] = off;
+    if (off + out_len[w] > r->cons_capacity) return VGC_ERR_CAPACITY;
+    std::memcpy(r->cons + off, out.data() + prep.out_off[w], out_len[w]);
+    off += out_len[w];
+  }
+  r->cons_off[b->n_windows] = off;
+  return VGC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// host_prep.h — host-side preparation of a vgc_batch for the device (pure C++, no CUDA).
+//
+// Everything here is work the reference does on the CPU *inside* Window::generate_consensus whose exact
+// result depends on libstdc++ / libm and therefore stays on the host:
+//   * layer rank: std::sort(rank.begin() + 1, rank.end(), by positions_.first) — unstable, same call,
+//     same comparator, same initial arrangement (src/window.cpp:90-97, :203-210)
+//   * quality -> weight LUT: (1 - pow(10, (33 - q) / 10.)) * 1000 truncated to uint32
+//     (vendor/spoa/src/graph.cpp:169, src/window.cpp:366)
+//   * average_weight: fp64 running sum in rank order (src/window.cpp:215-309)
+//   * add_layer's validation and silent drops (src/window.cpp:47-72)
+//   * windows with < 3 sequences return the backbone, polished = false (src/window.cpp:78-82, :188-192)
+#ifndef VGC_HOST_PREP_H_
+#define VGC_HOST_PREP_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "poa_core.h"
+#include "vgc.h"
+
+namespace vgc {
+
+inline void weight_lut(uint32_t lut[256]) {
+  for (int b = 0; b < 256; ++b) {
+    char q = static_cast<char>(b);
+    lut[b] = (1 - pow(10, (33 - q) / 10.)) * 1000;  // graph.cpp:169, same expression, same libm
+  }
+}
+
+struct Prepared {
+  std::vector<uint32_t> layer_rank;  // [n_layers]
+  std::vector<uint32_t> win_nseq;    // [n_windows]
+  std::vector<double> win_avgw;      // [n_windows]
+  std::vector<uint64_t> out_off;     // [n_windows]
+  std::vector<uint32_t> out_cap;     // [n_windows]
+  std::vector<uint32_t> device_windows;  // windows that need the device (>= 3 sequences), heaviest first
+  std::vector<uint64_t> win_work;    // estimated DP cells per window
+  uint8_t coder[256];
+  uint8_t decoder[kMaxCodes];
+  uint32_t num_codes = 0;
+  uint32_t wlut[256];
+  uint32_t max_len = 0;        // longest layer among device windows
+  uint64_t max_nodes_ub = 0;   // largest per-window node upper bound (sum of layer lengths)
+  uint64_t out_total = 0;
+};
+
+// Returns VGC_OK or VGC_ERR_INVALID / VGC_ERR_CAPACITY with a message.
+inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out, std::string* err) {
+  const uint32_t nw = b->n_windows, nl = b->n_layers;
+  if (p->gap > 0 || (p->num_prune == 0 && p->haplotype)) {
+    *err = "invalid params: gap must be non-positive, num_prune >= 1";
+    return VGC_ERR_INVALID;
+  }
+  if (nw && (!b->win_first || !b->seq_off || !b->bases || !b->begin || !b->end || !b->has_qual || !b->win_flags)) {
+    *err = "null array in batch";
+    return VGC_ERR_INVALID;
+  }
+  if (nw && b->win_first[nw] != nl) {
+    *err = "win_first[n_windows] != n_layers";
+    return VGC_ERR_INVALID;
+  }
+  weight_lut(out->wlut);
+  out->layer_rank.assign(nl, 0);
+  out->win_nseq.assign(nw, 0);
+  out->win_avgw.assign(nw, 0.0);
+  out->out_off.assign(nw, 0);
+  out->out_cap.assign(nw, 0);
+  out->win_work.assign(nw, 0);
+  out->device_windows.clear();
+  std::memset(out->coder, 0xFF, sizeof(out->coder));
+  std::memset(out->decoder, 0, sizeof(out->decoder));
+  // fixed part of the alphabet, then first-seen order for anything else
+  const char* acgt = "ACGT";
+  for (int i = 0; i < 4; ++i) {
+    out->coder[static_cast<uint8_t>(acgt[i])] = static_cast<uint8_t>(i);
+    out->decoder[i] = static_cast<uint8_t>(acgt[i]);
+  }
+  out->num_codes = 4;
+  uint64_t out_total = 0;
+  std::vector<uint32_t> rank;
+  for (uint32_t w = 0; w < nw; ++w) {
+    const uint32_t f = b->win_first[w], l = b->win_first[w + 1];
+    if (l <= f) {
+      *err = "window without a backbone";
+      return VGC_ERR_INVALID;
+    }
+    const uint64_t blen64 = b->seq_off[f + 1] - b->seq_off[f];
+    if (blen64 == 0 || blen64 > 65535) {  // createWindow (window.cpp:22-27); uint16 loop counters (:216,:232)
+      *err = "empty or oversized backbone";
+      return VGC_ERR_INVALID;
+    }
+    const uint32_t blen = static_cast<uint32_t>(blen64);
+    if (!b->has_qual[f] || !b->quals) {
+      *err = "backbone must carry a quality (real or dummy)";
+      return VGC_ERR_INVALID;
+    }
+    rank.clear();
+    rank.push_back(f);
+    uint64_t sum_len = blen;
+    uint32_t max_len = blen;
+    for (uint32_t i = f + 1; i < l; ++i) {
+      const uint64_t len = b->seq_off[i + 1] - b->seq_off[i];
+      const uint32_t bg = b->begin[i], en = b->end[i];
+      if (len == 0 || bg == en) continue;  // add_layer returns silently (window.cpp:51-54)
+      if (bg >= en || bg > blen || en > blen) {
+        *err = "layer begin and end positions are invalid";  // window.cpp:62-67
+        return VGC_ERR_INVALID;
+      }
+      if (len > 65535) {
+        *err = "layer longer than 65535";
+        return VGC_ERR_INVALID;
+      }
+      if (b->has_qual[i] && !b->quals) {
+        *err = "has_qual set but quals is NULL";
+        return VGC_ERR_INVALID;
+      }
+      rank.push_back(i);
+      sum_len += len;
+      max_len = std::max<uint32_t>(max_len, static_cast<uint32_t>(len));
+    }
+    const uint32_t nseq = static_cast<uint32_t>(rank.size());
+    out->win_nseq[w] = nseq;
+    std::sort(rank.begin() + 1, rank.end(),
+              [&](uint32_t lhs, uint32_t rhs) { return b->begin[lhs] < b->begin[rhs]; });
+    std::copy(rank.begin(), rank.end(), out->layer_rank.begin() + f);
+    // alphabet
+    for (uint32_t j = 0; j < nseq; ++j) {
+      const uint8_t* s = b->bases + b->seq_off[rank[j]];
+      const uint64_t len = b->seq_off[rank[j] + 1] - b->seq_off[rank[j]];
+      for (uint64_t k = 0; k < len; ++k) {
+        const uint8_t c = s[k];
+        if (out->coder[c] == 0xFF) {
+          if (c >= 128) {
+            *err = "base byte >= 128";
+            return VGC_ERR_INVALID;
+          }
+          if (out->num_codes >= static_cast<uint32_t>(kMaxCodes)) {
+            *err = "more than 8 distinct base bytes in one batch";
+            return VGC_ERR_CAPACITY;
+          }
+          out->coder[c] = static_cast<uint8_t>(out->num_codes);
+          out->decoder[out->num_codes++] = c;
+        }
+      }
+    }
+    // output capacity: < 3 sequences -> the backbone itself; otherwise nodes touched by an alignment
+    out->out_off[w] = out_total;
+    if (nseq < 3) {
+      out->out_cap[w] = blen;
+    } else {
+      out->out_cap[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 2ull * max_len + 2ull * blen + 64));
+      out->device_windows.push_back(w);
+      out->max_len = std::max(out->max_len, max_len);
+      out->max_nodes_ub = std::max(out->max_nodes_ub, sum_len);
+      out->win_work[w] = sum_len * static_cast<uint64_t>(blen) * (p->haplotype ? 3 : 1) * nseq / 8 + 1;
+    }
+    out_total += out->out_cap[w];
+    // average_weight (haplotype mode only): fp64 sum in rank order (window.cpp:215-309)
+    if (p->haplotype && nseq >= 3) {
+      double total = 0.0;
+      bool if_fasta = false;
+      const uint16_t window_len = static_cast<uint16_t>(blen);
+      if (b->win_flags[w] & VGC_WIN_DUMMY_QUAL) {
+        total += blen;
+        if_fasta = true;
+      } else {
+        const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[f]);
+        for (uint16_t k = 0; k < blen; ++k) total += 1 - pow(10, (33 - q[k]) / 10.0);
+      }
+      for (uint32_t j = 1; j < nseq; ++j) {
+        const uint32_t i = rank[j];
+        const uint32_t len = static_cast<uint32_t>(b->seq_off[i + 1] - b->seq_off[i]);
+        if (!b->has_qual[i]) {
+          total += len;
+        } else {
+          const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[i]);
+          for (uint16_t k = 0; k < len; ++k) total += (1 - pow(10, (33 - q[k]) / 10.0));
+        }
+      }
+      out->win_avgw[w] = if_fasta ? 2.0 * total / window_len : 2.0 * total / window_len * 1000;
+    }
+  }
+  out->out_total = out_total;
+  std::stable_sort(out->device_windows.begin(), out->device_windows.end(),
+                   [&](uint32_t a, uint32_t c) { return out->win_work[a] > out->win_work[c]; });
+  return VGC_OK;
+}
+
+// Bytes of one scratch slot for the given capacities, and the carving of a slot out of a flat buffer.
+struct SlotDims {
+  uint32_t max_nodes, max_edges, max_len, row_words;
+};
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+template <class F>
+inline uint64_t slot_walk(const SlotDims& d, F&& take) {
+  uint64_t off = 0;
+  auto t = [&](uint64_t bytes) {
+    uint64_t o = off;
+    off = align_up(off + bytes, 256);
+    return take(o);
+  };
+  const uint64_t N = d.max_nodes, E = d.max_edges;
+  (void)t;
+  // order must match slot_carve below
+  for (int gi = 0; gi < 2; ++gi) {
+    t(N);                      // code
+    t(N);                      // nal
+    t(N * kMaxAligned * 4);    // al
+    t(N * 4);                  // nin
+    t(N * 4);                  // nout
+    t(N * 4);                  // cov
+    t(E * 4);                  // etail
+    t(E * 4);                  // ehead
+    t(E * 4);                  // ew
+    t(E * 4);                  // ein_ord
+    t(E * 4);                  // eout_ord
+    t(E);                      // edead
+  }
+  t((N + 1) * 4);  // in_off
+  t(E * 4);        // in_eid
+  t(E * 4);        // in_tail
+  t((N + 1) * 4);  // out_off
+  t(E * 4);        // out_eid
+  t(N * 4);        // r2n
+  t(N * 4);        // order
+  t(N * 4);        // rank_of
+  t(N * 4);        // tmp0
+  t(N * 4);        // tmp1
+  t(N);            // flags
+  t(N * 16);       // rowprog
+  t(E * 4);        // ovf
+  t((N + 1) * 2);  // fc
+  t((N + 1) * static_cast<uint64_t>(d.row_words) * 4);  // H
+  t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_node
+  t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_pos
+  return off;
+}
+
+inline uint64_t slot_bytes(const SlotDims& d) {
+  return slot_walk(d, [](uint64_t) { return 0; });
+}
+
+inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
+  std::vector<uint64_t> offs;
+  slot_walk(d, [&](uint64_t o) {
+    offs.push_back(o);
+    return 0;
+  });
+  size_t i = 0;
+  auto P = [&](auto** p) {
+    using T = typename std::remove_pointer<typename std::remove_reference<decltype(*p)>::type>::type;
+    *p = reinterpret_cast<T*>(base + offs[i++]);
+  };
+  s->max_nodes = d.max_nodes;
+  s->max_edges = d.max_edges;
+  s->max_len = d.max_len;
+  s->row_words = d.row_words;
+  for (int gi = 0; gi < 2; ++gi) {
+    Graph& g = s->g[gi];
+    g.nV = g.nE = 0;
+    P(&g.code);
+    P(&g.nal);
+    P(&g.al);
+    P(&g.nin);
+    P(&g.nout);
+    P(&g.cov);
+    P(&g.etail);
+    P(&g.ehead);
+    P(&g.ew);
+    P(&g.ein_ord);
+    P(&g.eout_ord);
+    P(&g.edead);
+  }
+  P(&s->in_off);
+  P(&s->in_eid);
+  P(&s->in_tail);
+  P(&s->out_off);
+  P(&s->out_eid);
+  P(&s->r2n);
+  P(&s->order);
+  P(&s->rank_of);
+  P(&s->tmp0);
+  P(&s->tmp1);
+  P(&s->flags);
+  P(&s->rowprog);
+  P(&s->ovf);
+  P(&s->fc);
+  P(&s->H);
+  P(&s->aln_node);
+  P(&s->aln_pos);
+  s->aln_cap = d.max_len + d.max_nodes + 2;
+}
+
+}  // namespace vgc
+
+#endif  // VGC_HOST_PREP_H_

@@ -1,0 +1,1026 @@
+// poa_core.h — the window-correction algorithm on flat arrays, written once.
+//
+// The same template code is instantiated
+//   * in the CUDA engine (vgc_engine.cu) with a warp executor: one window per warp/CTA, 32 lanes,
+//     warp shuffles, shared memory, the packed int16x2 DP fill of poa_fill.cuh; and
+//   * in tests/host_model (g++, one "lane") so that the serial graph logic can be checked against the
+//     oracle on a machine without a GPU.  The host build is test-only: the product library never
+//     contains a CPU path.
+//
+// What it computes, with reference citations (paths under the reference tree):
+//   Window::generate_consensus haplotype  src/window.cpp:176-428      -> run_window()
+//   Window::generate_consensus linear     src/window.cpp:74-174       -> run_window() (haplotype == 0)
+//   Graph::AddAlignment / AddSequence     vendor/spoa/src/graph.cpp:109-130,182-299 -> add_alignment()
+//   Graph::TopologicalSort                graph.cpp:301-371           -> toposort()
+//   Graph::Subgraph / ExtractSubgraph     graph.cpp:640-732           -> extract_subgraph() + filtered toposort
+//   Graph::PruneGraph                     graph.cpp:811-982           -> prune()
+//   Graph::LargestSubgraph / DfsUtil      graph.cpp:984-1089          -> largest_subgraph()
+//   Graph::AddWeights                     graph.cpp:1104-1165         -> add_weights()
+//   Graph::GenerateCorrectedSequence      graph.cpp:1167-1179         -> emit_corrected()
+//   Graph::GenerateConsensus (+coverage)  graph.cpp:450-485,534-638   -> heaviest_bundle()
+//   Linear-gap NW/SW traceback            simd_alignment_engine_implementation.hpp:908-1105
+//                                         (scalar twin sisd_alignment_engine.cpp:362-460) -> traceback()
+//
+// Data layout (per window "slot", all in HBM unless noted):
+//   nodes : code u8, nin/nout u32, aligned list (<= kMaxAligned ids), coverage u32
+//   edges : tail, head, weight (u32), in_ord / out_ord (position inside head's in-list / tail's
+//           out-list; lists are "edges of that node in creation order", so CSR position =
+//           off[node] + ord), dead u8 (pruned hole)
+//   CSR   : in_off/in_eid/in_tail (rebuilt in parallel after every graph change), out_off/out_eid
+//   H     : one row of packed int16 score cells per graph node (+ virtual row 0), row = node id + 1
+//   fc    : int16 first-column value per row (NW border)
+#ifndef VGC_POA_CORE_H_
+#define VGC_POA_CORE_H_
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define VGC_HD __host__ __device__
+#define VGC_INL __forceinline__
+#else
+#define VGC_HD
+#define VGC_INL inline
+#endif
+
+namespace vgc {
+
+constexpr int kMaxAligned = 7;     // clique size - 1  (<= kMaxCodes - 1)
+constexpr int kMaxCodes = 8;       // distinct bytes per batch
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// window status codes (device -> host)
+enum : uint32_t {
+  kStOk = 0,
+  kStNodeOverflow = 1,   // arena too small: rerun with a larger slot
+  kStEdgeOverflow = 2,
+  kStOutOverflow = 3,
+  kStScoreRange = 4,     // int16 score range exceeded
+  kStTooLong = 5,        // layer longer than the row capacity
+  kStAlignedOverflow = 6,
+  kStInternal = 7,
+};
+
+enum : uint32_t { kModeNW = 0, kModeSW = 1 };
+
+// flags byte per node used by the sorts
+enum : uint8_t {
+  kFMarkMask = 3,
+  kFIgnored = 4,
+  kFHasAligned = 8,
+  kFMember = 16,
+};
+
+struct Scores {
+  int32_t m, x, g;
+};
+
+// Read-only batch, device-resident copy of vgc_batch + host-prepared per-window metadata.
+struct BatchView {
+  const uint8_t* bases;
+  const uint8_t* quals;
+  const uint64_t* seq_off;
+  const uint8_t* has_qual;
+  const uint32_t* begin;
+  const uint32_t* end;
+  const uint32_t* win_first;   // [n_windows + 1]
+  const uint8_t* win_flags;
+  const uint32_t* layer_rank;  // [n_layers]: for window w, entries win_first[w].. hold the GLOBAL layer
+                               // ids in the order std::sort left them (window.cpp:203-210); add_layer-
+                               // ignored layers are removed and the count is in win_nseq
+  const uint32_t* win_nseq;    // [n_windows] sequences_.size()
+  const double* win_avgw;      // [n_windows] average_weight (window.cpp:301-309), host fp64
+  const uint64_t* out_off;     // [n_windows] offset of the window's output bytes
+  const uint32_t* out_cap;     // [n_windows]
+  const uint8_t* coder;        // [256] byte -> code (batch-wide alphabet)
+  const uint8_t* decoder;      // [kMaxCodes]
+  const uint32_t* wlut;        // [256] quality byte -> weight
+  uint32_t num_codes;
+};
+
+struct Graph {
+  uint32_t nV, nE;
+  uint8_t* code;
+  uint8_t* nal;
+  uint32_t* al;        // [max_nodes * kMaxAligned]
+  uint32_t* nin;
+  uint32_t* nout;
+  uint32_t* cov;       // sequences through the node (linear mode coverage)
+  uint32_t* etail;
+  uint32_t* ehead;
+  uint32_t* ew;
+  uint32_t* ein_ord;
+  uint32_t* eout_ord;
+  uint8_t* edead;
+};
+
+// One slot of scratch in HBM.  Two graph buffers: LargestSubgraph writes the other one.
+struct Slot {
+  uint32_t max_nodes, max_edges, max_len, row_words;
+  Graph g[2];
+  uint32_t* in_off;    // [max_nodes + 1]
+  uint32_t* in_eid;    // [max_edges]
+  uint32_t* in_tail;   // [max_edges]
+  uint32_t* out_off;   // [max_nodes + 1]
+  uint32_t* out_eid;   // [max_edges]
+  uint32_t* r2n;       // [max_nodes] rank -> node of the whole current graph
+  uint32_t* order;     // [max_nodes] rank -> node of the rows the next alignment visits
+  uint32_t* rank_of;   // [max_nodes] node -> rank in `order`
+  uint32_t* tmp0;      // [max_nodes] scratch
+  uint32_t* tmp1;      // [max_nodes] scratch
+  uint8_t* flags;      // [max_nodes] (global fallback of the shared-memory flags)
+  uint32_t* rowprog;   // [max_nodes * 4] {node, meta, p0, p1}
+  uint32_t* ovf;       // [max_edges] predecessor rows of nodes with in-degree > 2
+  int16_t* fc;         // [max_nodes + 1]
+  uint32_t* H;         // [(max_nodes + 1) * row_words]; also the big scratch of the serial graph passes
+  int32_t* aln_node;   // [max_len + max_nodes + 2]
+  int32_t* aln_pos;
+  uint32_t aln_cap;
+};
+
+// rowprog meta word
+constexpr uint32_t kMetaSink = 1u << 31;
+VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink) {
+  return code | (npred << 8) | (sink ? kMetaSink : 0u);
+}
+VGC_HD VGC_INL uint32_t meta_code(uint32_t m) { return m & 0xFFu; }
+VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 8) & 0x7FFFFFu; }
+
+// Shared per-window state (shared memory on the device).
+struct WinState {
+  uint32_t cur;          // which graph buffer is live
+  uint32_t nR;           // rows of the pending alignment
+  uint32_t ovf_n;
+  uint32_t status;
+  uint32_t aln_len;      // pairs in aln_node/aln_pos, stored in REVERSE order
+  uint32_t best_row;     // row (node + 1) and DP column (1-based) the traceback starts from; 0,0 = none
+  uint32_t best_col;
+  int32_t best_score;
+  uint32_t nseq_added;
+  uint32_t scratch[4];
+  unsigned long long cells;
+  uint32_t alignments;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// H-matrix addressing.  A row holds 64*K cells as 32*K packed words: lane l owns words k of pair-slot
+// (k/2); low half = column l*K + k, high half = column 32*K + l*K + k.
+template <int K>
+struct RowMap {
+  static constexpr int kCols = 64 * K;
+  static constexpr int kWords = 32 * K;
+  VGC_HD static VGC_INL uint32_t word(int lane, int k) { return (k >> 1) * 64 + lane * 2 + (k & 1); }
+  VGC_HD static VGC_INL void locate(uint32_t c, int* half, int* lane, int* k) {
+    *half = c / (32 * K);
+    uint32_t r = c % (32 * K);
+    *lane = r / K;
+    *k = r % K;
+  }
+  VGC_HD static VGC_INL int32_t load(const uint32_t* row, uint32_t c) {
+    int h, l, k;
+    locate(c, &h, &l, &k);
+    uint32_t w = row[word(l, k)];
+    return static_cast<int16_t>(h ? (w >> 16) : (w & 0xFFFFu));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// The algorithm.  Ex (executor) provides: lane(), width(), leader(), sync(), atomic_add(u32*,u32),
+// excl_scan(v, &total), fill<K>(...) and the flag/CSR staging storage.
+template <class Ex, int K>
+struct Poa {
+  Ex& ex;
+  const BatchView& bv;
+  Slot& sl;
+  WinState& ws;
+  Scores nw;      // NW engine scores (params)
+  Scores sw;      // SW engine: 3/-5/-4 hard-wired (window.cpp:326)
+  using RM = RowMap<K>;
+
+  VGC_HD Poa(Ex& e, const BatchView& b, Slot& s, WinState& w, Scores nw_) : ex(e), bv(b), sl(s), ws(w), nw(nw_) {
+    sw.m = 3;
+    sw.x = -5;
+    sw.g = -4;
+  }
+
+  VGC_HD VGC_INL Graph& G() { return sl.g[ws.cur]; }
+
+  VGC_HD VGC_INL void fail(uint32_t st) {
+    if (ws.status == kStOk) ws.status = st;
+  }
+
+  // ---- CSR of in-edges (and out-edges) of the live graph: parallel over edges --------------------
+  VGC_HD void build_csr(bool with_out) {
+    Graph& g = G();
+    const uint32_t nV = g.nV, nE = g.nE;
+    // exclusive scan of nin -> in_off
+    uint32_t carry_in = 0, carry_out = 0;
+    for (uint32_t base = 0; base < nV; base += ex.width()) {
+      uint32_t v = base + ex.lane();
+      uint32_t a = v < nV ? g.nin[v] : 0, tot;
+      uint32_t p = ex.excl_scan(a, &tot);
+      if (v < nV) sl.in_off[v] = carry_in + p;
+      carry_in += tot;
+      if (with_out) {
+        uint32_t b = v < nV ? g.nout[v] : 0;
+        uint32_t q = ex.excl_scan(b, &tot);
+        if (v < nV) sl.out_off[v] = carry_out + q;
+        carry_out += tot;
+      }
+    }
+    if (ex.leader()) {
+      sl.in_off[nV] = carry_in;
+      if (with_out) sl.out_off[nV] = carry_out;
+    }
+    ex.sync();
+    for (uint32_t e = ex.lane(); e < nE; e += ex.width()) {
+      uint32_t pos = sl.in_off[g.ehead[e]] + g.ein_ord[e];
+      sl.in_eid[pos] = e;
+      sl.in_tail[pos] = g.etail[e];
+      if (with_out) sl.out_eid[sl.out_off[g.etail[e]] + g.eout_ord[e]] = e;
+    }
+    ex.sync();
+  }
+
+  // ---- graph.cpp:301-371.  Serial (leader).  `member_only`: the Subgraph view (graph.cpp:694-727):
+  //      roots, in-edges and aligned links restricted to nodes with kFMember.  Output: dst[0..n).
+  template <class IdxT>
+  VGC_HD uint32_t toposort_impl(uint8_t* flags, const IdxT* in_off, const IdxT* in_tail, IdxT* stack,
+                                uint32_t stack_cap, bool member_only, uint32_t* dst, bool* overflow) {
+    Graph& g = G();
+    const uint32_t nV = g.nV;
+    uint32_t n = 0, sp = 0;
+    *overflow = false;
+    for (uint32_t root = 0; root < nV; ++root) {
+      uint8_t fr = flags[root];
+      if ((fr & kFMarkMask) != 0) continue;
+      if (member_only && !(fr & kFMember)) continue;
+      stack[sp++] = static_cast<IdxT>(root);
+      while (sp > 0) {
+        const uint32_t curr = stack[sp - 1];
+        uint8_t fc = flags[curr];
+        bool valid = true;
+        if ((fc & kFMarkMask) != 2) {
+          const uint32_t b = in_off[curr], e = in_off[curr + 1];
+          if (sp + (e - b) + kMaxAligned + 1 > stack_cap) {
+            *overflow = true;
+            return 0;
+          }
+          for (uint32_t i = b; i < e; ++i) {
+            const uint32_t t = in_tail[i];
+            const uint8_t ft = flags[t];
+            if (member_only && !(ft & kFMember)) continue;
+            if ((ft & kFMarkMask) != 2) {
+              stack[sp++] = static_cast<IdxT>(t);
+              valid = false;
+            }
+          }
+          if (!(fc & kFIgnored) && (fc & kFHasAligned)) {
+            const uint32_t na = g.nal[curr];
+            for (uint32_t i = 0; i < na; ++i) {
+              const uint32_t a = g.al[curr * kMaxAligned + i];
+              const uint8_t fa = flags[a];
+              if (member_only && !(fa & kFMember)) continue;
+              if ((fa & kFMarkMask) != 2) {
+                stack[sp++] = static_cast<IdxT>(a);
+                flags[a] = fa | kFIgnored;
+                valid = false;
+              }
+            }
+          }
+          fc = flags[curr];  // (an aligned node cannot be curr itself, but keep the read ordered)
+          if (valid) {
+            flags[curr] = (fc & ~kFMarkMask) | 2;
+            if (!(fc & kFIgnored)) {
+              dst[n++] = curr;
+              if (fc & kFHasAligned) {
+                const uint32_t na = g.nal[curr];
+                for (uint32_t i = 0; i < na; ++i) {
+                  const uint32_t a = g.al[curr * kMaxAligned + i];
+                  if (member_only && !(flags[a] & kFMember)) continue;
+                  dst[n++] = a;
+                }
+              }
+            }
+          } else {
+            flags[curr] = (fc & ~kFMarkMask) | 1;
+          }
+        }
+        if (valid) --sp;
+      }
+    }
+    return n;
+  }
+
+  // ---- graph.cpp:640-666: nodes reachable backwards (in-edges + aligned links) from `from`, ids >= floor
+  template <class IdxT>
+  VGC_HD void extract_impl(uint8_t* flags, const IdxT* in_off, const IdxT* in_tail, uint32_t* stack,
+                           uint32_t from, uint32_t floor_id) {
+    Graph& g = G();
+    uint32_t sp = 0;
+    stack[sp++] = from;
+    while (sp > 0) {
+      const uint32_t curr = stack[--sp];
+      const uint8_t f = flags[curr];
+      if (!(f & kFMember) && curr >= floor_id) {
+        // pushes are bounded by nE + sum(nal) + 1: the stack is the H scratch, which is far larger
+        for (uint32_t i = in_off[curr]; i < in_off[curr + 1]; ++i) stack[sp++] = in_tail[i];
+        if (f & kFHasAligned) {
+          for (uint32_t i = 0; i < g.nal[curr]; ++i) stack[sp++] = g.al[curr * kMaxAligned + i];
+        }
+        flags[curr] = f | kFMember;
+      }
+    }
+  }
+
+  // Topological order of the live graph (or of the Subgraph view begin..end) into dst.
+  // Stages flags + CSR into the executor's fast storage when it fits.
+  VGC_HD uint32_t sort_graph(bool sub, uint32_t sub_begin, uint32_t sub_end, uint32_t* dst) {
+    Graph& g = G();
+    const uint32_t nV = g.nV, nE = g.nE;
+    uint8_t* fl;
+    uint16_t *off16, *tail16, *stk16;
+    uint32_t stk_cap;
+    const bool fast = ex.stage_fast(nV, nE, &fl, &off16, &tail16, &stk16, &stk_cap);
+    if (!fast) fl = sl.flags;
+    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) fl[v] = g.nal[v] ? kFHasAligned : 0;
+    if (fast) {
+      for (uint32_t v = ex.lane(); v <= nV; v += ex.width()) off16[v] = static_cast<uint16_t>(sl.in_off[v]);
+      for (uint32_t e = ex.lane(); e < nE; e += ex.width()) tail16[e] = static_cast<uint16_t>(sl.in_tail[e]);
+    }
+    ex.sync();
+    if (ex.leader()) {
+      uint32_t n = 0;
+      bool ovf = false;
+      if (fast) {
+        if (sub) extract_impl<uint16_t>(fl, off16, tail16, sl.H, sub_end, sub_begin);
+        n = toposort_impl<uint16_t>(fl, off16, tail16, stk16, stk_cap, sub, dst, &ovf);
+        if (ovf) {
+          // deep recursion: redo with the big stack in HBM (flags: clear marks/ignored, keep member)
+          for (uint32_t v = 0; v < nV; ++v) fl[v] &= (kFHasAligned | kFMember);
+          n = toposort_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, 0xFFFFFFFFu, sub, dst, &ovf);
+        }
+      } else {
+        if (sub) extract_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, sub_end, sub_begin);
+        n = toposort_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, 0xFFFFFFFFu, sub, dst, &ovf);
+      }
+      ws.scratch[0] = n;
+    }
+    ex.sync();
+    const uint32_t n = ws.scratch[0];
+    if (sub) {
+      // keep the membership where the row-program builder can see it
+      for (uint32_t v = ex.lane(); v < nV; v += ex.width()) sl.flags[v] = fl[v] & kFMember;
+      ex.sync();
+    }
+    return n;
+  }
+
+  // ---- row program: per rank {node, meta(code, npred, sink), p0, p1}; rows = node + 1, 0 = virtual.
+  //      npred > 2: p1 = offset into ovf[] holding predecessor rows 1..npred-1.
+  VGC_HD void build_rowprog(const uint32_t* order, uint32_t nR, bool sub) {
+    Graph& g = G();
+    if (ex.leader()) {
+      ws.ovf_n = 0;
+      ws.nR = nR;
+    }
+    if (sub) {
+      for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.tmp0[order[r]] = 0;
+      ex.sync();
+      for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
+        const uint32_t v = order[r];
+        for (uint32_t i = sl.in_off[v]; i < sl.in_off[v + 1]; ++i) {
+          const uint32_t t = sl.in_tail[i];
+          if (sl.flags[t] & kFMember) ex.atomic_add(&sl.tmp0[t], 1u);
+        }
+      }
+    }
+    ex.sync();
+    for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
+      const uint32_t v = order[r];
+      sl.rank_of[v] = r;
+      uint32_t np = 0, p0 = 0, p1 = 0;
+      const uint32_t b = sl.in_off[v], e = sl.in_off[v + 1];
+      for (uint32_t i = b; i < e; ++i) {
+        const uint32_t t = sl.in_tail[i];
+        if (sub && !(sl.flags[t] & kFMember)) continue;
+        if (np == 0) p0 = t + 1;
+        if (np == 1) p1 = t + 1;
+        ++np;
+      }
+      if (np > 2) {
+        const uint32_t o = ex.atomic_add(&ws.ovf_n, np - 1);
+        uint32_t k = 0, q = 0;
+        for (uint32_t i = b; i < e; ++i) {
+          const uint32_t t = sl.in_tail[i];
+          if (sub && !(sl.flags[t] & kFMember)) continue;
+          if (q++ > 0) sl.ovf[o + k++] = t + 1;
+        }
+        p1 = o;
+      }
+      const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
+      sl.rowprog[4 * r + 0] = v;
+      sl.rowprog[4 * r + 1] = meta_pack(g.code[v], np, sink);
+      sl.rowprog[4 * r + 2] = p0;
+      sl.rowprog[4 * r + 3] = p1;
+    }
+    ex.sync();
+  }
+
+  VGC_HD VGC_INL uint32_t pred_row(uint32_t r, uint32_t p) const {
+    const uint32_t np = meta_npred(sl.rowprog[4 * r + 1]);
+    if (np == 0) return 0;
+    if (p == 0) return sl.rowprog[4 * r + 2];
+    if (np == 2) return sl.rowprog[4 * r + 3];
+    return sl.ovf[sl.rowprog[4 * r + 3] + p - 1];
+  }
+
+  // ---- traceback (leader).  Priorities as simd_alignment_engine_implementation.hpp:1031-1061 /
+  //      sisd_alignment_engine.cpp:392-448: diagonal over predecessors in inedges order, then vertical
+  //      over predecessors, then horizontal.  Pairs are appended in reverse (end of alignment first).
+  VGC_HD VGC_INL int32_t hval(uint32_t row, uint32_t j, uint32_t mode, int32_t g) const {
+    if (mode == kModeSW) {
+      if (row == 0 || j == 0) return 0;
+    } else {
+      if (row == 0) return static_cast<int32_t>(j) * g;
+      if (j == 0) return sl.fc[row];
+    }
+    return RM::load(sl.H + static_cast<uint64_t>(row) * sl.row_words, j - 1);
+  }
+
+  VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
+    uint32_t n = 0;
+    uint32_t i = ws.best_row, j = ws.best_col;
+    if (i == 0 && j == 0) {
+      ws.aln_len = 0;
+      return;
+    }
+    while (true) {
+      if (mode == kModeSW) {
+        if (hval(i, j, mode, sc.g) == 0) break;
+      } else {
+        if (i == 0 && j == 0) break;
+      }
+      const int32_t h = hval(i, j, mode, sc.g);
+      uint32_t pi = i, pj = j;
+      bool found = false;
+      uint32_t r = 0, np = 0;
+      if (i != 0) {
+        r = sl.rank_of[i - 1];
+        np = meta_npred(sl.rowprog[4 * r + 1]);
+        if (np == 0) np = 1;  // no in-edges: the virtual row 0 is the predecessor
+      }
+      if (i != 0 && j != 0) {
+        const int32_t mc = (meta_code(sl.rowprog[4 * r + 1]) == seq_codes[j - 1]) ? sc.m : sc.x;
+        for (uint32_t p = 0; p < np; ++p) {
+          const uint32_t pr = pred_row(r, p);
+          if (h == hval(pr, j - 1, mode, sc.g) + mc) {
+            pi = pr;
+            pj = j - 1;
+            found = true;
+            break;
+          }
+        }
+      }
+      if (!found && i != 0) {
+        for (uint32_t p = 0; p < np; ++p) {
+          const uint32_t pr = pred_row(r, p);
+          if (h == hval(pr, j, mode, sc.g) + sc.g) {
+            pi = pr;
+            pj = j;
+            found = true;
+            break;
+          }
+        }
+      }
+      if (!found && j != 0 && h == hval(i, j - 1, mode, sc.g) + sc.g) {
+        pi = i;
+        pj = j - 1;
+        found = true;
+      }
+      if (!found || n >= sl.aln_cap) {
+        fail(kStInternal);
+        break;
+      }
+      sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(i - 1);
+      sl.aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+      ++n;
+      i = pi;
+      j = pj;
+    }
+    ws.aln_len = n;
+  }
+
+  // ---- sequence access ----------------------------------------------------------------------------
+  VGC_HD VGC_INL uint32_t weight_at(uint32_t layer, uint32_t pos) const {
+    if (!bv.has_qual[layer]) return 1u;
+    return bv.wlut[bv.quals[bv.seq_off[layer] + pos]];
+  }
+
+  // ---- graph.cpp:88-107 primitives (leader) -------------------------------------------------------
+  VGC_HD uint32_t add_node(Graph& g, uint32_t code) {
+    if (g.nV >= sl.max_nodes) {
+      fail(kStNodeOverflow);
+      return 0;
+    }
+    const uint32_t v = g.nV++;
+    g.code[v] = static_cast<uint8_t>(code);
+    g.nal[v] = 0;
+    g.nin[v] = 0;
+    g.nout[v] = 0;
+    g.cov[v] = 0;
+    return v;
+  }
+
+  // `nV0`: node count when the CSR was built — newer nodes have no CSR row and no older edges.
+  VGC_HD void add_edge(Graph& g, uint32_t tail, uint32_t head, uint32_t w, uint32_t nV0) {
+    if (head < nV0 && tail < nV0) {
+      for (uint32_t i = sl.in_off[head]; i < sl.in_off[head + 1]; ++i) {
+        if (sl.in_tail[i] == tail) {
+          g.ew[sl.in_eid[i]] += w;
+          return;
+        }
+      }
+    }
+    if (g.nE >= sl.max_edges) {
+      fail(kStEdgeOverflow);
+      return;
+    }
+    const uint32_t e = g.nE++;
+    g.etail[e] = tail;
+    g.ehead[e] = head;
+    g.ew[e] = w;
+    g.edead[e] = 0;
+    g.ein_ord[e] = g.nin[head]++;
+    g.eout_ord[e] = g.nout[tail]++;
+  }
+
+  // graph.cpp:109-130
+  VGC_HD uint32_t add_sequence(Graph& g, const uint8_t* codes, uint32_t layer, uint32_t begin, uint32_t end,
+                               uint32_t nV0) {
+    if (begin == end) return kNone;
+    uint32_t prev = kNone, first = kNone;
+    for (uint32_t i = begin; i < end; ++i) {
+      const uint32_t curr = add_node(g, codes[i]);
+      if (ws.status != kStOk) return kNone;
+      g.cov[curr] = ws.scratch[1];
+      if (first == kNone) first = curr;
+      if (prev != kNone) add_edge(g, prev, curr, weight_at(layer, i - 1) + weight_at(layer, i), nV0);
+      prev = curr;
+    }
+    return first;
+  }
+
+  // ---- graph.cpp:182-299 (leader).  The alignment is in aln_* in reverse order. --------------------
+  VGC_HD void add_alignment(const uint8_t* codes, uint32_t layer, uint32_t len) {
+    Graph& g = G();
+    const uint32_t nV0 = g.nV;
+    if (len == 0) return;
+    ws.scratch[1] = len > 1 ? 1u : 0u;  // Node::Coverage counts edge labels: a 1-base sequence has none
+    const uint32_t n = ws.aln_len;
+    if (n == 0) {
+      add_sequence(g, codes, layer, 0, len, nV0);
+      return;
+    }
+    // first / last aligned sequence position
+    uint32_t vfront = kNone, vback = kNone;
+    for (uint32_t t = n; t-- > 0;) {
+      if (sl.aln_pos[t] != -1) {
+        if (vfront == kNone) vfront = sl.aln_pos[t];
+        vback = sl.aln_pos[t];
+      }
+    }
+    if (vfront == kNone) {
+      fail(kStInternal);
+      return;
+    }
+    uint32_t begin = add_sequence(g, codes, layer, 0, vfront, nV0);
+    uint32_t prev = begin != kNone ? g.nV - 1 : kNone;
+    uint32_t last = add_sequence(g, codes, layer, vback + 1, len, nV0);
+    if (ws.status != kStOk) return;
+    for (uint32_t t = n; t-- > 0;) {
+      const int32_t pos = sl.aln_pos[t];
+      if (pos == -1) continue;
+      const int32_t nd = sl.aln_node[t];
+      const uint32_t code = codes[pos];
+      uint32_t curr = kNone;
+      if (nd == -1) {
+        curr = add_node(g, code);
+      } else {
+        const uint32_t jt = static_cast<uint32_t>(nd);
+        if (g.code[jt] == code) {
+          curr = jt;
+        } else {
+          const uint32_t na = g.nal[jt];
+          for (uint32_t i = 0; i < na; ++i) {
+            const uint32_t kt = g.al[jt * kMaxAligned + i];
+            if (g.code[kt] == code) {
+              curr = kt;
+              break;
+            }
+          }
+          if (curr == kNone) {
+            if (na + 1 > static_cast<uint32_t>(kMaxAligned)) {
+              fail(kStAlignedOverflow);
+              return;
+            }
+            curr = add_node(g, code);
+            if (ws.status != kStOk) return;
+            for (uint32_t i = 0; i < na; ++i) {
+              const uint32_t kt = g.al[jt * kMaxAligned + i];
+              g.al[kt * kMaxAligned + g.nal[kt]++] = curr;
+              g.al[curr * kMaxAligned + g.nal[curr]++] = kt;
+            }
+            g.al[jt * kMaxAligned + g.nal[jt]++] = curr;
+            g.al[curr * kMaxAligned + g.nal[curr]++] = jt;
+          }
+        }
+      }
+      if (ws.status != kStOk) return;
+      g.cov[curr] += ws.scratch[1];
+      if (begin == kNone) begin = curr;
+      if (prev != kNone) add_edge(g, prev, curr, weight_at(layer, pos - 1) + weight_at(layer, pos), nV0);
+      prev = curr;
+    }
+    if (last != kNone) add_edge(g, prev, last, weight_at(layer, vback) + weight_at(layer, vback + 1), nV0);
+  }
+
+  // ---- graph.cpp:1104-1165: parallel over alignment entries; weight adds commute --------------------
+  VGC_HD void add_weights(uint32_t layer) {
+    Graph& g = G();
+    const uint32_t n = ws.aln_len;
+    // entry t (reverse order) is preceded in sequence order by entry t + 1
+    for (uint32_t t = ex.lane(); t + 1 < n; t += ex.width()) {
+      const int32_t nd = sl.aln_node[t], pos = sl.aln_pos[t];
+      const int32_t pnd = sl.aln_node[t + 1], ppos = sl.aln_pos[t + 1];
+      if (nd == -1 || pos == -1 || pnd == -1 || ppos == -1) continue;
+      const uint32_t w = weight_at(layer, pos - 1) + weight_at(layer, pos);
+      bool hit = false;
+      for (uint32_t i = sl.in_off[nd]; i < sl.in_off[nd + 1]; ++i) {
+        if (sl.in_tail[i] == static_cast<uint32_t>(pnd)) {
+          ex.atomic_add(&g.ew[sl.in_eid[i]], w);
+          hit = true;
+          break;
+        }
+      }
+      if (!hit) fail(kStInternal);  // consecutive matched pairs always follow an edge of the graph
+    }
+    ex.sync();
+  }
+
+  // ---- graph.cpp:811-982: parallel over edges; fp64 divisions and >= compares exactly as written ----
+  VGC_HD void prune(double min_confidence, double min_support, double average_weight) {
+    Graph& g = G();
+    const uint32_t nV = g.nV, nE = g.nE;
+    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) {
+      sl.tmp0[v] = 0;
+      sl.tmp1[v] = 0;
+    }
+    ex.sync();
+    for (uint32_t e = ex.lane(); e < nE; e += ex.width()) {
+      ex.atomic_add(&sl.tmp0[g.etail[e]], g.ew[e]);  // sum over tail's out-edges
+      ex.atomic_add(&sl.tmp1[g.ehead[e]], g.ew[e]);  // sum over head's in-edges
+    }
+    ex.sync();
+    for (uint32_t e = ex.lane(); e < nE; e += ex.width()) {
+      const double w = static_cast<double>(static_cast<int64_t>(g.ew[e]));
+      const double cuv = w / static_cast<double>(static_cast<int64_t>(sl.tmp0[g.etail[e]]));
+      const double sup = w / average_weight;
+      const double cvu = w / static_cast<double>(static_cast<int64_t>(sl.tmp1[g.ehead[e]]));
+      const bool keep = (cuv >= min_confidence) && (cvu >= min_confidence) && (sup >= min_support);
+      g.edead[e] = keep ? 0 : 1;
+    }
+    ex.sync();
+  }
+
+  // ---- graph.cpp:984-1089 (leader): components by recursive pre-order over [live in-tails, live
+  //      out-heads]; last largest wins; rebuild with DFS-order ids, zero weights, no aligned links ----
+  VGC_HD void largest_subgraph() {
+    build_csr(true);
+    Graph& g = G();
+    Graph& h = sl.g[ws.cur ^ 1];
+    const uint32_t nV = g.nV;
+    uint32_t* comp = sl.tmp0;             // all components back to back
+    uint32_t* newid = sl.tmp1;
+    uint8_t* visited = sl.flags;
+    uint32_t* stk = sl.H;                 // frames: {node, cursor}
+    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) visited[v] = 0;
+    ex.sync();
+    if (ex.leader()) {
+      uint32_t ncomp = 0, best_start = 0, best_size = 0;
+      for (uint32_t v0 = 0; v0 < nV; ++v0) {
+        if (visited[v0]) continue;
+        const uint32_t start = ncomp;
+        uint32_t sp = 0;
+        visited[v0] = 1;
+        comp[ncomp++] = v0;
+        stk[0] = v0;
+        stk[1] = 0;
+        sp = 1;
+        while (sp > 0) {
+          const uint32_t v = stk[2 * (sp - 1)];
+          uint32_t c = stk[2 * (sp - 1) + 1];
+          const uint32_t nin = sl.in_off[v + 1] - sl.in_off[v];
+          const uint32_t nout = sl.out_off[v + 1] - sl.out_off[v];
+          uint32_t next = kNone;
+          while (c < nin + nout) {
+            uint32_t e, u;
+            if (c < nin) {
+              e = sl.in_eid[sl.in_off[v] + c];
+              u = g.etail[e];
+            } else {
+              e = sl.out_eid[sl.out_off[v] + (c - nin)];
+              u = g.ehead[e];
+            }
+            ++c;
+            if (g.edead[e]) continue;
+            if (!visited[u]) {
+              next = u;
+              break;
+            }
+          }
+          stk[2 * (sp - 1) + 1] = c;
+          if (next == kNone) {
+            --sp;
+          } else {
+            visited[next] = 1;
+            comp[ncomp++] = next;
+            stk[2 * sp] = next;
+            stk[2 * sp + 1] = 0;
+            ++sp;
+          }
+        }
+        if (ncomp - start >= best_size) {
+          best_size = ncomp - start;
+          best_start = start;
+        }
+      }
+      // rebuild
+      h.nV = best_size;
+      for (uint32_t i = 0; i < best_size; ++i) {
+        const uint32_t v = comp[best_start + i];
+        newid[v] = i;
+        h.code[i] = g.code[v];
+        h.nal[i] = 0;
+        h.nin[i] = 0;
+        h.nout[i] = 0;
+        h.cov[i] = 0;
+      }
+      uint32_t ne = 0;
+      for (uint32_t i = 0; i < best_size; ++i) {
+        const uint32_t v = comp[best_start + i];
+        for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) {
+          const uint32_t e = sl.out_eid[k];
+          if (g.edead[e]) continue;
+          const uint32_t hd = newid[g.ehead[e]];
+          h.etail[ne] = i;
+          h.ehead[ne] = hd;
+          h.ew[ne] = 0;
+          h.edead[ne] = 0;
+          h.ein_ord[ne] = h.nin[hd]++;
+          h.eout_ord[ne] = h.nout[i]++;
+          ++ne;
+        }
+      }
+      h.nE = ne;
+      ws.cur ^= 1;
+    }
+    ex.sync();
+  }
+
+  // ---- stage a layer: codes into fast storage (returned pointer), profile via the executor ---------
+  VGC_HD void align(uint32_t layer, uint32_t mode, const Scores& sc, const uint32_t* order, uint32_t nR,
+                    bool sub, bool rebuild_rowprog = true) {
+    const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
+    if (rebuild_rowprog) build_rowprog(order, nR, sub);
+    if (ex.leader()) {
+      ws.alignments += 1;
+      ws.cells += static_cast<unsigned long long>(nR + 1) * len;  // (R_a + 1) * L_a of the graph aligned to
+    }
+    uint8_t* codes = ex.seq_codes();
+    for (uint32_t i = ex.lane(); i < len; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[layer] + i]];
+    ex.sync();
+    // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
+    {
+      int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
+      if (-sc.g > a) a = -sc.g;
+      if (static_cast<int64_t>(nR + RM::kCols + 8) * a > 30000) {
+        if (ex.leader()) fail(kStScoreRange);
+        ex.sync();
+        return;
+      }
+    }
+    ex.template fill<K>(sl, ws, codes, len, mode, sc, bv.num_codes);
+    ex.sync();
+    if (ex.leader()) traceback(codes, mode, sc);
+    ex.sync();
+  }
+
+  VGC_HD uint32_t resort_main() {
+    build_csr(false);
+    const uint32_t n = sort_graph(false, 0, 0, sl.r2n);
+    return n;
+  }
+
+  // ---- graph.cpp:534-638 + 450-485 (leader): heaviest bundle consensus + coverage, linear mode ------
+  VGC_HD uint32_t heaviest_bundle(uint32_t nR, uint8_t* out, uint32_t out_cap, uint32_t* cov_out) {
+    Graph& g = G();
+    const uint32_t nV = g.nV;
+    // scores (int64) and predecessors live in the H scratch
+    long long* score = reinterpret_cast<long long*>(sl.H);
+    uint32_t* pred = reinterpret_cast<uint32_t*>(score + nV);
+    uint32_t* n2r = pred + nV;
+    for (uint32_t v = 0; v < nV; ++v) {
+      score[v] = -1;
+      pred[v] = kNone;
+    }
+    for (uint32_t r = 0; r < nR; ++r) n2r[sl.r2n[r]] = r;
+    uint32_t mx = kNone;
+    auto relax = [&](uint32_t it, bool skip_dead_tails) {
+      for (uint32_t i = sl.in_off[it]; i < sl.in_off[it + 1]; ++i) {
+        const uint32_t t = sl.in_tail[i];
+        const long long w = g.ew[sl.in_eid[i]];
+        if (skip_dead_tails && score[t] == -1) continue;
+        if (score[it] < w || (score[it] == w && score[pred[it]] <= score[t])) {
+          score[it] = w;
+          pred[it] = t;
+        }
+      }
+      if (pred[it] != kNone) score[it] += score[pred[it]];
+      if (mx == kNone || score[mx] < score[it]) mx = it;
+    };
+    for (uint32_t r = 0; r < nR; ++r) relax(sl.r2n[r], false);
+    while (g.nout[mx] != 0) {
+      // BranchCompletion (graph.cpp:590-638)
+      const uint32_t start = mx, rank = n2r[mx];
+      for (uint32_t k = sl.out_off[start]; k < sl.out_off[start + 1]; ++k) {
+        const uint32_t hd = g.ehead[sl.out_eid[k]];
+        for (uint32_t i = sl.in_off[hd]; i < sl.in_off[hd + 1]; ++i) {
+          if (sl.in_tail[i] != start) score[sl.in_tail[i]] = -1;
+        }
+      }
+      mx = kNone;
+      for (uint32_t r = rank + 1; r < nR; ++r) {
+        const uint32_t it = sl.r2n[r];
+        score[it] = -1;
+        pred[it] = kNone;
+        relax(it, true);
+      }
+    }
+    // traceback into out (reverse, then flip)
+    uint32_t n = 0;
+    uint32_t* path = n2r + nV;
+    while (true) {
+      path[n++] = mx;
+      if (pred[mx] == kNone) break;
+      mx = pred[mx];
+    }
+    if (n > out_cap) {
+      fail(kStOutOverflow);
+      return 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t v = path[n - 1 - i];
+      out[i] = bv.decoder[g.code[v]];
+      uint32_t c = g.cov[v];
+      for (uint32_t a = 0; a < g.nal[v]; ++a) c += g.cov[g.al[v * kMaxAligned + a]];
+      cov_out[i] = c;
+    }
+    return n;
+  }
+
+  // ---- the window (src/window.cpp:74-174 and :176-428) ---------------------------------------------
+  VGC_HD void run_window(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
+                         uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
+    const uint32_t first = bv.win_first[w];
+    const uint32_t nseq = bv.win_nseq[w];
+    const uint32_t* rank = bv.layer_rank + first;
+    const uint32_t bb = rank[0];
+    const uint32_t blen = static_cast<uint32_t>(bv.seq_off[bb + 1] - bv.seq_off[bb]);
+    const uint32_t offset = static_cast<uint32_t>(0.01 * blen);
+    const uint32_t out_cap = bv.out_cap[w];
+    if (ex.leader()) {
+      ws.cur = 0;
+      ws.status = kStOk;
+      ws.aln_len = 0;
+      ws.cells = 0;
+      ws.alignments = 0;
+      sl.g[0].nV = 0;
+      sl.g[0].nE = 0;
+      *out_len = 0;
+    }
+    ex.sync();
+    // every layer must fit one row of the H matrix
+    for (uint32_t j = 0; j < nseq; ++j) {
+      const uint32_t len = static_cast<uint32_t>(bv.seq_off[rank[j] + 1] - bv.seq_off[rank[j]]);
+      if (len > static_cast<uint32_t>(RM::kCols) || len > sl.max_len) {
+        if (ex.leader()) fail(kStTooLong);
+      }
+    }
+    ex.sync();
+    if (ws.status != kStOk) return;
+
+    // backbone: AddAlignment with an empty alignment (window.cpp:197-201)
+    {
+      uint8_t* codes = ex.seq_codes();
+      for (uint32_t i = ex.lane(); i < blen; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[bb] + i]];
+      ex.sync();
+      if (ex.leader()) {
+        ws.aln_len = 0;
+        add_alignment(codes, bb, blen);
+      }
+      ex.sync();
+      if (ws.status != kStOk) return;
+    }
+    uint32_t nMain = resort_main();
+
+    // build loop (window.cpp:239-298 / :100-136)
+    for (uint32_t j = 1; j < nseq; ++j) {
+      const uint32_t l = rank[j];
+      const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
+      const uint32_t lb = bv.begin[l], le = bv.end[l];
+      if (lb < offset && le > blen - offset) {
+        align(l, kModeNW, nw, sl.r2n, nMain, false);
+      } else {
+        const uint32_t nSub = sort_graph(true, lb, le, sl.order);
+        align(l, kModeNW, nw, sl.order, nSub, true);
+      }
+      if (ws.status != kStOk) return;
+      if (ex.leader()) add_alignment(ex.seq_codes(), l, len);
+      ex.sync();
+      if (ws.status != kStOk) return;
+      nMain = resort_main();
+    }
+
+    if (!haplotype) {
+      // linear mode: consensus + coverage trim (window.cpp:138-171)
+      build_csr(true);
+      if (ex.leader()) {
+        uint32_t* cov = sl.tmp0;
+        uint32_t n = heaviest_bundle(nMain, out, out_cap, cov);
+        if (ws.status == kStOk) {
+          uint32_t b = 0, e = n;
+          if ((bv.win_flags[w] & 1u) && trim) {
+            const uint32_t avg = (nseq - 1) / 2;
+            int32_t bi = 0, ei = static_cast<int32_t>(n) - 1;
+            for (; bi < static_cast<int32_t>(n); ++bi) {
+              if (cov[bi] >= avg) break;
+            }
+            for (; ei >= 0; --ei) {
+              if (cov[ei] >= avg) break;
+            }
+            if (bi < ei) {
+              b = bi;
+              e = ei + 1;
+            }
+          }
+          for (uint32_t i = b; i < e; ++i) out[i - b] = out[i];
+          *out_len = e - b;
+        }
+      }
+      ex.sync();
+      return;
+    }
+
+    // haplotype mode: prune + re-align rounds (window.cpp:300-394)
+    const double avgw = bv.win_avgw[w];
+    prune(min_confidence, min_support, avgw);
+    largest_subgraph();
+    for (uint32_t k = 0; k + 1 < num_prune; ++k) {
+      nMain = resort_main();
+      for (uint32_t j = 0; j < nseq; ++j) {
+        const uint32_t l = rank[j];
+        const uint32_t lb = bv.begin[l], le = bv.end[l];
+        const bool global = (j == 0) || (lb < offset && le > blen - offset);
+        align(l, global ? kModeNW : kModeSW, global ? nw : sw, sl.r2n, nMain, false, j == 0);
+        if (ws.status != kStOk) return;
+        add_weights(l);
+        if (ws.status != kStOk) return;
+      }
+      prune(min_confidence, min_support, avgw);
+      largest_subgraph();
+    }
+    nMain = resort_main();
+    align(bb, kModeSW, sw, sl.r2n, nMain, false);
+    if (ws.status != kStOk) return;
+    // graph.cpp:1167-1179
+    if (ex.leader()) {
+      Graph& g = G();
+      uint32_t n = 0;
+      for (uint32_t t = ws.aln_len; t-- > 0;) {
+        const int32_t nd = sl.aln_node[t];
+        if (nd == -1) continue;
+        if (n >= out_cap) {
+          fail(kStOutOverflow);
+          break;
+        }
+        out[n++] = bv.decoder[g.code[nd]];
+      }
+      *out_len = n;
+    }
+    ex.sync();
+  }
+};
+
+}  // namespace vgc
+
+#endif  // VGC_POA_CORE_H_
