@@ -1,0 +1,280 @@
+// poa_fill.cuh — the sequence-to-DAG DP fill for sm_100a: one warp per alignment, packed int16x2 cells.
+//
+// Replaces SimdAlignmentEngine::Linear's fill (vendor/spoa/src/simd_alignment_engine_implementation.hpp:
+// 760-906, scalar twin sisd_alignment_engine.cpp:292-360) and Initialize (:506-681):
+//   H[i][j] = max over predecessors p of max(H[p][j-1] + s(i,j), H[p][j] + g), then
+//   H[i][j] = max(H[i][j], H[i][j-1] + g)              (a max-plus prefix scan along the row)
+//   SW clamps at 0 and tracks the first row (rank order) / first column of the global maximum;
+//   NW ends at the first sink row with the best last-column score.
+//
+// Mapping.  A row of 64*K cells lives in K 32-bit registers per lane, two cells per register:
+// low half = column lane*K + k, high half = column 32*K + lane*K + k.  Every lane therefore owns two
+// runs of K consecutive columns and the two halves of a register never depend on each other, so the
+// whole recurrence runs on Blackwell's packed DPX integer ops (SASS VIADDMNMX.S16x2, VIMNMX.S16x2,
+// VIADD.16x2): one instruction per two cells.
+//   diagonal   : register k-1 of the predecessor row (lane boundary: one shuffle)
+//   horizontal : in-register running max over the lane's K cells, then a 5-step warp-shuffle max-scan of
+//                (segment end value - g * column) across the 64 segments, then one fused add-max per register
+// Rows are written once to HBM (2 B per cell, coalesced 8-byte stores) because the traceback re-reads
+// them; a predecessor that is the row just computed (the common case along chains) stays in registers.
+#ifndef VGC_POA_FILL_CUH_
+#define VGC_POA_FILL_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "poa_core.h"
+
+namespace vgc {
+
+__device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) {
+  return (static_cast<uint32_t>(lo) & 0xFFFFu) | (static_cast<uint32_t>(hi) << 16);
+}
+__device__ __forceinline__ int32_t lo16(uint32_t w) { return static_cast<int16_t>(w & 0xFFFFu); }
+__device__ __forceinline__ int32_t hi16(uint32_t w) { return static_cast<int16_t>(w >> 16); }
+
+template <int K>
+__device__ __forceinline__ void row_load(const uint32_t* __restrict__ row, int lane, uint32_t (&u)[K]) {
+  const uint2* p = reinterpret_cast<const uint2*>(row) + lane;
+#pragma unroll
+  for (int k = 0; k < K; k += 2) {
+    uint2 t = p[(k >> 1) * 32];
+    u[k] = t.x;
+    u[k + 1] = t.y;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void row_store(uint32_t* __restrict__ row, int lane, const uint32_t (&h)[K]) {
+  uint2* p = reinterpret_cast<uint2*>(row) + lane;
+#pragma unroll
+  for (int k = 0; k < K; k += 2) p[(k >> 1) * 32] = make_uint2(h[k], h[k + 1]);
+}
+
+// prof: shared memory, num_codes * 32*K words; stage: shared memory, 32 uint4.
+template <int K>
+__device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, uint32_t mode,
+                          const Scores sc, uint32_t num_codes, uint32_t* prof, uint4* stage) {
+  static_assert(K % 2 == 0, "K must be even");
+  using RM = RowMap<K>;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nR = ws.nR;
+  const int32_t g = sc.g;
+  const bool sw = mode == kModeSW;
+
+  // ---- query profile (Initialize, simd...:520-530): per code, match/mismatch per column, padding beyond len
+  {
+    int32_t pad = sc.m > -sc.x ? sc.m : -sc.x;
+    if (-g > pad) pad = -g;
+    pad = -pad;
+    for (uint32_t c = 0; c < num_codes; ++c) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const uint32_t cl = lane * K + k, ch = 32 * K + lane * K + k;
+        const int32_t vl = cl < len ? (codes[cl] == c ? sc.m : sc.x) : pad;
+        const int32_t vh = ch < len ? (codes[ch] == c ? sc.m : sc.x) : pad;
+        prof[c * RM::kWords + RM::word(lane, k)] = pack16(vl, vh);
+      }
+    }
+  }
+  // ---- per-lane constants
+  const int32_t c0l = lane * K, c0h = 32 * K + lane * K;
+  const uint32_t g2 = pack16(g, g);
+  const uint32_t voff = pack16(-g * (c0l + K - 1), -g * (c0h + K - 1));
+  const uint32_t gbase = pack16(g * c0l, g * c0h);
+
+  // ---- virtual row 0 (NW: j * g; SW: zeros) and its first column
+  uint32_t hp[K];  // the row computed last (registers)
+#pragma unroll
+  for (int k = 0; k < K; ++k) hp[k] = sw ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
+  row_store<K>(sl.H, lane, hp);
+  if (lane == 0) sl.fc[0] = 0;
+  uint32_t prev_row = 0;
+  int32_t fc_prev = 0;
+
+  // ---- best-cell tracking
+  uint32_t bestv = 0;                 // SW: per-lane packed running max (scores >= 0)
+  uint32_t bestr_lo = 0, bestr_hi = 0;  // rank at which each half first reached it
+  int32_t nw_best = INT32_MIN;
+  uint32_t nw_row = 0;
+  const uint32_t lc = len - 1;
+  const int lastH = lc / (32 * K), lastL = (lc % (32 * K)) / K, lastK = lc % K;
+
+  const uint4* rp = reinterpret_cast<const uint4*>(sl.rowprog);
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (static_cast<uint32_t>(lane) < nR) nxt = rp[lane];
+
+  for (uint32_t r0 = 0; r0 < nR; r0 += 32) {
+    __syncwarp();
+    stage[lane] = nxt;
+    if (r0 + 32 + lane < nR) nxt = rp[r0 + 32 + lane];
+    __syncwarp();
+    const uint32_t rn = nR - r0 < 32 ? nR - r0 : 32;
+    for (uint32_t rr = 0; rr < rn; ++rr) {
+      const uint4 e = stage[rr];
+      const uint32_t v = e.x, meta = e.y;
+      const uint32_t code = meta_code(meta);
+      uint32_t np = meta_npred(meta);
+      uint32_t pr[K];
+      {
+        const uint2* pp = reinterpret_cast<const uint2*>(prof + code * RM::kWords) + lane;
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+          uint2 t = pp[(k >> 1) * 32];
+          pr[k] = t.x;
+          pr[k + 1] = t.y;
+        }
+      }
+      uint32_t h[K];
+      int32_t fcmax = INT32_MIN;
+      const uint32_t npp = np == 0 ? 1 : np;
+      for (uint32_t p = 0; p < npp; ++p) {
+        uint32_t prow;
+        if (np == 0) prow = 0;
+        else if (p == 0) prow = e.z;
+        else if (np == 2) prow = e.w;
+        else prow = sl.ovf[e.w + p - 1];
+        uint32_t u[K];
+        int32_t fcp;
+        if (prow == prev_row) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) u[k] = hp[k];
+          fcp = fc_prev;
+        } else {
+          row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
+          fcp = 0;
+          if (!sw) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
+            if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
+            fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
+          }
+        }
+        fcmax = fcp > fcmax ? fcp : fcmax;
+        // diagonal of this lane's first cells: the previous lane's last cells
+        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, u[K - 1], 1);
+        const uint32_t y = __shfl_sync(0xFFFFFFFFu, u[K - 1], 31);
+        if (lane == 0) x = pack16(fcp, lo16(y));
+        if (p == 0) {
+          h[0] = __viaddmax_s16x2(x, pr[0], __vadd2(u[0], g2));
+#pragma unroll
+          for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k - 1], pr[k], __vadd2(u[k], g2));
+        } else {
+          h[0] = __viaddmax_s16x2(u[0], g2, __viaddmax_s16x2(x, pr[0], h[0]));
+#pragma unroll
+          for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k], g2, __viaddmax_s16x2(u[k - 1], pr[k], h[k]));
+        }
+      }
+      const int32_t fci = sw ? 0 : fcmax + g;
+      // ---- horizontal: in-lane running max, then the cross-lane max-plus scan
+#pragma unroll
+      for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(h[k - 1], g2, h[k]);
+      uint32_t V = __vadd2(h[K - 1], voff);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, V, d);
+        if (lane >= d) V = __vmaxs2(V, t);
+      }
+      const int32_t lowtot = lo16(__shfl_sync(0xFFFFFFFFu, V, 31));
+      const int32_t vfc = fci + g;
+      const uint32_t X = pack16(vfc, vfc > lowtot ? vfc : lowtot);
+      uint32_t E = __shfl_up_sync(0xFFFFFFFFu, V, 1);
+      E = lane == 0 ? X : __vmaxs2(E, X);
+      const uint32_t base = __vadd2(E, gbase);
+      if (sw) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = __viaddmax_s16x2_relu(base, pack16(g * k, g * k), h[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = __viaddmax_s16x2(base, pack16(g * k, g * k), h[k]);
+      }
+      // ---- write the row once
+      row_store<K>(sl.H + static_cast<uint64_t>(v + 1) * sl.row_words, lane, h);
+      if (!sw && lane == 0) sl.fc[v + 1] = static_cast<int16_t>(fci);
+      // ---- best cell
+      if (sw) {
+        uint32_t m = h[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = __vmaxs2(m, h[k]);
+        const uint32_t nb = __vmaxs2(bestv, m);
+        const uint32_t ch = nb ^ bestv;
+        if (ch & 0xFFFFu) bestr_lo = r0 + rr;
+        if (ch >> 16) bestr_hi = r0 + rr;
+        bestv = nb;
+      } else if (meta & kMetaSink) {
+        uint32_t sel = h[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          if (k == lastK) sel = h[k];
+        }
+        const uint32_t s = __shfl_sync(0xFFFFFFFFu, sel, lastL);
+        const int32_t val = lastH ? hi16(s) : lo16(s);
+        if (val > nw_best) {
+          nw_best = val;
+          nw_row = v + 1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) hp[k] = h[k];
+      prev_row = v + 1;
+      fc_prev = fci;
+    }
+  }
+
+  // ---- where the traceback starts
+  if (!sw) {
+    if (lane == 0) {
+      ws.best_row = nw_row;
+      ws.best_col = nw_row ? len : 0;
+      ws.best_score = nw_best;
+    }
+  } else {
+    // global max, then the first row in rank order that reached it, then its first column
+    int32_t mx = lo16(bestv) > hi16(bestv) ? lo16(bestv) : hi16(bestv);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const int32_t o = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
+      mx = o > mx ? o : mx;
+    }
+    uint32_t br = 0xFFFFFFFFu;
+    if (mx > 0) {
+      if (lo16(bestv) == mx) br = bestr_lo;
+      if (hi16(bestv) == mx && bestr_hi < br) br = bestr_hi;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, br, d);
+      br = o < br ? o : br;
+    }
+    uint32_t row = 0, col = 0;
+    if (mx > 0) {
+      row = sl.rowprog[4 * br] + 1;
+      uint32_t u[K];
+      __syncwarp();
+      row_load<K>(sl.H + static_cast<uint64_t>(row) * sl.row_words, lane, u);
+      uint32_t bc = 0xFFFFFFFFu;
+#pragma unroll
+      for (int k = K - 1; k >= 0; --k) {
+        if (hi16(u[k]) == mx) bc = c0h + k;
+      }
+#pragma unroll
+      for (int k = K - 1; k >= 0; --k) {
+        if (lo16(u[k]) == mx) bc = c0l + k;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, bc, d);
+        bc = o < bc ? o : bc;
+      }
+      col = bc + 1;
+    }
+    if (lane == 0) {
+      ws.best_row = row;
+      ws.best_col = col;
+      ws.best_score = mx;
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace vgc
+
+#endif  // VGC_POA_FILL_CUH_

@@ -1,0 +1,612 @@
+// vgc_engine.cu — C-ABI (include/vgc.h) + the persistent sm_100a POA kernel.
+//
+// One window per CTA, one warp per CTA (32 lanes): the DP rows are register-resident across the warp
+// (poa_fill.cuh), the graph lives in a per-CTA scratch slot in HBM with its sort-time working set staged in
+// shared memory, and the window algorithm itself is the template of poa_core.h.  CTAs are persistent: the
+// grid is (#SMs x resident CTAs per SM) and each CTA pulls windows, heaviest first, from an atomic cursor.
+//
+// Replaces Polisher::polish's per-window lambda (reference src/polisher.cpp:498-516) for a whole batch.
+// No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_prep.h"
+#include "poa_core.h"
+#include "poa_fill.cuh"
+#include "vgc.h"
+
+namespace vgc {
+
+constexpr int kSmemHeader = 768;  // Slot + WinState copies
+
+struct KernelArgs {
+  BatchView bv;
+  const uint32_t* work;    // window ids to process
+  uint32_t n_work;
+  uint32_t* cursor;        // atomic work cursor
+  const Slot* slots;       // one per CTA
+  uint8_t* out;            // output bytes (bv.out_off / out_cap index into it)
+  uint32_t* out_len;       // [n_windows]
+  uint32_t* status;        // [n_windows]
+  unsigned long long* totals;  // [2]: cells, alignments
+  Scores nw;
+  uint32_t haplotype, trim, num_prune;
+  double min_confidence, min_support;
+  uint32_t smem_bytes;     // dynamic shared memory per CTA
+};
+
+// Warp executor: the device side of poa_core.h's `Ex` concept.
+template <int K>
+struct WarpEx {
+  uint8_t* sm;        // shared memory after the header
+  uint32_t sm_bytes;
+  uint32_t max_len;
+  int lane_;
+
+  __device__ __forceinline__ int lane() const { return lane_; }
+  __device__ __forceinline__ int width() const { return 32; }
+  __device__ __forceinline__ bool leader() const { return lane_ == 0; }
+  __device__ __forceinline__ void sync() { __syncwarp(); }
+  __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+  __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane_ >= d) x += t;
+    }
+    *total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    return x - v;
+  }
+  // sort-time working set in shared memory: flags[nV] | off16[nV+1] | tail16[nE] | stack16[>=256]
+  __device__ bool stage_fast(uint32_t nV, uint32_t nE, uint8_t** f, uint16_t** o, uint16_t** t, uint16_t** s,
+                             uint32_t* cap) {
+    if (nV >= 65535u || nE >= 65535u) return false;
+    const uint32_t fo = 0;
+    const uint32_t oo = (nV + 3u) & ~3u;
+    const uint32_t to = oo + (((nV + 1u) * 2u + 3u) & ~3u);
+    const uint32_t so = to + ((nE * 2u + 3u) & ~3u);
+    if (so + 512u > sm_bytes) return false;
+    *f = sm + fo;
+    *o = reinterpret_cast<uint16_t*>(sm + oo);
+    *t = reinterpret_cast<uint16_t*>(sm + to);
+    *s = reinterpret_cast<uint16_t*>(sm + so);
+    *cap = (sm_bytes - so) / 2u;
+    return true;
+  }
+  // alignment-time layout: codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words]
+  __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
+  __device__ __forceinline__ uint4* stage() { return reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u)); }
+  __device__ __forceinline__ uint32_t* prof() { return reinterpret_cast<uint32_t*>(stage() + 32); }
+
+  template <int KK>
+  __device__ __forceinline__ void fill(Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, uint32_t mode,
+                                       const Scores& sc, uint32_t num_codes) {
+    warp_fill<KK>(sl, ws, codes, len, mode, sc, num_codes, prof(), stage());
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  Slot* sl = reinterpret_cast<Slot*>(smem);
+  WinState* ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
+  const int lane = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.slots + blockIdx.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sl);
+    for (uint32_t i = lane; i < sizeof(Slot) / 4; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  WarpEx<K> ex;
+  ex.sm = smem + kSmemHeader;
+  ex.sm_bytes = a.smem_bytes - kSmemHeader;
+  ex.max_len = sl->max_len;
+  ex.lane_ = lane;
+  Poa<WarpEx<K>, K> poa(ex, a.bv, *sl, *ws, a.nw);
+  while (true) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(a.cursor, 1u);
+    idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+    if (idx >= a.n_work) break;
+    const uint32_t w = a.work[idx];
+    poa.run_window(w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
+                   a.out + a.bv.out_off[w], a.out_len + w);
+    __syncwarp();
+    if (lane == 0) {
+      a.status[w] = ws->status;
+      atomicAdd(a.totals, ws->cells);
+      atomicAdd(a.totals + 1, static_cast<unsigned long long>(ws->alignments));
+    }
+    __syncwarp();
+  }
+}
+
+static_assert(sizeof(Slot) + sizeof(WinState) + 32 <= kSmemHeader, "shared-memory header too small");
+
+}  // namespace vgc
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+namespace {
+
+thread_local std::string g_err;
+
+void set_err(const std::string& s) { g_err = s; }
+
+#define VGC_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      set_err(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);          \
+      return VGC_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return VGC_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_err(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+      return VGC_ERR_NOMEM;
+    }
+    cap = want;
+    return VGC_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct vgc_engine {
+  int device = 0;
+  vgc_params params;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int sm_count = 0;
+  int ctas_per_sm = 16;
+  uint32_t smem_bytes = 0;
+  size_t mem_budget = 0;
+  // device copies of the batch
+  DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
+  DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
+  DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem;
+  // host staging (pinned)
+  uint8_t* h_out = nullptr;
+  size_t h_out_cap = 0;
+  uint32_t* h_out_len = nullptr;
+  uint32_t* h_status = nullptr;
+  size_t h_win_cap = 0;
+  // resident batch (vgc_upload)
+  bool resident = false;
+  vgc::Prepared prep;
+  std::vector<uint8_t> backbone_copy;  // backbones of < 3-sequence windows (resident mode)
+  std::vector<uint64_t> r_seq_off;
+  std::vector<uint32_t> r_win_first;
+  uint32_t r_n_windows = 0, r_n_layers = 0;
+  uint64_t r_input_bytes = 0;
+};
+
+namespace {
+
+using namespace vgc;
+
+int upload(vgc_engine* h, const vgc_batch* b, uint64_t* bytes_out) {
+  const uint32_t nw = b->n_windows, nl = b->n_layers;
+  const uint64_t nb = nl ? b->seq_off[nl] : 0;
+  Prepared& pr = h->prep;
+  uint64_t bytes = 0;
+  auto put = [&](DevBuf& d, const void* src, size_t n) -> int {
+    int rc = d.reserve(std::max<size_t>(n, 16));
+    if (rc != VGC_OK) return rc;
+    if (n) {
+      cudaError_t e = cudaMemcpyAsync(d.p, src, n, cudaMemcpyHostToDevice, h->stream);
+      if (e != cudaSuccess) {
+        set_err(std::string("H2D copy failed: ") + cudaGetErrorString(e));
+        return VGC_ERR_CUDA;
+      }
+    }
+    bytes += n;
+    return VGC_OK;
+  };
+  int rc;
+  if ((rc = put(h->d_bases, b->bases, nb))) return rc;
+  if ((rc = put(h->d_quals, b->quals, b->quals ? nb : 0))) return rc;
+  if ((rc = put(h->d_seq_off, b->seq_off, (nl + 1) * sizeof(uint64_t)))) return rc;
+  if ((rc = put(h->d_has_qual, b->has_qual, nl))) return rc;
+  if ((rc = put(h->d_begin, b->begin, nl * 4ull))) return rc;
+  if ((rc = put(h->d_end, b->end, nl * 4ull))) return rc;
+  if ((rc = put(h->d_win_first, b->win_first, (nw + 1) * 4ull))) return rc;
+  if ((rc = put(h->d_win_flags, b->win_flags, nw))) return rc;
+  if ((rc = put(h->d_rank, pr.layer_rank.data(), nl * 4ull))) return rc;
+  if ((rc = put(h->d_nseq, pr.win_nseq.data(), nw * 4ull))) return rc;
+  if ((rc = put(h->d_avgw, pr.win_avgw.data(), nw * 8ull))) return rc;
+  if ((rc = put(h->d_out_off, pr.out_off.data(), nw * 8ull))) return rc;
+  if ((rc = put(h->d_out_cap, pr.out_cap.data(), nw * 4ull))) return rc;
+  // tables: coder[256] | decoder[8] | pad | wlut[256]
+  std::vector<uint8_t> tab(256 + 16 + 1024);
+  std::memcpy(tab.data(), pr.coder, 256);
+  std::memcpy(tab.data() + 256, pr.decoder, kMaxCodes);
+  std::memcpy(tab.data() + 272, pr.wlut, 1024);
+  if ((rc = put(h->d_tables, tab.data(), tab.size()))) return rc;
+  if ((rc = put(h->d_work, pr.device_windows.data(), pr.device_windows.size() * 4ull))) return rc;
+  cudaError_t e = cudaStreamSynchronize(h->stream);  // `tab` and prep vectors must outlive the copies
+  if (e != cudaSuccess) {
+    set_err(std::string("H2D sync failed: ") + cudaGetErrorString(e));
+    return VGC_ERR_CUDA;
+  }
+  *bytes_out = bytes;
+  return VGC_OK;
+}
+
+BatchView make_view(vgc_engine* h) {
+  BatchView v;
+  v.bases = h->d_bases.as<uint8_t>();
+  v.quals = h->d_quals.as<uint8_t>();
+  v.seq_off = h->d_seq_off.as<uint64_t>();
+  v.has_qual = h->d_has_qual.as<uint8_t>();
+  v.begin = h->d_begin.as<uint32_t>();
+  v.end = h->d_end.as<uint32_t>();
+  v.win_first = h->d_win_first.as<uint32_t>();
+  v.win_flags = h->d_win_flags.as<uint8_t>();
+  v.layer_rank = h->d_rank.as<uint32_t>();
+  v.win_nseq = h->d_nseq.as<uint32_t>();
+  v.win_avgw = h->d_avgw.as<double>();
+  v.out_off = h->d_out_off.as<uint64_t>();
+  v.out_cap = h->d_out_cap.as<uint32_t>();
+  v.coder = h->d_tables.as<uint8_t>();
+  v.decoder = h->d_tables.as<uint8_t>() + 256;
+  v.wlut = reinterpret_cast<const uint32_t*>(h->d_tables.as<uint8_t>() + 272);
+  v.num_codes = h->prep.num_codes;
+  return v;
+}
+
+template <int K>
+int launch_k(vgc_engine* h, const KernelArgs& a, uint32_t grid) {
+  VGC_CUDA(cudaFuncSetAttribute(poa_window_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  VGC_CUDA(cudaFuncSetAttribute(poa_window_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(a.smem_bytes)));
+  poa_window_kernel<K><<<grid, 32, a.smem_bytes, h->stream>>>(a);
+  VGC_CUDA(cudaGetLastError());
+  return VGC_OK;
+}
+
+// Run the kernel over `work` (device array of window ids) with slots of the given dimensions.
+int run_pass(vgc_engine* h, uint32_t n_work, const uint32_t* d_work, uint32_t max_nodes, uint32_t max_len,
+             int K, uint32_t* launches) {
+  SlotDims d;
+  d.max_nodes = std::max<uint32_t>(max_nodes, 64);
+  d.max_edges = d.max_nodes;
+  d.max_len = std::max<uint32_t>(max_len, 16);
+  d.row_words = 32 * K;
+  const uint64_t per_slot = slot_bytes(d);
+  uint32_t grid = std::min<uint32_t>(n_work, h->sm_count * h->ctas_per_sm);
+  if (per_slot * grid > h->mem_budget) grid = static_cast<uint32_t>(h->mem_budget / per_slot);
+  if (grid == 0) {
+    set_err("a window needs more scratch than the device memory budget");
+    return VGC_ERR_CAPACITY;
+  }
+  int rc;
+  if ((rc = h->d_slot_mem.reserve(per_slot * grid))) return rc;
+  if ((rc = h->d_slots.reserve(sizeof(Slot) * grid))) return rc;
+  std::vector<Slot> slots(grid);
+  for (uint32_t i = 0; i < grid; ++i) slot_carve(d, h->d_slot_mem.as<uint8_t>() + per_slot * i, &slots[i]);
+  VGC_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), sizeof(Slot) * grid, cudaMemcpyHostToDevice, h->stream));
+  VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
+  KernelArgs a;
+  a.bv = make_view(h);
+  a.work = d_work;
+  a.n_work = n_work;
+  a.cursor = h->d_misc.as<uint32_t>();
+  a.slots = h->d_slots.as<Slot>();
+  a.out = h->d_out.as<uint8_t>();
+  a.out_len = h->d_out_len.as<uint32_t>();
+  a.status = h->d_status.as<uint32_t>();
+  a.totals = reinterpret_cast<unsigned long long*>(h->d_misc.as<uint8_t>() + 16);
+  a.nw.m = h->params.match;
+  a.nw.x = h->params.mismatch;
+  a.nw.g = h->params.gap;
+  a.haplotype = h->params.haplotype;
+  a.trim = h->params.trim;
+  a.num_prune = h->params.num_prune;
+  a.min_confidence = h->params.min_confidence;
+  a.min_support = h->params.min_support;
+  a.smem_bytes = h->smem_bytes;
+  if (K == 10) rc = launch_k<10>(h, a, grid);
+  else rc = launch_k<16>(h, a, grid);
+  if (rc != VGC_OK) return rc;
+  VGC_CUDA(cudaStreamSynchronize(h->stream));  // `slots` must outlive its copy; also surfaces kernel faults
+  ++*launches;
+  return VGC_OK;
+}
+
+int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t input_bytes,
+                  const uint8_t* host_bases, const uint64_t* seq_off, const uint32_t* win_first, uint32_t nw) {
+  Prepared& pr = h->prep;
+  int rc;
+  if ((rc = h->d_out.reserve(std::max<uint64_t>(pr.out_total, 16)))) return rc;
+  if ((rc = h->d_out_len.reserve(std::max<size_t>(nw, 4) * 4))) return rc;
+  if ((rc = h->d_status.reserve(std::max<size_t>(nw, 4) * 4))) return rc;
+  if ((rc = h->d_misc.reserve(256))) return rc;
+  if (h->h_win_cap < nw) {
+    if (h->h_out_len) cudaFreeHost(h->h_out_len);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    h->h_win_cap = nw + nw / 4 + 16;
+    VGC_CUDA(cudaMallocHost(&h->h_out_len, h->h_win_cap * 4));
+    VGC_CUDA(cudaMallocHost(&h->h_status, h->h_win_cap * 4));
+  }
+  if (h->h_out_cap < pr.out_total) {
+    if (h->h_out) cudaFreeHost(h->h_out);
+    h->h_out_cap = pr.out_total + pr.out_total / 4 + 256;
+    VGC_CUDA(cudaMallocHost(&h->h_out, h->h_out_cap));
+  }
+  const uint32_t n_dev = static_cast<uint32_t>(pr.device_windows.size());
+  uint32_t launches = 0, relaunched = 0;
+  unsigned long long totals[2] = {0, 0};
+  float kernel_ms = 0.f, d2h_ms = 0.f;
+  VGC_CUDA(cudaMemsetAsync(h->d_out_len.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
+  VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
+  if (n_dev) {
+    const int K = pr.max_len <= 640 ? 10 : 16;
+    if (pr.max_len > 1024) {
+      set_err("layer longer than 1024 bases: beyond the engine's row capacity");
+      return VGC_ERR_CAPACITY;
+    }
+    // first pass: slot sized for the largest node upper bound, capped by the memory budget
+    SlotDims probe;
+    probe.max_edges = probe.max_nodes = 1024;
+    probe.max_len = pr.max_len;
+    probe.row_words = 32 * K;
+    const uint64_t per_1k = slot_bytes(probe);
+    const uint32_t want_grid = std::min<uint32_t>(n_dev, h->sm_count * h->ctas_per_sm);
+    uint64_t cap_nodes = h->mem_budget / want_grid / per_1k * 1024;
+    uint32_t max_nodes = static_cast<uint32_t>(std::min<uint64_t>(pr.max_nodes_ub, std::max<uint64_t>(cap_nodes, 2048)));
+    VGC_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = run_pass(h, n_dev, h->d_work.as<uint32_t>(), max_nodes, pr.max_len, K, &launches))) return rc;
+    VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
+    VGC_CUDA(cudaStreamSynchronize(h->stream));
+    // second pass for windows whose graph outgrew the slot
+    std::vector<uint32_t> retry;
+    for (uint32_t w : pr.device_windows) {
+      if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow) retry.push_back(w);
+    }
+    if (!retry.empty() && max_nodes < pr.max_nodes_ub) {
+      relaunched = static_cast<uint32_t>(retry.size());
+      VGC_CUDA(cudaMemcpyAsync(h->d_work.p, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      if ((rc = run_pass(h, relaunched, h->d_work.as<uint32_t>(), static_cast<uint32_t>(pr.max_nodes_ub),
+                         pr.max_len, K, &launches)))
+        return rc;
+      VGC_CUDA(cudaMemcpyAsync(h->d_work.p, pr.device_windows.data(), n_dev * 4ull, cudaMemcpyHostToDevice,
+                               h->stream));
+    }
+    VGC_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  }
+  VGC_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
+  VGC_CUDA(cudaMemcpyAsync(h->h_out_len, h->d_out_len.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
+  if (result && pr.out_total) {
+    VGC_CUDA(cudaMemcpyAsync(h->h_out, h->d_out.p, pr.out_total, cudaMemcpyDeviceToHost, h->stream));
+  }
+  VGC_CUDA(cudaMemcpyAsync(totals, h->d_misc.as<uint8_t>() + 16, 16, cudaMemcpyDeviceToHost, h->stream));
+  VGC_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  VGC_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_dev) VGC_CUDA(cudaEventElapsedTime(&kernel_ms, h->ev[0], h->ev[1]));
+  VGC_CUDA(cudaEventElapsedTime(&d2h_ms, h->ev[2], h->ev[3]));
+  // status check: anything but OK is an engine limit (there is no CPU fallback)
+  for (uint32_t w : pr.device_windows) {
+    if (h->h_status[w] != kStOk) {
+      char msg[160];
+      std::snprintf(msg, sizeof(msg), "window %u failed on the device with status %u (see poa_core.h kSt*)", w,
+                    h->h_status[w]);
+      set_err(msg);
+      return h->h_status[w] == kStInternal ? VGC_ERR_CUDA : VGC_ERR_CAPACITY;
+    }
+  }
+  if (result) {
+    // stitch: windows in order; < 3 sequences -> backbone, polished = false (window.cpp:188-192)
+    uint64_t off = 0;
+    for (uint32_t w = 0; w < nw; ++w) {
+      result->cons_off[w] = off;
+      uint32_t n;
+      const uint8_t* src;
+      if (pr.win_nseq[w] < 3) {
+        const uint32_t f = win_first[w];
+        n = static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]);
+        src = host_bases + seq_off[f];
+        result->polished[w] = 0;
+      } else {
+        n = h->h_out_len[w];
+        src = h->h_out + pr.out_off[w];
+        result->polished[w] = 1;
+      }
+      if (off + n > result->cons_capacity) {
+        set_err("vgc_result.cons too small (use vgc_result_bound)");
+        return VGC_ERR_INVALID;
+      }
+      std::memcpy(result->cons + off, src, n);
+      off += n;
+    }
+    result->cons_off[nw] = off;
+  }
+  if (stats) {
+    stats->cells = totals[0];
+    stats->alignments = totals[1];
+    stats->input_bytes = input_bytes;
+    stats->output_bytes = (result ? pr.out_total : 0) + nw * 8ull + 16;
+    stats->kernel_ms = kernel_ms;
+    stats->d2h_ms = d2h_ms;
+    stats->kernel_launches = launches;
+    stats->relaunched_windows = relaunched;
+  }
+  return VGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vgc_last_error(void) { return g_err.c_str(); }
+const char* vgc_version(void) { return "vechat_b200 0.1 (sm_100a)"; }
+
+void vgc_weight_lut(uint32_t lut[256]) { vgc::weight_lut(lut); }
+
+int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
+  if (!out || !params) {
+    set_err("null argument");
+    return VGC_ERR_INVALID;
+  }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    set_err(std::string("no usable CUDA device (the engine has no CPU fallback): ") +
+            (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range"));
+    cudaGetLastError();
+    return VGC_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  VGC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_err("device is not sm_100-class (Blackwell); this library carries sm_100a code only");
+    return VGC_ERR_NO_DEVICE;
+  }
+  VGC_CUDA(cudaSetDevice(device));
+  auto* h = new vgc_engine();
+  h->device = device;
+  h->params = *params;
+  h->sm_count = prop.multiProcessorCount;
+  VGC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) VGC_CUDA(cudaEventCreate(&ev));
+  // 16 one-warp CTAs per SM: (228 KB - 16 x 1 KB reserved) / 16
+  h->ctas_per_sm = 16;
+  h->smem_bytes = 13568;
+  if (const char* s = std::getenv("VGC_CTAS_PER_SM")) {
+    int c = std::atoi(s);
+    if (c >= 1 && c <= 32) {
+      h->ctas_per_sm = c;
+      h->smem_bytes = std::min<uint32_t>(((228 * 1024 - c * 1024) / c) & ~255u, 200 * 1024);
+    }
+  }
+  size_t free_b = 0, total_b = 0;
+  VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  h->mem_budget = static_cast<size_t>(free_b * 0.70);
+  if (const char* s = std::getenv("VGC_MEM_BUDGET_MB")) h->mem_budget = static_cast<size_t>(std::atoll(s)) << 20;
+  *out = h;
+  return VGC_OK;
+}
+
+int vgc_destroy(vgc_handle h) {
+  if (!h) return VGC_OK;
+  cudaSetDevice(h->device);
+  for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
+                    &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
+                    &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
+                    &h->d_misc, &h->d_slots, &h->d_slot_mem})
+    d->release();
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_out_len) cudaFreeHost(h->h_out_len);
+  if (h->h_status) cudaFreeHost(h->h_status);
+  for (auto& ev : h->ev) {
+    if (ev) cudaEventDestroy(ev);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VGC_OK;
+}
+
+uint64_t vgc_result_bound(const vgc_batch* batch) {
+  if (!batch || !batch->seq_off) return 0;
+  return batch->seq_off[batch->n_layers] + 16;
+}
+
+int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_stats* stats) {
+  if (!h || !batch || !result) {
+    set_err("null argument");
+    return VGC_ERR_INVALID;
+  }
+  VGC_CUDA(cudaSetDevice(h->device));
+  h->resident = false;
+  std::string err;
+  int rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
+  if (rc != VGC_OK) {
+    set_err(err);
+    return rc;
+  }
+  uint64_t in_bytes = 0;
+  float h2d_ms = 0.f;
+  VGC_CUDA(cudaEventRecord(h->ev[4], h->stream));
+  if ((rc = upload(h, batch, &in_bytes))) return rc;
+  VGC_CUDA(cudaEventRecord(h->ev[5], h->stream));
+  rc = polish_device(h, result, stats, in_bytes, batch->bases, batch->seq_off, batch->win_first, batch->n_windows);
+  if (rc != VGC_OK) return rc;
+  if (stats) {
+    VGC_CUDA(cudaEventElapsedTime(&h2d_ms, h->ev[4], h->ev[5]));
+    stats->h2d_ms = h2d_ms;
+  }
+  return VGC_OK;
+}
+
+int vgc_upload(vgc_handle h, const vgc_batch* batch) {
+  if (!h || !batch) {
+    set_err("null argument");
+    return VGC_ERR_INVALID;
+  }
+  VGC_CUDA(cudaSetDevice(h->device));
+  h->resident = false;
+  std::string err;
+  int rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
+  if (rc != VGC_OK) {
+    set_err(err);
+    return rc;
+  }
+  if ((rc = upload(h, batch, &h->r_input_bytes))) return rc;
+  // keep what the stitcher needs from the host batch
+  h->r_n_windows = batch->n_windows;
+  h->r_n_layers = batch->n_layers;
+  h->r_seq_off.assign(batch->seq_off, batch->seq_off + batch->n_layers + 1);
+  h->r_win_first.assign(batch->win_first, batch->win_first + batch->n_windows + 1);
+  h->backbone_copy.assign(batch->bases, batch->bases + (batch->n_layers ? batch->seq_off[batch->n_layers] : 0));
+  h->resident = true;
+  return VGC_OK;
+}
+
+int vgc_polish_resident(vgc_handle h, vgc_result* result, vgc_stats* stats) {
+  if (!h || !h->resident) {
+    set_err("no resident batch: call vgc_upload first");
+    return VGC_ERR_INVALID;
+  }
+  VGC_CUDA(cudaSetDevice(h->device));
+  int rc = polish_device(h, result, stats, 0, h->backbone_copy.data(), h->r_seq_off.data(), h->r_win_first.data(),
+                         h->r_n_windows);
+  if (rc == VGC_OK && stats) stats->h2d_ms = 0.0;
+  return rc;
+}
+
+}  // extern "C"
