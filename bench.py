@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — the POA window-correction path on BASELINE.json's config[1] workload.
+
+  python bench.py [--gpus N --steps K --warmup W]                      our arm (CUDA engine through the C-ABI)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   one rank per GPU, weak scaling
+  python bench.py --impl reference [--steps K --warmup W]              the reference's own CPU path (oracle/_ref)
+
+Workload ("step" = one pass of the hot path over one batch): synthetic PacBio CLR of SURVEY.md §8(d) config 2
+(10k reads x 10 kb over a 3.33 Mb genome, 15 % error 9:4.5:1.5, Q~N(12,2), ground-truth overlaps, 500 bp
+windows, m=3 x=-5 g=-4 -p -d 0.2 -s 0.2 -k 3).  One batch = all windows of `--targets` consecutive target reads
+(default 400 reads = 8000 windows, depth ~30) per GPU; rank r takes targets [r*T, (r+1)*T) (weak scaling, no
+data-path collective; the gather of corrected reads to rank 0 is part of the e2e leg).
+
+Legs of our arm:
+  value : windows/s with the batch already resident in HBM (vgc_upload once; each timed step = kernels + D2H of
+          the corrected windows), timed on the device with CUDA events on the engine's launch stream, max over ranks
+  e2e   : windows/s through the public call (vechat_b200.polisher.Polisher -> vgc_polish): pinned HOST buffers in,
+          host buffers out; host prep + H2D + kernels + D2H + stitch (+ NCCL gather at N > 1) inside the timed region
+  roofline / cpu_baseline: see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "pb_clr_10k_x_10kb"
+METRIC = "poa_windows_per_sec"
+UNIT = "windows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--targets", type=int, default=400, help="target reads per GPU per step (20 windows each)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "%s: synthetic PacBio CLR 10k reads x 10 kb, 15%% error, 500 bp windows, haplotype mode "
+                        "(-p -d 0.2 -s 0.2 -k 3, m=3 x=-5 g=-4); batch = all windows of %d target reads per GPU "
+                        "per step" % (WORKLOAD, args.targets),
+            "targets_per_gpu": args.targets, "window_length": 500, "ranks": world,
+            "sharding": "whole target reads per rank, no data-path collective; gather of corrected reads in e2e",
+            "l2": "inputs per step (~240 MB) and DP scratch (GBs) exceed the 126 MB L2; no explicit flush"}
+
+
+def make_batch(args, rank):
+    from vechat_b200.sim import Simulator
+    sim = Simulator(WORKLOAD)
+    b = sim.windows(rank * args.targets, (rank + 1) * args.targets)
+    return sim, b
+
+
+def pin_batch(batch):
+    """Re-home the batch arrays in pinned host memory (the e2e leg copies from pinned memory)."""
+    import torch
+    from vechat_b200._ffi import WindowBatch
+    keep = []
+
+    def pin(a):
+        t = torch.empty(max(a.nbytes, 8), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.nbytes].view(a.dtype)
+        v[...] = a
+        keep.append(t)
+        return v
+
+    nb = WindowBatch(pin(batch.bases), pin(batch.quals), pin(batch.seq_off), pin(batch.has_qual), pin(batch.begin),
+                     pin(batch.end), pin(batch.win_first), pin(batch.win_flags))
+    for attr in ("win_target", "win_rank", "target_coverage"):
+        setattr(nb, attr, getattr(batch, attr))
+    nb._pinned = keep
+    return nb
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def cpu_leg(batch, params, seconds, threads=None):
+    """The reference's CPU path (oracle/_ref if it travelled, else the oracle port) on a bounded sample of the
+    same batch: every k-th window, sized by a pilot so the run takes about `seconds`."""
+    from oracle import checker
+    kind = "reference" if checker.have_ref() else "port"
+    fn = checker.ref_polish if kind == "reference" else checker.oracle_polish
+    cores = threads or os.cpu_count() or 1
+    nw = batch.n_windows
+    pilot_idx = np.linspace(0, nw - 1, num=min(nw, 2 * cores)).astype(int)
+    pb = batch.select(pilot_idx)
+    t0 = time.perf_counter()
+    fn(pb, params, threads=cores)
+    rate = len(pilot_idx) / max(time.perf_counter() - t0, 1e-6)
+    n = int(max(cores, min(nw, rate * seconds)))
+    idx = np.linspace(0, nw - 1, num=n).astype(int)
+    sb = batch.select(idx)
+    return kind, cores, sb, fn
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from vechat_b200._ffi import make_params
+    _, batch = make_batch(args, 0)
+    params = make_params()
+    # sample sized so that (warmup + steps) passes stay within a few minutes
+    per_step = max(2.0, min(10.0, 150.0 / max(1, args.steps + args.warmup)))
+    kind, cores, sb, fn = cpu_leg(batch, params, per_step)
+    bases = 0
+    for _ in range(args.warmup):
+        fn(sb, params, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = fn(sb, params, threads=cores)
+        bases += r.total_bases()
+    dt = time.perf_counter() - t0
+    value = sb.n_windows * args.steps / dt
+    sample = "%d of the batch's %d windows (every k-th), %d host threads, %s" % (
+        sb.n_windows, batch.n_windows, cores,
+        "unmodified reference window.cpp + spoa compiled -O3 -msse4.1" if kind == "reference" else "oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": workload_config(args, 1), "corrected_bases_per_sec": bases / dt,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from vechat_b200._ffi import make_params
+    from vechat_b200.engine import Engine
+    from vechat_b200.polisher import Polisher, stitch, _gather_records
+
+    sim, batch = make_batch(args, rank)
+    batch = pin_batch(batch)
+    params = make_params()
+    eng = Engine(local)
+    pol = Polisher(local, rank=rank, world=world, engine=eng)
+    dev = torch.device("cuda", local)
+    names = lambda t: "read%d" % t  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_step():
+        result = pol.polish_shard(batch)
+        recs = stitch(result, batch.win_target, batch.win_rank, names, batch.target_coverage)
+        if world > 1:
+            recs, _ = _gather_records(recs, rank, world, None, dev)
+        return result, recs, pol.last_stats
+
+    # ---- warm-up (both legs) ----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        e2e_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- e2e leg: host buffers through the public call ---------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stats = []
+    for _ in range(args.steps):
+        result, recs, st = e2e_step()
+        e2e_stats.append(st)
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    corrected = result.total_bases()
+
+    # ---- resident leg: inputs already in HBM; device-event timing ------------------------------------
+    eng.upload(batch)
+    for _ in range(args.warmup):
+        eng.polish_resident()
+    barrier()
+    t0 = time.perf_counter()
+    res_stats = []
+    for _ in range(args.steps):
+        _, st = eng.polish_resident()
+        res_stats.append(st)
+    barrier()
+    res_wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    dev_ms = sum(s["device_ms"] for s in res_stats)
+    kern_ms = sum(s["kernel_ms"] for s in res_stats)
+    launches = sum(s["kernel_launches"] for s in res_stats) + sum(s["kernel_launches"] for s in e2e_stats)
+    cells = res_stats[-1]["cells"]
+    agg = torch.tensor([dev_ms, e2e_dt * 1e3, res_wall * 1e3, kern_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([batch.n_windows, corrected, launches, cells], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, res_wall_max, kern_ms_max = [float(x) for x in agg.tolist()]
+    n_windows, n_bases, n_launch, n_cells = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # roofline of the dominant (only) kernel: algorithmic bytes = 2 B x sum over alignments of (R_a+1) x L_a
+        # of THIS rank's launch / its average launch duration (CUDA events on the launch stream, in the library)
+        k_launches = sum(s["kernel_launches"] for s in res_stats)
+        alg_bytes_per_launch = 2.0 * cells * len(res_stats) / max(k_launches, 1)
+        k_avg_s = kern_ms / 1e3 / max(k_launches, 1)
+        achieved = alg_bytes_per_launch / k_avg_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": n_windows * args.steps / (dev_ms_max / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "corrected_bases_per_sec": n_bases * args.steps / (dev_ms_max / 1e3),
+            "windows_per_step": n_windows, "ms_per_step_wall": res_wall_max / args.steps,
+            "e2e": {"value": n_windows * args.steps / (e2e_ms_max / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(e2e_stats[-1]["input_bytes"]),
+                    "d2h_bytes_per_step": int(e2e_stats[-1]["output_bytes"]),
+                    "ms_per_step": e2e_ms_max / args.steps,
+                    "corrected_bases_per_sec": n_bases * args.steps / (e2e_ms_max / 1e3),
+                    "host_prep_ms": e2e_stats[-1]["host_prep_ms"], "h2d_ms": e2e_stats[-1]["h2d_ms"],
+                    "kernel_ms": e2e_stats[-1]["kernel_ms"], "d2h_ms": e2e_stats[-1]["d2h_ms"]},
+            "gpu_launches": int(n_launch),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "poa_window_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "dp_cells_per_launch": cells, "kernel_ms_per_launch": k_avg_s * 1e3,
+                         "gcups": cells / k_avg_s / 1e9},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            kind, cores, sb, fn = cpu_leg(batch, params, args.cpu_seconds)
+            t0 = time.perf_counter()
+            r = fn(sb, params, threads=cores)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": sb.n_windows / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                "corrected_bases_per_sec": r.total_bases() / dt,
+                "sample": "%d of the batch's %d windows (every k-th) in %.1f s on %d host threads" % (
+                    sb.n_windows, batch.n_windows, dt, cores)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,6 +98,8 @@ typedef struct {
   double   kernel_ms;      /* device time of the POA kernel(s), CUDA events on the launch stream  */
   double   h2d_ms;
   double   d2h_ms;
+  double   device_ms;      /* first device op of the call -> last (H2D if any + kernels + D2H), CUDA events   */
+  double   host_prep_ms;   /* host-side batch preparation (rank sort, average weights), wall clock          */
   uint32_t kernel_launches;
   uint32_t relaunched_windows; /* windows re-run with a larger scratch arena                      */
 } vgc_stats;

@@ -1,0 +1,164 @@
+"""-m gpu: the CUDA engine, called through the C-ABI (include/vgc.h via ctypes), against
+  * the committed outputs of the unmodified reference (tests/golden/windows_*.npz),
+  * the oracle (and the compiled reference when its .so travelled) on seeded windows incl. the edge cases the
+    reference's window code distinguishes (empty batch, < 3 sequences, dropped layers, FASTA dummy quality, N
+    bases, missing qualities, partial spans, long layers, deep windows with > 16 equal sort keys),
+  * size-independent properties at the bench workload's size (determinism, resident == host-buffer path,
+    polished flags, per-window independence: a window's result does not depend on its batch neighbours).
+Bit-exact: this is byte/integer work."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_same, golden_names, load_golden
+from oracle import checker
+from vechat_b200._ffi import WindowBatch, make_params, VGC_WIN_TGS
+from vechat_b200.engine import Engine, VgcError
+from vechat_b200.sim import Simulator, fuzz_batch, fuzz_window
+
+pytestmark = pytest.mark.gpu
+
+_engines = {}
+
+
+def eng(**pkw):
+    key = tuple(sorted(pkw.items()))
+    if key not in _engines:
+        _engines[key] = Engine(0, **pkw)
+    return _engines[key]
+
+
+def check(batch, pkw, label):
+    got, st = eng(**pkw).polish(batch)
+    p = make_params(**pkw)
+    want = checker.ref_polish(batch, p, threads=8) if checker.have_ref() else checker.oracle_polish(batch, p, threads=8)
+    assert_same(got, want, label)
+    return st
+
+
+def test_gpu_present_and_native_library_loaded():
+    assert torch.cuda.is_available()
+    e = eng()
+    assert e.lib.vgc_version().startswith(b"vechat_b200")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name):
+    batch, pkw, want = load_golden(name)
+    got, st = eng(**pkw).polish(batch)
+    assert_same(got, want, name)
+    assert st["kernel_launches"] >= 1 and st["cells"] > 0
+
+
+@pytest.mark.parametrize("seed,kw,pkw", [
+    (401, dict(n_windows=32), dict()),
+    (402, dict(n_windows=32, partial=0.8), dict()),
+    (403, dict(n_windows=32, fastq=False), dict()),
+    (404, dict(n_windows=32, n_frac=0.05, null_qual=0.5), dict()),
+    (405, dict(n_windows=32), dict(haplotype=0)),
+    (406, dict(n_windows=32, partial=0.8), dict(haplotype=0, trim=0)),
+    (407, dict(n_windows=8, depth=70, length=100), dict()),
+    (408, dict(n_windows=16, err=0.4), dict(num_prune=4)),
+    (409, dict(n_windows=16), dict(num_prune=1)),
+    (410, dict(n_windows=16), dict(min_confidence=1.0, min_support=1.0)),
+    (411, dict(n_windows=16), dict(min_confidence=0.0, min_support=0.0)),
+    (412, dict(n_windows=16), dict(match=5, mismatch=-4, gap=-8)),
+    (413, dict(n_windows=8, length=560, depth=12), dict()),           # rows up to ~640 columns
+    (414, dict(n_windows=4, length=800, depth=8), dict()),            # wide-row template (K = 16)
+    (415, dict(n_windows=4, length=800, depth=8, partial=0.6), dict(haplotype=0)),
+])
+def test_fuzz(seed, kw, pkw):
+    check(fuzz_batch(seed, **kw), pkw, "seed %d" % seed)
+
+
+def test_empty_batch():
+    b = WindowBatch.from_windows([])
+    r, st = eng().polish(b)
+    assert r.total_bases() == 0 and len(r.polished) == 0
+
+
+def test_windows_below_three_sequences_return_backbone():
+    rng = np.random.default_rng(5)
+    wins = [fuzz_window(rng, depth=d) for d in (0, 1, 0, 1)]
+    b = WindowBatch.from_windows(wins)
+    r, _ = eng().polish(b)
+    for w in range(4):
+        assert r.window(w) == wins[w][0][0][0] and r.polished[w] == 0
+
+
+def test_dropped_layers_do_not_count():
+    """add_layer drops empty layers and begin == end silently (src/window.cpp:51-54): a window whose third
+    sequence is such a layer has < 3 sequences."""
+    rng = np.random.default_rng(6)
+    layers, flags = fuzz_window(rng, depth=2, partial=0.0)
+    layers[2] = (layers[2][0], layers[2][1], 7, 7)
+    b = WindowBatch.from_windows([(layers, flags)])
+    check(b, dict(), "dropped layer")
+    r, _ = eng().polish(b)
+    assert r.polished[0] == 0
+
+
+def test_invalid_layer_positions_are_rejected():
+    rng = np.random.default_rng(7)
+    layers, flags = fuzz_window(rng, depth=3, partial=0.0)
+    layers[1] = (layers[1][0], layers[1][1], 10, 5)    # begin > end: the reference exits (src/window.cpp:62-67)
+    with pytest.raises(VgcError) as ei:
+        eng().polish(WindowBatch.from_windows([(layers, flags)]))
+    assert ei.value.code == 1
+
+
+def test_mixed_batch_with_tiny_and_large_windows():
+    rng = np.random.default_rng(8)
+    wins = []
+    for i in range(40):
+        wins.append(fuzz_window(rng, length=int(rng.integers(4, 500)), depth=int(rng.integers(0, 30)),
+                                partial=float(rng.random())))
+    check(WindowBatch.from_windows(wins), dict(), "mixed")
+    check(WindowBatch.from_windows(wins), dict(haplotype=0), "mixed linear")
+
+
+def test_scratch_regrow_path(monkeypatch):
+    """A tiny memory budget forces small slots -> node overflow -> relaunch with larger slots."""
+    monkeypatch.setenv("VGC_MEM_BUDGET_MB", "2048")
+    e = Engine(0)
+    b = fuzz_batch(420, n_windows=6, depth=45, length=400)
+    got, st = e.polish(b)
+    p = make_params()
+    assert_same(got, checker.oracle_polish(b, p, threads=8), "regrow")
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def pb_batch():
+    sim = Simulator("pb_clr_10k_x_10kb", n_reads=1500, genome_len=500_000)
+    return sim.windows(0, 60)     # 60 targets x 20 windows, depth ~30
+
+
+def test_sim_pb_sample_vs_checker(pb_batch):
+    sub = pb_batch.select(range(0, pb_batch.n_windows, 10))
+    check(sub, dict(), "sim pb haplotype")
+    check(sub, dict(haplotype=0), "sim pb linear")
+
+
+def test_properties_at_scale(pb_batch):
+    e = eng()
+    r1, st1 = e.polish(pb_batch)
+    r2, st2 = e.polish(pb_batch)
+    assert r1.cons.tobytes() == r2.cons.tobytes() and st1["cells"] == st2["cells"]        # deterministic
+    e.upload(pb_batch)
+    r3, st3 = e.polish_resident()
+    assert r3.cons.tobytes() == r1.cons.tobytes()                                        # resident == host path
+    # independence: a permuted batch gives the permuted result
+    perm = np.random.default_rng(1).permutation(pb_batch.n_windows)[:200]
+    rp, _ = e.polish(pb_batch.select(perm))
+    for i, w in enumerate(perm):
+        assert rp.window(i) == r1.window(int(w))
+    # every window with >= 3 sequences is polished; corrected length stays near the backbone's
+    nseq = np.diff(pb_batch.win_first)
+    assert all(int(r1.polished[w]) == int(nseq[w] >= 3) for w in range(pb_batch.n_windows))
+    blen = np.array([int(pb_batch.seq_off[f + 1] - pb_batch.seq_off[f]) for f in pb_batch.win_first[:-1]])
+    clen = np.diff(r1.cons_off.astype(np.int64))[:pb_batch.n_windows]
+    assert np.all(clen[nseq >= 3] > 0.5 * blen[nseq >= 3]) and np.all(clen < 2.0 * blen + 64)
+    assert st1["alignments"] == sum(3 * (int(n) - 1) + 3 for n in nseq if n >= 3)    # 3*depth+3

@@ -1,0 +1,75 @@
+"""The engine's algorithm template (vechat_b200/csrc/poa_core.h + host_prep.h) instantiated on the host with a
+one-lane executor (tests/host_model/host_model.cpp) and compared with the oracle / committed reference outputs.
+This checks, without a GPU, every serial piece that runs inside the kernel: AddAlignment, TopologicalSort,
+Subgraph, PruneGraph, LargestSubgraph, AddWeights, traceback, heaviest bundle, the host-side rank sort and
+average-weight arithmetic.  (The CUDA fill itself is covered by the -m gpu tests.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_same, golden_names, load_golden
+from oracle import checker
+from vechat_b200._ffi import VgcBatch, VgcParams, VgcResult, alloc_result, finish_result, make_params
+from vechat_b200.sim import fuzz_batch
+
+SRC = os.path.join(ROOT, "tests", "host_model", "host_model.cpp")
+OUT = os.path.join(ROOT, "tests", "host_model", "_build", "libhostmodel.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        csrc = os.path.join(ROOT, "vechat_b200", "csrc")
+        deps = [SRC, os.path.join(csrc, "poa_core.h"), os.path.join(csrc, "host_prep.h")]
+        if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+            os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                            "-o", OUT, SRC], check=True)
+        _lib = C.CDLL(OUT)
+        _lib.hm_polish.restype = C.c_int
+        _lib.hm_polish.argtypes = [C.POINTER(VgcBatch), C.POINTER(VgcParams), C.POINTER(VgcResult), C.c_int, C.c_int,
+                                   C.POINTER(C.c_uint32)]
+    return _lib
+
+
+def hm_polish(batch, params, flags=0, k=10):
+    b = batch.c_struct()
+    r, arrays = alloc_result(batch)
+    status = (C.c_uint32 * max(batch.n_windows, 1))()
+    rc = lib().hm_polish(C.byref(b), C.byref(params), C.byref(r), flags, k, status)
+    assert rc == 0, "hm_polish rc=%d" % rc
+    assert all(s == 0 for s in status), "window status %s" % list(status)
+    return finish_result(batch, arrays)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_host_model_vs_committed_reference_outputs(name):
+    batch, pkw, want = load_golden(name)
+    got = hm_polish(batch, make_params(**pkw))
+    assert_same(got, want, name)
+
+
+@pytest.mark.parametrize("flags,k", [(1, 10), (8 << 8, 10), (0, 16)])
+def test_host_model_slow_paths(flags, k):
+    """flags bit0: sort without the staged 16-bit CSR; flags>>8: tiny DFS stack -> overflow redo; k=16: wide rows."""
+    for seed, kw, pkw in [(301, dict(n_windows=8), dict()), (302, dict(n_windows=8, partial=0.7), dict(haplotype=0))]:
+        batch = fuzz_batch(seed, **kw)
+        p = make_params(**pkw)
+        assert_same(hm_polish(batch, p, flags, k), checker.oracle_polish(batch, p, threads=4), "seed %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(310, 316))
+def test_host_model_fuzz_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    kw = dict(n_windows=10, partial=float(rng.random()), err=float(rng.uniform(0.02, 0.35)),
+              fastq=bool(rng.integers(0, 2)), null_qual=float(rng.choice([0.0, 0.4])),
+              n_frac=float(rng.choice([0.0, 0.03])))
+    pkw = dict(haplotype=int(rng.integers(0, 2)), num_prune=int(rng.integers(1, 4)),
+               min_confidence=float(rng.choice([0.0, 0.2, 0.5])), min_support=float(rng.choice([0.0, 0.2, 1.0])))
+    batch = fuzz_batch(seed, **kw)
+    p = make_params(**pkw)
+    assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d %r %r" % (seed, kw, pkw))

@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU session: parity tests, smoke, bench (both arms), ncu launch list (+ optional full capture).
+# Usage (under gpurun): bash tools/gpu_round.sh [tests] [bench] [ncu] [ncufull]
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+for what in "$@"; do
+  case $what in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+      tail -5 gpurun_out/pytest_gpu.log
+      timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+      tail -6 gpurun_out/smoke.log ;;
+    bench)
+      timeout 900 python bench.py --steps ${STEPS:-5} --warmup ${WARMUP:-3} ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+      tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json ;;
+    benchref)
+      timeout 600 python bench.py --impl reference --steps ${STEPS:-5} --warmup ${WARMUP:-3} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"
+      cat gpurun_out/bench_ref.json ;;
+    ncu)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 2 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+      tail -12 gpurun_out/launches.csv ;;
+    ncufull)
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:poa_window -s 1 -c 1 -f -o gpurun_out/prof \
+        python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "ncufull rc=$?"
+      ls -la gpurun_out/prof.ncu-rep ;;
+  esac
+done

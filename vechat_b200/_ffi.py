@@ -55,6 +55,8 @@ class VgcStats(C.Structure):
         ("kernel_ms", C.c_double),
         ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double),
+        ("device_ms", C.c_double),
+        ("host_prep_ms", C.c_double),
         ("kernel_launches", C.c_uint32),
         ("relaunched_windows", C.c_uint32),
     ]
@@ -140,7 +142,28 @@ class WindowBatch:
 
     def select(self, windows):
         """New batch holding only the given window indices (in that order)."""
-        return WindowBatch.from_windows([(self.window(w), int(self.win_flags[w])) for w in windows])
+        windows = [int(w) for w in windows]
+        b = WindowBatch.from_windows([(self.window(w), int(self.win_flags[w])) for w in windows])
+        for attr in ("win_target", "win_rank"):
+            if hasattr(self, attr):
+                setattr(b, attr, np.asarray(getattr(self, attr))[windows].copy())
+        if hasattr(self, "target_coverage"):
+            b.target_coverage = self.target_coverage
+        return b
+
+    def slice(self, w0, w1):
+        """Contiguous window range [w0, w1) as a new batch (array slicing, no per-window Python work)."""
+        l0, l1 = int(self.win_first[w0]), int(self.win_first[w1])
+        o0, o1 = int(self.seq_off[l0]), int(self.seq_off[l1])
+        b = WindowBatch(self.bases[o0:o1], self.quals[o0:o1], self.seq_off[l0:l1 + 1] - np.uint64(o0),
+                        self.has_qual[l0:l1], self.begin[l0:l1], self.end[l0:l1],
+                        self.win_first[w0:w1 + 1] - np.uint32(l0), self.win_flags[w0:w1])
+        for attr in ("win_target", "win_rank"):
+            if hasattr(self, attr):
+                setattr(b, attr, np.asarray(getattr(self, attr))[w0:w1].copy())
+        if hasattr(self, "target_coverage"):
+            b.target_coverage = self.target_coverage
+        return b
 
     @staticmethod
     def from_windows(windows):

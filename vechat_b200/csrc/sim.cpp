@@ -182,6 +182,7 @@ struct sim_batch {
   std::vector<uint64_t> seq_off;
   std::vector<uint32_t> begin, end, win_first;
   std::vector<uint32_t> win_target, win_rank;  // which read / which window of it
+  std::vector<uint32_t> tgt_cov;               // overlaps per target t0..t1-1 (targets_coverages_, src/polisher.cpp:411)
   uint64_t n_overlaps;
 };
 
@@ -242,6 +243,7 @@ sim_batch* sim_windows(const sim_state* st, uint32_t t0, uint32_t t1, double qua
       qids.push_back(q);
     }
     qcache.resize(qids.size());
+    sb->tgt_cov.push_back(static_cast<uint32_t>(qids.size()));
     for (size_t qi = 0; qi < qids.size(); ++qi) {
       orient(st->reads[qids[qi]], flip, &qcache[qi]);
       const Oriented& QQ = qcache[qi];
@@ -341,6 +343,8 @@ sim_batch* sim_windows(const sim_state* st, uint32_t t0, uint32_t t1, double qua
 const vgc_batch* sim_batch_view(const sim_batch* sb) { return &sb->b; }
 const uint32_t* sim_batch_targets(const sim_batch* sb) { return sb->win_target.data(); }
 const uint32_t* sim_batch_ranks(const sim_batch* sb) { return sb->win_rank.data(); }
+const uint32_t* sim_batch_target_coverages(const sim_batch* sb) { return sb->tgt_cov.data(); }
+uint32_t sim_batch_num_targets(const sim_batch* sb) { return static_cast<uint32_t>(sb->tgt_cov.size()); }
 uint64_t sim_batch_overlaps(const sim_batch* sb) { return sb->n_overlaps; }
 void sim_free_batch(sim_batch* sb) { delete sb; }
 

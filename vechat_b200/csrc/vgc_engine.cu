@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -189,7 +190,8 @@ struct vgc_engine {
   int device = 0;
   vgc_params params;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int ctas_per_sm = 16;
   uint32_t smem_bytes = 0;
@@ -339,10 +341,15 @@ int run_pass(vgc_engine* h, uint32_t n_work, const uint32_t* d_work, uint32_t ma
   a.min_confidence = h->params.min_confidence;
   a.min_support = h->params.min_support;
   a.smem_bytes = h->smem_bytes;
+  VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
   if (K == 10) rc = launch_k<10>(h, a, grid);
   else rc = launch_k<16>(h, a, grid);
   if (rc != VGC_OK) return rc;
+  VGC_CUDA(cudaEventRecord(h->ev[7], h->stream));
   VGC_CUDA(cudaStreamSynchronize(h->stream));  // `slots` must outlive its copy; also surfaces kernel faults
+  float kms = 0.f;
+  VGC_CUDA(cudaEventElapsedTime(&kms, h->ev[6], h->ev[7]));
+  h->pass_kernel_ms += kms;
   ++*launches;
   return VGC_OK;
 }
@@ -371,6 +378,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   uint32_t launches = 0, relaunched = 0;
   unsigned long long totals[2] = {0, 0};
   float kernel_ms = 0.f, d2h_ms = 0.f;
+  h->pass_kernel_ms = 0.0;
   VGC_CUDA(cudaMemsetAsync(h->d_out_len.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   if (n_dev) {
@@ -417,7 +425,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   VGC_CUDA(cudaMemcpyAsync(totals, h->d_misc.as<uint8_t>() + 16, 16, cudaMemcpyDeviceToHost, h->stream));
   VGC_CUDA(cudaEventRecord(h->ev[3], h->stream));
   VGC_CUDA(cudaStreamSynchronize(h->stream));
-  if (n_dev) VGC_CUDA(cudaEventElapsedTime(&kernel_ms, h->ev[0], h->ev[1]));
+  kernel_ms = static_cast<float>(h->pass_kernel_ms);
   VGC_CUDA(cudaEventElapsedTime(&d2h_ms, h->ev[2], h->ev[3]));
   // status check: anything but OK is an engine limit (there is no CPU fallback)
   for (uint32_t w : pr.device_windows) {
@@ -462,6 +470,10 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     stats->output_bytes = (result ? pr.out_total : 0) + nw * 8ull + 16;
     stats->kernel_ms = kernel_ms;
     stats->d2h_ms = d2h_ms;
+    float dev_ms = 0.f;
+    VGC_CUDA(cudaEventElapsedTime(&dev_ms, h->ev[n_dev ? 0 : 2], h->ev[3]));
+    stats->device_ms = dev_ms;
+    stats->host_prep_ms = 0.0;
     stats->kernel_launches = launches;
     stats->relaunched_windows = relaunched;
   }
@@ -554,7 +566,9 @@ int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_sta
   VGC_CUDA(cudaSetDevice(h->device));
   h->resident = false;
   std::string err;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
+  const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (rc != VGC_OK) {
     set_err(err);
     return rc;
@@ -569,6 +583,10 @@ int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_sta
   if (stats) {
     VGC_CUDA(cudaEventElapsedTime(&h2d_ms, h->ev[4], h->ev[5]));
     stats->h2d_ms = h2d_ms;
+    float dev_ms = 0.f;
+    VGC_CUDA(cudaEventElapsedTime(&dev_ms, h->ev[4], h->ev[3]));
+    stats->device_ms = dev_ms;
+    stats->host_prep_ms = prep_ms;
   }
   return VGC_OK;
 }

@@ -67,6 +67,11 @@ def _lib():
         lib.sim_windows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_double]
         lib.sim_batch_view.restype = C.POINTER(VgcBatch)
         lib.sim_batch_view.argtypes = [C.c_void_p]
+        for fn in ("sim_batch_targets", "sim_batch_ranks", "sim_batch_target_coverages"):
+            getattr(lib, fn).restype = C.POINTER(C.c_uint32)
+            getattr(lib, fn).argtypes = [C.c_void_p]
+        lib.sim_batch_num_targets.restype = C.c_uint32
+        lib.sim_batch_num_targets.argtypes = [C.c_void_p]
         lib.sim_batch_overlaps.restype = C.c_uint64
         lib.sim_batch_overlaps.argtypes = [C.c_void_p]
         lib.sim_free_batch.argtypes = [C.c_void_p]
@@ -104,9 +109,19 @@ class Simulator:
         return s.raw[:n], q.raw[:n]
 
     def windows(self, t0, t1, quality_threshold=10.0):
-        sb = _lib().sim_windows(self._h, t0, t1, quality_threshold)
+        """Windows of target reads [t0, t1).  The returned batch also carries win_target / win_rank (read id and
+        window index, Window::id_/rank_) and target_coverage {read id: #overlaps} for the stitcher."""
+        L = _lib()
+        sb = L.sim_windows(self._h, t0, t1, quality_threshold)
         try:
-            return WindowBatch.from_c(_lib().sim_batch_view(sb))
+            b = WindowBatch.from_c(L.sim_batch_view(sb))
+            nw = b.n_windows
+            b.win_target = np.ctypeslib.as_array(L.sim_batch_targets(sb), shape=(max(nw, 1),))[:nw].copy()
+            b.win_rank = np.ctypeslib.as_array(L.sim_batch_ranks(sb), shape=(max(nw, 1),))[:nw].copy()
+            nt = L.sim_batch_num_targets(sb)
+            cov = np.ctypeslib.as_array(L.sim_batch_target_coverages(sb), shape=(max(nt, 1),))[:nt].copy()
+            b.target_coverage = {int(t0 + i): int(c) for i, c in enumerate(cov)}
+            return b
         finally:
             _lib().sim_free_batch(sb)
 
