@@ -303,6 +303,9 @@ def main():
                          "gcups": cells / k_avg_s / 1e9},
             "clocks": sampler.summary(),
         }
+        ph = eng.phase_profile()
+        tot_ph = sum(ph.values()) or 1.0
+        line["phase_share"] = {k: round(v / tot_ph, 4) for k, v in ph.items()}
         if world == 1 and not args.no_cpu_baseline:
             kind, cores, sb, fn = cpu_leg(batch, params, args.cpu_seconds)
             t0 = time.perf_counter()

@@ -25,6 +25,7 @@ struct HostEx {
   bool allow_fast = true;
   uint32_t small_stack = 0;  // test hook: tiny fast stack to force the overflow path
 
+  unsigned long long clock() const { return 0; }
   int lane() const { return 0; }
   int width() const { return 1; }
   bool leader() const { return true; }

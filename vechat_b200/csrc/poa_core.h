@@ -159,6 +159,14 @@ struct WinState {
   uint32_t scratch[4];
   unsigned long long cells;
   uint32_t alignments;
+  // per-phase cycle counters (leader lane, clock64): see kPh*
+  unsigned long long t_last;
+  unsigned long long phase[12];
+};
+
+enum : int {
+  kPhCsr = 0, kPhSort = 1, kPhRowprog = 2, kPhFill = 3, kPhTrace = 4, kPhAddAln = 5, kPhAddW = 6, kPhPrune = 7,
+  kPhLargest = 8, kPhEmit = 9, kPhOther = 10, kPhCount = 11,
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -203,6 +211,15 @@ struct Poa {
   }
 
   VGC_HD VGC_INL Graph& G() { return sl.g[ws.cur]; }
+
+  // attribute the cycles since the previous tick to `phase`
+  VGC_HD VGC_INL void tick(int phase) {
+    if (ex.leader()) {
+      const unsigned long long now = ex.clock();
+      ws.phase[phase] += now - ws.t_last;
+      ws.t_last = now;
+    }
+  }
 
   VGC_HD VGC_INL void fail(uint32_t st) {
     if (ws.status == kStOk) ws.status = st;
@@ -791,7 +808,9 @@ struct Poa {
   VGC_HD void align(uint32_t layer, uint32_t mode, const Scores& sc, const uint32_t* order, uint32_t nR,
                     bool sub, bool rebuild_rowprog = true) {
     const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
+    tick(kPhOther);
     if (rebuild_rowprog) build_rowprog(order, nR, sub);
+    tick(kPhRowprog);
     if (ex.leader()) {
       ws.alignments += 1;
       ws.cells += static_cast<unsigned long long>(nR + 1) * len;  // (R_a + 1) * L_a of the graph aligned to
@@ -809,15 +828,21 @@ struct Poa {
         return;
       }
     }
+    tick(kPhOther);
     ex.template fill<K>(sl, ws, codes, len, mode, sc, bv.num_codes);
     ex.sync();
+    tick(kPhFill);
     if (ex.leader()) traceback(codes, mode, sc);
     ex.sync();
+    tick(kPhTrace);
   }
 
   VGC_HD uint32_t resort_main() {
+    tick(kPhOther);
     build_csr(false);
+    tick(kPhCsr);
     const uint32_t n = sort_graph(false, 0, 0, sl.r2n);
+    tick(kPhSort);
     return n;
   }
 
@@ -907,6 +932,8 @@ struct Poa {
       sl.g[0].nV = 0;
       sl.g[0].nE = 0;
       *out_len = 0;
+      ws.t_last = ex.clock();
+      for (int i = 0; i < kPhCount; ++i) ws.phase[i] = 0;
     }
     ex.sync();
     // every layer must fit one row of the H matrix
@@ -941,12 +968,15 @@ struct Poa {
       if (lb < offset && le > blen - offset) {
         align(l, kModeNW, nw, sl.r2n, nMain, false);
       } else {
+        tick(kPhOther);
         const uint32_t nSub = sort_graph(true, lb, le, sl.order);
+        tick(kPhSort);
         align(l, kModeNW, nw, sl.order, nSub, true);
       }
       if (ws.status != kStOk) return;
       if (ex.leader()) add_alignment(ex.seq_codes(), l, len);
       ex.sync();
+      tick(kPhAddAln);
       if (ws.status != kStOk) return;
       nMain = resort_main();
     }
@@ -983,8 +1013,11 @@ struct Poa {
 
     // haplotype mode: prune + re-align rounds (window.cpp:300-394)
     const double avgw = bv.win_avgw[w];
+    tick(kPhOther);
     prune(min_confidence, min_support, avgw);
+    tick(kPhPrune);
     largest_subgraph();
+    tick(kPhLargest);
     for (uint32_t k = 0; k + 1 < num_prune; ++k) {
       nMain = resort_main();
       for (uint32_t j = 0; j < nseq; ++j) {
@@ -994,10 +1027,13 @@ struct Poa {
         align(l, global ? kModeNW : kModeSW, global ? nw : sw, sl.r2n, nMain, false, j == 0);
         if (ws.status != kStOk) return;
         add_weights(l);
+        tick(kPhAddW);
         if (ws.status != kStOk) return;
       }
       prune(min_confidence, min_support, avgw);
+      tick(kPhPrune);
       largest_subgraph();
+      tick(kPhLargest);
     }
     nMain = resort_main();
     align(bb, kModeSW, sw, sl.r2n, nMain, false);
@@ -1018,6 +1054,7 @@ struct Poa {
       *out_len = n;
     }
     ex.sync();
+    tick(kPhEmit);
   }
 };
 

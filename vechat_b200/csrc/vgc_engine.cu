@@ -25,7 +25,7 @@
 
 namespace vgc {
 
-constexpr int kSmemHeader = 768;  // Slot + WinState copies
+constexpr int kSmemHeader = 896;  // Slot + WinState copies
 
 struct KernelArgs {
   BatchView bv;
@@ -36,7 +36,7 @@ struct KernelArgs {
   uint8_t* out;            // output bytes (bv.out_off / out_cap index into it)
   uint32_t* out_len;       // [n_windows]
   uint32_t* status;        // [n_windows]
-  unsigned long long* totals;  // [2]: cells, alignments
+  unsigned long long* totals;  // [2 + kPhCount]: cells, alignments, per-phase cycles
   Scores nw;
   uint32_t haplotype, trim, num_prune;
   double min_confidence, min_support;
@@ -51,6 +51,7 @@ struct WarpEx {
   uint32_t max_len;
   int lane_;
 
+  __device__ __forceinline__ unsigned long long clock() const { return clock64(); }
   __device__ __forceinline__ int lane() const { return lane_; }
   __device__ __forceinline__ int width() const { return 32; }
   __device__ __forceinline__ bool leader() const { return lane_ == 0; }
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) 
       a.status[w] = ws->status;
       atomicAdd(a.totals, ws->cells);
       atomicAdd(a.totals + 1, static_cast<unsigned long long>(ws->alignments));
+      for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, ws->phase[i]);
     }
     __syncwarp();
   }
@@ -191,6 +193,7 @@ struct vgc_engine {
   vgc_params params;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int ctas_per_sm = 16;
@@ -321,7 +324,7 @@ int run_pass(vgc_engine* h, uint32_t n_work, const uint32_t* d_work, uint32_t ma
   std::vector<Slot> slots(grid);
   for (uint32_t i = 0; i < grid; ++i) slot_carve(d, h->d_slot_mem.as<uint8_t>() + per_slot * i, &slots[i]);
   VGC_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), sizeof(Slot) * grid, cudaMemcpyHostToDevice, h->stream));
-  VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
+  VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 16, h->stream));  // work cursor (totals accumulate over passes)
   KernelArgs a;
   a.bv = make_view(h);
   a.work = d_work;
@@ -376,9 +379,10 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   }
   const uint32_t n_dev = static_cast<uint32_t>(pr.device_windows.size());
   uint32_t launches = 0, relaunched = 0;
-  unsigned long long totals[2] = {0, 0};
+  unsigned long long totals[2 + vgc::kPhCount] = {0};
   float kernel_ms = 0.f, d2h_ms = 0.f;
   h->pass_kernel_ms = 0.0;
+  VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 256, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_out_len.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   if (n_dev) {
@@ -422,7 +426,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   if (result && pr.out_total) {
     VGC_CUDA(cudaMemcpyAsync(h->h_out, h->d_out.p, pr.out_total, cudaMemcpyDeviceToHost, h->stream));
   }
-  VGC_CUDA(cudaMemcpyAsync(totals, h->d_misc.as<uint8_t>() + 16, 16, cudaMemcpyDeviceToHost, h->stream));
+  VGC_CUDA(cudaMemcpyAsync(totals, h->d_misc.as<uint8_t>() + 16, sizeof(totals), cudaMemcpyDeviceToHost, h->stream));
   VGC_CUDA(cudaEventRecord(h->ev[3], h->stream));
   VGC_CUDA(cudaStreamSynchronize(h->stream));
   kernel_ms = static_cast<float>(h->pass_kernel_ms);
@@ -464,6 +468,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     result->cons_off[nw] = off;
   }
   if (stats) {
+    for (int i = 0; i < vgc::kPhCount; ++i) h->phase_cycles[i] = static_cast<double>(totals[2 + i]);
     stats->cells = totals[0];
     stats->alignments = totals[1];
     stats->input_bytes = input_bytes;
@@ -485,6 +490,12 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
 extern "C" {
 
 const char* vgc_last_error(void) { return g_err.c_str(); }
+int vgc_phase_profile(vgc_handle h, double out[16]) {
+  if (!h || !out) return VGC_ERR_INVALID;
+  for (int i = 0; i < 16; ++i) out[i] = h->phase_cycles[i];
+  return VGC_OK;
+}
+
 const char* vgc_version(void) { return "vechat_b200 0.1 (sm_100a)"; }
 
 void vgc_weight_lut(uint32_t lut[256]) { vgc::weight_lut(lut); }

@@ -15,7 +15,7 @@ _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvgc.so")
 
 EXPORTS = ["vgc_create", "vgc_destroy", "vgc_result_bound", "vgc_polish", "vgc_upload", "vgc_polish_resident",
-           "vgc_last_error", "vgc_version", "vgc_weight_lut"]
+           "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile"]
 
 
 class VgcError(RuntimeError):
@@ -43,6 +43,8 @@ def load_library():
         lib.vgc_upload.argtypes = [C.c_void_p, C.POINTER(VgcBatch)]
         lib.vgc_polish_resident.restype = C.c_int
         lib.vgc_polish_resident.argtypes = [C.c_void_p, C.POINTER(VgcResult), C.POINTER(VgcStats)]
+        lib.vgc_phase_profile.restype = C.c_int
+        lib.vgc_phase_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.vgc_last_error.restype = C.c_char_p
         lib.vgc_version.restype = C.c_char_p
         lib.vgc_weight_lut.argtypes = [C.POINTER(C.c_uint32)]
@@ -99,6 +101,19 @@ class Engine:
             return finish_result(batch, arrays), _stats(st)
         self._check(self.lib.vgc_polish_resident(self._h, None, C.byref(st)))
         return None, _stats(st)
+
+
+PHASES = ["csr", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
+          "largest_subgraph", "emit", "other"]
+
+
+def _phase_profile(engine):
+    out = (C.c_double * 16)()
+    engine.lib.vgc_phase_profile(engine._h, out)
+    return {n: out[i] for i, n in enumerate(PHASES)}
+
+
+Engine.phase_profile = _phase_profile
 
 
 def _stats(st):
