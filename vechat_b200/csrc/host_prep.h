@@ -228,7 +228,7 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
   for (int gi = 0; gi < 2; ++gi) {
     t(N);                      // code
     t(N);                      // nal
-    t(N * kMaxAligned * 4);    // al
+    t(N * kAlStride * 4);      // al
     t(N * 4);                  // nin
     t(N * 4);                  // nout
     t(N * 4);                  // cov

@@ -45,6 +45,10 @@
 namespace vgc {
 
 constexpr int kMaxAligned = 7;     // clique size - 1  (<= kMaxCodes - 1)
+constexpr int kAlStride = 8;       // aligned-list stride per node (32 B: the first four ids load as one 16 B vector)
+struct alignas(16) U4 {
+  uint32_t x, y, z, w;
+};
 constexpr int kMaxCodes = 8;       // distinct bytes per batch
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -68,6 +72,7 @@ enum : uint8_t {
   kFIgnored = 4,
   kFHasAligned = 8,
   kFMember = 16,
+  kFNalShift = 5,   // bits 5..7: number of aligned nodes (<= kMaxAligned)
 };
 
 struct Scores {
@@ -101,7 +106,7 @@ struct Graph {
   uint32_t nV, nE;
   uint8_t* code;
   uint8_t* nal;
-  uint32_t* al;        // [max_nodes * kMaxAligned]
+  uint32_t* al;        // [max_nodes * kAlStride]
   uint32_t* nin;
   uint32_t* nout;
   uint32_t* cov;       // sequences through the node (linear mode coverage)
@@ -277,6 +282,11 @@ struct Poa {
         uint8_t fc = flags[curr];
         bool valid = true;
         if ((fc & kFMarkMask) != 2) {
+          // aligned ids: one vector load, issued before the in-edge scan so its latency overlaps it
+          const uint32_t na = fc >> kFNalShift;
+          const bool has_al = !(fc & kFIgnored) && na != 0;
+          U4 q = {0, 0, 0, 0};
+          if (has_al) q = *reinterpret_cast<const U4*>(g.al + curr * kAlStride);
           const uint32_t b = in_off[curr], e = in_off[curr + 1];
           if (sp + (e - b) + kMaxAligned + 1 > stack_cap) {
             *overflow = true;
@@ -291,10 +301,11 @@ struct Poa {
               valid = false;
             }
           }
-          if (!(fc & kFIgnored) && (fc & kFHasAligned)) {
-            const uint32_t na = g.nal[curr];
-            for (uint32_t i = 0; i < na; ++i) {
-              const uint32_t a = g.al[curr * kMaxAligned + i];
+          if (has_al) {
+#pragma unroll
+            for (int i = 0; i < kMaxAligned; ++i) {
+              if (static_cast<uint32_t>(i) >= na) break;
+              const uint32_t a = i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : i == 3 ? q.w : g.al[curr * kAlStride + i];
               const uint8_t fa = flags[a];
               if (member_only && !(fa & kFMember)) continue;
               if ((fa & kFMarkMask) != 2) {
@@ -309,10 +320,11 @@ struct Poa {
             flags[curr] = (fc & ~kFMarkMask) | 2;
             if (!(fc & kFIgnored)) {
               dst[n++] = curr;
-              if (fc & kFHasAligned) {
-                const uint32_t na = g.nal[curr];
-                for (uint32_t i = 0; i < na; ++i) {
-                  const uint32_t a = g.al[curr * kMaxAligned + i];
+              if (has_al) {
+#pragma unroll
+                for (int i = 0; i < kMaxAligned; ++i) {
+                  if (static_cast<uint32_t>(i) >= na) break;
+                  const uint32_t a = i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : i == 3 ? q.w : g.al[curr * kAlStride + i];
                   if (member_only && !(flags[a] & kFMember)) continue;
                   dst[n++] = a;
                 }
@@ -342,7 +354,7 @@ struct Poa {
         // pushes are bounded by nE + sum(nal) + 1: the stack is the H scratch, which is far larger
         for (uint32_t i = in_off[curr]; i < in_off[curr + 1]; ++i) stack[sp++] = in_tail[i];
         if (f & kFHasAligned) {
-          for (uint32_t i = 0; i < g.nal[curr]; ++i) stack[sp++] = g.al[curr * kMaxAligned + i];
+          for (uint32_t i = 0; i < g.nal[curr]; ++i) stack[sp++] = g.al[curr * kAlStride + i];
         }
         flags[curr] = f | kFMember;
       }
@@ -359,7 +371,10 @@ struct Poa {
     uint32_t stk_cap;
     const bool fast = ex.stage_fast(nV, nE, &fl, &off16, &tail16, &stk16, &stk_cap);
     if (!fast) fl = sl.flags;
-    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) fl[v] = g.nal[v] ? kFHasAligned : 0;
+    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) {
+      const uint32_t na = g.nal[v];
+      fl[v] = static_cast<uint8_t>((na ? kFHasAligned : 0) | (na << kFNalShift));
+    }
     if (fast) {
       for (uint32_t v = ex.lane(); v <= nV; v += ex.width()) off16[v] = static_cast<uint16_t>(sl.in_off[v]);
       for (uint32_t e = ex.lane(); e < nE; e += ex.width()) tail16[e] = static_cast<uint16_t>(sl.in_tail[e]);
@@ -373,7 +388,7 @@ struct Poa {
         n = toposort_impl<uint16_t>(fl, off16, tail16, stk16, stk_cap, sub, dst, &ovf);
         if (ovf) {
           // deep recursion: redo with the big stack in HBM (flags: clear marks/ignored, keep member)
-          for (uint32_t v = 0; v < nV; ++v) fl[v] &= (kFHasAligned | kFMember);
+          for (uint32_t v = 0; v < nV; ++v) fl[v] &= static_cast<uint8_t>(kFHasAligned | kFMember | (7u << kFNalShift));
           n = toposort_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, 0xFFFFFFFFu, sub, dst, &ovf);
         }
       } else {
@@ -464,7 +479,7 @@ struct Poa {
     return RM::load(sl.H + static_cast<uint64_t>(row) * sl.row_words, j - 1);
   }
 
-  VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
+  VGC_HD void traceback_serial(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
     uint32_t n = 0;
     uint32_t i = ws.best_row, j = ws.best_col;
     if (i == 0 && j == 0) {
@@ -527,138 +542,291 @@ struct Poa {
     ws.aln_len = n;
   }
 
+  // Warp-cooperative traceback.  One step = one round of parallel loads: every candidate of the current cell
+  // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order) is
+  // fetched and compared by its own lane, and the first match wins (reduce_min over the candidate index).
+  // Node facts come from a table indexed by node id — word {p0 row:16, min(np,15):4, code:8} plus a u16 second
+  // predecessor row / overflow offset — kept in the executor's fast storage when it fits.
+  VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
+    Graph& g = G();
+    const int W = ex.width(), L = ex.lane();
+    uint32_t i = ws.best_row, j = ws.best_col;
+    if (i == 0 && j == 0) {
+      if (ex.leader()) ws.aln_len = 0;
+      ex.sync();
+      return;
+    }
+    if (g.nV >= 65535u || ws.ovf_n >= 65535u) {  // ids beyond the 16-bit tables: plain serial walk
+      if (ex.leader()) traceback_serial(seq_codes, mode, sc);
+      ex.sync();
+      return;
+    }
+    uint32_t* ni;
+    uint16_t* p1t;
+    if (!ex.trace_tables(g.nV, &ni, &p1t)) {
+      ni = sl.tmp0;
+      p1t = reinterpret_cast<uint16_t*>(sl.tmp1);
+    }
+    const uint32_t nR = ws.nR;
+    for (uint32_t r = L; r < nR; r += W) {
+      const uint32_t v = sl.rowprog[4 * r], meta = sl.rowprog[4 * r + 1];
+      const uint32_t np = meta_npred(meta);
+      ni[v] = (sl.rowprog[4 * r + 2] & 0xFFFFu) | ((np < 15u ? np : 15u) << 16) | (meta_code(meta) << 20);
+      p1t[v] = static_cast<uint16_t>(sl.rowprog[4 * r + 3]);
+    }
+    ex.sync();
+    const int32_t gp = sc.g;
+    int32_t h = hval(i, j, mode, gp);
+    uint32_t n = 0;
+    bool bad = false;
+    while (true) {
+      if (mode == kModeSW) {
+        if (h == 0) break;
+      } else {
+        if (i == 0 && j == 0) break;
+      }
+      uint32_t np = 0, p0 = 0, code = 0;
+      if (i != 0) {
+        const uint32_t info = ni[i - 1];
+        p0 = info & 0xFFFFu;
+        np = (info >> 16) & 15u;
+        code = info >> 20;
+        if (np == 15u) np = meta_npred(sl.rowprog[4 * sl.rank_of[i - 1] + 1]);
+      }
+      const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;  // no in-edges: the virtual row 0 is the predecessor
+      const uint32_t ncand = 2 * npp + 1;
+      const int32_t mc = (i != 0 && j != 0) ? (code == seq_codes[j - 1] ? sc.m : sc.x) : 0;
+      uint32_t first = kNone, pr_next = 0;
+      int32_t hv_next = 0;
+      for (uint32_t c0 = 0; c0 < ncand; c0 += W) {
+        const uint32_t c = c0 + L;
+        bool ok = false;
+        int32_t hv = 0;
+        uint32_t pr = i;
+        if (c < 2 * npp) {
+          const uint32_t p = c < npp ? c : c - npp;
+          if (p == 0) pr = p0;
+          else if (np == 2) pr = p1t[i - 1];
+          else pr = sl.ovf[static_cast<uint32_t>(p1t[i - 1]) + p - 1];
+          if (c < npp) {
+            if (j != 0) {
+              hv = hval(pr, j - 1, mode, gp);
+              ok = h == hv + mc;
+            }
+          } else {
+            hv = hval(pr, j, mode, gp);
+            ok = h == hv + gp;
+          }
+        } else if (c == 2 * npp && j != 0) {
+          hv = hval(i, j - 1, mode, gp);
+          ok = h == hv + gp;
+        }
+        const uint32_t f = ex.reduce_min(ok ? c : kNone);
+        if (f != kNone) {
+          first = f;
+          hv_next = static_cast<int32_t>(ex.bcast(static_cast<uint32_t>(hv), f - c0));
+          pr_next = ex.bcast(pr, f - c0);
+          break;
+        }
+      }
+      if (first == kNone || n >= sl.aln_cap) {
+        bad = true;
+        break;
+      }
+      const uint32_t pi = pr_next;
+      const uint32_t pj = (first >= npp && first < 2 * npp) ? j : j - 1;
+      if (ex.leader()) {
+        sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(i - 1);
+        sl.aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+      }
+      ++n;
+      i = pi;
+      j = pj;
+      h = hv_next;
+    }
+    if (ex.leader()) {
+      if (bad) fail(kStInternal);
+      ws.aln_len = n;
+    }
+    ex.sync();
+  }
+
   // ---- sequence access ----------------------------------------------------------------------------
   VGC_HD VGC_INL uint32_t weight_at(uint32_t layer, uint32_t pos) const {
     if (!bv.has_qual[layer]) return 1u;
     return bv.wlut[bv.quals[bv.seq_off[layer] + pos]];
   }
 
-  // ---- graph.cpp:88-107 primitives (leader) -------------------------------------------------------
-  VGC_HD uint32_t add_node(Graph& g, uint32_t code) {
-    if (g.nV >= sl.max_nodes) {
-      fail(kStNodeOverflow);
-      return 0;
-    }
-    const uint32_t v = g.nV++;
-    g.code[v] = static_cast<uint8_t>(code);
-    g.nal[v] = 0;
-    g.nin[v] = 0;
-    g.nout[v] = 0;
-    g.cov[v] = 0;
-    return v;
-  }
-
-  // `nV0`: node count when the CSR was built — newer nodes have no CSR row and no older edges.
-  VGC_HD void add_edge(Graph& g, uint32_t tail, uint32_t head, uint32_t w, uint32_t nV0) {
-    if (head < nV0 && tail < nV0) {
-      for (uint32_t i = sl.in_off[head]; i < sl.in_off[head + 1]; ++i) {
-        if (sl.in_tail[i] == tail) {
-          g.ew[sl.in_eid[i]] += w;
-          return;
-        }
-      }
-    }
-    if (g.nE >= sl.max_edges) {
-      fail(kStEdgeOverflow);
-      return;
-    }
-    const uint32_t e = g.nE++;
-    g.etail[e] = tail;
-    g.ehead[e] = head;
-    g.ew[e] = w;
-    g.edead[e] = 0;
-    g.ein_ord[e] = g.nin[head]++;
-    g.eout_ord[e] = g.nout[tail]++;
-  }
-
-  // graph.cpp:109-130
-  VGC_HD uint32_t add_sequence(Graph& g, const uint8_t* codes, uint32_t layer, uint32_t begin, uint32_t end,
-                               uint32_t nV0) {
-    if (begin == end) return kNone;
-    uint32_t prev = kNone, first = kNone;
-    for (uint32_t i = begin; i < end; ++i) {
-      const uint32_t curr = add_node(g, codes[i]);
-      if (ws.status != kStOk) return kNone;
-      g.cov[curr] = ws.scratch[1];
-      if (first == kNone) first = curr;
-      if (prev != kNone) add_edge(g, prev, curr, weight_at(layer, i - 1) + weight_at(layer, i), nV0);
-      prev = curr;
-    }
-    return first;
-  }
-
-  // ---- graph.cpp:182-299 (leader).  The alignment is in aln_* in reverse order. --------------------
+  // ---- graph.cpp:182-299, all lanes.  The alignment is in aln_* in reverse order (entry n-1 is the first
+  //      pair).  The reference walks the alignment once, serially; the same result is produced here in
+  //      parallel because along one alignment
+  //        * the aligned sequence positions are the contiguous run [vfront, vback], in increasing order;
+  //        * new nodes are numbered prefix chain, suffix chain, then aligned-part nodes in alignment order
+  //          (graph.cpp:230-236) — an exclusive scan over "needs a new node";
+  //        * a path visits at most one node of an aligned clique, and gives every node at most one new in-edge
+  //          and one new out-edge, so clique updates and in/out-list appends of different positions never touch
+  //          the same list (list order = creation order is therefore preserved).
+  //      Needs the CSR of the graph as it was before the call (in_off/in_tail/in_eid for ids < nV0).
   VGC_HD void add_alignment(const uint8_t* codes, uint32_t layer, uint32_t len) {
     Graph& g = G();
-    const uint32_t nV0 = g.nV;
+    const uint32_t nV0 = g.nV, nE0 = g.nE;
     if (len == 0) return;
-    ws.scratch[1] = len > 1 ? 1u : 0u;  // Node::Coverage counts edge labels: a 1-base sequence has none
+    // conservative capacity check: every position may need a node and an edge (the regrow pass sizes slots
+    // for the sum of all layer lengths, which always suffices)
+    if (nV0 + len > sl.max_nodes || nE0 + len > sl.max_edges) {
+      if (ex.leader()) fail(nV0 + len > sl.max_nodes ? kStNodeOverflow : kStEdgeOverflow);
+      ex.sync();
+      return;
+    }
+    const uint32_t covinc = len > 1 ? 1u : 0u;  // Node::Coverage counts edge labels: a 1-base sequence has none
     const uint32_t n = ws.aln_len;
+    uint32_t* npos = sl.tmp1;  // node id of every sequence position
+    const int W = ex.width(), L = ex.lane();
+    auto new_node = [&](uint32_t v, uint32_t code) {
+      g.code[v] = static_cast<uint8_t>(code);
+      g.nal[v] = 0;
+      g.nin[v] = 0;
+      g.nout[v] = 0;
+      g.cov[v] = covinc;
+    };
+    uint32_t newV = 0;
     if (n == 0) {
-      add_sequence(g, codes, layer, 0, len, nV0);
-      return;
-    }
-    // first / last aligned sequence position
-    uint32_t vfront = kNone, vback = kNone;
-    for (uint32_t t = n; t-- > 0;) {
-      if (sl.aln_pos[t] != -1) {
-        if (vfront == kNone) vfront = sl.aln_pos[t];
-        vback = sl.aln_pos[t];
+      for (uint32_t pos = L; pos < len; pos += W) {
+        new_node(nV0 + pos, codes[pos]);
+        npos[pos] = nV0 + pos;
       }
+      newV = len;
+    } else {
+      uint32_t mn = kNone, mx = 0;
+      for (uint32_t t = L; t < n; t += W) {
+        const int32_t p = sl.aln_pos[t];
+        if (p != -1) {
+          mn = static_cast<uint32_t>(p) < mn ? static_cast<uint32_t>(p) : mn;
+          mx = static_cast<uint32_t>(p) > mx ? static_cast<uint32_t>(p) : mx;
+        }
+      }
+      mn = ex.reduce_min(mn);
+      mx = ex.reduce_max(mx);
+      if (mn == kNone) {
+        if (ex.leader()) fail(kStInternal);
+        ex.sync();
+        return;
+      }
+      const uint32_t vfront = mn, vback = mx;
+      const uint32_t nPre = vfront, nSuf = len - vback - 1;
+      for (uint32_t pos = L; pos < vfront; pos += W) {
+        new_node(nV0 + pos, codes[pos]);
+        npos[pos] = nV0 + pos;
+      }
+      for (uint32_t pos = vback + 1 + L; pos < len; pos += W) {
+        const uint32_t v = nV0 + nPre + (pos - vback - 1);
+        new_node(v, codes[pos]);
+        npos[pos] = v;
+      }
+      const uint32_t base = nV0 + nPre + nSuf;
+      uint32_t carry = 0;
+      for (uint32_t f0 = 0; f0 < n; f0 += W) {
+        const uint32_t f = f0 + L;
+        int32_t pos = -1, nd = -1;
+        if (f < n) {
+          pos = sl.aln_pos[n - 1 - f];
+          nd = sl.aln_node[n - 1 - f];
+        }
+        uint32_t curr = kNone, code = 0, kind = 0;  // kind: 0 none/existing, 1 new unaligned, 2 new aligned
+        if (pos != -1) {
+          code = codes[pos];
+          if (nd == -1) {
+            kind = 1;
+          } else {
+            const uint32_t jt = static_cast<uint32_t>(nd);
+            if (g.code[jt] == code) {
+              curr = jt;
+            } else {
+              const uint32_t na = g.nal[jt];
+              for (uint32_t i = 0; i < na; ++i) {
+                const uint32_t kt = g.al[jt * kAlStride + i];
+                if (g.code[kt] == code) {
+                  curr = kt;
+                  break;
+                }
+              }
+              if (curr == kNone) kind = 2;
+            }
+          }
+        }
+        uint32_t tot;
+        const uint32_t idx = ex.excl_scan(kind ? 1u : 0u, &tot);
+        if (kind) {
+          curr = base + carry + idx;
+          new_node(curr, code);
+          if (kind == 2) {
+            const uint32_t jt = static_cast<uint32_t>(nd);
+            const uint32_t na = g.nal[jt];
+            if (na + 1 > static_cast<uint32_t>(kMaxAligned)) {
+              fail(kStAlignedOverflow);
+            } else {
+              for (uint32_t i = 0; i < na; ++i) {
+                const uint32_t kt = g.al[jt * kAlStride + i];
+                g.al[kt * kAlStride + g.nal[kt]] = curr;
+                g.nal[kt] = g.nal[kt] + 1;
+                g.al[curr * kAlStride + i] = kt;
+              }
+              g.al[jt * kAlStride + na] = curr;
+              g.nal[jt] = static_cast<uint8_t>(na + 1);
+              g.al[curr * kAlStride + na] = jt;
+              g.nal[curr] = static_cast<uint8_t>(na + 1);
+            }
+          }
+        } else if (pos != -1) {
+          g.cov[curr] += covinc;
+        }
+        if (pos != -1) npos[pos] = curr;
+        carry += tot;
+      }
+      newV = nPre + nSuf + carry;
     }
-    if (vfront == kNone) {
-      fail(kStInternal);
-      return;
-    }
-    uint32_t begin = add_sequence(g, codes, layer, 0, vfront, nV0);
-    uint32_t prev = begin != kNone ? g.nV - 1 : kNone;
-    uint32_t last = add_sequence(g, codes, layer, vback + 1, len, nV0);
+    ex.sync();
     if (ws.status != kStOk) return;
-    for (uint32_t t = n; t-- > 0;) {
-      const int32_t pos = sl.aln_pos[t];
-      if (pos == -1) continue;
-      const int32_t nd = sl.aln_node[t];
-      const uint32_t code = codes[pos];
-      uint32_t curr = kNone;
-      if (nd == -1) {
-        curr = add_node(g, code);
-      } else {
-        const uint32_t jt = static_cast<uint32_t>(nd);
-        if (g.code[jt] == code) {
-          curr = jt;
-        } else {
-          const uint32_t na = g.nal[jt];
-          for (uint32_t i = 0; i < na; ++i) {
-            const uint32_t kt = g.al[jt * kMaxAligned + i];
-            if (g.code[kt] == code) {
-              curr = kt;
+    // edges between consecutive sequence positions (weight = w[pos-1] + w[pos], graph.cpp:126,290,296)
+    uint32_t ecarry = 0;
+    for (uint32_t p0 = 1; p0 < len; p0 += W) {
+      const uint32_t pos = p0 + L;
+      bool need = pos < len;
+      uint32_t tail = 0, head = 0, w = 0;
+      if (need) {
+        tail = npos[pos - 1];
+        head = npos[pos];
+        w = weight_at(layer, pos - 1) + weight_at(layer, pos);
+        if (tail < nV0 && head < nV0) {
+          for (uint32_t i = sl.in_off[head]; i < sl.in_off[head + 1]; ++i) {
+            if (sl.in_tail[i] == tail) {
+              g.ew[sl.in_eid[i]] += w;
+              need = false;
               break;
             }
           }
-          if (curr == kNone) {
-            if (na + 1 > static_cast<uint32_t>(kMaxAligned)) {
-              fail(kStAlignedOverflow);
-              return;
-            }
-            curr = add_node(g, code);
-            if (ws.status != kStOk) return;
-            for (uint32_t i = 0; i < na; ++i) {
-              const uint32_t kt = g.al[jt * kMaxAligned + i];
-              g.al[kt * kMaxAligned + g.nal[kt]++] = curr;
-              g.al[curr * kMaxAligned + g.nal[curr]++] = kt;
-            }
-            g.al[jt * kMaxAligned + g.nal[jt]++] = curr;
-            g.al[curr * kMaxAligned + g.nal[curr]++] = jt;
-          }
         }
       }
-      if (ws.status != kStOk) return;
-      g.cov[curr] += ws.scratch[1];
-      if (begin == kNone) begin = curr;
-      if (prev != kNone) add_edge(g, prev, curr, weight_at(layer, pos - 1) + weight_at(layer, pos), nV0);
-      prev = curr;
+      uint32_t tot;
+      const uint32_t idx = ex.excl_scan(need ? 1u : 0u, &tot);
+      if (need) {
+        const uint32_t e = nE0 + ecarry + idx;
+        g.etail[e] = tail;
+        g.ehead[e] = head;
+        g.ew[e] = w;
+        g.edead[e] = 0;
+        g.ein_ord[e] = g.nin[head];
+        g.nin[head] = g.nin[head] + 1;
+        g.eout_ord[e] = g.nout[tail];
+        g.nout[tail] = g.nout[tail] + 1;
+      }
+      ecarry += tot;
     }
-    if (last != kNone) add_edge(g, prev, last, weight_at(layer, vback) + weight_at(layer, vback + 1), nV0);
+    if (ex.leader()) {
+      g.nV = nV0 + newV;
+      g.nE = nE0 + ecarry;
+    }
+    ex.sync();
   }
 
   // ---- graph.cpp:1104-1165: parallel over alignment entries; weight adds commute --------------------
@@ -832,8 +1000,7 @@ struct Poa {
     ex.template fill<K>(sl, ws, codes, len, mode, sc, bv.num_codes);
     ex.sync();
     tick(kPhFill);
-    if (ex.leader()) traceback(codes, mode, sc);
-    ex.sync();
+    traceback(codes, mode, sc);
     tick(kPhTrace);
   }
 
@@ -907,7 +1074,7 @@ struct Poa {
       const uint32_t v = path[n - 1 - i];
       out[i] = bv.decoder[g.code[v]];
       uint32_t c = g.cov[v];
-      for (uint32_t a = 0; a < g.nal[v]; ++a) c += g.cov[g.al[v * kMaxAligned + a]];
+      for (uint32_t a = 0; a < g.nal[v]; ++a) c += g.cov[g.al[v * kAlStride + a]];
       cov_out[i] = c;
     }
     return n;
@@ -951,11 +1118,9 @@ struct Poa {
       uint8_t* codes = ex.seq_codes();
       for (uint32_t i = ex.lane(); i < blen; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[bb] + i]];
       ex.sync();
-      if (ex.leader()) {
-        ws.aln_len = 0;
-        add_alignment(codes, bb, blen);
-      }
+      if (ex.leader()) ws.aln_len = 0;
       ex.sync();
+      add_alignment(codes, bb, blen);
       if (ws.status != kStOk) return;
     }
     uint32_t nMain = resort_main();
@@ -974,8 +1139,7 @@ struct Poa {
         align(l, kModeNW, nw, sl.order, nSub, true);
       }
       if (ws.status != kStOk) return;
-      if (ex.leader()) add_alignment(ex.seq_codes(), l, len);
-      ex.sync();
+      add_alignment(ex.seq_codes(), l, len);
       tick(kPhAddAln);
       if (ws.status != kStOk) return;
       nMain = resort_main();

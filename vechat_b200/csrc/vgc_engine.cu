@@ -57,6 +57,19 @@ struct WarpEx {
   __device__ __forceinline__ bool leader() const { return lane_ == 0; }
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+  __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+  // traceback-time layout: codes[max_len] | stage | ni[nV] u32 | p1[nV] u16  (the profile is dead by then)
+  __device__ bool trace_tables(uint32_t nV, uint32_t** ni, uint16_t** p1) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(prof());
+    const uint32_t avail = sm_bytes - static_cast<uint32_t>(base - sm);
+    const uint32_t need = ((nV * 4u + 15u) & ~15u) + nV * 2u;
+    if (need > avail) return false;
+    *ni = reinterpret_cast<uint32_t*>(base);
+    *p1 = reinterpret_cast<uint16_t*>(base + ((nV * 4u + 15u) & ~15u));
+    return true;
+  }
+  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+  __device__ __forceinline__ uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
   __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
     uint32_t x = v;
 #pragma unroll
