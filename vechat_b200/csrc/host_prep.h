@@ -53,6 +53,9 @@ struct Prepared {
   std::vector<uint32_t> out_cap;     // [n_windows]
   std::vector<uint32_t> device_windows;  // windows that need the device (>= 3 sequences), heaviest first
   std::vector<uint64_t> win_work;    // estimated DP cells per window
+  std::vector<uint32_t> win_sum_len; // sum of layer lengths (upper bound of graph nodes)
+  std::vector<uint32_t> win_max_len; // longest layer
+  std::vector<uint32_t> win_nfill;   // alignments (DP fills) the window program runs
   uint8_t coder[256];
   uint8_t decoder[kMaxCodes];
   uint32_t num_codes = 0;
@@ -84,6 +87,9 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
   out->out_off.assign(nw, 0);
   out->out_cap.assign(nw, 0);
   out->win_work.assign(nw, 0);
+  out->win_sum_len.assign(nw, 0);
+  out->win_max_len.assign(nw, 0);
+  out->win_nfill.assign(nw, 0);
   out->device_windows.clear();
   std::memset(out->coder, 0xFF, sizeof(out->coder));
   std::memset(out->decoder, 0, sizeof(out->decoder));
@@ -171,6 +177,10 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
       out->max_len = std::max(out->max_len, max_len);
       out->max_nodes_ub = std::max(out->max_nodes_ub, sum_len);
       out->win_work[w] = sum_len * static_cast<uint64_t>(blen) * (p->haplotype ? 3 : 1) * nseq / 8 + 1;
+      out->win_sum_len[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 0xFFFFFFFFu));
+      out->win_max_len[w] = max_len;
+      // fills of the window program (poa_core.h advance()): build + realign rounds + final, or build only
+      out->win_nfill[w] = p->haplotype ? (nseq - 1) + (p->num_prune - 1) * nseq + 1 : (nseq - 1);
     }
     out_total += out->out_cap[w];
     // average_weight (haplotype mode only): fp64 sum in rank order (window.cpp:215-309).  The addend
@@ -203,7 +213,10 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
   }
   out->out_total = out_total;
   std::stable_sort(out->device_windows.begin(), out->device_windows.end(),
-                   [&](uint32_t a, uint32_t c) { return out->win_work[a] > out->win_work[c]; });
+                   [&](uint32_t a, uint32_t c) {
+                     if (out->win_nfill[a] != out->win_nfill[c]) return out->win_nfill[a] > out->win_nfill[c];
+                     return out->win_work[a] > out->win_work[c];
+                   });
   return VGC_OK;
 }
 

@@ -65,6 +65,7 @@ enum : uint32_t {
 };
 
 enum : uint32_t { kModeNW = 0, kModeSW = 1 };
+enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRealignPost = 2, kPcFinalPost = 3, kPcDone = 4 };
 
 // flags byte per node used by the sorts
 enum : uint8_t {
@@ -162,6 +163,14 @@ struct WinState {
   int32_t best_score;
   uint32_t nseq_added;
   uint32_t scratch[4];
+  // resumable window program (Poa::advance): the fill of the pending alignment runs between two advances
+  uint32_t pc;           // kPc*
+  uint32_t j;            // layer cursor of the current phase
+  uint32_t k;            // prune round
+  uint32_t nMain;        // rows of the whole current graph (rank order in r2n)
+  uint32_t fill_layer;   // pending alignment: layer id, mode, sub-graph flag
+  uint32_t fill_mode;
+  uint32_t fill_pending;
   unsigned long long cells;
   uint32_t alignments;
   // per-phase cycle counters (leader lane, clock64): see kPh*
@@ -972,36 +981,35 @@ struct Poa {
     ex.sync();
   }
 
-  // ---- stage a layer: codes into fast storage (returned pointer), profile via the executor ---------
-  VGC_HD void align(uint32_t layer, uint32_t mode, const Scores& sc, const uint32_t* order, uint32_t nR,
-                    bool sub, bool rebuild_rowprog = true) {
+  // ---- stage a layer's codes into the executor's fast storage ------------------------------------
+  VGC_HD uint8_t* stage_codes(uint32_t layer) {
     const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
-    tick(kPhOther);
-    if (rebuild_rowprog) build_rowprog(order, nR, sub);
-    tick(kPhRowprog);
-    if (ex.leader()) {
-      ws.alignments += 1;
-      ws.cells += static_cast<unsigned long long>(nR + 1) * len;  // (R_a + 1) * L_a of the graph aligned to
-    }
     uint8_t* codes = ex.seq_codes();
     for (uint32_t i = ex.lane(); i < len; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[layer] + i]];
     ex.sync();
-    // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
-    {
-      int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
-      if (-sc.g > a) a = -sc.g;
-      if (static_cast<int64_t>(nR + RM::kCols + 8) * a > 30000) {
-        if (ex.leader()) fail(kStScoreRange);
-        ex.sync();
-        return;
-      }
-    }
+    return codes;
+  }
+
+  // ---- make the next alignment pending: row program over order[0..nR) + bookkeeping.  The fill itself runs
+  //      outside (fill kernel on the device, HostEx::fill in the host model), then advance() resumes.
+  VGC_HD void schedule(uint32_t layer, uint32_t mode, const uint32_t* order, uint32_t nR, bool sub, bool rebuild) {
+    const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
     tick(kPhOther);
-    ex.template fill<K>(sl, ws, codes, len, mode, sc, bv.num_codes);
+    if (rebuild) build_rowprog(order, nR, sub);
+    tick(kPhRowprog);
+    // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
+    const Scores& sc = mode == kModeNW ? nw : sw;
+    int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
+    if (-sc.g > a) a = -sc.g;
+    if (ex.leader()) {
+      if (static_cast<int64_t>(nR + RM::kCols + 8) * a > 30000) fail(kStScoreRange);
+      ws.alignments += 1;
+      ws.cells += static_cast<unsigned long long>(nR + 1) * len;  // (R_a + 1) * L_a of the graph aligned to
+      ws.fill_layer = layer;
+      ws.fill_mode = mode;
+      ws.fill_pending = 1;
+    }
     ex.sync();
-    tick(kPhFill);
-    traceback(codes, mode, sc);
-    tick(kPhTrace);
   }
 
   VGC_HD uint32_t resort_main() {
@@ -1080,9 +1088,13 @@ struct Poa {
     return n;
   }
 
-  // ---- the window (src/window.cpp:74-174 and :176-428) ---------------------------------------------
-  VGC_HD void run_window(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
-                         uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
+  // ---- the window (src/window.cpp:74-174 and :176-428) as a resumable program -------------------------
+  //      advance() runs the window up to (and including) the scheduling of its next alignment and returns;
+  //      ws.fill_pending says whether a fill must run before the next advance().  ws.pc == kPcDone: finished
+  //      (ws.status tells how).  The number of fills of a window is known on the host:
+  //      haplotype: (nseq-1) + (num_prune-1)*nseq + 1, linear: nseq-1.
+  VGC_HD void advance(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
+                      uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
     const uint32_t first = bv.win_first[w];
     const uint32_t nseq = bv.win_nseq[w];
     const uint32_t* rank = bv.layer_rank + first;
@@ -1090,135 +1102,214 @@ struct Poa {
     const uint32_t blen = static_cast<uint32_t>(bv.seq_off[bb + 1] - bv.seq_off[bb]);
     const uint32_t offset = static_cast<uint32_t>(0.01 * blen);
     const uint32_t out_cap = bv.out_cap[w];
-    if (ex.leader()) {
-      ws.cur = 0;
-      ws.status = kStOk;
-      ws.aln_len = 0;
-      ws.cells = 0;
-      ws.alignments = 0;
-      sl.g[0].nV = 0;
-      sl.g[0].nE = 0;
-      *out_len = 0;
-      ws.t_last = ex.clock();
-      for (int i = 0; i < kPhCount; ++i) ws.phase[i] = 0;
-    }
+    const double avgw = bv.win_avgw[w];
+    const uint32_t pc = ws.pc;
+    if (pc == kPcDone) return;
+    enum Act { kBuildNext, kRoundStart, kRealignNext, kFinalSchedule };
+    Act act = kBuildNext;
+    uint32_t j = ws.j, k = ws.k, nMain = ws.nMain;
     ex.sync();
-    // every layer must fit one row of the H matrix
-    for (uint32_t j = 0; j < nseq; ++j) {
-      const uint32_t len = static_cast<uint32_t>(bv.seq_off[rank[j] + 1] - bv.seq_off[rank[j]]);
-      if (len > static_cast<uint32_t>(RM::kCols) || len > sl.max_len) {
-        if (ex.leader()) fail(kStTooLong);
-      }
-    }
-    ex.sync();
-    if (ws.status != kStOk) return;
-
-    // backbone: AddAlignment with an empty alignment (window.cpp:197-201)
-    {
-      uint8_t* codes = ex.seq_codes();
-      for (uint32_t i = ex.lane(); i < blen; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[bb] + i]];
-      ex.sync();
-      if (ex.leader()) ws.aln_len = 0;
-      ex.sync();
-      add_alignment(codes, bb, blen);
-      if (ws.status != kStOk) return;
-    }
-    uint32_t nMain = resort_main();
-
-    // build loop (window.cpp:239-298 / :100-136)
-    for (uint32_t j = 1; j < nseq; ++j) {
-      const uint32_t l = rank[j];
-      const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
-      const uint32_t lb = bv.begin[l], le = bv.end[l];
-      if (lb < offset && le > blen - offset) {
-        align(l, kModeNW, nw, sl.r2n, nMain, false);
-      } else {
-        tick(kPhOther);
-        const uint32_t nSub = sort_graph(true, lb, le, sl.order);
-        tick(kPhSort);
-        align(l, kModeNW, nw, sl.order, nSub, true);
-      }
-      if (ws.status != kStOk) return;
-      add_alignment(ex.seq_codes(), l, len);
-      tick(kPhAddAln);
-      if (ws.status != kStOk) return;
-      nMain = resort_main();
-    }
-
-    if (!haplotype) {
-      // linear mode: consensus + coverage trim (window.cpp:138-171)
-      build_csr(true);
+    if (ex.leader()) ws.t_last = ex.clock();
+    auto finish = [&]() {
       if (ex.leader()) {
-        uint32_t* cov = sl.tmp0;
-        uint32_t n = heaviest_bundle(nMain, out, out_cap, cov);
-        if (ws.status == kStOk) {
-          uint32_t b = 0, e = n;
-          if ((bv.win_flags[w] & 1u) && trim) {
-            const uint32_t avg = (nseq - 1) / 2;
-            int32_t bi = 0, ei = static_cast<int32_t>(n) - 1;
-            for (; bi < static_cast<int32_t>(n); ++bi) {
-              if (cov[bi] >= avg) break;
-            }
-            for (; ei >= 0; --ei) {
-              if (cov[ei] >= avg) break;
-            }
-            if (bi < ei) {
-              b = bi;
-              e = ei + 1;
-            }
-          }
-          for (uint32_t i = b; i < e; ++i) out[i - b] = out[i];
-          *out_len = e - b;
+        ws.pc = kPcDone;
+        ws.fill_pending = 0;
+      }
+      ex.sync();
+    };
+    auto commit = [&](uint32_t next_pc) {
+      if (ex.leader()) {
+        ws.pc = ws.status == kStOk ? next_pc : kPcDone;
+        if (ws.status != kStOk) ws.fill_pending = 0;
+        ws.j = j;
+        ws.k = k;
+        ws.nMain = nMain;
+      }
+      ex.sync();
+    };
+
+    if (pc == kPcInit) {
+      if (ex.leader()) {
+        ws.cur = 0;
+        ws.status = kStOk;
+        ws.aln_len = 0;
+        ws.cells = 0;
+        ws.alignments = 0;
+        ws.fill_pending = 0;
+        sl.g[0].nV = 0;
+        sl.g[0].nE = 0;
+        *out_len = 0;
+        for (int i = 0; i < kPhCount; ++i) ws.phase[i] = 0;
+      }
+      ex.sync();
+      // every layer must fit one row of the H matrix
+      for (uint32_t t = 0; t < nseq; ++t) {
+        const uint32_t len = static_cast<uint32_t>(bv.seq_off[rank[t] + 1] - bv.seq_off[rank[t]]);
+        if (len > static_cast<uint32_t>(RM::kCols) || len > sl.max_len) {
+          if (ex.leader()) fail(kStTooLong);
         }
       }
       ex.sync();
-      return;
-    }
-
-    // haplotype mode: prune + re-align rounds (window.cpp:300-394)
-    const double avgw = bv.win_avgw[w];
-    tick(kPhOther);
-    prune(min_confidence, min_support, avgw);
-    tick(kPhPrune);
-    largest_subgraph();
-    tick(kPhLargest);
-    for (uint32_t k = 0; k + 1 < num_prune; ++k) {
+      if (ws.status != kStOk) return finish();
+      // backbone: AddAlignment with an empty alignment (window.cpp:197-201)
+      uint8_t* codes = stage_codes(bb);
+      add_alignment(codes, bb, blen);
+      if (ws.status != kStOk) return finish();
       nMain = resort_main();
-      for (uint32_t j = 0; j < nseq; ++j) {
-        const uint32_t l = rank[j];
-        const uint32_t lb = bv.begin[l], le = bv.end[l];
-        const bool global = (j == 0) || (lb < offset && le > blen - offset);
-        align(l, global ? kModeNW : kModeSW, global ? nw : sw, sl.r2n, nMain, false, j == 0);
-        if (ws.status != kStOk) return;
+      j = 1;
+      act = kBuildNext;
+    } else {
+      // resume after the fill of the pending alignment
+      const uint32_t l = ws.fill_layer, mode = ws.fill_mode;
+      const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
+      uint8_t* codes = stage_codes(l);
+      if (ex.leader()) ws.fill_pending = 0;
+      tick(kPhOther);
+      traceback(codes, mode, mode == kModeNW ? nw : sw);
+      tick(kPhTrace);
+      if (ws.status != kStOk) return finish();
+      if (pc == kPcBuildPost) {
+        add_alignment(codes, l, len);
+        tick(kPhAddAln);
+        if (ws.status != kStOk) return finish();
+        nMain = resort_main();
+        ++j;
+        act = kBuildNext;
+      } else if (pc == kPcRealignPost) {
         add_weights(l);
         tick(kPhAddW);
-        if (ws.status != kStOk) return;
-      }
-      prune(min_confidence, min_support, avgw);
-      tick(kPhPrune);
-      largest_subgraph();
-      tick(kPhLargest);
-    }
-    nMain = resort_main();
-    align(bb, kModeSW, sw, sl.r2n, nMain, false);
-    if (ws.status != kStOk) return;
-    // graph.cpp:1167-1179
-    if (ex.leader()) {
-      Graph& g = G();
-      uint32_t n = 0;
-      for (uint32_t t = ws.aln_len; t-- > 0;) {
-        const int32_t nd = sl.aln_node[t];
-        if (nd == -1) continue;
-        if (n >= out_cap) {
-          fail(kStOutOverflow);
-          break;
+        if (ws.status != kStOk) return finish();
+        ++j;
+        act = kRealignNext;
+      } else {
+        // graph.cpp:1167-1179
+        if (ex.leader()) {
+          Graph& g = G();
+          uint32_t n = 0;
+          for (uint32_t t = ws.aln_len; t-- > 0;) {
+            const int32_t nd = sl.aln_node[t];
+            if (nd == -1) continue;
+            if (n >= out_cap) {
+              fail(kStOutOverflow);
+              break;
+            }
+            out[n++] = bv.decoder[g.code[nd]];
+          }
+          *out_len = n;
         }
-        out[n++] = bv.decoder[g.code[nd]];
+        ex.sync();
+        tick(kPhEmit);
+        return finish();
       }
-      *out_len = n;
+    }
+
+    while (true) {
+      if (act == kBuildNext) {
+        // build loop (window.cpp:239-298 / :100-136)
+        if (j < nseq) {
+          const uint32_t l = rank[j];
+          const uint32_t lb = bv.begin[l], le = bv.end[l];
+          if (lb < offset && le > blen - offset) {
+            schedule(l, kModeNW, sl.r2n, nMain, false, true);
+          } else {
+            tick(kPhOther);
+            const uint32_t nSub = sort_graph(true, lb, le, sl.order);
+            tick(kPhSort);
+            schedule(l, kModeNW, sl.order, nSub, true, true);
+          }
+          return commit(kPcBuildPost);
+        }
+        if (!haplotype) {
+          // linear mode: consensus + coverage trim (window.cpp:138-171)
+          build_csr(true);
+          if (ex.leader()) {
+            uint32_t* cov = sl.tmp0;
+            uint32_t n = heaviest_bundle(nMain, out, out_cap, cov);
+            if (ws.status == kStOk) {
+              uint32_t b = 0, e = n;
+              if ((bv.win_flags[w] & 1u) && trim) {
+                const uint32_t avg = (nseq - 1) / 2;
+                int32_t bi = 0, ei = static_cast<int32_t>(n) - 1;
+                for (; bi < static_cast<int32_t>(n); ++bi) {
+                  if (cov[bi] >= avg) break;
+                }
+                for (; ei >= 0; --ei) {
+                  if (cov[ei] >= avg) break;
+                }
+                if (bi < ei) {
+                  b = bi;
+                  e = ei + 1;
+                }
+              }
+              for (uint32_t i = b; i < e; ++i) out[i - b] = out[i];
+              *out_len = e - b;
+            }
+          }
+          ex.sync();
+          tick(kPhEmit);
+          return finish();
+        }
+        // haplotype mode: prune (window.cpp:300-319)
+        tick(kPhOther);
+        prune(min_confidence, min_support, avgw);
+        tick(kPhPrune);
+        largest_subgraph();
+        tick(kPhLargest);
+        k = 0;
+        act = kRoundStart;
+      } else if (act == kRoundStart) {
+        if (k + 1 < num_prune) {
+          nMain = resort_main();
+          j = 0;
+          act = kRealignNext;
+        } else {
+          act = kFinalSchedule;
+        }
+      } else if (act == kRealignNext) {
+        // re-align + re-weight rounds (window.cpp:329-386)
+        if (j < nseq) {
+          const uint32_t l = rank[j];
+          const uint32_t lb = bv.begin[l], le = bv.end[l];
+          const bool global = (j == 0) || (lb < offset && le > blen - offset);
+          schedule(l, global ? kModeNW : kModeSW, sl.r2n, nMain, false, j == 0);
+          return commit(kPcRealignPost);
+        }
+        tick(kPhOther);
+        prune(min_confidence, min_support, avgw);
+        tick(kPhPrune);
+        largest_subgraph();
+        tick(kPhLargest);
+        ++k;
+        act = kRoundStart;
+      } else {
+        // final local alignment of the backbone (window.cpp:391-394)
+        nMain = resort_main();
+        schedule(bb, kModeSW, sl.r2n, nMain, false, true);
+        return commit(kPcFinalPost);
+      }
+    }
+  }
+
+  // Whole window in one go (host model; a single-kernel device build could use it too).
+  VGC_HD void run_window(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
+                         uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
+    if (ex.leader()) {
+      ws.pc = kPcInit;
+      ws.j = ws.k = ws.nMain = 0;
+      ws.fill_pending = 0;
     }
     ex.sync();
-    tick(kPhEmit);
+    while (true) {
+      advance(w, haplotype, trim, min_confidence, min_support, num_prune, out, out_len);
+      if (ws.pc == kPcDone) break;
+      if (ws.fill_pending) {
+        const uint32_t l = ws.fill_layer;
+        const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
+        uint8_t* codes = stage_codes(l);
+        ex.template fill<K>(sl, ws, codes, len, ws.fill_mode, ws.fill_mode == kModeNW ? nw : sw, bv.num_codes);
+        ex.sync();
+      }
+    }
   }
 };
 

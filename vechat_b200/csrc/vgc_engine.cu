@@ -27,12 +27,13 @@ namespace vgc {
 
 constexpr int kSmemHeader = 896;  // Slot + WinState copies
 
+// Arguments shared by the two kernels of a lockstep pass.  `idx` below is the position of a window in the
+// pass's work list (windows ordered group by group, inside a group by decreasing number of fills).
 struct KernelArgs {
   BatchView bv;
-  const uint32_t* work;    // window ids to process
-  uint32_t n_work;
-  uint32_t* cursor;        // atomic work cursor
-  const Slot* slots;       // one per CTA
+  const uint32_t* work;    // [n] window ids
+  const Slot* slots;       // [n] scratch slot of work[idx]
+  WinState* wstates;       // [n] resumable program state of work[idx]
   uint8_t* out;            // output bytes (bv.out_off / out_cap index into it)
   uint32_t* out_len;       // [n_windows]
   uint32_t* status;        // [n_windows]
@@ -40,7 +41,7 @@ struct KernelArgs {
   Scores nw;
   uint32_t haplotype, trim, num_prune;
   double min_confidence, min_support;
-  uint32_t smem_bytes;     // dynamic shared memory per CTA
+  uint32_t smem_bytes;     // dynamic shared memory per CTA of the launched kernel
 };
 
 // Warp executor: the device side of poa_core.h's `Ex` concept.
@@ -58,16 +59,6 @@ struct WarpEx {
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-  // traceback-time layout: codes[max_len] | stage | ni[nV] u32 | p1[nV] u16  (the profile is dead by then)
-  __device__ bool trace_tables(uint32_t nV, uint32_t** ni, uint16_t** p1) {
-    uint8_t* base = reinterpret_cast<uint8_t*>(prof());
-    const uint32_t avail = sm_bytes - static_cast<uint32_t>(base - sm);
-    const uint32_t need = ((nV * 4u + 15u) & ~15u) + nV * 2u;
-    if (need > avail) return false;
-    *ni = reinterpret_cast<uint32_t*>(base);
-    *p1 = reinterpret_cast<uint16_t*>(base + ((nV * 4u + 15u) & ~15u));
-    return true;
-  }
   __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
   __device__ __forceinline__ uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
   __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
@@ -80,45 +71,65 @@ struct WarpEx {
     *total = __shfl_sync(0xFFFFFFFFu, x, 31);
     return x - v;
   }
-  // sort-time working set in shared memory: flags[nV] | off16[nV+1] | tail16[nE] | stack16[>=256]
+  // layout: codes[max_len] | arena.  The arena is reused phase by phase:
+  //   sort      : flags[nV] | off16[nV+1] | tail16[nE] | stack16[>=256]
+  //   traceback : ni[nV] u32 | p1[nV] u16
+  __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
+  __device__ __forceinline__ uint8_t* arena() { return sm + ((max_len + 15u) & ~15u); }
+  __device__ __forceinline__ uint32_t arena_bytes() { return sm_bytes - ((max_len + 15u) & ~15u); }
   __device__ bool stage_fast(uint32_t nV, uint32_t nE, uint8_t** f, uint16_t** o, uint16_t** t, uint16_t** s,
                              uint32_t* cap) {
     if (nV >= 65535u || nE >= 65535u) return false;
-    const uint32_t fo = 0;
     const uint32_t oo = (nV + 3u) & ~3u;
     const uint32_t to = oo + (((nV + 1u) * 2u + 3u) & ~3u);
     const uint32_t so = to + ((nE * 2u + 3u) & ~3u);
-    if (so + 512u > sm_bytes) return false;
-    *f = sm + fo;
-    *o = reinterpret_cast<uint16_t*>(sm + oo);
-    *t = reinterpret_cast<uint16_t*>(sm + to);
-    *s = reinterpret_cast<uint16_t*>(sm + so);
-    *cap = (sm_bytes - so) / 2u;
+    const uint32_t avail = arena_bytes();
+    if (so + 512u > avail) return false;
+    uint8_t* base = arena();
+    *f = base;
+    *o = reinterpret_cast<uint16_t*>(base + oo);
+    *t = reinterpret_cast<uint16_t*>(base + to);
+    *s = reinterpret_cast<uint16_t*>(base + so);
+    *cap = (avail - so) / 2u;
     return true;
   }
-  // alignment-time layout: codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words]
-  __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
-  __device__ __forceinline__ uint4* stage() { return reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u)); }
-  __device__ __forceinline__ uint32_t* prof() { return reinterpret_cast<uint32_t*>(stage() + 32); }
-
-  template <int KK>
-  __device__ __forceinline__ void fill(Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, uint32_t mode,
-                                       const Scores& sc, uint32_t num_codes) {
-    warp_fill<KK>(sl, ws, codes, len, mode, sc, num_codes, prof(), stage());
+  __device__ bool trace_tables(uint32_t nV, uint32_t** ni, uint16_t** p1) {
+    uint8_t* base = arena();
+    const uint32_t need = ((nV * 4u + 15u) & ~15u) + nV * 2u;
+    if (need > arena_bytes()) return false;
+    *ni = reinterpret_cast<uint32_t*>(base);
+    *p1 = reinterpret_cast<uint16_t*>(base + ((nV * 4u + 15u) & ~15u));
+    return true;
   }
+  // the fill runs in its own kernel (fill_kernel): never called through the executor on the device
+  template <int KK>
+  __device__ __forceinline__ void fill(Slot&, WinState&, const uint8_t*, uint32_t, uint32_t, const Scores&, uint32_t) {}
 };
 
+__device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t bytes, int lane) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (uint32_t i = lane; i < bytes / 4; i += 32) d[i] = s[i];
+}
+
+#ifndef VGC_GRAPH_CTAS
+#define VGC_GRAPH_CTAS 24
+#endif
+
+// Graph kernel: one warp per window.  Resumes the window program (poa_core.h advance()): traceback of the
+// alignment just filled, graph update (AddAlignment / AddWeights / prune / LargestSubgraph), re-sort, and the row
+// program of the next alignment.  Replaces everything of Window::generate_consensus except the DP fill.
 template <int K>
-__global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32, VGC_GRAPH_CTAS) graph_kernel(const KernelArgs a, uint32_t base) {
   extern __shared__ __align__(16) uint8_t smem[];
   Slot* sl = reinterpret_cast<Slot*>(smem);
   WinState* ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
   const int lane = threadIdx.x;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.slots + blockIdx.x);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sl);
-    for (uint32_t i = lane; i < sizeof(Slot) / 4; i += 32) dst[i] = src[i];
-  }
+  const uint32_t idx = base + blockIdx.x;
+  WinState* gws = a.wstates + idx;
+  if (gws->pc == kPcDone) return;
+  copy_words(sl, a.slots + idx, sizeof(Slot), lane);
+  copy_words(ws, gws, sizeof(WinState), lane);
   __syncwarp();
   WarpEx<K> ex;
   ex.sm = smem + kSmemHeader;
@@ -126,22 +137,63 @@ __global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) 
   ex.max_len = sl->max_len;
   ex.lane_ = lane;
   Poa<WarpEx<K>, K> poa(ex, a.bv, *sl, *ws, a.nw);
-  while (true) {
-    uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(a.cursor, 1u);
-    idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-    if (idx >= a.n_work) break;
-    const uint32_t w = a.work[idx];
-    poa.run_window(w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
-                   a.out + a.bv.out_off[w], a.out_len + w);
-    __syncwarp();
-    if (lane == 0) {
-      a.status[w] = ws->status;
-      atomicAdd(a.totals, ws->cells);
-      atomicAdd(a.totals + 1, static_cast<unsigned long long>(ws->alignments));
-      for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, ws->phase[i]);
-    }
-    __syncwarp();
+  const uint32_t w = a.work[idx];
+  poa.advance(w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
+              a.out + a.bv.out_off[w], a.out_len + w);
+  __syncwarp();
+  // the graph headers (nV, nE) live in the Slot copy: write them back with the program state
+  if (lane == 0) {
+    Slot* gs = const_cast<Slot*>(a.slots + idx);
+    gs->g[0].nV = sl->g[0].nV;
+    gs->g[0].nE = sl->g[0].nE;
+    gs->g[1].nV = sl->g[1].nV;
+    gs->g[1].nE = sl->g[1].nE;
+  }
+  copy_words(gws, ws, sizeof(WinState), lane);
+  if (lane == 0 && ws->pc == kPcDone) {
+    a.status[w] = ws->status;
+    atomicAdd(a.totals, ws->cells);
+    atomicAdd(a.totals + 1, static_cast<unsigned long long>(ws->alignments));
+    for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, ws->phase[i]);
+  }
+}
+
+// Fill kernel: one warp per pending alignment (poa_fill.cuh).  Replaces SimdAlignmentEngine::Linear's fill.
+// shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words]
+template <int K>
+__global__ void __launch_bounds__(32, 16) fill_kernel(const KernelArgs a, uint32_t base) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  Slot* sl = reinterpret_cast<Slot*>(smem);
+  WinState* ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
+  const int lane = threadIdx.x;
+  const uint32_t idx = base + blockIdx.x;
+  WinState* gws = a.wstates + idx;
+  if (gws->pc == kPcDone || gws->fill_pending == 0) return;
+  const unsigned long long t0 = clock64();
+  copy_words(sl, a.slots + idx, sizeof(Slot), lane);
+  copy_words(ws, gws, sizeof(WinState), lane);
+  __syncwarp();
+  uint8_t* sm = smem + kSmemHeader;
+  const uint32_t max_len = sl->max_len;
+  uint8_t* codes = sm;
+  uint4* stage = reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u));
+  uint32_t* prof = reinterpret_cast<uint32_t*>(stage + 32);
+  const uint32_t l = ws->fill_layer;
+  const uint64_t o = a.bv.seq_off[l];
+  const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
+  for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
+  __syncwarp();
+  Scores sw;
+  sw.m = 3;
+  sw.x = -5;
+  sw.g = -4;
+  const uint32_t mode = ws->fill_mode;
+  warp_fill<K>(*sl, *ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage);
+  if (lane == 0) {
+    gws->best_row = ws->best_row;
+    gws->best_col = ws->best_col;
+    gws->best_score = ws->best_score;
+    gws->phase[kPhFill] += clock64() - t0;
   }
 }
 
@@ -209,13 +261,15 @@ struct vgc_engine {
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
-  int ctas_per_sm = 16;
-  uint32_t smem_bytes = 0;
+  int groups = 4;                 // streams of a lockstep pass
+  cudaStream_t gstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t gev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t smem_graph = 0, smem_fill = 0;
   size_t mem_budget = 0;
   // device copies of the batch
   DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
   DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
-  DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem;
+  DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem, d_wstates;
   // host staging (pinned)
   uint8_t* h_out = nullptr;
   size_t h_out_cap = 0;
@@ -274,7 +328,6 @@ int upload(vgc_engine* h, const vgc_batch* b, uint64_t* bytes_out) {
   std::memcpy(tab.data() + 256, pr.decoder, kMaxCodes);
   std::memcpy(tab.data() + 272, pr.wlut, 1024);
   if ((rc = put(h->d_tables, tab.data(), tab.size()))) return rc;
-  if ((rc = put(h->d_work, pr.device_windows.data(), pr.device_windows.size() * 4ull))) return rc;
   cudaError_t e = cudaStreamSynchronize(h->stream);  // `tab` and prep vectors must outlive the copies
   if (e != cudaSuccess) {
     set_err(std::string("H2D sync failed: ") + cudaGetErrorString(e));
@@ -306,67 +359,153 @@ BatchView make_view(vgc_engine* h) {
   return v;
 }
 
+constexpr int kMaxGroups = 8;
+
 template <int K>
-int launch_k(vgc_engine* h, const KernelArgs& a, uint32_t grid) {
-  VGC_CUDA(cudaFuncSetAttribute(poa_window_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  VGC_CUDA(cudaFuncSetAttribute(poa_window_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(a.smem_bytes)));
-  poa_window_kernel<K><<<grid, 32, a.smem_bytes, h->stream>>>(a);
-  VGC_CUDA(cudaGetLastError());
+int set_kernel_attrs(uint32_t smem_graph, uint32_t smem_fill) {
+  VGC_CUDA(cudaFuncSetAttribute(graph_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  VGC_CUDA(cudaFuncSetAttribute(graph_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem_graph)));
+  VGC_CUDA(cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  VGC_CUDA(cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem_fill)));
   return VGC_OK;
 }
 
-// Run the kernel over `work` (device array of window ids) with slots of the given dimensions.
-int run_pass(vgc_engine* h, uint32_t n_work, const uint32_t* d_work, uint32_t max_nodes, uint32_t max_len,
-             int K, uint32_t* launches) {
-  SlotDims d;
-  d.max_nodes = std::max<uint32_t>(max_nodes, 64);
-  d.max_edges = d.max_nodes;
-  d.max_len = std::max<uint32_t>(max_len, 16);
-  d.row_words = 32 * K;
-  const uint64_t per_slot = slot_bytes(d);
-  uint32_t grid = std::min<uint32_t>(n_work, h->sm_count * h->ctas_per_sm);
-  if (per_slot * grid > h->mem_budget) grid = static_cast<uint32_t>(h->mem_budget / per_slot);
-  if (grid == 0) {
-    set_err("a window needs more scratch than the device memory budget");
-    return VGC_ERR_CAPACITY;
+template <int K>
+void launch_graph(const KernelArgs& a, uint32_t base, uint32_t count, cudaStream_t st) {
+  graph_kernel<K><<<count, 32, a.smem_bytes, st>>>(a, base);
+}
+template <int K>
+void launch_fill(const KernelArgs& a, uint32_t base, uint32_t count, cudaStream_t st) {
+  fill_kernel<K><<<count, 32, a.smem_bytes, st>>>(a, base);
+}
+
+// Node capacity of a window's slot on the first pass: backbone + a share of the layer bases (a read adds a node
+// only where it disagrees with the graph) + one layer of head-room for AddAlignment's conservative check.  Windows
+// that outgrow it are re-run with the exact upper bound (sum of layer lengths).
+uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exact) {
+  const uint64_t ub = static_cast<uint64_t>(pr.win_sum_len[w]) + 64;
+  if (exact) return static_cast<uint32_t>(ub);
+  const uint64_t est = blen + pr.win_sum_len[w] / 6 + pr.win_max_len[w] + 64;
+  return static_cast<uint32_t>(std::min(ub, est));
+}
+
+// One lockstep pass over `wins` (ordered by decreasing number of fills): every window gets its own scratch slot,
+// the windows are dealt round-robin to `groups` streams, and each stream alternates graph_kernel / fill_kernel
+// launches — step s resumes the program of every window that still has >= s fills to go.  Chunked by the memory
+// budget.  Windows are independent, so no synchronisation other than stream order is needed.
+int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K, const uint64_t* seq_off,
+             const uint32_t* win_first, uint32_t* launches) {
+  const Prepared& pr = h->prep;
+  const uint32_t row_words = 32 * K;
+  size_t pos = 0;
+  while (pos < wins.size()) {
+    // ---- chunk: as many windows as the budget holds
+    std::vector<SlotDims> dims;
+    std::vector<uint64_t> offs;
+    uint64_t bytes = 0;
+    size_t e = pos;
+    while (e < wins.size()) {
+      const uint32_t w = wins[e];
+      const uint32_t f = win_first[w];
+      SlotDims d;
+      d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact), 64);
+      d.max_edges = d.max_nodes;
+      d.max_len = std::max<uint32_t>(pr.max_len, 16);
+      d.row_words = row_words;
+      const uint64_t sb = slot_bytes(d);
+      if (bytes + sb > h->mem_budget && e > pos) break;
+      if (sb > h->mem_budget) {
+        set_err("a window needs more scratch than the device memory budget");
+        return VGC_ERR_CAPACITY;
+      }
+      dims.push_back(d);
+      offs.push_back(bytes);
+      bytes += sb;
+      ++e;
+    }
+    const uint32_t n = static_cast<uint32_t>(e - pos);
+    int rc;
+    if ((rc = h->d_slot_mem.reserve(bytes))) return rc;
+    if ((rc = h->d_slots.reserve(sizeof(Slot) * n))) return rc;
+    if ((rc = h->d_wstates.reserve(sizeof(WinState) * n))) return rc;
+    if ((rc = h->d_work.reserve(4ull * n))) return rc;
+    // ---- deal the chunk's windows to groups: group g takes sorted positions g, g+G, g+2G, ...
+    const int G = std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)));
+    std::vector<uint32_t> work(n);
+    std::vector<Slot> slots(n);
+    std::vector<uint32_t> gbase(G + 1, 0);
+    std::vector<std::vector<uint32_t>> gfill(G);  // fills of each window of the group, in list order
+    uint32_t k = 0;
+    for (int g = 0; g < G; ++g) {
+      gbase[g] = k;
+      for (uint32_t i = g; i < n; i += G) {
+        work[k] = wins[pos + i];
+        slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
+        gfill[g].push_back(pr.win_nfill[wins[pos + i]]);
+        ++k;
+      }
+    }
+    gbase[G] = k;
+    VGC_CUDA(cudaMemcpyAsync(h->d_work.p, work.data(), 4ull * n, cudaMemcpyHostToDevice, h->stream));
+    VGC_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), sizeof(Slot) * n, cudaMemcpyHostToDevice, h->stream));
+    VGC_CUDA(cudaMemsetAsync(h->d_wstates.p, 0, sizeof(WinState) * n, h->stream));
+    KernelArgs a;
+    a.bv = make_view(h);
+    a.work = h->d_work.as<uint32_t>();
+    a.slots = h->d_slots.as<Slot>();
+    a.wstates = h->d_wstates.as<WinState>();
+    a.out = h->d_out.as<uint8_t>();
+    a.out_len = h->d_out_len.as<uint32_t>();
+    a.status = h->d_status.as<uint32_t>();
+    a.totals = reinterpret_cast<unsigned long long*>(h->d_misc.as<uint8_t>() + 16);
+    a.nw.m = h->params.match;
+    a.nw.x = h->params.mismatch;
+    a.nw.g = h->params.gap;
+    a.haplotype = h->params.haplotype;
+    a.trim = h->params.trim;
+    a.num_prune = h->params.num_prune;
+    a.min_confidence = h->params.min_confidence;
+    a.min_support = h->params.min_support;
+    KernelArgs ag = a, af = a;
+    ag.smem_bytes = h->smem_graph;
+    af.smem_bytes = h->smem_fill;
+    VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
+    // ---- lockstep: the lists are sorted by decreasing fills, so the live windows of step s are a prefix
+    std::vector<uint32_t> liveG(G), liveF(G);
+    for (int g = 0; g < G; ++g) liveG[g] = liveF[g] = static_cast<uint32_t>(gfill[g].size());
+    const uint32_t max_fill = pr.win_nfill[wins[pos]];
+    for (uint32_t s = 0; s <= max_fill; ++s) {
+      for (int g = 0; g < G; ++g) {
+        const std::vector<uint32_t>& nf = gfill[g];
+        while (liveG[g] > 0 && nf[liveG[g] - 1] < s) --liveG[g];       // advance #s exists iff fills >= s
+        while (liveF[g] > 0 && nf[liveF[g] - 1] <= s) --liveF[g];      // fill #s exists iff fills > s
+        if (liveG[g]) {
+          if (K == 10) launch_graph<10>(ag, gbase[g], liveG[g], h->gstream[g]);
+          else launch_graph<16>(ag, gbase[g], liveG[g], h->gstream[g]);
+          ++*launches;
+        }
+        if (liveF[g]) {
+          if (K == 10) launch_fill<10>(af, gbase[g], liveF[g], h->gstream[g]);
+          else launch_fill<16>(af, gbase[g], liveF[g], h->gstream[g]);
+          ++*launches;
+        }
+      }
+    }
+    VGC_CUDA(cudaGetLastError());
+    for (int g = 0; g < G; ++g) {
+      VGC_CUDA(cudaEventRecord(h->gev[g], h->gstream[g]));
+      VGC_CUDA(cudaStreamWaitEvent(h->stream, h->gev[g], 0));
+    }
+    VGC_CUDA(cudaEventRecord(h->ev[7], h->stream));
+    VGC_CUDA(cudaStreamSynchronize(h->stream));  // host vectors must outlive their copies; surfaces kernel faults
+    float kms = 0.f;
+    VGC_CUDA(cudaEventElapsedTime(&kms, h->ev[6], h->ev[7]));
+    h->pass_kernel_ms += kms;
+    pos = e;
   }
-  int rc;
-  if ((rc = h->d_slot_mem.reserve(per_slot * grid))) return rc;
-  if ((rc = h->d_slots.reserve(sizeof(Slot) * grid))) return rc;
-  std::vector<Slot> slots(grid);
-  for (uint32_t i = 0; i < grid; ++i) slot_carve(d, h->d_slot_mem.as<uint8_t>() + per_slot * i, &slots[i]);
-  VGC_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), sizeof(Slot) * grid, cudaMemcpyHostToDevice, h->stream));
-  VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 16, h->stream));  // work cursor (totals accumulate over passes)
-  KernelArgs a;
-  a.bv = make_view(h);
-  a.work = d_work;
-  a.n_work = n_work;
-  a.cursor = h->d_misc.as<uint32_t>();
-  a.slots = h->d_slots.as<Slot>();
-  a.out = h->d_out.as<uint8_t>();
-  a.out_len = h->d_out_len.as<uint32_t>();
-  a.status = h->d_status.as<uint32_t>();
-  a.totals = reinterpret_cast<unsigned long long*>(h->d_misc.as<uint8_t>() + 16);
-  a.nw.m = h->params.match;
-  a.nw.x = h->params.mismatch;
-  a.nw.g = h->params.gap;
-  a.haplotype = h->params.haplotype;
-  a.trim = h->params.trim;
-  a.num_prune = h->params.num_prune;
-  a.min_confidence = h->params.min_confidence;
-  a.min_support = h->params.min_support;
-  a.smem_bytes = h->smem_bytes;
-  VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
-  if (K == 10) rc = launch_k<10>(h, a, grid);
-  else rc = launch_k<16>(h, a, grid);
-  if (rc != VGC_OK) return rc;
-  VGC_CUDA(cudaEventRecord(h->ev[7], h->stream));
-  VGC_CUDA(cudaStreamSynchronize(h->stream));  // `slots` must outlive its copy; also surfaces kernel faults
-  float kms = 0.f;
-  VGC_CUDA(cudaEventElapsedTime(&kms, h->ev[6], h->ev[7]));
-  h->pass_kernel_ms += kms;
-  ++*launches;
   return VGC_OK;
 }
 
@@ -404,32 +543,21 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
       set_err("layer longer than 1024 bases: beyond the engine's row capacity");
       return VGC_ERR_CAPACITY;
     }
-    // first pass: slot sized for the largest node upper bound, capped by the memory budget
-    SlotDims probe;
-    probe.max_edges = probe.max_nodes = 1024;
-    probe.max_len = pr.max_len;
-    probe.row_words = 32 * K;
-    const uint64_t per_1k = slot_bytes(probe);
-    const uint32_t want_grid = std::min<uint32_t>(n_dev, h->sm_count * h->ctas_per_sm);
-    uint64_t cap_nodes = h->mem_budget / want_grid / per_1k * 1024;
-    uint32_t max_nodes = static_cast<uint32_t>(std::min<uint64_t>(pr.max_nodes_ub, std::max<uint64_t>(cap_nodes, 2048)));
+    if (K == 10) rc = set_kernel_attrs<10>(h->smem_graph, h->smem_fill);
+    else rc = set_kernel_attrs<16>(h->smem_graph, h->smem_fill);
+    if (rc) return rc;
     VGC_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = run_pass(h, n_dev, h->d_work.as<uint32_t>(), max_nodes, pr.max_len, K, &launches))) return rc;
+    if ((rc = run_pass(h, pr.device_windows, false, K, seq_off, win_first, &launches))) return rc;
     VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
     VGC_CUDA(cudaStreamSynchronize(h->stream));
-    // second pass for windows whose graph outgrew the slot
+    // second pass, exact capacities, for windows whose graph outgrew the estimate
     std::vector<uint32_t> retry;
     for (uint32_t w : pr.device_windows) {
       if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow) retry.push_back(w);
     }
-    if (!retry.empty() && max_nodes < pr.max_nodes_ub) {
+    if (!retry.empty()) {
       relaunched = static_cast<uint32_t>(retry.size());
-      VGC_CUDA(cudaMemcpyAsync(h->d_work.p, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, h->stream));
-      if ((rc = run_pass(h, relaunched, h->d_work.as<uint32_t>(), static_cast<uint32_t>(pr.max_nodes_ub),
-                         pr.max_len, K, &launches)))
-        return rc;
-      VGC_CUDA(cudaMemcpyAsync(h->d_work.p, pr.device_windows.data(), n_dev * 4ull, cudaMemcpyHostToDevice,
-                               h->stream));
+      if ((rc = run_pass(h, retry, true, K, seq_off, win_first, &launches))) return rc;
     }
     VGC_CUDA(cudaEventRecord(h->ev[1], h->stream));
   }
@@ -540,16 +668,15 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->sm_count = prop.multiProcessorCount;
   VGC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) VGC_CUDA(cudaEventCreate(&ev));
-  // 16 one-warp CTAs per SM: (228 KB - 16 x 1 KB reserved) / 16
-  h->ctas_per_sm = 16;
-  h->smem_bytes = 13568;
-  if (const char* s = std::getenv("VGC_CTAS_PER_SM")) {
-    int c = std::atoi(s);
-    if (c >= 1 && c <= 32) {
-      h->ctas_per_sm = c;
-      h->smem_bytes = std::min<uint32_t>(((228 * 1024 - c * 1024) / c) & ~255u, 200 * 1024);
-    }
+  for (int g = 0; g < kMaxGroups; ++g) {
+    VGC_CUDA(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    VGC_CUDA(cudaEventCreateWithFlags(&h->gev[g], cudaEventDisableTiming));
   }
+  // shared memory per one-warp CTA: fill kernel 16 CTAs / SM, graph kernel VGC_GRAPH_CTAS / SM
+  h->smem_fill = 13568;
+  h->smem_graph = ((228 * 1024 - VGC_GRAPH_CTAS * 1024) / VGC_GRAPH_CTAS) & ~255u;
+  if (const char* s = std::getenv("VGC_GRAPH_SMEM")) h->smem_graph = static_cast<uint32_t>(std::atoi(s));
+  if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
   h->mem_budget = static_cast<size_t>(free_b * 0.70);
@@ -564,13 +691,17 @@ int vgc_destroy(vgc_handle h) {
   for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
                     &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
                     &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
-                    &h->d_misc, &h->d_slots, &h->d_slot_mem})
+                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates})
     d->release();
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_out_len) cudaFreeHost(h->h_out_len);
   if (h->h_status) cudaFreeHost(h->h_status);
   for (auto& ev : h->ev) {
     if (ev) cudaEventDestroy(ev);
+  }
+  for (int g = 0; g < 8; ++g) {
+    if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+    if (h->gev[g]) cudaEventDestroy(h->gev[g]);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
