@@ -36,16 +36,6 @@ struct HostEx {
     return o;
   }
   uint32_t bcast(uint32_t v, uint32_t /*src*/) { return v; }
-  std::vector<uint32_t> tt_ni;
-  std::vector<uint16_t> tt_p1;
-  bool trace_tables(uint32_t nV, uint32_t** ni, uint16_t** p1) {
-    if (!allow_fast) return false;
-    tt_ni.assign(nV + 1, 0);
-    tt_p1.assign(nV + 1, 0);
-    *ni = tt_ni.data();
-    *p1 = tt_p1.data();
-    return true;
-  }
   uint32_t reduce_min(uint32_t v) { return v; }
   uint32_t reduce_max(uint32_t v) { return v; }
   uint32_t excl_scan(uint32_t v, uint32_t* total) {

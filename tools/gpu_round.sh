@@ -20,6 +20,14 @@ for what in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 2 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
       tail -12 gpurun_out/launches.csv ;;
+    ncugraph)
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:graph_kernel -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_graph \
+        python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncugraph.log 2>&1; echo "ncugraph rc=$?"
+      ls -la gpurun_out/prof_graph.ncu-rep ;;
+    ncufill)
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:fill_kernel -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_fill \
+        python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncufill.log 2>&1; echo "ncufill rc=$?"
+      ls -la gpurun_out/prof_fill.ncu-rep ;;
     ncufull)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:poa_window -s 1 -c 1 -f -o gpurun_out/prof \
         python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "ncufull rc=$?"

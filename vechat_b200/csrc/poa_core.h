@@ -65,7 +65,11 @@ enum : uint32_t {
 };
 
 enum : uint32_t { kModeNW = 0, kModeSW = 1 };
-enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRealignPost = 2, kPcFinalPost = 3, kPcDone = 4 };
+enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRealignPost = 2, kPcFinalPost = 3, kPcDone = 4, kPcLinearFinal = 5 };
+// step a window waits for (WinState::need); a zeroed WinState starts at kPcInit / kNeedUpdate
+enum : uint32_t { kNeedUpdate = 0, kNeedPrepare = 1, kNeedFill = 2, kNeedTrace = 3, kNeedNone = 4 };
+// what step_prepare must do (WinState::prep)
+enum : uint32_t { kPrepMainSort = 1, kPrepSubSort = 2, kPrepRowprog = 4, kPrepFill = 8 };
 
 // flags byte per node used by the sorts
 enum : uint8_t {
@@ -134,7 +138,8 @@ struct Slot {
   uint32_t* tmp0;      // [max_nodes] scratch
   uint32_t* tmp1;      // [max_nodes] scratch
   uint8_t* flags;      // [max_nodes] (global fallback of the shared-memory flags)
-  uint32_t* rowprog;   // [max_nodes * 4] {node, meta, p0, p1}
+  uint32_t* rowprog;   // [max_nodes * 4] by rank: {node, meta, p0, p1 | ovf offset}
+  uint32_t* nodeprog;  // [max_nodes * 4] by node: {meta, p0, p1, p2 | ovf offset (npred >= 4)}
   uint32_t* ovf;       // [max_edges] predecessor rows of nodes with in-degree > 2
   int16_t* fc;         // [max_nodes + 1]
   uint32_t* H;         // [(max_nodes + 1) * row_words]; also the big scratch of the serial graph passes
@@ -170,7 +175,8 @@ struct WinState {
   uint32_t nMain;        // rows of the whole current graph (rank order in r2n)
   uint32_t fill_layer;   // pending alignment: layer id, mode, sub-graph flag
   uint32_t fill_mode;
-  uint32_t fill_pending;
+  uint32_t need;         // kNeed*
+  uint32_t prep;         // kPrep* flags for step_prepare
   unsigned long long cells;
   uint32_t alignments;
   // per-phase cycle counters (leader lane, clock64): see kPh*
@@ -272,78 +278,72 @@ struct Poa {
     ex.sync();
   }
 
+  // ---- adjacency view of the sorts: adj[off[v] .. off[v+1]) = in-edge tails of v in creation order followed
+  //      by its aligned nodes in list order; flags[v] bits 5..7 = number of aligned entries.
+
   // ---- graph.cpp:301-371.  Serial (leader).  `member_only`: the Subgraph view (graph.cpp:694-727):
   //      roots, in-edges and aligned links restricted to nodes with kFMember.  Output: dst[0..n).
-  template <class IdxT>
-  VGC_HD uint32_t toposort_impl(uint8_t* flags, const IdxT* in_off, const IdxT* in_tail, IdxT* stack,
-                                uint32_t stack_cap, bool member_only, uint32_t* dst, bool* overflow) {
-    Graph& g = G();
-    const uint32_t nV = g.nV;
+  template <class IdxT, class StkT>
+  VGC_HD uint32_t toposort_impl(uint8_t* flags, const IdxT* off, const IdxT* adj, StkT* stack, uint32_t stack_cap,
+                                bool member_only, uint32_t* dst, bool* overflow) {
+    const uint32_t nV = G().nV;
     uint32_t n = 0, sp = 0;
     *overflow = false;
     for (uint32_t root = 0; root < nV; ++root) {
-      uint8_t fr = flags[root];
+      const uint8_t fr = flags[root];
       if ((fr & kFMarkMask) != 0) continue;
       if (member_only && !(fr & kFMember)) continue;
-      stack[sp++] = static_cast<IdxT>(root);
+      stack[sp++] = static_cast<StkT>(root);
       while (sp > 0) {
         const uint32_t curr = stack[sp - 1];
-        uint8_t fc = flags[curr];
+        const uint8_t fc = flags[curr];
+        if ((fc & kFMarkMask) == 2) {
+          --sp;
+          continue;
+        }
+        const uint32_t b = off[curr], e = off[curr + 1];
+        const uint32_t in_e = e - (fc >> kFNalShift);
+        if (sp + (e - b) + 1 > stack_cap) {
+          *overflow = true;
+          return 0;
+        }
         bool valid = true;
-        if ((fc & kFMarkMask) != 2) {
-          // aligned ids: one vector load, issued before the in-edge scan so its latency overlaps it
-          const uint32_t na = fc >> kFNalShift;
-          const bool has_al = !(fc & kFIgnored) && na != 0;
-          U4 q = {0, 0, 0, 0};
-          if (has_al) q = *reinterpret_cast<const U4*>(g.al + curr * kAlStride);
-          const uint32_t b = in_off[curr], e = in_off[curr + 1];
-          if (sp + (e - b) + kMaxAligned + 1 > stack_cap) {
-            *overflow = true;
-            return 0;
+        for (uint32_t i = b; i < in_e; ++i) {
+          const uint32_t t = adj[i];
+          const uint8_t ft = flags[t];
+          if (member_only && !(ft & kFMember)) continue;
+          if ((ft & kFMarkMask) != 2) {
+            stack[sp++] = static_cast<StkT>(t);
+            valid = false;
           }
-          for (uint32_t i = b; i < e; ++i) {
-            const uint32_t t = in_tail[i];
-            const uint8_t ft = flags[t];
-            if (member_only && !(ft & kFMember)) continue;
-            if ((ft & kFMarkMask) != 2) {
-              stack[sp++] = static_cast<IdxT>(t);
+        }
+        const bool primary = !(fc & kFIgnored);
+        if (primary) {
+          for (uint32_t i = in_e; i < e; ++i) {
+            const uint32_t a = adj[i];
+            const uint8_t fa = flags[a];
+            if (member_only && !(fa & kFMember)) continue;
+            if ((fa & kFMarkMask) != 2) {
+              stack[sp++] = static_cast<StkT>(a);
+              flags[a] = fa | kFIgnored;
               valid = false;
             }
           }
-          if (has_al) {
-#pragma unroll
-            for (int i = 0; i < kMaxAligned; ++i) {
-              if (static_cast<uint32_t>(i) >= na) break;
-              const uint32_t a = i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : i == 3 ? q.w : g.al[curr * kAlStride + i];
-              const uint8_t fa = flags[a];
-              if (member_only && !(fa & kFMember)) continue;
-              if ((fa & kFMarkMask) != 2) {
-                stack[sp++] = static_cast<IdxT>(a);
-                flags[a] = fa | kFIgnored;
-                valid = false;
-              }
-            }
-          }
-          fc = flags[curr];  // (an aligned node cannot be curr itself, but keep the read ordered)
-          if (valid) {
-            flags[curr] = (fc & ~kFMarkMask) | 2;
-            if (!(fc & kFIgnored)) {
-              dst[n++] = curr;
-              if (has_al) {
-#pragma unroll
-                for (int i = 0; i < kMaxAligned; ++i) {
-                  if (static_cast<uint32_t>(i) >= na) break;
-                  const uint32_t a = i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : i == 3 ? q.w : g.al[curr * kAlStride + i];
-                  if (member_only && !(flags[a] & kFMember)) continue;
-                  dst[n++] = a;
-                }
-              }
-            }
-          } else {
-            flags[curr] = (fc & ~kFMarkMask) | 1;
-          }
         }
-        if (valid) --sp;
+        if (valid) {
+          flags[curr] = (fc & ~kFMarkMask) | 2;
+          if (primary) {
+            dst[n++] = curr;
+            for (uint32_t i = in_e; i < e; ++i) {
+              const uint32_t a = adj[i];
+              if (member_only && !(flags[a] & kFMember)) continue;
+              dst[n++] = a;
+            }
+          }
+          --sp;
+        } else {
+          flags[curr] = (fc & ~kFMarkMask) | 1;
+        }
       }
     }
     return n;
@@ -351,58 +351,82 @@ struct Poa {
 
   // ---- graph.cpp:640-666: nodes reachable backwards (in-edges + aligned links) from `from`, ids >= floor
   template <class IdxT>
-  VGC_HD void extract_impl(uint8_t* flags, const IdxT* in_off, const IdxT* in_tail, uint32_t* stack,
-                           uint32_t from, uint32_t floor_id) {
-    Graph& g = G();
+  VGC_HD void extract_impl(uint8_t* flags, const IdxT* off, const IdxT* adj, uint32_t* stack, uint32_t from,
+                           uint32_t floor_id) {
     uint32_t sp = 0;
     stack[sp++] = from;
     while (sp > 0) {
       const uint32_t curr = stack[--sp];
       const uint8_t f = flags[curr];
       if (!(f & kFMember) && curr >= floor_id) {
-        // pushes are bounded by nE + sum(nal) + 1: the stack is the H scratch, which is far larger
-        for (uint32_t i = in_off[curr]; i < in_off[curr + 1]; ++i) stack[sp++] = in_tail[i];
-        if (f & kFHasAligned) {
-          for (uint32_t i = 0; i < g.nal[curr]; ++i) stack[sp++] = g.al[curr * kAlStride + i];
-        }
+        // pushes are bounded by nE + sum(nal) + 1: the stack is scratch far larger than that
+        for (uint32_t i = off[curr]; i < off[curr + 1]; ++i) stack[sp++] = adj[i];
         flags[curr] = f | kFMember;
       }
     }
   }
 
-  // Topological order of the live graph (or of the Subgraph view begin..end) into dst.
-  // Stages flags + CSR into the executor's fast storage when it fits.
+  // Topological order of the live graph (or of the Subgraph view begin..end) into dst.  Builds the adjacency
+  // view in the executor's fast storage (16-bit ids) when it fits, else in the H scratch (32-bit ids).
+  // H scratch layout (words): [0, nV] offsets | [nV+1, nV+1+nA) adjacency | big stack after that.
   VGC_HD uint32_t sort_graph(bool sub, uint32_t sub_begin, uint32_t sub_end, uint32_t* dst) {
     Graph& g = G();
     const uint32_t nV = g.nV, nE = g.nE;
+    const int W = ex.width(), L = ex.lane();
+    uint32_t* goff = sl.H;
+    // offsets = exclusive scan of (in-degree + aligned count)
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nV; base += W) {
+      const uint32_t v = base + L;
+      const uint32_t c = v < nV ? g.nin[v] + g.nal[v] : 0;
+      uint32_t tot;
+      const uint32_t p = ex.excl_scan(c, &tot);
+      if (v < nV) goff[v] = carry + p;
+      carry += tot;
+    }
+    const uint32_t nA = carry;
+    if (ex.leader()) goff[nV] = nA;
+    ex.sync();
     uint8_t* fl;
-    uint16_t *off16, *tail16, *stk16;
+    uint16_t *off16, *adj16, *stk16;
     uint32_t stk_cap;
-    const bool fast = ex.stage_fast(nV, nE, &fl, &off16, &tail16, &stk16, &stk_cap);
+    const bool fast = ex.stage_fast(nV, nA, &fl, &off16, &adj16, &stk16, &stk_cap);
+    uint32_t* gadj = sl.H + nV + 1;
+    uint32_t* gstack = gadj + nA;
     if (!fast) fl = sl.flags;
-    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) {
+    for (uint32_t v = L; v < nV; v += W) {
       const uint32_t na = g.nal[v];
       fl[v] = static_cast<uint8_t>((na ? kFHasAligned : 0) | (na << kFNalShift));
+      const uint32_t o = goff[v] + g.nin[v];
+      for (uint32_t i = 0; i < na; ++i) {
+        const uint32_t a = g.al[v * kAlStride + i];
+        if (fast) adj16[o + i] = static_cast<uint16_t>(a);
+        else gadj[o + i] = a;
+      }
+      if (fast) off16[v] = static_cast<uint16_t>(goff[v]);
     }
-    if (fast) {
-      for (uint32_t v = ex.lane(); v <= nV; v += ex.width()) off16[v] = static_cast<uint16_t>(sl.in_off[v]);
-      for (uint32_t e = ex.lane(); e < nE; e += ex.width()) tail16[e] = static_cast<uint16_t>(sl.in_tail[e]);
+    if (fast && L == 0) off16[nV] = static_cast<uint16_t>(nA);
+    for (uint32_t e = L; e < nE; e += W) {
+      const uint32_t pos = goff[g.ehead[e]] + g.ein_ord[e];
+      if (fast) adj16[pos] = static_cast<uint16_t>(g.etail[e]);
+      else gadj[pos] = g.etail[e];
     }
     ex.sync();
     if (ex.leader()) {
       uint32_t n = 0;
       bool ovf = false;
       if (fast) {
-        if (sub) extract_impl<uint16_t>(fl, off16, tail16, sl.H, sub_end, sub_begin);
-        n = toposort_impl<uint16_t>(fl, off16, tail16, stk16, stk_cap, sub, dst, &ovf);
+        if (sub) extract_impl<uint16_t>(fl, off16, adj16, gstack, sub_end, sub_begin);
+        n = toposort_impl<uint16_t, uint16_t>(fl, off16, adj16, stk16, stk_cap, sub, dst, &ovf);
         if (ovf) {
-          // deep recursion: redo with the big stack in HBM (flags: clear marks/ignored, keep member)
+          // deep recursion: redo with the big stack in HBM (flags: clear marks/ignored, keep member + counts);
+          // 16-bit ids in a 32-bit stack
           for (uint32_t v = 0; v < nV; ++v) fl[v] &= static_cast<uint8_t>(kFHasAligned | kFMember | (7u << kFNalShift));
-          n = toposort_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, 0xFFFFFFFFu, sub, dst, &ovf);
+          n = toposort_impl<uint16_t, uint32_t>(fl, off16, adj16, gstack, 0xFFFFFFFFu, sub, dst, &ovf);
         }
       } else {
-        if (sub) extract_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, sub_end, sub_begin);
-        n = toposort_impl<uint32_t>(fl, sl.in_off, sl.in_tail, sl.H, 0xFFFFFFFFu, sub, dst, &ovf);
+        if (sub) extract_impl<uint32_t>(fl, goff, gadj, gstack, sub_end, sub_begin);
+        n = toposort_impl<uint32_t, uint32_t>(fl, goff, gadj, gstack, 0xFFFFFFFFu, sub, dst, &ovf);
       }
       ws.scratch[0] = n;
     }
@@ -410,7 +434,7 @@ struct Poa {
     const uint32_t n = ws.scratch[0];
     if (sub) {
       // keep the membership where the row-program builder can see it
-      for (uint32_t v = ex.lane(); v < nV; v += ex.width()) sl.flags[v] = fl[v] & kFMember;
+      for (uint32_t v = L; v < nV; v += W) sl.flags[v] = fl[v] & kFMember;
       ex.sync();
     }
     return n;
@@ -459,25 +483,27 @@ struct Poa {
         p1 = o;
       }
       const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
+      const uint32_t meta = meta_pack(g.code[v], np, sink);
       sl.rowprog[4 * r + 0] = v;
-      sl.rowprog[4 * r + 1] = meta_pack(g.code[v], np, sink);
+      sl.rowprog[4 * r + 1] = meta;
       sl.rowprog[4 * r + 2] = p0;
       sl.rowprog[4 * r + 3] = p1;
+      // by-node copy for the traceback: up to three predecessors inline
+      uint32_t q1 = p1, q2 = 0;
+      if (np == 3) {
+        q1 = sl.ovf[p1];
+        q2 = sl.ovf[p1 + 1];
+      } else if (np > 3) {
+        q1 = sl.ovf[p1];
+        q2 = p1;  // ovf offset: predecessor p (>= 1) is ovf[q2 + p - 1]
+      }
+      U4 np4 = {meta, p0, q1, q2};
+      *reinterpret_cast<U4*>(sl.nodeprog + 4 * static_cast<size_t>(v)) = np4;
     }
     ex.sync();
   }
 
-  VGC_HD VGC_INL uint32_t pred_row(uint32_t r, uint32_t p) const {
-    const uint32_t np = meta_npred(sl.rowprog[4 * r + 1]);
-    if (np == 0) return 0;
-    if (p == 0) return sl.rowprog[4 * r + 2];
-    if (np == 2) return sl.rowprog[4 * r + 3];
-    return sl.ovf[sl.rowprog[4 * r + 3] + p - 1];
-  }
-
-  // ---- traceback (leader).  Priorities as simd_alignment_engine_implementation.hpp:1031-1061 /
-  //      sisd_alignment_engine.cpp:392-448: diagonal over predecessors in inedges order, then vertical
-  //      over predecessors, then horizontal.  Pairs are appended in reverse (end of alignment first).
+  // ---- traceback.  Pairs are appended in reverse (end of alignment first).
   VGC_HD VGC_INL int32_t hval(uint32_t row, uint32_t j, uint32_t mode, int32_t g) const {
     if (mode == kModeSW) {
       if (row == 0 || j == 0) return 0;
@@ -488,76 +514,20 @@ struct Poa {
     return RM::load(sl.H + static_cast<uint64_t>(row) * sl.row_words, j - 1);
   }
 
-  VGC_HD void traceback_serial(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
-    uint32_t n = 0;
-    uint32_t i = ws.best_row, j = ws.best_col;
-    if (i == 0 && j == 0) {
-      ws.aln_len = 0;
-      return;
+  // Warp-cooperative traceback.  One step = one round of parallel loads: every candidate of the current cell
+  // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order,
+  // simd_alignment_engine_implementation.hpp:1031-1061) is fetched and compared by its own lane and the first
+  // match wins (reduce_min over the candidate index).  The lane of a candidate also fetches the node record of
+  // the row the walk would move to (nodeprog, one 16-byte load), so the next step starts without a dependent load.
+  VGC_HD VGC_INL U4 node_rec(uint32_t row) const {
+    if (row == 0) {
+      U4 z = {0, 0, 0, 0};
+      return z;
     }
-    while (true) {
-      if (mode == kModeSW) {
-        if (hval(i, j, mode, sc.g) == 0) break;
-      } else {
-        if (i == 0 && j == 0) break;
-      }
-      const int32_t h = hval(i, j, mode, sc.g);
-      uint32_t pi = i, pj = j;
-      bool found = false;
-      uint32_t r = 0, np = 0;
-      if (i != 0) {
-        r = sl.rank_of[i - 1];
-        np = meta_npred(sl.rowprog[4 * r + 1]);
-        if (np == 0) np = 1;  // no in-edges: the virtual row 0 is the predecessor
-      }
-      if (i != 0 && j != 0) {
-        const int32_t mc = (meta_code(sl.rowprog[4 * r + 1]) == seq_codes[j - 1]) ? sc.m : sc.x;
-        for (uint32_t p = 0; p < np; ++p) {
-          const uint32_t pr = pred_row(r, p);
-          if (h == hval(pr, j - 1, mode, sc.g) + mc) {
-            pi = pr;
-            pj = j - 1;
-            found = true;
-            break;
-          }
-        }
-      }
-      if (!found && i != 0) {
-        for (uint32_t p = 0; p < np; ++p) {
-          const uint32_t pr = pred_row(r, p);
-          if (h == hval(pr, j, mode, sc.g) + sc.g) {
-            pi = pr;
-            pj = j;
-            found = true;
-            break;
-          }
-        }
-      }
-      if (!found && j != 0 && h == hval(i, j - 1, mode, sc.g) + sc.g) {
-        pi = i;
-        pj = j - 1;
-        found = true;
-      }
-      if (!found || n >= sl.aln_cap) {
-        fail(kStInternal);
-        break;
-      }
-      sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(i - 1);
-      sl.aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
-      ++n;
-      i = pi;
-      j = pj;
-    }
-    ws.aln_len = n;
+    return *reinterpret_cast<const U4*>(sl.nodeprog + 4 * static_cast<size_t>(row - 1));
   }
 
-  // Warp-cooperative traceback.  One step = one round of parallel loads: every candidate of the current cell
-  // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order) is
-  // fetched and compared by its own lane, and the first match wins (reduce_min over the candidate index).
-  // Node facts come from a table indexed by node id — word {p0 row:16, min(np,15):4, code:8} plus a u16 second
-  // predecessor row / overflow offset — kept in the executor's fast storage when it fits.
   VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
-    Graph& g = G();
     const int W = ex.width(), L = ex.lane();
     uint32_t i = ws.best_row, j = ws.best_col;
     if (i == 0 && j == 0) {
@@ -565,27 +535,9 @@ struct Poa {
       ex.sync();
       return;
     }
-    if (g.nV >= 65535u || ws.ovf_n >= 65535u) {  // ids beyond the 16-bit tables: plain serial walk
-      if (ex.leader()) traceback_serial(seq_codes, mode, sc);
-      ex.sync();
-      return;
-    }
-    uint32_t* ni;
-    uint16_t* p1t;
-    if (!ex.trace_tables(g.nV, &ni, &p1t)) {
-      ni = sl.tmp0;
-      p1t = reinterpret_cast<uint16_t*>(sl.tmp1);
-    }
-    const uint32_t nR = ws.nR;
-    for (uint32_t r = L; r < nR; r += W) {
-      const uint32_t v = sl.rowprog[4 * r], meta = sl.rowprog[4 * r + 1];
-      const uint32_t np = meta_npred(meta);
-      ni[v] = (sl.rowprog[4 * r + 2] & 0xFFFFu) | ((np < 15u ? np : 15u) << 16) | (meta_code(meta) << 20);
-      p1t[v] = static_cast<uint16_t>(sl.rowprog[4 * r + 3]);
-    }
-    ex.sync();
     const int32_t gp = sc.g;
     int32_t h = hval(i, j, mode, gp);
+    U4 rec = node_rec(i);
     uint32_t n = 0;
     bool bad = false;
     while (true) {
@@ -594,29 +546,27 @@ struct Poa {
       } else {
         if (i == 0 && j == 0) break;
       }
-      uint32_t np = 0, p0 = 0, code = 0;
-      if (i != 0) {
-        const uint32_t info = ni[i - 1];
-        p0 = info & 0xFFFFu;
-        np = (info >> 16) & 15u;
-        code = info >> 20;
-        if (np == 15u) np = meta_npred(sl.rowprog[4 * sl.rank_of[i - 1] + 1]);
-      }
+      const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
       const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;  // no in-edges: the virtual row 0 is the predecessor
       const uint32_t ncand = 2 * npp + 1;
-      const int32_t mc = (i != 0 && j != 0) ? (code == seq_codes[j - 1] ? sc.m : sc.x) : 0;
+      const int32_t mc = (i != 0 && j != 0) ? (meta_code(rec.x) == seq_codes[j - 1] ? sc.m : sc.x) : 0;
       uint32_t first = kNone, pr_next = 0;
       int32_t hv_next = 0;
+      U4 rec_next = rec;
       for (uint32_t c0 = 0; c0 < ncand; c0 += W) {
         const uint32_t c = c0 + L;
         bool ok = false;
         int32_t hv = 0;
         uint32_t pr = i;
+        U4 nr = rec;
         if (c < 2 * npp) {
           const uint32_t p = c < npp ? c : c - npp;
-          if (p == 0) pr = p0;
-          else if (np == 2) pr = p1t[i - 1];
-          else pr = sl.ovf[static_cast<uint32_t>(p1t[i - 1]) + p - 1];
+          if (np == 0) pr = 0;
+          else if (p == 0) pr = rec.y;
+          else if (p == 1) pr = rec.z;
+          else if (np == 3) pr = rec.w;
+          else pr = sl.ovf[rec.w + p - 1];
+          nr = node_rec(pr);
           if (c < npp) {
             if (j != 0) {
               hv = hval(pr, j - 1, mode, gp);
@@ -632,9 +582,14 @@ struct Poa {
         }
         const uint32_t f = ex.reduce_min(ok ? c : kNone);
         if (f != kNone) {
+          const uint32_t src = f - c0;
           first = f;
-          hv_next = static_cast<int32_t>(ex.bcast(static_cast<uint32_t>(hv), f - c0));
-          pr_next = ex.bcast(pr, f - c0);
+          hv_next = static_cast<int32_t>(ex.bcast(static_cast<uint32_t>(hv), src));
+          pr_next = ex.bcast(pr, src);
+          rec_next.x = ex.bcast(nr.x, src);
+          rec_next.y = ex.bcast(nr.y, src);
+          rec_next.z = ex.bcast(nr.z, src);
+          rec_next.w = ex.bcast(nr.w, src);
           break;
         }
       }
@@ -652,6 +607,7 @@ struct Poa {
       i = pi;
       j = pj;
       h = hv_next;
+      rec = rec_next;
     }
     if (ex.leader()) {
       if (bad) fail(kStInternal);
@@ -990,37 +946,6 @@ struct Poa {
     return codes;
   }
 
-  // ---- make the next alignment pending: row program over order[0..nR) + bookkeeping.  The fill itself runs
-  //      outside (fill kernel on the device, HostEx::fill in the host model), then advance() resumes.
-  VGC_HD void schedule(uint32_t layer, uint32_t mode, const uint32_t* order, uint32_t nR, bool sub, bool rebuild) {
-    const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
-    tick(kPhOther);
-    if (rebuild) build_rowprog(order, nR, sub);
-    tick(kPhRowprog);
-    // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
-    const Scores& sc = mode == kModeNW ? nw : sw;
-    int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
-    if (-sc.g > a) a = -sc.g;
-    if (ex.leader()) {
-      if (static_cast<int64_t>(nR + RM::kCols + 8) * a > 30000) fail(kStScoreRange);
-      ws.alignments += 1;
-      ws.cells += static_cast<unsigned long long>(nR + 1) * len;  // (R_a + 1) * L_a of the graph aligned to
-      ws.fill_layer = layer;
-      ws.fill_mode = mode;
-      ws.fill_pending = 1;
-    }
-    ex.sync();
-  }
-
-  VGC_HD uint32_t resort_main() {
-    tick(kPhOther);
-    build_csr(false);
-    tick(kPhCsr);
-    const uint32_t n = sort_graph(false, 0, 0, sl.r2n);
-    tick(kPhSort);
-    return n;
-  }
-
   // ---- graph.cpp:534-638 + 450-485 (leader): heaviest bundle consensus + coverage, linear mode ------
   VGC_HD uint32_t heaviest_bundle(uint32_t nR, uint8_t* out, uint32_t out_cap, uint32_t* cov_out) {
     Graph& g = G();
@@ -1089,41 +1014,121 @@ struct Poa {
   }
 
   // ---- the window (src/window.cpp:74-174 and :176-428) as a resumable program -------------------------
-  //      advance() runs the window up to (and including) the scheduling of its next alignment and returns;
-  //      ws.fill_pending says whether a fill must run before the next advance().  ws.pc == kPcDone: finished
-  //      (ws.status tells how).  The number of fills of a window is known on the host:
-  //      haplotype: (nseq-1) + (num_prune-1)*nseq + 1, linear: nseq-1.
-  VGC_HD void advance(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
-                      uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
+  // A window cycles through four steps, each of which the device runs in its own kernel with the occupancy
+  // that suits it (vgc_engine.cu); ws.need names the step the window is waiting for:
+  //   step_update  (kNeedUpdate) : consume the alignment just traced (AddAlignment / AddWeights / emit), run
+  //                                the phase transitions (prune, LargestSubgraph, consensus), choose the next
+  //                                alignment and record what must be prepared for it in ws.prep
+  //   step_prepare (kNeedPrepare): re-sort the graph (serial DFS), Subgraph view of a partial layer, row program
+  //   fill         (kNeedFill)   : the DP fill (poa_fill.cuh on the device, HostEx::fill in the host model)
+  //   step_trace   (kNeedTrace)  : traceback of the filled matrix
+  // Fills of a window: haplotype (nseq-1) + (num_prune-1)*nseq + 1, linear nseq-1 (known on the host).
+  VGC_HD VGC_INL uint32_t layer_len(uint32_t l) const {
+    return static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
+  }
+
+  VGC_HD void finish() {
+    if (ex.leader()) {
+      ws.pc = kPcDone;
+      ws.need = kNeedNone;
+    }
+    ex.sync();
+  }
+
+  VGC_HD void step_trace() {
+    if (ws.need != kNeedTrace) return;
+    ex.sync();
+    if (ex.leader()) ws.t_last = ex.clock();
+    const uint32_t l = ws.fill_layer, mode = ws.fill_mode;
+    uint8_t* codes = stage_codes(l);
+    traceback(codes, mode, mode == kModeNW ? nw : sw);
+    tick(kPhTrace);
+    if (ws.status != kStOk) return finish();
+    if (ex.leader()) ws.need = kNeedUpdate;
+    ex.sync();
+  }
+
+  VGC_HD void step_prepare() {
+    if (ws.need != kNeedPrepare) return;
+    ex.sync();
+    if (ex.leader()) ws.t_last = ex.clock();
+    const uint32_t prep = ws.prep;
+    uint32_t nMain = ws.nMain;
+    if (prep & kPrepMainSort) {
+      nMain = sort_graph(false, 0, 0, sl.r2n);
+      tick(kPhSort);
+    }
+    const uint32_t l = ws.fill_layer;
+    const uint32_t* order = sl.r2n;
+    uint32_t nR = nMain;
+    const bool sub = (prep & kPrepSubSort) != 0;
+    if (sub) {
+      nR = sort_graph(true, bv.begin[l], bv.end[l], sl.order);
+      order = sl.order;
+      tick(kPhSort);
+    }
+    if (prep & kPrepRowprog) {
+      build_rowprog(order, nR, sub);
+      tick(kPhRowprog);
+    }
+    if (prep & kPrepFill) {
+      // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
+      const uint32_t mode = ws.fill_mode;
+      const Scores& sc = mode == kModeNW ? nw : sw;
+      int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
+      if (-sc.g > a) a = -sc.g;
+      if (ex.leader()) {
+        if (static_cast<int64_t>(ws.nR + RM::kCols + 8) * a > 30000) fail(kStScoreRange);
+        ws.alignments += 1;
+        ws.cells += static_cast<unsigned long long>(ws.nR + 1) * layer_len(l);  // (R_a + 1) * L_a
+      }
+      ex.sync();
+      if (ws.status != kStOk) return finish();
+    }
+    if (ex.leader()) {
+      ws.nMain = nMain;
+      ws.need = (prep & kPrepFill) ? kNeedFill : kNeedUpdate;
+    }
+    ex.sync();
+  }
+
+  VGC_HD void step_update(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
+                          uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
+    if (ws.need != kNeedUpdate) return;
     const uint32_t first = bv.win_first[w];
     const uint32_t nseq = bv.win_nseq[w];
     const uint32_t* rank = bv.layer_rank + first;
     const uint32_t bb = rank[0];
-    const uint32_t blen = static_cast<uint32_t>(bv.seq_off[bb + 1] - bv.seq_off[bb]);
+    const uint32_t blen = layer_len(bb);
     const uint32_t offset = static_cast<uint32_t>(0.01 * blen);
     const uint32_t out_cap = bv.out_cap[w];
     const double avgw = bv.win_avgw[w];
     const uint32_t pc = ws.pc;
-    if (pc == kPcDone) return;
     enum Act { kBuildNext, kRoundStart, kRealignNext, kFinalSchedule };
     Act act = kBuildNext;
-    uint32_t j = ws.j, k = ws.k, nMain = ws.nMain;
+    uint32_t j = ws.j, k = ws.k;
+    bool changed = false;  // graph changed since the last sort
     ex.sync();
     if (ex.leader()) ws.t_last = ex.clock();
-    auto finish = [&]() {
-      if (ex.leader()) {
-        ws.pc = kPcDone;
-        ws.fill_pending = 0;
+    // plan: make the next alignment (or sort-only step) pending
+    auto plan = [&](uint32_t next_pc, uint32_t prep, uint32_t layer, uint32_t mode) {
+      if (changed) {
+        tick(kPhOther);
+        build_csr(false);
+        tick(kPhCsr);
       }
-      ex.sync();
-    };
-    auto commit = [&](uint32_t next_pc) {
       if (ex.leader()) {
-        ws.pc = ws.status == kStOk ? next_pc : kPcDone;
-        if (ws.status != kStOk) ws.fill_pending = 0;
+        ws.pc = next_pc;
         ws.j = j;
         ws.k = k;
-        ws.nMain = nMain;
+        ws.prep = prep | (changed ? kPrepMainSort : 0u);
+        ws.fill_layer = layer;
+        ws.fill_mode = mode;
+        ws.need = (ws.prep == kPrepFill) ? kNeedFill : kNeedPrepare;
+        if (ws.prep == kPrepFill) {
+          ws.alignments += 1;
+          ws.cells += static_cast<unsigned long long>(ws.nR + 1) * layer_len(layer);
+        }
       }
       ex.sync();
     };
@@ -1135,7 +1140,7 @@ struct Poa {
         ws.aln_len = 0;
         ws.cells = 0;
         ws.alignments = 0;
-        ws.fill_pending = 0;
+        ws.nMain = 0;
         sl.g[0].nV = 0;
         sl.g[0].nE = 0;
         *out_len = 0;
@@ -1144,7 +1149,7 @@ struct Poa {
       ex.sync();
       // every layer must fit one row of the H matrix
       for (uint32_t t = 0; t < nseq; ++t) {
-        const uint32_t len = static_cast<uint32_t>(bv.seq_off[rank[t] + 1] - bv.seq_off[rank[t]]);
+        const uint32_t len = layer_len(rank[t]);
         if (len > static_cast<uint32_t>(RM::kCols) || len > sl.max_len) {
           if (ex.leader()) fail(kStTooLong);
         }
@@ -1154,53 +1159,76 @@ struct Poa {
       // backbone: AddAlignment with an empty alignment (window.cpp:197-201)
       uint8_t* codes = stage_codes(bb);
       add_alignment(codes, bb, blen);
+      tick(kPhAddAln);
       if (ws.status != kStOk) return finish();
-      nMain = resort_main();
+      changed = true;
       j = 1;
       act = kBuildNext;
-    } else {
-      // resume after the fill of the pending alignment
-      const uint32_t l = ws.fill_layer, mode = ws.fill_mode;
-      const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
+    } else if (pc == kPcBuildPost) {
+      const uint32_t l = ws.fill_layer;
       uint8_t* codes = stage_codes(l);
-      if (ex.leader()) ws.fill_pending = 0;
-      tick(kPhOther);
-      traceback(codes, mode, mode == kModeNW ? nw : sw);
-      tick(kPhTrace);
+      add_alignment(codes, l, layer_len(l));
+      tick(kPhAddAln);
       if (ws.status != kStOk) return finish();
-      if (pc == kPcBuildPost) {
-        add_alignment(codes, l, len);
-        tick(kPhAddAln);
-        if (ws.status != kStOk) return finish();
-        nMain = resort_main();
-        ++j;
-        act = kBuildNext;
-      } else if (pc == kPcRealignPost) {
-        add_weights(l);
-        tick(kPhAddW);
-        if (ws.status != kStOk) return finish();
-        ++j;
-        act = kRealignNext;
-      } else {
-        // graph.cpp:1167-1179
-        if (ex.leader()) {
-          Graph& g = G();
-          uint32_t n = 0;
-          for (uint32_t t = ws.aln_len; t-- > 0;) {
-            const int32_t nd = sl.aln_node[t];
-            if (nd == -1) continue;
-            if (n >= out_cap) {
-              fail(kStOutOverflow);
-              break;
-            }
-            out[n++] = bv.decoder[g.code[nd]];
+      changed = true;
+      ++j;
+      act = kBuildNext;
+    } else if (pc == kPcRealignPost) {
+      add_weights(ws.fill_layer);
+      tick(kPhAddW);
+      if (ws.status != kStOk) return finish();
+      ++j;
+      act = kRealignNext;
+    } else if (pc == kPcFinalPost) {
+      // graph.cpp:1167-1179
+      if (ex.leader()) {
+        Graph& g = G();
+        uint32_t n = 0;
+        for (uint32_t t = ws.aln_len; t-- > 0;) {
+          const int32_t nd = sl.aln_node[t];
+          if (nd == -1) continue;
+          if (n >= out_cap) {
+            fail(kStOutOverflow);
+            break;
           }
-          *out_len = n;
+          out[n++] = bv.decoder[g.code[nd]];
         }
-        ex.sync();
-        tick(kPhEmit);
-        return finish();
+        *out_len = n;
       }
+      ex.sync();
+      tick(kPhEmit);
+      return finish();
+    } else if (pc == kPcLinearFinal) {
+      // linear mode: consensus + coverage trim (window.cpp:138-171); the graph was re-sorted by step_prepare
+      build_csr(true);
+      if (ex.leader()) {
+        uint32_t* cov = sl.tmp0;
+        uint32_t n = heaviest_bundle(ws.nMain, out, out_cap, cov);
+        if (ws.status == kStOk) {
+          uint32_t b = 0, e = n;
+          if ((bv.win_flags[w] & 1u) && trim) {
+            const uint32_t avg = (nseq - 1) / 2;
+            int32_t bi = 0, ei = static_cast<int32_t>(n) - 1;
+            for (; bi < static_cast<int32_t>(n); ++bi) {
+              if (cov[bi] >= avg) break;
+            }
+            for (; ei >= 0; --ei) {
+              if (cov[ei] >= avg) break;
+            }
+            if (bi < ei) {
+              b = bi;
+              e = ei + 1;
+            }
+          }
+          for (uint32_t i = b; i < e; ++i) out[i - b] = out[i];
+          *out_len = e - b;
+        }
+      }
+      ex.sync();
+      tick(kPhEmit);
+      return finish();
+    } else {
+      return;
     }
 
     while (true) {
@@ -1209,57 +1237,20 @@ struct Poa {
         if (j < nseq) {
           const uint32_t l = rank[j];
           const uint32_t lb = bv.begin[l], le = bv.end[l];
-          if (lb < offset && le > blen - offset) {
-            schedule(l, kModeNW, sl.r2n, nMain, false, true);
-          } else {
-            tick(kPhOther);
-            const uint32_t nSub = sort_graph(true, lb, le, sl.order);
-            tick(kPhSort);
-            schedule(l, kModeNW, sl.order, nSub, true, true);
-          }
-          return commit(kPcBuildPost);
+          const bool full = lb < offset && le > blen - offset;
+          return plan(kPcBuildPost, kPrepFill | kPrepRowprog | (full ? 0u : kPrepSubSort), l, kModeNW);
         }
-        if (!haplotype) {
-          // linear mode: consensus + coverage trim (window.cpp:138-171)
-          build_csr(true);
-          if (ex.leader()) {
-            uint32_t* cov = sl.tmp0;
-            uint32_t n = heaviest_bundle(nMain, out, out_cap, cov);
-            if (ws.status == kStOk) {
-              uint32_t b = 0, e = n;
-              if ((bv.win_flags[w] & 1u) && trim) {
-                const uint32_t avg = (nseq - 1) / 2;
-                int32_t bi = 0, ei = static_cast<int32_t>(n) - 1;
-                for (; bi < static_cast<int32_t>(n); ++bi) {
-                  if (cov[bi] >= avg) break;
-                }
-                for (; ei >= 0; --ei) {
-                  if (cov[ei] >= avg) break;
-                }
-                if (bi < ei) {
-                  b = bi;
-                  e = ei + 1;
-                }
-              }
-              for (uint32_t i = b; i < e; ++i) out[i - b] = out[i];
-              *out_len = e - b;
-            }
-          }
-          ex.sync();
-          tick(kPhEmit);
-          return finish();
-        }
-        // haplotype mode: prune (window.cpp:300-319)
-        tick(kPhOther);
+        if (!haplotype) return plan(kPcLinearFinal, 0u, bb, kModeNW);
+        // haplotype mode: prune (window.cpp:300-319); LargestSubgraph rebuilds the CSR it needs
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
         largest_subgraph();
         tick(kPhLargest);
+        changed = true;
         k = 0;
         act = kRoundStart;
       } else if (act == kRoundStart) {
         if (k + 1 < num_prune) {
-          nMain = resort_main();
           j = 0;
           act = kRealignNext;
         } else {
@@ -1271,42 +1262,41 @@ struct Poa {
           const uint32_t l = rank[j];
           const uint32_t lb = bv.begin[l], le = bv.end[l];
           const bool global = (j == 0) || (lb < offset && le > blen - offset);
-          schedule(l, global ? kModeNW : kModeSW, sl.r2n, nMain, false, j == 0);
-          return commit(kPcRealignPost);
+          return plan(kPcRealignPost, kPrepFill | (j == 0 ? kPrepRowprog : 0u), l, global ? kModeNW : kModeSW);
         }
-        tick(kPhOther);
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
         largest_subgraph();
         tick(kPhLargest);
+        changed = true;
         ++k;
         act = kRoundStart;
       } else {
         // final local alignment of the backbone (window.cpp:391-394)
-        nMain = resort_main();
-        schedule(bb, kModeSW, sl.r2n, nMain, false, true);
-        return commit(kPcFinalPost);
+        return plan(kPcFinalPost, kPrepFill | kPrepRowprog, bb, kModeSW);
       }
     }
   }
 
-  // Whole window in one go (host model; a single-kernel device build could use it too).
+  // Whole window in one go (host model).
   VGC_HD void run_window(uint32_t w, bool haplotype, bool trim, double min_confidence, double min_support,
                          uint32_t num_prune, uint8_t* out, uint32_t* out_len) {
     if (ex.leader()) {
       ws.pc = kPcInit;
-      ws.j = ws.k = ws.nMain = 0;
-      ws.fill_pending = 0;
+      ws.need = kNeedUpdate;
+      ws.j = ws.k = ws.nMain = ws.prep = 0;
     }
     ex.sync();
-    while (true) {
-      advance(w, haplotype, trim, min_confidence, min_support, num_prune, out, out_len);
-      if (ws.pc == kPcDone) break;
-      if (ws.fill_pending) {
+    while (ws.pc != kPcDone) {
+      step_trace();
+      step_update(w, haplotype, trim, min_confidence, min_support, num_prune, out, out_len);
+      step_prepare();
+      if (ws.pc != kPcDone && ws.need == kNeedFill) {
         const uint32_t l = ws.fill_layer;
-        const uint32_t len = static_cast<uint32_t>(bv.seq_off[l + 1] - bv.seq_off[l]);
         uint8_t* codes = stage_codes(l);
-        ex.template fill<K>(sl, ws, codes, len, ws.fill_mode, ws.fill_mode == kModeNW ? nw : sw, bv.num_codes);
+        ex.template fill<K>(sl, ws, codes, layer_len(l), ws.fill_mode, ws.fill_mode == kModeNW ? nw : sw, bv.num_codes);
+        ex.sync();
+        if (ex.leader()) ws.need = kNeedTrace;
         ex.sync();
       }
     }

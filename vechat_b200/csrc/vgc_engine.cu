@@ -73,7 +73,6 @@ struct WarpEx {
   }
   // layout: codes[max_len] | arena.  The arena is reused phase by phase:
   //   sort      : flags[nV] | off16[nV+1] | tail16[nE] | stack16[>=256]
-  //   traceback : ni[nV] u32 | p1[nV] u16
   __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
   __device__ __forceinline__ uint8_t* arena() { return sm + ((max_len + 15u) & ~15u); }
   __device__ __forceinline__ uint32_t arena_bytes() { return sm_bytes - ((max_len + 15u) & ~15u); }
@@ -93,14 +92,6 @@ struct WarpEx {
     *cap = (avail - so) / 2u;
     return true;
   }
-  __device__ bool trace_tables(uint32_t nV, uint32_t** ni, uint16_t** p1) {
-    uint8_t* base = arena();
-    const uint32_t need = ((nV * 4u + 15u) & ~15u) + nV * 2u;
-    if (need > arena_bytes()) return false;
-    *ni = reinterpret_cast<uint32_t*>(base);
-    *p1 = reinterpret_cast<uint16_t*>(base + ((nV * 4u + 15u) & ~15u));
-    return true;
-  }
   // the fill runs in its own kernel (fill_kernel): never called through the executor on the device
   template <int KK>
   __device__ __forceinline__ void fill(Slot&, WinState&, const uint8_t*, uint32_t, uint32_t, const Scores&, uint32_t) {}
@@ -112,73 +103,128 @@ __device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t 
   for (uint32_t i = lane; i < bytes / 4; i += 32) d[i] = s[i];
 }
 
-#ifndef VGC_GRAPH_CTAS
-#define VGC_GRAPH_CTAS 24
+// ---- the four kernels of a lockstep cycle (one warp = one CTA = one window in each of them) -------------
+// CTAs per SM each kernel is compiled and sized for (registers via __launch_bounds__, shared memory via the
+// dynamic size the host passes): the traceback wants many warps (one DRAM round trip per step, no shared state
+// beyond the sequence), the update is parallel and light, the sort is a serial DFS over a graph staged in shared
+// memory, the fill is register-heavy.
+#ifndef VGC_TRACE_CTAS
+#define VGC_TRACE_CTAS 32
 #endif
+#ifndef VGC_UPDATE_CTAS
+#define VGC_UPDATE_CTAS 24
+#endif
+#ifndef VGC_SORT_CTAS
+#define VGC_SORT_CTAS 12
+#endif
+#define VGC_FILL_CTAS 16
 
-// Graph kernel: one warp per window.  Resumes the window program (poa_core.h advance()): traceback of the
-// alignment just filled, graph update (AddAlignment / AddWeights / prune / LargestSubgraph), re-sort, and the row
-// program of the next alignment.  Replaces everything of Window::generate_consensus except the DP fill.
-template <int K>
-__global__ void __launch_bounds__(32, VGC_GRAPH_CTAS) graph_kernel(const KernelArgs a, uint32_t base) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  Slot* sl = reinterpret_cast<Slot*>(smem);
-  WinState* ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
+struct WinCtx {
+  Slot* sl;
+  WinState* ws;
+  WinState* gws;
+  uint32_t idx, w;
+};
+
+// Load the window's Slot + WinState into the shared-memory header; false if the window does not wait for `need`.
+__device__ __forceinline__ bool win_enter(const KernelArgs& a, uint32_t base, uint32_t need, uint8_t* smem, WinCtx* c) {
   const int lane = threadIdx.x;
-  const uint32_t idx = base + blockIdx.x;
-  WinState* gws = a.wstates + idx;
-  if (gws->pc == kPcDone) return;
-  copy_words(sl, a.slots + idx, sizeof(Slot), lane);
-  copy_words(ws, gws, sizeof(WinState), lane);
+  c->idx = base + blockIdx.x;
+  c->gws = a.wstates + c->idx;
+  if (c->gws->pc == kPcDone || c->gws->need != need) return false;
+  c->sl = reinterpret_cast<Slot*>(smem);
+  c->ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
+  copy_words(c->sl, a.slots + c->idx, sizeof(Slot), lane);
+  copy_words(c->ws, c->gws, sizeof(WinState), lane);
   __syncwarp();
+  c->w = a.work[c->idx];
+  return true;
+}
+
+// Write the program state (and the graph headers that live in the Slot copy) back; publish a finished window.
+__device__ __forceinline__ void win_leave(const KernelArgs& a, const WinCtx& c) {
+  const int lane = threadIdx.x;
+  __syncwarp();
+  if (lane == 0) {
+    Slot* gs = const_cast<Slot*>(a.slots + c.idx);
+    gs->g[0].nV = c.sl->g[0].nV;
+    gs->g[0].nE = c.sl->g[0].nE;
+    gs->g[1].nV = c.sl->g[1].nV;
+    gs->g[1].nE = c.sl->g[1].nE;
+  }
+  copy_words(c.gws, c.ws, sizeof(WinState), lane);
+  if (lane == 0 && c.ws->pc == kPcDone) {
+    a.status[c.w] = c.ws->status;
+    atomicAdd(a.totals, c.ws->cells);
+    atomicAdd(a.totals + 1, static_cast<unsigned long long>(c.ws->alignments));
+    for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, c.ws->phase[i]);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem, const Slot* sl) {
   WarpEx<K> ex;
   ex.sm = smem + kSmemHeader;
   ex.sm_bytes = a.smem_bytes - kSmemHeader;
   ex.max_len = sl->max_len;
-  ex.lane_ = lane;
-  Poa<WarpEx<K>, K> poa(ex, a.bv, *sl, *ws, a.nw);
-  const uint32_t w = a.work[idx];
-  poa.advance(w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
-              a.out + a.bv.out_off[w], a.out_len + w);
-  __syncwarp();
-  // the graph headers (nV, nE) live in the Slot copy: write them back with the program state
-  if (lane == 0) {
-    Slot* gs = const_cast<Slot*>(a.slots + idx);
-    gs->g[0].nV = sl->g[0].nV;
-    gs->g[0].nE = sl->g[0].nE;
-    gs->g[1].nV = sl->g[1].nV;
-    gs->g[1].nE = sl->g[1].nE;
-  }
-  copy_words(gws, ws, sizeof(WinState), lane);
-  if (lane == 0 && ws->pc == kPcDone) {
-    a.status[w] = ws->status;
-    atomicAdd(a.totals, ws->cells);
-    atomicAdd(a.totals + 1, static_cast<unsigned long long>(ws->alignments));
-    for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, ws->phase[i]);
-  }
+  ex.lane_ = threadIdx.x;
+  return ex;
 }
 
-// Fill kernel: one warp per pending alignment (poa_fill.cuh).  Replaces SimdAlignmentEngine::Linear's fill.
+// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback).
+template <int K>
+__global__ void __launch_bounds__(32, VGC_TRACE_CTAS) trace_kernel(const KernelArgs a, uint32_t base) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  WinCtx c;
+  if (!win_enter(a, base, kNeedTrace, smem, &c)) return;
+  WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
+  Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
+  poa.step_trace();
+  win_leave(a, c);
+}
+
+// U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, AddWeights,
+// PruneGraph, LargestSubgraph, GenerateCorrectedSequence / GenerateConsensus, and Window::generate_consensus'
+// control flow).
+template <int K>
+__global__ void __launch_bounds__(32, VGC_UPDATE_CTAS) update_kernel(const KernelArgs a, uint32_t base) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  WinCtx c;
+  if (!win_enter(a, base, kNeedUpdate, smem, &c)) return;
+  WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
+  Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
+  poa.step_update(c.w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
+                  a.out + a.bv.out_off[c.w], a.out_len + c.w);
+  win_leave(a, c);
+}
+
+// T: Graph::TopologicalSort (+ Subgraph view of a partial layer) and the row program of the next alignment.
+template <int K>
+__global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArgs a, uint32_t base) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  WinCtx c;
+  if (!win_enter(a, base, kNeedPrepare, smem, &c)) return;
+  WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
+  Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
+  poa.step_prepare();
+  win_leave(a, c);
+}
+
+// F: the DP fill of the pending alignment (poa_fill.cuh; replaces SimdAlignmentEngine::Linear's fill).
 // shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words]
 template <int K>
-__global__ void __launch_bounds__(32, 16) fill_kernel(const KernelArgs a, uint32_t base) {
+__global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArgs a, uint32_t base) {
   extern __shared__ __align__(16) uint8_t smem[];
-  Slot* sl = reinterpret_cast<Slot*>(smem);
-  WinState* ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
-  const int lane = threadIdx.x;
-  const uint32_t idx = base + blockIdx.x;
-  WinState* gws = a.wstates + idx;
-  if (gws->pc == kPcDone || gws->fill_pending == 0) return;
   const unsigned long long t0 = clock64();
-  copy_words(sl, a.slots + idx, sizeof(Slot), lane);
-  copy_words(ws, gws, sizeof(WinState), lane);
-  __syncwarp();
+  WinCtx c;
+  if (!win_enter(a, base, kNeedFill, smem, &c)) return;
+  const int lane = threadIdx.x;
   uint8_t* sm = smem + kSmemHeader;
-  const uint32_t max_len = sl->max_len;
+  const uint32_t max_len = c.sl->max_len;
   uint8_t* codes = sm;
   uint4* stage = reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u));
   uint32_t* prof = reinterpret_cast<uint32_t*>(stage + 32);
-  const uint32_t l = ws->fill_layer;
+  const uint32_t l = c.ws->fill_layer;
   const uint64_t o = a.bv.seq_off[l];
   const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
   for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
@@ -187,13 +233,14 @@ __global__ void __launch_bounds__(32, 16) fill_kernel(const KernelArgs a, uint32
   sw.m = 3;
   sw.x = -5;
   sw.g = -4;
-  const uint32_t mode = ws->fill_mode;
-  warp_fill<K>(*sl, *ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage);
+  const uint32_t mode = c.ws->fill_mode;
+  warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage);
   if (lane == 0) {
-    gws->best_row = ws->best_row;
-    gws->best_col = ws->best_col;
-    gws->best_score = ws->best_score;
-    gws->phase[kPhFill] += clock64() - t0;
+    c.gws->best_row = c.ws->best_row;
+    c.gws->best_col = c.ws->best_col;
+    c.gws->best_score = c.ws->best_score;
+    c.gws->need = kNeedTrace;
+    c.gws->phase[kPhFill] += clock64() - t0;
   }
 }
 
@@ -264,7 +311,7 @@ struct vgc_engine {
   int groups = 4;                 // streams of a lockstep pass
   cudaStream_t gstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t gev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  uint32_t smem_graph = 0, smem_fill = 0;
+  uint32_t smem_trace = 0, smem_update = 0, smem_sort = 0, smem_fill = 0;
   size_t mem_budget = 0;
   // device copies of the batch
   DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
@@ -362,23 +409,43 @@ BatchView make_view(vgc_engine* h) {
 constexpr int kMaxGroups = 8;
 
 template <int K>
-int set_kernel_attrs(uint32_t smem_graph, uint32_t smem_fill) {
-  VGC_CUDA(cudaFuncSetAttribute(graph_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  VGC_CUDA(cudaFuncSetAttribute(graph_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem_graph)));
-  VGC_CUDA(cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  VGC_CUDA(cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem_fill)));
+int set_kernel_attrs(const vgc_engine* h) {
+  auto set = [](const void* f, uint32_t smem) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  };
+  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), h->smem_trace));
+  VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), h->smem_update));
+  VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
+  VGC_CUDA(set(reinterpret_cast<const void*>(fill_kernel<K>), h->smem_fill));
   return VGC_OK;
 }
 
+// one lockstep cycle for the first `nru` (trace, update) / `ntf` (sort, fill) windows of a group
 template <int K>
-void launch_graph(const KernelArgs& a, uint32_t base, uint32_t count, cudaStream_t st) {
-  graph_kernel<K><<<count, 32, a.smem_bytes, st>>>(a, base);
-}
-template <int K>
-void launch_fill(const KernelArgs& a, uint32_t base, uint32_t count, cudaStream_t st) {
-  fill_kernel<K><<<count, 32, a.smem_bytes, st>>>(a, base);
+uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, uint32_t nru, uint32_t ntf, bool first,
+                      cudaStream_t st) {
+  KernelArgs k = a;
+  uint32_t n = 0;
+  if (nru && !first) {
+    k.smem_bytes = h->smem_trace;
+    trace_kernel<K><<<nru, 32, k.smem_bytes, st>>>(k, base);
+    ++n;
+  }
+  if (nru) {
+    k.smem_bytes = h->smem_update;
+    update_kernel<K><<<nru, 32, k.smem_bytes, st>>>(k, base);
+    ++n;
+  }
+  if (ntf) {
+    k.smem_bytes = h->smem_sort;
+    sort_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
+    k.smem_bytes = h->smem_fill;
+    fill_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
+    n += 2;
+  }
+  return n;
 }
 
 // Node capacity of a window's slot on the first pass: backbone + a share of the layer bases (a read adds a node
@@ -468,30 +535,23 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     a.num_prune = h->params.num_prune;
     a.min_confidence = h->params.min_confidence;
     a.min_support = h->params.min_support;
-    KernelArgs ag = a, af = a;
-    ag.smem_bytes = h->smem_graph;
-    af.smem_bytes = h->smem_fill;
+    a.smem_bytes = 0;
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
-    // ---- lockstep: the lists are sorted by decreasing fills, so the live windows of step s are a prefix
-    std::vector<uint32_t> liveG(G), liveF(G);
-    for (int g = 0; g < G; ++g) liveG[g] = liveF[g] = static_cast<uint32_t>(gfill[g].size());
-    const uint32_t max_fill = pr.win_nfill[wins[pos]];
-    for (uint32_t s = 0; s <= max_fill; ++s) {
+    // ---- lockstep: the lists are sorted by decreasing fills, so the live windows of a cycle are a prefix.
+    // Cycle c runs trace + update for windows with fills + extra >= c (extra = 1 in linear mode: its consensus
+    // needs one more update after the last sort) and sort + fill for windows with fills + extra > c.
+    const uint32_t extra = h->params.haplotype ? 0u : 1u;
+    std::vector<uint32_t> liveA(G), liveB(G);
+    for (int g = 0; g < G; ++g) liveA[g] = liveB[g] = static_cast<uint32_t>(gfill[g].size());
+    const uint32_t max_fill = pr.win_nfill[wins[pos]] + extra;
+    for (uint32_t c = 0; c <= max_fill; ++c) {
       for (int g = 0; g < G; ++g) {
         const std::vector<uint32_t>& nf = gfill[g];
-        while (liveG[g] > 0 && nf[liveG[g] - 1] < s) --liveG[g];       // advance #s exists iff fills >= s
-        while (liveF[g] > 0 && nf[liveF[g] - 1] <= s) --liveF[g];      // fill #s exists iff fills > s
-        if (liveG[g]) {
-          if (K == 10) launch_graph<10>(ag, gbase[g], liveG[g], h->gstream[g]);
-          else launch_graph<16>(ag, gbase[g], liveG[g], h->gstream[g]);
-          ++*launches;
-        }
-        if (liveF[g]) {
-          if (K == 10) launch_fill<10>(af, gbase[g], liveF[g], h->gstream[g]);
-          else launch_fill<16>(af, gbase[g], liveF[g], h->gstream[g]);
-          ++*launches;
-        }
+        while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
+        while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
+        if (K == 10) *launches += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
+        else *launches += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
       }
     }
     VGC_CUDA(cudaGetLastError());
@@ -543,8 +603,8 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
       set_err("layer longer than 1024 bases: beyond the engine's row capacity");
       return VGC_ERR_CAPACITY;
     }
-    if (K == 10) rc = set_kernel_attrs<10>(h->smem_graph, h->smem_fill);
-    else rc = set_kernel_attrs<16>(h->smem_graph, h->smem_fill);
+    if (K == 10) rc = set_kernel_attrs<10>(h);
+    else rc = set_kernel_attrs<16>(h);
     if (rc) return rc;
     VGC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = run_pass(h, pr.device_windows, false, K, seq_off, win_first, &launches))) return rc;
@@ -672,10 +732,13 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
     VGC_CUDA(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
     VGC_CUDA(cudaEventCreateWithFlags(&h->gev[g], cudaEventDisableTiming));
   }
-  // shared memory per one-warp CTA: fill kernel 16 CTAs / SM, graph kernel VGC_GRAPH_CTAS / SM
+  // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
+  auto smem_for = [](int ctas) { return static_cast<uint32_t>(((228 * 1024 - ctas * 1024) / ctas) & ~255); };
   h->smem_fill = 13568;
-  h->smem_graph = ((228 * 1024 - VGC_GRAPH_CTAS * 1024) / VGC_GRAPH_CTAS) & ~255u;
-  if (const char* s = std::getenv("VGC_GRAPH_SMEM")) h->smem_graph = static_cast<uint32_t>(std::atoi(s));
+  h->smem_sort = smem_for(VGC_SORT_CTAS);
+  h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
+  h->smem_trace = 2048;
+  if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
