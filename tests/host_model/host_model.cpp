@@ -36,6 +36,7 @@ struct HostEx {
     return o;
   }
   uint32_t bcast(uint32_t v, uint32_t /*src*/) { return v; }
+  const uint16_t* col_lut() const { return nullptr; }
   uint32_t reduce_min(uint32_t v) { return v; }
   uint32_t reduce_max(uint32_t v) { return v; }
   uint32_t excl_scan(uint32_t v, uint32_t* total) {
@@ -145,6 +146,8 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   d.max_edges = d.max_nodes;
   d.max_len = std::max<uint32_t>(prep.max_len, 16);
   d.row_words = 32 * K;
+  d.in_stride = 8;
+  for (uint32_t w = 0; w < b->n_windows; ++w) d.in_stride = std::max(d.in_stride, prep.win_nseq[w] + 1);
   std::vector<uint8_t> buf(slot_bytes(d));
   Slot sl;
   slot_carve(d, buf.data(), &sl);

@@ -17,13 +17,18 @@ for what in "$@"; do
       timeout 600 python bench.py --impl reference --steps ${STEPS:-5} --warmup ${WARMUP:-3} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"
       cat gpurun_out/bench_ref.json ;;
     ncu)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
-        python bench.py --steps 2 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
-      tail -12 gpurun_out/launches.csv ;;
+      VGC_GROUPS=${NCU_GROUPS:-1} timeout 1500 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-3000} --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+      python tools/launch_summary.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt ;;
     ncugraph)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:graph_kernel -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_graph \
         python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncugraph.log 2>&1; echo "ncugraph rc=$?"
       ls -la gpurun_out/prof_graph.ncu-rep ;;
+    ncuk)
+      # generic: NCU_KERNEL regex, NCU_SKIP, output gpurun_out/prof_${NCU_NAME}
+      VGC_GROUPS=${NCU_GROUPS:-1} timeout 1500 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL} -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_${NCU_NAME:-k} \
+        python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncuk.log 2>&1; echo "ncuk rc=$?"
+      ls -la gpurun_out/prof_${NCU_NAME:-k}.ncu-rep ;;
     ncufill)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:fill_kernel -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_fill \
         python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncufill.log 2>&1; echo "ncufill rc=$?"

@@ -223,6 +223,7 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
 // Bytes of one scratch slot for the given capacities, and the carving of a slot out of a flat buffer.
 struct SlotDims {
   uint32_t max_nodes, max_edges, max_len, row_words;
+  uint32_t in_stride = 8;  // in-list capacity per node (exact bound: the number of sequences of the window)
 };
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -251,10 +252,9 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
     t(E * 4);                  // ein_ord
     t(E * 4);                  // eout_ord
     t(E);                      // edead
+    t(N * d.in_stride * 4);    // itail
+    t(N * d.in_stride * 4);    // ieid
   }
-  t((N + 1) * 4);  // in_off
-  t(E * 4);        // in_eid
-  t(E * 4);        // in_tail
   t((N + 1) * 4);  // out_off
   t(E * 4);        // out_eid
   t(N * 4);        // r2n
@@ -292,6 +292,7 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
   s->max_edges = d.max_edges;
   s->max_len = d.max_len;
   s->row_words = d.row_words;
+  s->in_stride = d.in_stride;
   for (int gi = 0; gi < 2; ++gi) {
     Graph& g = s->g[gi];
     g.nV = g.nE = 0;
@@ -307,10 +308,9 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
     P(&g.ein_ord);
     P(&g.eout_ord);
     P(&g.edead);
+    P(&g.itail);
+    P(&g.ieid);
   }
-  P(&s->in_off);
-  P(&s->in_eid);
-  P(&s->in_tail);
   P(&s->out_off);
   P(&s->out_eid);
   P(&s->r2n);

@@ -26,7 +26,8 @@
 //   edges : tail, head, weight (u32), in_ord / out_ord (position inside head's in-list / tail's
 //           out-list; lists are "edges of that node in creation order", so CSR position =
 //           off[node] + ord), dead u8 (pruned hole)
-//   CSR   : in_off/in_eid/in_tail (rebuilt in parallel after every graph change), out_off/out_eid
+//   in-lists: per node a fixed-stride row of (tail, edge id) in creation order — appended in place, never
+//           rebuilt; out_off/out_eid: CSR of out-edges, built only where a pass needs it
 //   H     : one row of packed int16 score cells per graph node (+ virtual row 0), row = node id + 1
 //   fc    : int16 first-column value per row (NW border)
 #ifndef VGC_POA_CORE_H_
@@ -62,6 +63,7 @@ enum : uint32_t {
   kStTooLong = 5,        // layer longer than the row capacity
   kStAlignedOverflow = 6,
   kStInternal = 7,
+  kStDegreeOverflow = 8, // a node's in-degree outgrew the slot's in-list stride: rerun with a larger one
 };
 
 enum : uint32_t { kModeNW = 0, kModeSW = 1 };
@@ -121,15 +123,15 @@ struct Graph {
   uint32_t* ein_ord;
   uint32_t* eout_ord;
   uint8_t* edead;
+  uint32_t* itail;     // [max_nodes * in_stride] in-edge tails of each node, creation order
+  uint32_t* ieid;      // [max_nodes * in_stride] ... and their edge ids
 };
 
 // One slot of scratch in HBM.  Two graph buffers: LargestSubgraph writes the other one.
 struct Slot {
   uint32_t max_nodes, max_edges, max_len, row_words;
+  uint32_t in_stride;  // capacity of a node's in-list
   Graph g[2];
-  uint32_t* in_off;    // [max_nodes + 1]
-  uint32_t* in_eid;    // [max_edges]
-  uint32_t* in_tail;   // [max_edges]
   uint32_t* out_off;   // [max_nodes + 1]
   uint32_t* out_eid;   // [max_edges]
   uint32_t* r2n;       // [max_nodes] rank -> node of the whole current graph
@@ -203,6 +205,12 @@ struct RowMap {
     *lane = r / K;
     *k = r % K;
   }
+  // (word index << 1) | half of column c: what the traceback's column table holds
+  VGC_HD static VGC_INL uint32_t lut_entry(uint32_t c) {
+    int h, l, k;
+    locate(c, &h, &l, &k);
+    return (word(l, k) << 1) | static_cast<uint32_t>(h);
+  }
   VGC_HD static VGC_INL int32_t load(const uint32_t* row, uint32_t c) {
     int h, l, k;
     locate(c, &h, &l, &k);
@@ -245,36 +253,21 @@ struct Poa {
     if (ws.status == kStOk) ws.status = st;
   }
 
-  // ---- CSR of in-edges (and out-edges) of the live graph: parallel over edges --------------------
-  VGC_HD void build_csr(bool with_out) {
+  // ---- CSR of the out-edges of the live graph (LargestSubgraph, heaviest bundle): parallel over edges ----
+  VGC_HD void build_out_csr() {
     Graph& g = G();
     const uint32_t nV = g.nV, nE = g.nE;
-    // exclusive scan of nin -> in_off
-    uint32_t carry_in = 0, carry_out = 0;
+    uint32_t carry = 0;
     for (uint32_t base = 0; base < nV; base += ex.width()) {
-      uint32_t v = base + ex.lane();
-      uint32_t a = v < nV ? g.nin[v] : 0, tot;
-      uint32_t p = ex.excl_scan(a, &tot);
-      if (v < nV) sl.in_off[v] = carry_in + p;
-      carry_in += tot;
-      if (with_out) {
-        uint32_t b = v < nV ? g.nout[v] : 0;
-        uint32_t q = ex.excl_scan(b, &tot);
-        if (v < nV) sl.out_off[v] = carry_out + q;
-        carry_out += tot;
-      }
+      const uint32_t v = base + ex.lane();
+      uint32_t tot;
+      const uint32_t q = ex.excl_scan(v < nV ? g.nout[v] : 0, &tot);
+      if (v < nV) sl.out_off[v] = carry + q;
+      carry += tot;
     }
-    if (ex.leader()) {
-      sl.in_off[nV] = carry_in;
-      if (with_out) sl.out_off[nV] = carry_out;
-    }
+    if (ex.leader()) sl.out_off[nV] = carry;
     ex.sync();
-    for (uint32_t e = ex.lane(); e < nE; e += ex.width()) {
-      uint32_t pos = sl.in_off[g.ehead[e]] + g.ein_ord[e];
-      sl.in_eid[pos] = e;
-      sl.in_tail[pos] = g.etail[e];
-      if (with_out) sl.out_eid[sl.out_off[g.etail[e]] + g.eout_ord[e]] = e;
-    }
+    for (uint32_t e = ex.lane(); e < nE; e += ex.width()) sl.out_eid[sl.out_off[g.etail[e]] + g.eout_ord[e]] = e;
     ex.sync();
   }
 
@@ -444,6 +437,7 @@ struct Poa {
   //      npred > 2: p1 = offset into ovf[] holding predecessor rows 1..npred-1.
   VGC_HD void build_rowprog(const uint32_t* order, uint32_t nR, bool sub) {
     Graph& g = G();
+    const uint32_t S = sl.in_stride;
     if (ex.leader()) {
       ws.ovf_n = 0;
       ws.nR = nR;
@@ -453,8 +447,8 @@ struct Poa {
       ex.sync();
       for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
         const uint32_t v = order[r];
-        for (uint32_t i = sl.in_off[v]; i < sl.in_off[v + 1]; ++i) {
-          const uint32_t t = sl.in_tail[i];
+        for (uint32_t i = 0; i < g.nin[v]; ++i) {
+          const uint32_t t = g.itail[v * S + i];
           if (sl.flags[t] & kFMember) ex.atomic_add(&sl.tmp0[t], 1u);
         }
       }
@@ -464,9 +458,9 @@ struct Poa {
       const uint32_t v = order[r];
       sl.rank_of[v] = r;
       uint32_t np = 0, p0 = 0, p1 = 0;
-      const uint32_t b = sl.in_off[v], e = sl.in_off[v + 1];
+      const uint32_t b = v * S, e = v * S + g.nin[v];
       for (uint32_t i = b; i < e; ++i) {
-        const uint32_t t = sl.in_tail[i];
+        const uint32_t t = g.itail[i];
         if (sub && !(sl.flags[t] & kFMember)) continue;
         if (np == 0) p0 = t + 1;
         if (np == 1) p1 = t + 1;
@@ -476,7 +470,7 @@ struct Poa {
         const uint32_t o = ex.atomic_add(&ws.ovf_n, np - 1);
         uint32_t k = 0, q = 0;
         for (uint32_t i = b; i < e; ++i) {
-          const uint32_t t = sl.in_tail[i];
+          const uint32_t t = g.itail[i];
           if (sub && !(sl.flags[t] & kFMember)) continue;
           if (q++ > 0) sl.ovf[o + k++] = t + 1;
         }
@@ -504,16 +498,6 @@ struct Poa {
   }
 
   // ---- traceback.  Pairs are appended in reverse (end of alignment first).
-  VGC_HD VGC_INL int32_t hval(uint32_t row, uint32_t j, uint32_t mode, int32_t g) const {
-    if (mode == kModeSW) {
-      if (row == 0 || j == 0) return 0;
-    } else {
-      if (row == 0) return static_cast<int32_t>(j) * g;
-      if (j == 0) return sl.fc[row];
-    }
-    return RM::load(sl.H + static_cast<uint64_t>(row) * sl.row_words, j - 1);
-  }
-
   // Warp-cooperative traceback.  One step = one round of parallel loads: every candidate of the current cell
   // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order,
   // simd_alignment_engine_implementation.hpp:1031-1061) is fetched and compared by its own lane and the first
@@ -528,6 +512,12 @@ struct Poa {
   }
 
   VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
+    if (mode == kModeSW) traceback_t<true>(seq_codes, sc);
+    else traceback_t<false>(seq_codes, sc);
+  }
+
+  template <bool SW>
+  VGC_HD void traceback_t(const uint8_t* seq_codes, const Scores& sc) {
     const int W = ex.width(), L = ex.lane();
     uint32_t i = ws.best_row, j = ws.best_col;
     if (i == 0 && j == 0) {
@@ -535,13 +525,25 @@ struct Poa {
       ex.sync();
       return;
     }
+    const uint16_t* lut = ex.col_lut();  // [kCols] RowMap::lut_entry per column, or nullptr
+    const uint32_t rw = sl.row_words;
+    const uint32_t* Hb = sl.H;
+    const int16_t* fcb = sl.fc;
+    // H(row, j) with j the 1-based DP column; j == 0 is the first column (NW border / 0 in SW).  The virtual
+    // row 0 is materialised in H by the fill, so only the column needs a special case.
+    auto hv_at = [&](uint32_t row, uint32_t jj) -> int32_t {
+      if (jj == 0) return SW ? 0 : static_cast<int32_t>(fcb[row]);
+      const uint32_t e = lut ? static_cast<uint32_t>(lut[jj - 1]) : RM::lut_entry(jj - 1);
+      const uint32_t wv = Hb[static_cast<uint64_t>(row) * rw + (e >> 1)];
+      return static_cast<int16_t>((e & 1u) ? (wv >> 16) : (wv & 0xFFFFu));
+    };
     const int32_t gp = sc.g;
-    int32_t h = hval(i, j, mode, gp);
+    int32_t h = hv_at(i, j);
     U4 rec = node_rec(i);
     uint32_t n = 0;
     bool bad = false;
     while (true) {
-      if (mode == kModeSW) {
+      if (SW) {
         if (h == 0) break;
       } else {
         if (i == 0 && j == 0) break;
@@ -569,15 +571,15 @@ struct Poa {
           nr = node_rec(pr);
           if (c < npp) {
             if (j != 0) {
-              hv = hval(pr, j - 1, mode, gp);
+              hv = hv_at(pr, j - 1);
               ok = h == hv + mc;
             }
           } else {
-            hv = hval(pr, j, mode, gp);
+            hv = hv_at(pr, j);
             ok = h == hv + gp;
           }
         } else if (c == 2 * npp && j != 0) {
-          hv = hval(i, j - 1, mode, gp);
+          hv = hv_at(i, j - 1);
           ok = h == hv + gp;
         }
         const uint32_t f = ex.reduce_min(ok ? c : kNone);
@@ -631,7 +633,6 @@ struct Poa {
   //        * a path visits at most one node of an aligned clique, and gives every node at most one new in-edge
   //          and one new out-edge, so clique updates and in/out-list appends of different positions never touch
   //          the same list (list order = creation order is therefore preserved).
-  //      Needs the CSR of the graph as it was before the call (in_off/in_tail/in_eid for ids < nV0).
   VGC_HD void add_alignment(const uint8_t* codes, uint32_t layer, uint32_t len) {
     Graph& g = G();
     const uint32_t nV0 = g.nV, nE0 = g.nE;
@@ -643,6 +644,7 @@ struct Poa {
       ex.sync();
       return;
     }
+    const uint32_t S = sl.in_stride;
     const uint32_t covinc = len > 1 ? 1u : 0u;  // Node::Coverage counts edge labels: a 1-base sequence has none
     const uint32_t n = ws.aln_len;
     uint32_t* npos = sl.tmp1;  // node id of every sequence position
@@ -763,9 +765,10 @@ struct Poa {
         head = npos[pos];
         w = weight_at(layer, pos - 1) + weight_at(layer, pos);
         if (tail < nV0 && head < nV0) {
-          for (uint32_t i = sl.in_off[head]; i < sl.in_off[head + 1]; ++i) {
-            if (sl.in_tail[i] == tail) {
-              g.ew[sl.in_eid[i]] += w;
+          const uint32_t ni = g.nin[head];
+          for (uint32_t i = 0; i < ni; ++i) {
+            if (g.itail[head * S + i] == tail) {
+              g.ew[g.ieid[head * S + i]] += w;
               need = false;
               break;
             }
@@ -780,8 +783,15 @@ struct Poa {
         g.ehead[e] = head;
         g.ew[e] = w;
         g.edead[e] = 0;
-        g.ein_ord[e] = g.nin[head];
-        g.nin[head] = g.nin[head] + 1;
+        const uint32_t slot = g.nin[head];
+        if (slot >= S) {
+          fail(kStDegreeOverflow);
+        } else {
+          g.itail[head * S + slot] = tail;
+          g.ieid[head * S + slot] = e;
+          g.nin[head] = slot + 1;
+        }
+        g.ein_ord[e] = slot;
         g.eout_ord[e] = g.nout[tail];
         g.nout[tail] = g.nout[tail] + 1;
       }
@@ -805,9 +815,10 @@ struct Poa {
       if (nd == -1 || pos == -1 || pnd == -1 || ppos == -1) continue;
       const uint32_t w = weight_at(layer, pos - 1) + weight_at(layer, pos);
       bool hit = false;
-      for (uint32_t i = sl.in_off[nd]; i < sl.in_off[nd + 1]; ++i) {
-        if (sl.in_tail[i] == static_cast<uint32_t>(pnd)) {
-          ex.atomic_add(&g.ew[sl.in_eid[i]], w);
+      const uint32_t S = sl.in_stride;
+      for (uint32_t i = 0; i < g.nin[nd]; ++i) {
+        if (g.itail[nd * S + i] == static_cast<uint32_t>(pnd)) {
+          ex.atomic_add(&g.ew[g.ieid[nd * S + i]], w);
           hit = true;
           break;
         }
@@ -845,8 +856,9 @@ struct Poa {
   // ---- graph.cpp:984-1089 (leader): components by recursive pre-order over [live in-tails, live
   //      out-heads]; last largest wins; rebuild with DFS-order ids, zero weights, no aligned links ----
   VGC_HD void largest_subgraph() {
-    build_csr(true);
+    build_out_csr();
     Graph& g = G();
+    const uint32_t S = sl.in_stride;
     Graph& h = sl.g[ws.cur ^ 1];
     const uint32_t nV = g.nV;
     uint32_t* comp = sl.tmp0;             // all components back to back
@@ -869,13 +881,13 @@ struct Poa {
         while (sp > 0) {
           const uint32_t v = stk[2 * (sp - 1)];
           uint32_t c = stk[2 * (sp - 1) + 1];
-          const uint32_t nin = sl.in_off[v + 1] - sl.in_off[v];
+          const uint32_t nin = g.nin[v];
           const uint32_t nout = sl.out_off[v + 1] - sl.out_off[v];
           uint32_t next = kNone;
           while (c < nin + nout) {
             uint32_t e, u;
             if (c < nin) {
-              e = sl.in_eid[sl.in_off[v] + c];
+              e = g.ieid[v * S + c];
               u = g.etail[e];
             } else {
               e = sl.out_eid[sl.out_off[v] + (c - nin)];
@@ -926,7 +938,10 @@ struct Poa {
           h.ehead[ne] = hd;
           h.ew[ne] = 0;
           h.edead[ne] = 0;
-          h.ein_ord[ne] = h.nin[hd]++;
+          const uint32_t slot = h.nin[hd]++;  // <= the node's in-degree in g, which fits the stride
+          h.itail[hd * S + slot] = i;
+          h.ieid[hd * S + slot] = ne;
+          h.ein_ord[ne] = slot;
           h.eout_ord[ne] = h.nout[i]++;
           ++ne;
         }
@@ -949,6 +964,7 @@ struct Poa {
   // ---- graph.cpp:534-638 + 450-485 (leader): heaviest bundle consensus + coverage, linear mode ------
   VGC_HD uint32_t heaviest_bundle(uint32_t nR, uint8_t* out, uint32_t out_cap, uint32_t* cov_out) {
     Graph& g = G();
+    const uint32_t S = sl.in_stride;
     const uint32_t nV = g.nV;
     // scores (int64) and predecessors live in the H scratch
     long long* score = reinterpret_cast<long long*>(sl.H);
@@ -961,9 +977,9 @@ struct Poa {
     for (uint32_t r = 0; r < nR; ++r) n2r[sl.r2n[r]] = r;
     uint32_t mx = kNone;
     auto relax = [&](uint32_t it, bool skip_dead_tails) {
-      for (uint32_t i = sl.in_off[it]; i < sl.in_off[it + 1]; ++i) {
-        const uint32_t t = sl.in_tail[i];
-        const long long w = g.ew[sl.in_eid[i]];
+      for (uint32_t i = it * S; i < it * S + g.nin[it]; ++i) {
+        const uint32_t t = g.itail[i];
+        const long long w = g.ew[g.ieid[i]];
         if (skip_dead_tails && score[t] == -1) continue;
         if (score[it] < w || (score[it] == w && score[pred[it]] <= score[t])) {
           score[it] = w;
@@ -979,8 +995,8 @@ struct Poa {
       const uint32_t start = mx, rank = n2r[mx];
       for (uint32_t k = sl.out_off[start]; k < sl.out_off[start + 1]; ++k) {
         const uint32_t hd = g.ehead[sl.out_eid[k]];
-        for (uint32_t i = sl.in_off[hd]; i < sl.in_off[hd + 1]; ++i) {
-          if (sl.in_tail[i] != start) score[sl.in_tail[i]] = -1;
+        for (uint32_t i = hd * S; i < hd * S + g.nin[hd]; ++i) {
+          if (g.itail[i] != start) score[g.itail[i]] = -1;
         }
       }
       mx = kNone;
@@ -1112,11 +1128,6 @@ struct Poa {
     if (ex.leader()) ws.t_last = ex.clock();
     // plan: make the next alignment (or sort-only step) pending
     auto plan = [&](uint32_t next_pc, uint32_t prep, uint32_t layer, uint32_t mode) {
-      if (changed) {
-        tick(kPhOther);
-        build_csr(false);
-        tick(kPhCsr);
-      }
       if (ex.leader()) {
         ws.pc = next_pc;
         ws.j = j;
@@ -1200,7 +1211,8 @@ struct Poa {
       return finish();
     } else if (pc == kPcLinearFinal) {
       // linear mode: consensus + coverage trim (window.cpp:138-171); the graph was re-sorted by step_prepare
-      build_csr(true);
+      build_out_csr();
+      tick(kPhCsr);
       if (ex.leader()) {
         uint32_t* cov = sl.tmp0;
         uint32_t n = heaviest_bundle(ws.nMain, out, out_cap, cov);

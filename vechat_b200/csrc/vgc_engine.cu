@@ -44,35 +44,49 @@ struct KernelArgs {
   uint32_t smem_bytes;     // dynamic shared memory per CTA of the launched kernel
 };
 
-// Warp executor: the device side of poa_core.h's `Ex` concept.
-template <int K>
+// Executor: the device side of poa_core.h's `Ex` concept.  G lanes work on one window (G = 32: a whole warp;
+// G = 8: four windows per warp, used where a step keeps only a handful of lanes busy).
+template <int K, int G = 32>
 struct WarpEx {
-  uint8_t* sm;        // shared memory after the header
+  uint8_t* sm;        // this window's shared memory after the header
   uint32_t sm_bytes;
   uint32_t max_len;
-  int lane_;
+  int lane_;          // lane inside the group
+  uint32_t mask_;     // the group's lanes inside the warp
+  const uint16_t* lut_ = nullptr;
 
   __device__ __forceinline__ unsigned long long clock() const { return clock64(); }
   __device__ __forceinline__ int lane() const { return lane_; }
-  __device__ __forceinline__ int width() const { return 32; }
+  __device__ __forceinline__ int width() const { return G; }
   __device__ __forceinline__ bool leader() const { return lane_ == 0; }
-  __device__ __forceinline__ void sync() { __syncwarp(); }
+  __device__ __forceinline__ void sync() { __syncwarp(mask_); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-  __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
-  __device__ __forceinline__ uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+  __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(mask_, v, src, G); }
+  __device__ __forceinline__ const uint16_t* col_lut() const { return lut_; }
+  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) {
+    if (G == 32) return __reduce_min_sync(0xFFFFFFFFu, v);
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(mask_, v, d, G));
+    return v;
+  }
+  __device__ __forceinline__ uint32_t reduce_max(uint32_t v) {
+    if (G == 32) return __reduce_max_sync(0xFFFFFFFFu, v);
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(mask_, v, d, G));
+    return v;
+  }
   __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
     uint32_t x = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    for (int d = 1; d < G; d <<= 1) {
+      uint32_t t = __shfl_up_sync(mask_, x, d, G);
       if (lane_ >= d) x += t;
     }
-    *total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    *total = __shfl_sync(mask_, x, G - 1, G);
     return x - v;
   }
-  // layout: codes[max_len] | arena.  The arena is reused phase by phase:
-  //   sort      : flags[nV] | off16[nV+1] | tail16[nE] | stack16[>=256]
+  // layout: codes[max_len] | arena.  The arena holds the sort's staged graph:
+  //   flags[nV] | off16[nV+1] | adj16[nA] | stack16[>=256]
   __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
   __device__ __forceinline__ uint8_t* arena() { return sm + ((max_len + 15u) & ~15u); }
   __device__ __forceinline__ uint32_t arena_bytes() { return sm_bytes - ((max_len + 15u) & ~15u); }
@@ -97,10 +111,10 @@ struct WarpEx {
   __device__ __forceinline__ void fill(Slot&, WinState&, const uint8_t*, uint32_t, uint32_t, const Scores&, uint32_t) {}
 };
 
-__device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t bytes, int lane) {
+__device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t bytes, int lane, int width = 32) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
   uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-  for (uint32_t i = lane; i < bytes / 4; i += 32) d[i] = s[i];
+  for (uint32_t i = lane; i < bytes / 4; i += width) d[i] = s[i];
 }
 
 // ---- the four kernels of a lockstep cycle (one warp = one CTA = one window in each of them) -------------
@@ -124,36 +138,41 @@ struct WinCtx {
   WinState* ws;
   WinState* gws;
   uint32_t idx, w;
+  int lane, width;
+  uint32_t mask;
 };
 
-// Load the window's Slot + WinState into the shared-memory header; false if the window does not wait for `need`.
-__device__ __forceinline__ bool win_enter(const KernelArgs& a, uint32_t base, uint32_t need, uint8_t* smem, WinCtx* c) {
-  const int lane = threadIdx.x;
-  c->idx = base + blockIdx.x;
-  c->gws = a.wstates + c->idx;
+// Load the window's Slot + WinState into its shared-memory header; false if the window does not wait for `need`.
+// `lane`/`width`/`mask`: the lanes working on this window (a whole warp unless the kernel packs several per warp).
+__device__ __forceinline__ bool win_enter(const KernelArgs& a, uint32_t idx, uint32_t need, uint8_t* hdr, WinCtx* c,
+                                          int lane = threadIdx.x, int width = 32, uint32_t mask = 0xFFFFFFFFu) {
+  c->idx = idx;
+  c->lane = lane;
+  c->width = width;
+  c->mask = mask;
+  c->gws = a.wstates + idx;
   if (c->gws->pc == kPcDone || c->gws->need != need) return false;
-  c->sl = reinterpret_cast<Slot*>(smem);
-  c->ws = reinterpret_cast<WinState*>(smem + ((sizeof(Slot) + 15) & ~size_t(15)));
-  copy_words(c->sl, a.slots + c->idx, sizeof(Slot), lane);
-  copy_words(c->ws, c->gws, sizeof(WinState), lane);
-  __syncwarp();
-  c->w = a.work[c->idx];
+  c->sl = reinterpret_cast<Slot*>(hdr);
+  c->ws = reinterpret_cast<WinState*>(hdr + ((sizeof(Slot) + 15) & ~size_t(15)));
+  copy_words(c->sl, a.slots + idx, sizeof(Slot), lane, width);
+  copy_words(c->ws, c->gws, sizeof(WinState), lane, width);
+  __syncwarp(mask);
+  c->w = a.work[idx];
   return true;
 }
 
 // Write the program state (and the graph headers that live in the Slot copy) back; publish a finished window.
 __device__ __forceinline__ void win_leave(const KernelArgs& a, const WinCtx& c) {
-  const int lane = threadIdx.x;
-  __syncwarp();
-  if (lane == 0) {
+  __syncwarp(c.mask);
+  if (c.lane == 0) {
     Slot* gs = const_cast<Slot*>(a.slots + c.idx);
     gs->g[0].nV = c.sl->g[0].nV;
     gs->g[0].nE = c.sl->g[0].nE;
     gs->g[1].nV = c.sl->g[1].nV;
     gs->g[1].nE = c.sl->g[1].nE;
   }
-  copy_words(c.gws, c.ws, sizeof(WinState), lane);
-  if (lane == 0 && c.ws->pc == kPcDone) {
+  copy_words(c.gws, c.ws, sizeof(WinState), c.lane, c.width);
+  if (c.lane == 0 && c.ws->pc == kPcDone) {
     a.status[c.w] = c.ws->status;
     atomicAdd(a.totals, c.ws->cells);
     atomicAdd(a.totals + 1, static_cast<unsigned long long>(c.ws->alignments));
@@ -168,17 +187,47 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
   ex.sm_bytes = a.smem_bytes - kSmemHeader;
   ex.max_len = sl->max_len;
   ex.lane_ = threadIdx.x;
+  ex.mask_ = 0xFFFFFFFFu;
   return ex;
 }
 
-// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback).
+// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback).  A step of the
+// walk compares at most 2 * in-degree + 1 candidate cells, so 8 lanes per window are plenty: a warp walks four
+// windows at once and a 128-thread block sixteen.  shared memory: column table (RowMap::lut_entry per column) |
+// per window: Slot/WinState header + codes[max_len].
+constexpr int kTraceLanes = 8;
+constexpr int kTraceWins = 16;   // windows per block
+
 template <int K>
-__global__ void __launch_bounds__(32, VGC_TRACE_CTAS) trace_kernel(const KernelArgs a, uint32_t base) {
+__host__ __device__ constexpr uint32_t trace_lut_bytes() {
+  return (RowMap<K>::kCols * 2u + 255u) & ~255u;
+}
+__host__ __device__ inline uint32_t trace_win_bytes(uint32_t max_len) { return kSmemHeader + ((max_len + 15u) & ~15u); }
+
+template <int K>
+__global__ void __launch_bounds__(kTraceLanes * kTraceWins, 4) trace_kernel(const KernelArgs a, uint32_t base,
+                                                                          uint32_t count, uint32_t max_len) {
   extern __shared__ __align__(16) uint8_t smem[];
+  uint16_t* lut = reinterpret_cast<uint16_t*>(smem);
+  for (uint32_t c = threadIdx.x; c < static_cast<uint32_t>(RowMap<K>::kCols); c += blockDim.x)
+    lut[c] = static_cast<uint16_t>(RowMap<K>::lut_entry(c));
+  __syncthreads();
+  const uint32_t slot = threadIdx.x / kTraceLanes;
+  const uint32_t i = blockIdx.x * kTraceWins + slot;
+  if (i >= count) return;
+  const int gl = threadIdx.x % kTraceLanes;
+  const uint32_t mask = ((1u << kTraceLanes) - 1u) << ((threadIdx.x & 31) / kTraceLanes * kTraceLanes);
+  uint8_t* mine = smem + trace_lut_bytes<K>() + slot * trace_win_bytes(max_len);
   WinCtx c;
-  if (!win_enter(a, base, kNeedTrace, smem, &c)) return;
-  WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
-  Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
+  if (!win_enter(a, base + i, kNeedTrace, mine, &c, gl, kTraceLanes, mask)) return;
+  WarpEx<K, kTraceLanes> ex;
+  ex.sm = mine + kSmemHeader;
+  ex.sm_bytes = trace_win_bytes(max_len) - kSmemHeader;
+  ex.max_len = max_len;
+  ex.lane_ = gl;
+  ex.mask_ = mask;
+  ex.lut_ = lut;
+  Poa<WarpEx<K, kTraceLanes>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_trace();
   win_leave(a, c);
 }
@@ -190,7 +239,7 @@ template <int K>
 __global__ void __launch_bounds__(32, VGC_UPDATE_CTAS) update_kernel(const KernelArgs a, uint32_t base) {
   extern __shared__ __align__(16) uint8_t smem[];
   WinCtx c;
-  if (!win_enter(a, base, kNeedUpdate, smem, &c)) return;
+  if (!win_enter(a, base + blockIdx.x, kNeedUpdate, smem, &c)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_update(c.w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
@@ -203,7 +252,7 @@ template <int K>
 __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArgs a, uint32_t base) {
   extern __shared__ __align__(16) uint8_t smem[];
   WinCtx c;
-  if (!win_enter(a, base, kNeedPrepare, smem, &c)) return;
+  if (!win_enter(a, base + blockIdx.x, kNeedPrepare, smem, &c)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_prepare();
@@ -217,7 +266,7 @@ __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArg
   extern __shared__ __align__(16) uint8_t smem[];
   const unsigned long long t0 = clock64();
   WinCtx c;
-  if (!win_enter(a, base, kNeedFill, smem, &c)) return;
+  if (!win_enter(a, base + blockIdx.x, kNeedFill, smem, &c)) return;
   const int lane = threadIdx.x;
   uint8_t* sm = smem + kSmemHeader;
   const uint32_t max_len = c.sl->max_len;
@@ -415,7 +464,7 @@ int set_kernel_attrs(const vgc_engine* h) {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   };
-  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), h->smem_trace));
+  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), trace_lut_bytes<K>() + kTraceWins * trace_win_bytes(1024)));
   VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), h->smem_update));
   VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
   VGC_CUDA(set(reinterpret_cast<const void*>(fill_kernel<K>), h->smem_fill));
@@ -429,8 +478,9 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
   KernelArgs k = a;
   uint32_t n = 0;
   if (nru && !first) {
-    k.smem_bytes = h->smem_trace;
-    trace_kernel<K><<<nru, 32, k.smem_bytes, st>>>(k, base);
+    const uint32_t ml = std::max<uint32_t>(h->prep.max_len, 16);
+    k.smem_bytes = trace_lut_bytes<K>() + kTraceWins * trace_win_bytes(ml);
+    trace_kernel<K><<<(nru + kTraceWins - 1) / kTraceWins, kTraceLanes * kTraceWins, k.smem_bytes, st>>>(k, base, nru, ml);
     ++n;
   }
   if (nru) {
@@ -481,6 +531,7 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       d.max_edges = d.max_nodes;
       d.max_len = std::max<uint32_t>(pr.max_len, 16);
       d.row_words = row_words;
+      d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : 8;
       const uint64_t sb = slot_bytes(d);
       if (bytes + sb > h->mem_budget && e > pos) break;
       if (sb > h->mem_budget) {
@@ -613,7 +664,8 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     // second pass, exact capacities, for windows whose graph outgrew the estimate
     std::vector<uint32_t> retry;
     for (uint32_t w : pr.device_windows) {
-      if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow) retry.push_back(w);
+      if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow || h->h_status[w] == kStDegreeOverflow)
+        retry.push_back(w);
     }
     if (!retry.empty()) {
       relaunched = static_cast<uint32_t>(retry.size());
