@@ -37,6 +37,14 @@ struct HostEx {
   }
   uint32_t bcast(uint32_t v, uint32_t /*src*/) { return v; }
   const uint16_t* col_lut() const { return nullptr; }
+  std::vector<int16_t> tile_h;
+  std::vector<U4> tile_r;
+  void trace_tile(int16_t** th, U4** tr) {
+    tile_h.assign(16 * 8, 0);
+    tile_r.assign(16, U4{0, 0, 0, 0});
+    *th = tile_h.data();
+    *tr = tile_r.data();
+  }
   uint32_t reduce_min(uint32_t v) { return v; }
   uint32_t reduce_max(uint32_t v) { return v; }
   uint32_t excl_scan(uint32_t v, uint32_t* total) {
@@ -83,19 +91,20 @@ struct HostEx {
     uint32_t best_row = 0, best_col = 0;
     std::vector<int32_t> row(len + 1);
     for (uint32_t r = 0; r < nR; ++r) {
-      const uint32_t v = sl.rowprog[4 * r], meta = sl.rowprog[4 * r + 1];
+      // rows live in rank space: row = r + 1; rowprog[r] = {meta, p0, p1, p2 | ovf offset}, predecessors as rows
+      const uint32_t meta = sl.rowprog[4 * r];
       const uint32_t code = meta_code(meta);
-      uint32_t np = meta_npred(meta);
-      const bool nopred = np == 0;
-      if (nopred) np = 1;
+      const uint32_t npred = meta_npred(meta);
+      const uint32_t np = npred == 0 ? 1 : npred;
       int32_t fcv = INT32_MIN;
       for (uint32_t j = 1; j <= len; ++j) row[j] = INT32_MIN;
       for (uint32_t p = 0; p < np; ++p) {
         uint32_t pr;
-        if (nopred) pr = 0;
-        else if (p == 0) pr = sl.rowprog[4 * r + 2];
-        else if (meta_npred(meta) == 2) pr = sl.rowprog[4 * r + 3];
-        else pr = sl.ovf[sl.rowprog[4 * r + 3] + p - 1];
+        if (npred == 0) pr = 0;
+        else if (p == 0) pr = sl.rowprog[4 * r + 1];
+        else if (p == 1) pr = sl.rowprog[4 * r + 2];
+        else if (npred == 3) pr = sl.rowprog[4 * r + 3];
+        else pr = sl.ovf[sl.rowprog[4 * r + 3] + p - 2];
         fcv = std::max(fcv, H(pr, 0));
         for (uint32_t j = 1; j <= len; ++j) {
           const int32_t s = codes_[j - 1] == code ? sc.m : sc.x;
@@ -103,21 +112,21 @@ struct HostEx {
         }
       }
       row[0] = mode == kModeSW ? 0 : fcv + sc.g;
-      sl.fc[v + 1] = static_cast<int16_t>(row[0]);
+      sl.fc[r + 1] = static_cast<int16_t>(row[0]);
       for (uint32_t j = 1; j <= len; ++j) {
         row[j] = std::max(row[j], row[j - 1] + sc.g);
         if (mode == kModeSW) row[j] = std::max(row[j], 0);
-        *cell(v + 1, j - 1) = static_cast<int16_t>(row[j]);
+        *cell(r + 1, j - 1) = static_cast<int16_t>(row[j]);
         if (mode == kModeSW) {
           if (best < row[j]) {
             best = row[j];
-            best_row = v + 1;
+            best_row = r + 1;
             best_col = j;
           }
         } else if ((meta & kMetaSink) && j == len) {
           if (best < row[j]) {
             best = row[j];
-            best_row = v + 1;
+            best_row = r + 1;
             best_col = j;
           }
         }

@@ -264,7 +264,6 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
   t(N * 4);        // tmp1
   t(N);            // flags
   t(N * 16);       // rowprog
-  t(N * 16);       // nodeprog
   t(E * 4);        // ovf
   t((N + 1) * 2);  // fc
   t((N + 1) * static_cast<uint64_t>(d.row_words) * 4);  // H
@@ -320,7 +319,6 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
   P(&s->tmp1);
   P(&s->flags);
   P(&s->rowprog);
-  P(&s->nodeprog);
   P(&s->ovf);
   P(&s->fc);
   P(&s->H);

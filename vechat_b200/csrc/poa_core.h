@@ -140,8 +140,7 @@ struct Slot {
   uint32_t* tmp0;      // [max_nodes] scratch
   uint32_t* tmp1;      // [max_nodes] scratch
   uint8_t* flags;      // [max_nodes] (global fallback of the shared-memory flags)
-  uint32_t* rowprog;   // [max_nodes * 4] by rank: {node, meta, p0, p1 | ovf offset}
-  uint32_t* nodeprog;  // [max_nodes * 4] by node: {meta, p0, p1, p2 | ovf offset (npred >= 4)}
+  uint32_t* rowprog;   // [max_nodes * 4] by rank: {meta, p0, p1, p2 | ovf offset (npred >= 4)}; predecessors as rows
   uint32_t* ovf;       // [max_edges] predecessor rows of nodes with in-degree > 2
   int16_t* fc;         // [max_nodes + 1]
   uint32_t* H;         // [(max_nodes + 1) * row_words]; also the big scratch of the serial graph passes
@@ -177,6 +176,7 @@ struct WinState {
   uint32_t nMain;        // rows of the whole current graph (rank order in r2n)
   uint32_t fill_layer;   // pending alignment: layer id, mode, sub-graph flag
   uint32_t fill_mode;
+  uint32_t sub;          // the pending alignment runs on a Subgraph view (rank -> node through sl.order)
   uint32_t need;         // kNeed*
   uint32_t prep;         // kPrep* flags for step_prepare
   unsigned long long cells;
@@ -441,6 +441,7 @@ struct Poa {
     if (ex.leader()) {
       ws.ovf_n = 0;
       ws.nR = nR;
+      ws.sub = sub ? 1u : 0u;
     }
     if (sub) {
       for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.tmp0[order[r]] = 0;
@@ -453,46 +454,35 @@ struct Poa {
         }
       }
     }
+    for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.rank_of[order[r]] = r;
     ex.sync();
+    // DP rows live in rank space: row = rank + 1 (0 = the virtual row), predecessors are given as rows
     for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
       const uint32_t v = order[r];
-      sl.rank_of[v] = r;
-      uint32_t np = 0, p0 = 0, p1 = 0;
+      uint32_t np = 0, p0 = 0, p1 = 0, p2 = 0;
       const uint32_t b = v * S, e = v * S + g.nin[v];
       for (uint32_t i = b; i < e; ++i) {
         const uint32_t t = g.itail[i];
         if (sub && !(sl.flags[t] & kFMember)) continue;
-        if (np == 0) p0 = t + 1;
-        if (np == 1) p1 = t + 1;
+        const uint32_t row = sl.rank_of[t] + 1;
+        if (np == 0) p0 = row;
+        if (np == 1) p1 = row;
+        if (np == 2) p2 = row;
         ++np;
       }
-      if (np > 2) {
-        const uint32_t o = ex.atomic_add(&ws.ovf_n, np - 1);
+      if (np > 3) {
+        const uint32_t o = ex.atomic_add(&ws.ovf_n, np - 2);
         uint32_t k = 0, q = 0;
         for (uint32_t i = b; i < e; ++i) {
           const uint32_t t = g.itail[i];
           if (sub && !(sl.flags[t] & kFMember)) continue;
-          if (q++ > 0) sl.ovf[o + k++] = t + 1;
+          if (q++ > 1) sl.ovf[o + k++] = sl.rank_of[t] + 1;
         }
-        p1 = o;
+        p2 = o;  // predecessor p (>= 2) is ovf[p2 + p - 2]
       }
       const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
-      const uint32_t meta = meta_pack(g.code[v], np, sink);
-      sl.rowprog[4 * r + 0] = v;
-      sl.rowprog[4 * r + 1] = meta;
-      sl.rowprog[4 * r + 2] = p0;
-      sl.rowprog[4 * r + 3] = p1;
-      // by-node copy for the traceback: up to three predecessors inline
-      uint32_t q1 = p1, q2 = 0;
-      if (np == 3) {
-        q1 = sl.ovf[p1];
-        q2 = sl.ovf[p1 + 1];
-      } else if (np > 3) {
-        q1 = sl.ovf[p1];
-        q2 = p1;  // ovf offset: predecessor p (>= 1) is ovf[q2 + p - 1]
-      }
-      U4 np4 = {meta, p0, q1, q2};
-      *reinterpret_cast<U4*>(sl.nodeprog + 4 * static_cast<size_t>(v)) = np4;
+      U4 rec = {meta_pack(g.code[v], np, sink), p0, p1, p2};
+      *reinterpret_cast<U4*>(sl.rowprog + 4 * static_cast<size_t>(r)) = rec;
     }
     ex.sync();
   }
@@ -502,24 +492,21 @@ struct Poa {
   // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order,
   // simd_alignment_engine_implementation.hpp:1031-1061) is fetched and compared by its own lane and the first
   // match wins (reduce_min over the candidate index).  The lane of a candidate also fetches the node record of
-  // the row the walk would move to (nodeprog, one 16-byte load), so the next step starts without a dependent load.
-  VGC_HD VGC_INL U4 node_rec(uint32_t row) const {
-    if (row == 0) {
-      U4 z = {0, 0, 0, 0};
-      return z;
-    }
-    return *reinterpret_cast<const U4*>(sl.nodeprog + 4 * static_cast<size_t>(row - 1));
-  }
-
+  // the row the walk would move to, so the next step starts without a dependent load.
   VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
     if (mode == kModeSW) traceback_t<true>(seq_codes, sc);
     else traceback_t<false>(seq_codes, sc);
   }
 
+  // Tile of the DP matrix around the walk: kTR consecutive rows (ranks) x kTC columns, fetched in one round of
+  // parallel loads together with the rows' records, then walked out of the executor's fast storage.  DRAM
+  // latency is paid once per tile instead of once per step.
+  static constexpr int kTR = 16, kTC = 8;
+
   template <bool SW>
   VGC_HD void traceback_t(const uint8_t* seq_codes, const Scores& sc) {
     const int W = ex.width(), L = ex.lane();
-    uint32_t i = ws.best_row, j = ws.best_col;
+    uint32_t i = ws.best_row, j = ws.best_col;  // row = rank + 1 (0 = virtual row), DP column (0 = first column)
     if (i == 0 && j == 0) {
       if (ex.leader()) ws.aln_len = 0;
       ex.sync();
@@ -529,17 +516,31 @@ struct Poa {
     const uint32_t rw = sl.row_words;
     const uint32_t* Hb = sl.H;
     const int16_t* fcb = sl.fc;
-    // H(row, j) with j the 1-based DP column; j == 0 is the first column (NW border / 0 in SW).  The virtual
-    // row 0 is materialised in H by the fill, so only the column needs a special case.
+    const U4* rp = reinterpret_cast<const U4*>(sl.rowprog);
+    const uint32_t* nodes = ws.sub ? sl.order : sl.r2n;  // rank -> node id
+    // H(row, j) with j the DP column; j == 0 is the first column (NW border / 0 in SW).  The virtual row 0 is
+    // materialised in H by the fill, so only the column needs a special case.
     auto hv_at = [&](uint32_t row, uint32_t jj) -> int32_t {
       if (jj == 0) return SW ? 0 : static_cast<int32_t>(fcb[row]);
       const uint32_t e = lut ? static_cast<uint32_t>(lut[jj - 1]) : RM::lut_entry(jj - 1);
       const uint32_t wv = Hb[static_cast<uint64_t>(row) * rw + (e >> 1)];
       return static_cast<int16_t>((e & 1u) ? (wv >> 16) : (wv & 0xFFFFu));
     };
+    auto rec_at = [&](uint32_t row) -> U4 {
+      if (row == 0) {
+        U4 z = {0, 0, 0, 0};
+        return z;
+      }
+      return rp[row - 1];
+    };
+    int16_t* th;
+    U4* tr;
+    ex.trace_tile(&th, &tr);  // th[kTR * kTC], tr[kTR]
+    uint32_t ti = 0, tj = 0;  // tile anchor: rows (ti - kTR, ti], columns (tj - kTC, tj]
+    bool have_tile = false;
     const int32_t gp = sc.g;
     int32_t h = hv_at(i, j);
-    U4 rec = node_rec(i);
+    U4 rec = rec_at(i);
     uint32_t n = 0;
     bool bad = false;
     while (true) {
@@ -555,32 +556,52 @@ struct Poa {
       uint32_t first = kNone, pr_next = 0;
       int32_t hv_next = 0;
       U4 rec_next = rec;
+      bool retile = false;
       for (uint32_t c0 = 0; c0 < ncand; c0 += W) {
         const uint32_t c = c0 + L;
-        bool ok = false;
-        int32_t hv = 0;
-        uint32_t pr = i;
-        U4 nr = rec;
+        // this lane's candidate: row pr, column cj; kind 0 diagonal, 1 vertical, 2 horizontal, 3 none
+        uint32_t pr = i, cj = j, kind = 3;
         if (c < 2 * npp) {
           const uint32_t p = c < npp ? c : c - npp;
           if (np == 0) pr = 0;
           else if (p == 0) pr = rec.y;
           else if (p == 1) pr = rec.z;
           else if (np == 3) pr = rec.w;
-          else pr = sl.ovf[rec.w + p - 1];
-          nr = node_rec(pr);
+          else pr = sl.ovf[rec.w + p - 2];
           if (c < npp) {
             if (j != 0) {
-              hv = hv_at(pr, j - 1);
-              ok = h == hv + mc;
+              kind = 0;
+              cj = j - 1;
             }
           } else {
-            hv = hv_at(pr, j);
-            ok = h == hv + gp;
+            kind = 1;
           }
         } else if (c == 2 * npp && j != 0) {
-          hv = hv_at(i, j - 1);
-          ok = h == hv + gp;
+          kind = 2;
+          cj = j - 1;
+        }
+        const bool in_tile = have_tile && pr <= ti && pr + kTR > ti && cj <= tj && cj + kTC > tj;
+        const bool direct = have_tile && ti == i && tj == j;  // just anchored here: what is still outside is far away
+        if (!direct) {
+          // all candidates of this chunk must be in the tile, else fetch a tile anchored at the current cell
+          const uint32_t miss = ex.reduce_max((kind != 3 && !in_tile) ? 1u : 0u);
+          if (miss) {
+            retile = true;
+            break;
+          }
+        }
+        bool ok = false;
+        int32_t hv = 0;
+        U4 nr = rec;
+        if (kind != 3) {
+          if (in_tile) {
+            hv = th[(ti - pr) * kTC + (tj - cj)];
+            if (kind != 2) nr = tr[ti - pr];
+          } else {
+            hv = hv_at(pr, cj);
+            if (kind != 2) nr = rec_at(pr);
+          }
+          ok = h == hv + (kind == 0 ? mc : gp);
         }
         const uint32_t f = ex.reduce_min(ok ? c : kNone);
         if (f != kNone) {
@@ -595,6 +616,21 @@ struct Poa {
           break;
         }
       }
+      if (retile) {
+        ex.sync();
+        ti = i;
+        tj = j;
+        for (uint32_t t = L; t < static_cast<uint32_t>(kTR * kTC); t += W) {
+          const uint32_t rr = t / kTC, cc = t % kTC;
+          if (rr <= ti && cc <= tj) th[t] = static_cast<int16_t>(hv_at(ti - rr, tj - cc));
+        }
+        for (uint32_t t = L; t < static_cast<uint32_t>(kTR); t += W) {
+          if (t <= ti) tr[t] = rec_at(ti - t);
+        }
+        have_tile = true;
+        ex.sync();
+        continue;
+      }
       if (first == kNone || n >= sl.aln_cap) {
         bad = true;
         break;
@@ -602,7 +638,7 @@ struct Poa {
       const uint32_t pi = pr_next;
       const uint32_t pj = (first >= npp && first < 2 * npp) ? j : j - 1;
       if (ex.leader()) {
-        sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(i - 1);
+        sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(nodes[i - 1]);
         sl.aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
       }
       ++n;

@@ -16,7 +16,9 @@
 //   horizontal : in-register running max over the lane's K cells, then a 5-step warp-shuffle max-scan of
 //                (segment end value - g * column) across the 64 segments, then one fused add-max per register
 // Rows are written once to HBM (2 B per cell, coalesced 8-byte stores) because the traceback re-reads
-// them; a predecessor that is the row just computed (the common case along chains) stays in registers.
+// them.  Predecessor rows come, in order of preference, from registers (the row just computed: the
+// common case along chains, updated in place), from a small ring of the most recent rows in shared
+// memory, or from HBM/L2.
 #ifndef VGC_POA_FILL_CUH_
 #define VGC_POA_FILL_CUH_
 
@@ -26,6 +28,8 @@
 #include "poa_core.h"
 
 namespace vgc {
+
+constexpr int kRingRows = 4;  // recent rows kept in shared memory (when the space is there)
 
 __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) {
   return (static_cast<uint32_t>(lo) & 0xFFFFu) | (static_cast<uint32_t>(hi) << 16);
@@ -51,28 +55,34 @@ __device__ __forceinline__ void row_store(uint32_t* __restrict__ row, int lane, 
   for (int k = 0; k < K; k += 2) p[(k >> 1) * 32] = make_uint2(h[k], h[k + 1]);
 }
 
-// prof: shared memory, num_codes * 32*K words; stage: shared memory, 32 uint4.
-template <int K>
-__device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, uint32_t mode,
-                          const Scores sc, uint32_t num_codes, uint32_t* prof, uint4* stage) {
+// prof : shared memory, num_codes * 32*K words;  stage: shared memory, 32 uint4
+// ring : shared memory, ring_rows * 32*K words (ring_rows <= kRingRows, may be 0)
+template <int K, bool SW>
+__device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, const Scores sc,
+                            uint32_t num_codes, uint32_t* prof, uint4* stage, uint32_t* ring, int ring_rows) {
   static_assert(K % 2 == 0, "K must be even");
   using RM = RowMap<K>;
   const int lane = threadIdx.x & 31;
   const uint32_t nR = ws.nR;
   const int32_t g = sc.g;
-  const bool sw = mode == kModeSW;
 
   // ---- query profile (Initialize, simd...:520-530): per code, match/mismatch per column, padding beyond len
   {
     int32_t pad = sc.m > -sc.x ? sc.m : -sc.x;
     if (-g > pad) pad = -g;
     pad = -pad;
+    uint32_t cl[K], ch[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint32_t a = lane * K + k, b = 32 * K + lane * K + k;
+      cl[k] = a < len ? codes[a] : 0xFFu;
+      ch[k] = b < len ? codes[b] : 0xFFu;
+    }
     for (uint32_t c = 0; c < num_codes; ++c) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const uint32_t cl = lane * K + k, ch = 32 * K + lane * K + k;
-        const int32_t vl = cl < len ? (codes[cl] == c ? sc.m : sc.x) : pad;
-        const int32_t vh = ch < len ? (codes[ch] == c ? sc.m : sc.x) : pad;
+        const int32_t vl = cl[k] == 0xFFu ? pad : (cl[k] == c ? sc.m : sc.x);
+        const int32_t vh = ch[k] == 0xFFu ? pad : (ch[k] == c ? sc.m : sc.x);
         prof[c * RM::kWords + RM::word(lane, k)] = pack16(vl, vh);
       }
     }
@@ -84,16 +94,26 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
   const uint32_t gbase = pack16(g * c0l, g * c0h);
 
   // ---- virtual row 0 (NW: j * g; SW: zeros) and its first column
-  uint32_t hp[K];  // the row computed last (registers)
+  uint32_t hp[K];  // the row computed last (registers); chain rows are updated in place
 #pragma unroll
-  for (int k = 0; k < K; ++k) hp[k] = sw ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
+  for (int k = 0; k < K; ++k) hp[k] = SW ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
   row_store<K>(sl.H, lane, hp);
   if (lane == 0) sl.fc[0] = 0;
   uint32_t prev_row = 0;
   int32_t fc_prev = 0;
 
+  // ring of recent rows: tags (row ids) and first-column values live in registers (uniform across the warp)
+  uint32_t tag[kRingRows];
+  int32_t rfc[kRingRows];
+#pragma unroll
+  for (int r = 0; r < kRingRows; ++r) {
+    tag[r] = 0xFFFFFFFFu;
+    rfc[r] = 0;
+  }
+  int rpos = 0;
+
   // ---- best-cell tracking
-  uint32_t bestv = 0;                 // SW: per-lane packed running max (scores >= 0)
+  uint32_t bestv = 0;                   // SW: per-lane packed running max (scores >= 0)
   uint32_t bestr_lo = 0, bestr_hi = 0;  // rank at which each half first reached it
   int32_t nw_best = INT32_MIN;
   uint32_t nw_row = 0;
@@ -111,13 +131,13 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
     __syncwarp();
     const uint32_t rn = nR - r0 < 32 ? nR - r0 : 32;
     for (uint32_t rr = 0; rr < rn; ++rr) {
+      // rows live in rank space: this is row r0 + rr + 1; e = {meta, p0, p1, p2 | ovf offset}, predecessors as rows
       const uint4 e = stage[rr];
-      const uint32_t v = e.x, meta = e.y;
-      const uint32_t code = meta_code(meta);
-      uint32_t np = meta_npred(meta);
+      const uint32_t row = r0 + rr + 1, meta = e.x;
+      const uint32_t np = meta_npred(meta);
       uint32_t pr[K];
       {
-        const uint2* pp = reinterpret_cast<const uint2*>(prof + code * RM::kWords) + lane;
+        const uint2* pp = reinterpret_cast<const uint2*>(prof + meta_code(meta) * RM::kWords) + lane;
 #pragma unroll
         for (int k = 0; k < K; k += 2) {
           uint2 t = pp[(k >> 1) * 32];
@@ -125,49 +145,77 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
           pr[k + 1] = t.y;
         }
       }
-      uint32_t h[K];
-      int32_t fcmax = INT32_MIN;
-      const uint32_t npp = np == 0 ? 1 : np;
-      for (uint32_t p = 0; p < npp; ++p) {
-        uint32_t prow;
-        if (np == 0) prow = 0;
-        else if (p == 0) prow = e.z;
-        else if (np == 2) prow = e.w;
-        else prow = sl.ovf[e.w + p - 1];
-        uint32_t u[K];
-        int32_t fcp;
-        if (prow == prev_row) {
+      const uint32_t p0 = np == 0 ? 0u : e.y;
+      int32_t fcmax;
+      if (np <= 1 && p0 == prev_row) {
+        // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
+        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, hp[K - 1], 1);
+        const uint32_t y = __shfl_sync(0xFFFFFFFFu, hp[K - 1], 31);
+        if (lane == 0) x = pack16(fc_prev, lo16(y));
 #pragma unroll
-          for (int k = 0; k < K; ++k) u[k] = hp[k];
-          fcp = fc_prev;
-        } else {
-          row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
-          fcp = 0;
-          if (!sw) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
-            if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
-            fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
+        for (int k = K - 1; k >= 1; --k) hp[k] = __viaddmax_s16x2(hp[k - 1], pr[k], __vadd2(hp[k], g2));
+        hp[0] = __viaddmax_s16x2(x, pr[0], __vadd2(hp[0], g2));
+        fcmax = fc_prev;
+      } else {
+        // ---- general row: maximum over all predecessors, each from registers, the ring or memory
+        uint32_t h[K];
+        fcmax = INT32_MIN;
+        const uint32_t npp = np == 0 ? 1 : np;
+        for (uint32_t p = 0; p < npp; ++p) {
+          uint32_t prow;
+          if (p == 0) prow = p0;
+          else if (p == 1) prow = e.z;
+          else if (np == 3) prow = e.w;
+          else prow = sl.ovf[e.w + p - 2];
+          uint32_t u[K];
+          int32_t fcp;
+          int hit = -1;
+#pragma unroll
+          for (int r = 0; r < kRingRows; ++r) {
+            if (tag[r] == prow) hit = r;
+          }
+          if (prow == prev_row) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) u[k] = hp[k];
+            fcp = fc_prev;
+          } else if (hit >= 0) {
+            row_load<K>(ring + hit * RM::kWords, lane, u);
+            fcp = rfc[0];
+#pragma unroll
+            for (int r = 1; r < kRingRows; ++r) {
+              if (hit == r) fcp = rfc[r];
+            }
+          } else {
+            row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
+            fcp = 0;
+            if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
+              if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
+              fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
+            }
+          }
+          fcmax = fcp > fcmax ? fcp : fcmax;
+          // diagonal of this lane's first cells: the previous lane's last cells
+          uint32_t x = __shfl_up_sync(0xFFFFFFFFu, u[K - 1], 1);
+          const uint32_t y = __shfl_sync(0xFFFFFFFFu, u[K - 1], 31);
+          if (lane == 0) x = pack16(fcp, lo16(y));
+          if (p == 0) {
+            h[0] = __viaddmax_s16x2(x, pr[0], __vadd2(u[0], g2));
+#pragma unroll
+            for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k - 1], pr[k], __vadd2(u[k], g2));
+          } else {
+            h[0] = __viaddmax_s16x2(u[0], g2, __viaddmax_s16x2(x, pr[0], h[0]));
+#pragma unroll
+            for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k], g2, __viaddmax_s16x2(u[k - 1], pr[k], h[k]));
           }
         }
-        fcmax = fcp > fcmax ? fcp : fcmax;
-        // diagonal of this lane's first cells: the previous lane's last cells
-        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, u[K - 1], 1);
-        const uint32_t y = __shfl_sync(0xFFFFFFFFu, u[K - 1], 31);
-        if (lane == 0) x = pack16(fcp, lo16(y));
-        if (p == 0) {
-          h[0] = __viaddmax_s16x2(x, pr[0], __vadd2(u[0], g2));
 #pragma unroll
-          for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k - 1], pr[k], __vadd2(u[k], g2));
-        } else {
-          h[0] = __viaddmax_s16x2(u[0], g2, __viaddmax_s16x2(x, pr[0], h[0]));
-#pragma unroll
-          for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k], g2, __viaddmax_s16x2(u[k - 1], pr[k], h[k]));
-        }
+        for (int k = 0; k < K; ++k) hp[k] = h[k];
       }
-      const int32_t fci = sw ? 0 : fcmax + g;
+      const int32_t fci = SW ? 0 : fcmax + g;
       // ---- horizontal: in-lane running max, then the cross-lane max-plus scan
 #pragma unroll
-      for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(h[k - 1], g2, h[k]);
-      uint32_t V = __vadd2(h[K - 1], voff);
+      for (int k = 1; k < K; ++k) hp[k] = __viaddmax_s16x2(hp[k - 1], g2, hp[k]);
+      uint32_t V = __vadd2(hp[K - 1], voff);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, V, d);
@@ -179,48 +227,57 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
       uint32_t E = __shfl_up_sync(0xFFFFFFFFu, V, 1);
       E = lane == 0 ? X : __vmaxs2(E, X);
       const uint32_t base = __vadd2(E, gbase);
-      if (sw) {
+      if (SW) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) h[k] = __viaddmax_s16x2_relu(base, pack16(g * k, g * k), h[k]);
+        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2_relu(base, pack16(g * k, g * k), hp[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) h[k] = __viaddmax_s16x2(base, pack16(g * k, g * k), h[k]);
+        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2(base, pack16(g * k, g * k), hp[k]);
       }
-      // ---- write the row once
-      row_store<K>(sl.H + static_cast<uint64_t>(v + 1) * sl.row_words, lane, h);
-      if (!sw && lane == 0) sl.fc[v + 1] = static_cast<int16_t>(fci);
-      // ---- best cell
-      if (sw) {
-        uint32_t m = h[0];
+      // ---- write the row once (HBM) and keep it in the ring
+      row_store<K>(sl.H + static_cast<uint64_t>(row) * sl.row_words, lane, hp);
+      if (!SW && lane == 0) sl.fc[row] = static_cast<int16_t>(fci);
+      if (ring_rows > 0) {
+        row_store<K>(ring + rpos * RM::kWords, lane, hp);
 #pragma unroll
-        for (int k = 1; k < K; ++k) m = __vmaxs2(m, h[k]);
+        for (int r = 0; r < kRingRows; ++r) {
+          if (r == rpos) {
+            tag[r] = row;
+            rfc[r] = fci;
+          }
+        }
+        rpos = rpos + 1 == ring_rows ? 0 : rpos + 1;
+      }
+      // ---- best cell
+      if (SW) {
+        uint32_t m = hp[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = __vmaxs2(m, hp[k]);
         const uint32_t nb = __vmaxs2(bestv, m);
-        const uint32_t ch = nb ^ bestv;
-        if (ch & 0xFFFFu) bestr_lo = r0 + rr;
-        if (ch >> 16) bestr_hi = r0 + rr;
+        const uint32_t chg = nb ^ bestv;
+        if (chg & 0xFFFFu) bestr_lo = r0 + rr;
+        if (chg >> 16) bestr_hi = r0 + rr;
         bestv = nb;
       } else if (meta & kMetaSink) {
-        uint32_t sel = h[0];
+        uint32_t sel = hp[0];
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          if (k == lastK) sel = h[k];
+          if (k == lastK) sel = hp[k];
         }
         const uint32_t s = __shfl_sync(0xFFFFFFFFu, sel, lastL);
         const int32_t val = lastH ? hi16(s) : lo16(s);
         if (val > nw_best) {
           nw_best = val;
-          nw_row = v + 1;
+          nw_row = row;
         }
       }
-#pragma unroll
-      for (int k = 0; k < K; ++k) hp[k] = h[k];
-      prev_row = v + 1;
+      prev_row = row;
       fc_prev = fci;
     }
   }
 
   // ---- where the traceback starts
-  if (!sw) {
+  if (!SW) {
     if (lane == 0) {
       ws.best_row = nw_row;
       ws.best_col = nw_row ? len : 0;
@@ -244,12 +301,12 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
       const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, br, d);
       br = o < br ? o : br;
     }
-    uint32_t row = 0, col = 0;
+    uint32_t brow = 0, col = 0;
     if (mx > 0) {
-      row = sl.rowprog[4 * br] + 1;
+      brow = br + 1;
       uint32_t u[K];
       __syncwarp();
-      row_load<K>(sl.H + static_cast<uint64_t>(row) * sl.row_words, lane, u);
+      row_load<K>(sl.H + static_cast<uint64_t>(brow) * sl.row_words, lane, u);
       uint32_t bc = 0xFFFFFFFFu;
 #pragma unroll
       for (int k = K - 1; k >= 0; --k) {
@@ -267,12 +324,20 @@ __device__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, ui
       col = bc + 1;
     }
     if (lane == 0) {
-      ws.best_row = row;
+      ws.best_row = brow;
       ws.best_col = col;
       ws.best_score = mx;
     }
   }
   __syncwarp();
+}
+
+template <int K>
+__device__ __forceinline__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len,
+                                          uint32_t mode, const Scores sc, uint32_t num_codes, uint32_t* prof,
+                                          uint4* stage, uint32_t* ring, int ring_rows) {
+  if (mode == kModeSW) warp_fill_t<K, true>(sl, ws, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
+  else warp_fill_t<K, false>(sl, ws, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
 }
 
 }  // namespace vgc

@@ -25,7 +25,7 @@
 
 namespace vgc {
 
-constexpr int kSmemHeader = 896;  // Slot + WinState copies
+constexpr int kSmemHeader = 640;  // Slot + WinState copies
 
 // Arguments shared by the two kernels of a lockstep pass.  `idx` below is the position of a window in the
 // pass's work list (windows ordered group by group, inside a group by decreasing number of fills).
@@ -63,17 +63,28 @@ struct WarpEx {
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(mask_, v, src, G); }
   __device__ __forceinline__ const uint16_t* col_lut() const { return lut_; }
+  // traceback tile (poa_core.h kTR x kTC cells + kTR records) at the start of the arena
+  __device__ __forceinline__ void trace_tile(int16_t** th, U4** tr) {
+    *tr = reinterpret_cast<U4*>(arena());
+    *th = reinterpret_cast<int16_t*>(arena() + 16 * sizeof(U4));
+  }
   __device__ __forceinline__ uint32_t reduce_min(uint32_t v) {
-    if (G == 32) return __reduce_min_sync(0xFFFFFFFFu, v);
+    if constexpr (G == 32) {
+      return __reduce_min_sync(0xFFFFFFFFu, v);
+    } else {
 #pragma unroll
-    for (int d = G / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(mask_, v, d, G));
-    return v;
+      for (int d = G / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(mask_, v, d, G));
+      return v;
+    }
   }
   __device__ __forceinline__ uint32_t reduce_max(uint32_t v) {
-    if (G == 32) return __reduce_max_sync(0xFFFFFFFFu, v);
+    if constexpr (G == 32) {
+      return __reduce_max_sync(0xFFFFFFFFu, v);
+    } else {
 #pragma unroll
-    for (int d = G / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(mask_, v, d, G));
-    return v;
+      for (int d = G / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(mask_, v, d, G));
+      return v;
+    }
   }
   __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
     uint32_t x = v;
@@ -174,6 +185,7 @@ __device__ __forceinline__ void win_leave(const KernelArgs& a, const WinCtx& c) 
   copy_words(c.gws, c.ws, sizeof(WinState), c.lane, c.width);
   if (c.lane == 0 && c.ws->pc == kPcDone) {
     a.status[c.w] = c.ws->status;
+    if (c.ws->status != kStOk) return;  // a window that is re-run counts once, when it completes
     atomicAdd(a.totals, c.ws->cells);
     atomicAdd(a.totals + 1, static_cast<unsigned long long>(c.ws->alignments));
     for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, c.ws->phase[i]);
@@ -202,7 +214,8 @@ template <int K>
 __host__ __device__ constexpr uint32_t trace_lut_bytes() {
   return (RowMap<K>::kCols * 2u + 255u) & ~255u;
 }
-__host__ __device__ inline uint32_t trace_win_bytes(uint32_t max_len) { return kSmemHeader + ((max_len + 15u) & ~15u); }
+// header | codes[max_len] | tile records 16 x 16 B | tile cells 16 x 8 x 2 B
+__host__ __device__ inline uint32_t trace_win_bytes(uint32_t max_len) { return kSmemHeader + ((max_len + 15u) & ~15u) + 512; }
 
 template <int K>
 __global__ void __launch_bounds__(kTraceLanes * kTraceWins, 4) trace_kernel(const KernelArgs a, uint32_t base,
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
 }
 
 // F: the DP fill of the pending alignment (poa_fill.cuh; replaces SimdAlignmentEngine::Linear's fill).
-// shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words]
+// shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words] | ring
 template <int K>
 __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArgs a, uint32_t base) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -283,7 +296,13 @@ __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArg
   sw.x = -5;
   sw.g = -4;
   const uint32_t mode = c.ws->fill_mode;
-  warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage);
+  // the rest of the shared memory is the ring of recent rows
+  uint32_t* ring = prof + a.bv.num_codes * RowMap<K>::kWords;
+  const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
+  int ring_rows = used < a.smem_bytes ? static_cast<int>((a.smem_bytes - used) / (RowMap<K>::kWords * 4)) : 0;
+  if (ring_rows > kRingRows) ring_rows = kRingRows;
+  warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage, ring,
+               ring_rows);
   if (lane == 0) {
     c.gws->best_row = c.ws->best_row;
     c.gws->best_col = c.ws->best_col;
@@ -357,9 +376,10 @@ struct vgc_engine {
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
-  int groups = 4;                 // streams of a lockstep pass
-  cudaStream_t gstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t gev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int groups = 8;                 // streams of a lockstep pass
+  int group_mode = 1;             // 1: contiguous blocks of the depth-sorted window list, 0: round-robin
+  cudaStream_t gstream[32] = {};
+  cudaEvent_t gev[32] = {};
   uint32_t smem_trace = 0, smem_update = 0, smem_sort = 0, smem_fill = 0;
   size_t mem_budget = 0;
   // device copies of the batch
@@ -455,7 +475,7 @@ BatchView make_view(vgc_engine* h) {
   return v;
 }
 
-constexpr int kMaxGroups = 8;
+constexpr int kMaxGroups = 32;
 
 template <int K>
 int set_kernel_attrs(const vgc_engine* h) {
@@ -531,7 +551,8 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       d.max_edges = d.max_nodes;
       d.max_len = std::max<uint32_t>(pr.max_len, 16);
       d.row_words = row_words;
-      d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : 8;
+      // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
+      d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : std::min<uint32_t>(16, std::max<uint32_t>(8, pr.win_nseq[w] + 1));
       const uint64_t sb = slot_bytes(d);
       if (bytes + sb > h->mem_budget && e > pos) break;
       if (sb > h->mem_budget) {
@@ -549,7 +570,9 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     if ((rc = h->d_slots.reserve(sizeof(Slot) * n))) return rc;
     if ((rc = h->d_wstates.reserve(sizeof(WinState) * n))) return rc;
     if ((rc = h->d_work.reserve(4ull * n))) return rc;
-    // ---- deal the chunk's windows to groups: group g takes sorted positions g, g+G, g+2G, ...
+    // ---- deal the chunk's windows to groups.  VGC_GROUP_MODE=0: group g takes sorted positions g, g+G, ... (every
+    // group sees the whole depth range); 1 (default): contiguous blocks of the sorted list (a group's windows run
+    // the same program in step: the serial phase transitions of a cycle do not stall the other windows)
     const int G = std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)));
     std::vector<uint32_t> work(n);
     std::vector<Slot> slots(n);
@@ -558,7 +581,9 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     uint32_t k = 0;
     for (int g = 0; g < G; ++g) {
       gbase[g] = k;
-      for (uint32_t i = g; i < n; i += G) {
+      const uint32_t b0 = h->group_mode ? static_cast<uint32_t>(static_cast<uint64_t>(n) * g / G) : g;
+      const uint32_t b1 = h->group_mode ? static_cast<uint32_t>(static_cast<uint64_t>(n) * (g + 1) / G) : n;
+      for (uint32_t i = b0; i < b1; i += h->group_mode ? 1 : G) {
         work[k] = wins[pos + i];
         slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
         gfill[g].push_back(pr.win_nfill[wins[pos + i]]);
@@ -599,6 +624,7 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     for (uint32_t c = 0; c <= max_fill; ++c) {
       for (int g = 0; g < G; ++g) {
         const std::vector<uint32_t>& nf = gfill[g];
+        if (nf.empty() || nf[0] + extra < c) continue;
         while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
         while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
         if (K == 10) *launches += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
@@ -791,6 +817,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
   h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
+  if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::atoi(s) ? 1 : 0;
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -814,7 +841,7 @@ int vgc_destroy(vgc_handle h) {
   for (auto& ev : h->ev) {
     if (ev) cudaEventDestroy(ev);
   }
-  for (int g = 0; g < 8; ++g) {
+  for (int g = 0; g < 32; ++g) {
     if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
     if (h->gev[g]) cudaEventDestroy(h->gev[g]);
   }
