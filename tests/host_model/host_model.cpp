@@ -36,13 +36,11 @@ struct HostEx {
     return o;
   }
   uint32_t bcast(uint32_t v, uint32_t /*src*/) { return v; }
-  const uint16_t* col_lut() const { return nullptr; }
-  std::vector<int16_t> tile_h;
-  std::vector<U4> tile_r;
-  void trace_tile(int16_t** th, U4** tr) {
-    tile_h.assign(16 * 8, 0);
-    tile_r.assign(16, U4{0, 0, 0, 0});
-    *th = tile_h.data();
+  std::vector<U4> tile_h, tile_r;  // U4: the walker fetches 16-byte vectors
+  void trace_tile(uint32_t** th, U4** tr) {
+    tile_h.assign(kTR * kTW / 4, U4{0, 0, 0, 0});
+    tile_r.assign(kTR, U4{0, 0, 0, 0});
+    *th = reinterpret_cast<uint32_t*>(tile_h.data());
     *tr = tile_r.data();
   }
   uint32_t reduce_min(uint32_t v) { return v; }
@@ -75,10 +73,9 @@ struct HostEx {
             uint32_t /*num_codes*/) {
     using RM = RowMap<K>;
     const uint32_t nR = ws.nR;
-    auto cell = [&](uint32_t row, uint32_t c) -> int16_t* {
-      int h, l, k;
-      RM::locate(c, &h, &l, &k);
-      return reinterpret_cast<int16_t*>(sl.H + static_cast<uint64_t>(row) * sl.row_words + RM::word(l, k)) + h;
+    auto cell = [&](uint32_t row, uint32_t c) -> int16_t* {  // lane-major words: low half = column w, high = 32K + w
+      const uint32_t h = c >= static_cast<uint32_t>(RM::kWords) ? 1u : 0u;
+      return reinterpret_cast<int16_t*>(sl.H + static_cast<uint64_t>(row) * sl.row_words + (h ? c - RM::kWords : c)) + h;
     };
     auto H = [&](uint32_t row, uint32_t j) -> int32_t {  // j = DP column, 0 = first column
       if (j == 0) return mode == kModeSW ? 0 : sl.fc[row];

@@ -192,30 +192,206 @@ enum : int {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// H-matrix addressing.  A row holds 64*K cells as 32*K packed words: lane l owns words k of pair-slot
-// (k/2); low half = column l*K + k, high half = column 32*K + l*K + k.
+// H-matrix addressing.  A row holds 64*K cells as 32*K packed words, "lane-major": word w (0 <= w < 32*K) holds
+// column w in its low half and column 32*K + w in its high half.  The fill's lane l owns the K consecutive
+// words [l*K, l*K + K) (two runs of K consecutive columns); a run of consecutive columns of one half is a run
+// of consecutive words, which is what the traceback's tiles fetch (16 B vectors).
 template <int K>
 struct RowMap {
   static constexpr int kCols = 64 * K;
   static constexpr int kWords = 32 * K;
-  VGC_HD static VGC_INL uint32_t word(int lane, int k) { return (k >> 1) * 64 + lane * 2 + (k & 1); }
-  VGC_HD static VGC_INL void locate(uint32_t c, int* half, int* lane, int* k) {
-    *half = c / (32 * K);
-    uint32_t r = c % (32 * K);
-    *lane = r / K;
-    *k = r % K;
-  }
-  // (word index << 1) | half of column c: what the traceback's column table holds
-  VGC_HD static VGC_INL uint32_t lut_entry(uint32_t c) {
-    int h, l, k;
-    locate(c, &h, &l, &k);
-    return (word(l, k) << 1) | static_cast<uint32_t>(h);
-  }
+  VGC_HD static VGC_INL uint32_t word(int lane, int k) { return lane * K + k; }
   VGC_HD static VGC_INL int32_t load(const uint32_t* row, uint32_t c) {
-    int h, l, k;
-    locate(c, &h, &l, &k);
-    uint32_t w = row[word(l, k)];
+    const uint32_t h = c >= static_cast<uint32_t>(kWords) ? 1u : 0u;
+    const uint32_t w = row[h ? c - kWords : c];
     return static_cast<int16_t>(h ? (w >> 16) : (w & 0xFFFFu));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Traceback walker: ONE thread per alignment (the device runs 32 alignments per warp, the host model one).
+// Replaces the traceback of SimdAlignmentEngine::Linear (simd_alignment_engine_implementation.hpp:908-1105,
+// scalar twin sisd_alignment_engine.cpp:362-460).  A step compares the current cell with its candidates in the
+// reference's priority order — diagonal over the predecessors (in-edge order), vertical over the predecessors,
+// horizontal — and takes the first that reproduces the score.  The cells come from a private tile of the DP
+// matrix (kTR consecutive rows in rank space x kTW consecutive words of the lane-major row) that the thread
+// fetches with 16-byte loads whenever the walk leaves it: DRAM latency is paid once per tile, not once per step.
+// Pairs are appended in reverse (end of the alignment first).
+constexpr int kTR = 32;  // tile rows (ranks ti, ti-1, ..)
+constexpr int kTW = 16;  // tile words per row
+enum : int { kWalkStep = 0, kWalkMiss = 1, kWalkDone = 2, kWalkBad = 3 };
+
+struct TraceWalker {
+  // the alignment's DP matrix and row program
+  const uint32_t* H;
+  const int16_t* fc;
+  const U4* rp;
+  const uint32_t* ovf;
+  const uint32_t* nodes;   // rank -> node id
+  const uint8_t* seq;      // the sequence's bases
+  const uint8_t* coder;    // byte -> code
+  int32_t* aln_node;
+  int32_t* aln_pos;
+  uint32_t aln_cap, rw, half_words;
+  int32_t m, x, g;
+  bool sw;
+  // tile storage (kTR * kTW words, kTR records)
+  uint32_t* th;
+  U4* tr;
+  // walk state
+  uint32_t i, j, n;
+  int32_t h;
+  U4 rec;
+  uint32_t ti, wb;
+  bool have, fresh, started;
+
+  VGC_HD VGC_INL void start(uint32_t row, uint32_t col) {
+    i = row;
+    j = col;
+    n = 0;
+    h = 0;
+    rec = U4{0, 0, 0, 0};
+    ti = wb = 0;
+    have = fresh = started = false;
+  }
+
+  // fetch the tile anchored at the current cell
+  VGC_HD VGC_INL void refill() {
+    ti = i;
+    const uint32_t c = j ? j - 1 : 0;
+    const uint32_t w = c >= half_words ? c - half_words : c;
+    uint32_t b = w & ~3u;
+    b = b >= static_cast<uint32_t>(kTW - 4) ? b - (kTW - 4) : 0u;
+    if (b + kTW > half_words) b = half_words - kTW;
+    wb = b;
+#ifdef __CUDA_ARCH__
+    // asynchronous 16-byte copies global -> shared (LDGSTS): no registers are tied up, so every load of the tile
+    // is in flight at once and the refill costs one DRAM round trip
+    for (uint32_t r = 0; r < static_cast<uint32_t>(kTR); ++r) {
+      if (r > ti) break;
+      const uint32_t row = ti - r;
+      const uint32_t* src = H + static_cast<uint64_t>(row) * rw + wb;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(th + r * kTW));
+#pragma unroll
+      for (int q = 0; q < kTW / 4; ++q)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 4) : "memory");
+      const uint32_t rdst = static_cast<uint32_t>(__cvta_generic_to_shared(tr + r));
+      if (row) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rdst), "l"(rp + (row - 1)) : "memory");
+      else tr[r] = U4{0, 0, 0, 0};
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#else
+    for (uint32_t r = 0; r < static_cast<uint32_t>(kTR); ++r) {
+      if (r > ti) break;
+      const uint32_t row = ti - r;
+      const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(row) * rw + wb);
+      U4* dst = reinterpret_cast<U4*>(th + r * kTW);
+      for (int q = 0; q < kTW / 4; ++q) dst[q] = src[q];
+      tr[r] = row ? rp[row - 1] : U4{0, 0, 0, 0};
+    }
+#endif
+    have = true;
+    fresh = true;
+  }
+
+  // H(row, jj), jj = DP column (0 = first column).  false: not in the tile (and the tile is not fresh)
+  VGC_HD VGC_INL bool cell(uint32_t row, uint32_t jj, int32_t* out) const {
+    if (jj == 0) {
+      *out = sw ? 0 : static_cast<int32_t>(fc[row]);
+      return true;
+    }
+    const uint32_t c = jj - 1;
+    const uint32_t hi = c >= half_words ? 1u : 0u;
+    const uint32_t w = hi ? c - half_words : c;
+    const uint32_t dr = ti - row, dq = w - wb;
+    uint32_t v;
+    if (have && dr < static_cast<uint32_t>(kTR) && dq < static_cast<uint32_t>(kTW)) v = th[dr * kTW + dq];
+    else if (fresh) v = H[static_cast<uint64_t>(row) * rw + w];
+    else return false;
+    *out = static_cast<int16_t>(hi ? (v >> 16) : (v & 0xFFFFu));
+    return true;
+  }
+  VGC_HD VGC_INL U4 rec_of(uint32_t row) const {
+    if (row == 0) return U4{0, 0, 0, 0};
+    const uint32_t dr = ti - row;
+    if (have && dr < static_cast<uint32_t>(kTR)) return tr[dr];
+    return rp[row - 1];
+  }
+  VGC_HD VGC_INL uint32_t pred(uint32_t np, uint32_t p) const {
+    if (np == 0) return 0u;  // no in-edges: the virtual row 0 is the predecessor
+    if (p == 0) return rec.y;
+    if (p == 1) return rec.z;
+    if (np == 3) return rec.w;
+    return ovf[rec.w + p - 2];
+  }
+
+  VGC_HD VGC_INL int step() {
+    if (!have) return kWalkMiss;  // first call: fetch the tile, then read the start cell
+    if (!started) {
+      int32_t v = 0;
+      cell(i, j, &v);
+      h = v;
+      rec = rec_of(i);
+      started = true;
+    }
+    if (sw) {
+      if (h == 0) return kWalkDone;
+    } else {
+      if (i == 0 && j == 0) return kWalkDone;
+    }
+    const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
+    const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;
+    int32_t mc = 0;
+    if (i != 0 && j != 0) mc = (meta_code(rec.x) == coder[seq[j - 1]]) ? m : x;
+    uint32_t pi = i, pj = j;
+    int32_t hn = 0;
+    bool found = false;
+    if (j != 0) {
+      for (uint32_t p = 0; p < npp; ++p) {
+        const uint32_t pr = pred(np, p);
+        int32_t hv;
+        if (!cell(pr, j - 1, &hv)) return kWalkMiss;
+        if (h == hv + mc) {
+          found = true;
+          pi = pr;
+          pj = j - 1;
+          hn = hv;
+          break;
+        }
+      }
+    }
+    if (!found) {
+      for (uint32_t p = 0; p < npp; ++p) {
+        const uint32_t pr = pred(np, p);
+        int32_t hv;
+        if (!cell(pr, j, &hv)) return kWalkMiss;
+        if (h == hv + g) {
+          found = true;
+          pi = pr;
+          hn = hv;
+          break;
+        }
+      }
+    }
+    if (!found && j != 0) {
+      int32_t hv;
+      if (!cell(i, j - 1, &hv)) return kWalkMiss;
+      if (h == hv + g) {
+        found = true;
+        pj = j - 1;
+        hn = hv;
+      }
+    }
+    if (!found || n >= aln_cap) return kWalkBad;
+    aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(nodes[i - 1]);
+    aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+    ++n;
+    if (pi != i) rec = rec_of(pi);
+    i = pi;
+    j = pj;
+    h = hn;
+    fresh = false;
+    return kWalkStep;
   }
 };
 
@@ -487,169 +663,48 @@ struct Poa {
     ex.sync();
   }
 
-  // ---- traceback.  Pairs are appended in reverse (end of alignment first).
-  // Warp-cooperative traceback.  One step = one round of parallel loads: every candidate of the current cell
-  // (diagonal over predecessors, vertical over predecessors, horizontal — the reference's priority order,
-  // simd_alignment_engine_implementation.hpp:1031-1061) is fetched and compared by its own lane and the first
-  // match wins (reduce_min over the candidate index).  The lane of a candidate also fetches the node record of
-  // the row the walk would move to, so the next step starts without a dependent load.
-  VGC_HD void traceback(const uint8_t* seq_codes, uint32_t mode, const Scores& sc) {
-    if (mode == kModeSW) traceback_t<true>(seq_codes, sc);
-    else traceback_t<false>(seq_codes, sc);
+  // ---- traceback (host model / single-lane executors): drive one TraceWalker to the end.  The device runs the
+  //      same walker, 32 alignments per warp, in trace_kernel (vgc_engine.cu).
+  VGC_HD void init_walker(TraceWalker& t, uint32_t layer, uint32_t mode, uint32_t* th, U4* tr) {
+    const Scores& sc = mode == kModeNW ? nw : sw;
+    t.H = sl.H;
+    t.fc = sl.fc;
+    t.rp = reinterpret_cast<const U4*>(sl.rowprog);
+    t.ovf = sl.ovf;
+    t.nodes = ws.sub ? sl.order : sl.r2n;
+    t.seq = bv.bases + bv.seq_off[layer];
+    t.coder = bv.coder;
+    t.aln_node = sl.aln_node;
+    t.aln_pos = sl.aln_pos;
+    t.aln_cap = sl.aln_cap;
+    t.rw = sl.row_words;
+    t.half_words = RM::kWords;
+    t.m = sc.m;
+    t.x = sc.x;
+    t.g = sc.g;
+    t.sw = mode == kModeSW;
+    t.th = th;
+    t.tr = tr;
+    t.start(ws.best_row, ws.best_col);
   }
 
-  // Tile of the DP matrix around the walk: kTR consecutive rows (ranks) x kTC columns, fetched in one round of
-  // parallel loads together with the rows' records, then walked out of the executor's fast storage.  DRAM
-  // latency is paid once per tile instead of once per step.
-  static constexpr int kTR = 16, kTC = 8;
-
-  template <bool SW>
-  VGC_HD void traceback_t(const uint8_t* seq_codes, const Scores& sc) {
-    const int W = ex.width(), L = ex.lane();
-    uint32_t i = ws.best_row, j = ws.best_col;  // row = rank + 1 (0 = virtual row), DP column (0 = first column)
-    if (i == 0 && j == 0) {
-      if (ex.leader()) ws.aln_len = 0;
-      ex.sync();
-      return;
-    }
-    const uint16_t* lut = ex.col_lut();  // [kCols] RowMap::lut_entry per column, or nullptr
-    const uint32_t rw = sl.row_words;
-    const uint32_t* Hb = sl.H;
-    const int16_t* fcb = sl.fc;
-    const U4* rp = reinterpret_cast<const U4*>(sl.rowprog);
-    const uint32_t* nodes = ws.sub ? sl.order : sl.r2n;  // rank -> node id
-    // H(row, j) with j the DP column; j == 0 is the first column (NW border / 0 in SW).  The virtual row 0 is
-    // materialised in H by the fill, so only the column needs a special case.
-    auto hv_at = [&](uint32_t row, uint32_t jj) -> int32_t {
-      if (jj == 0) return SW ? 0 : static_cast<int32_t>(fcb[row]);
-      const uint32_t e = lut ? static_cast<uint32_t>(lut[jj - 1]) : RM::lut_entry(jj - 1);
-      const uint32_t wv = Hb[static_cast<uint64_t>(row) * rw + (e >> 1)];
-      return static_cast<int16_t>((e & 1u) ? (wv >> 16) : (wv & 0xFFFFu));
-    };
-    auto rec_at = [&](uint32_t row) -> U4 {
-      if (row == 0) {
-        U4 z = {0, 0, 0, 0};
-        return z;
-      }
-      return rp[row - 1];
-    };
-    int16_t* th;
-    U4* tr;
-    ex.trace_tile(&th, &tr);  // th[kTR * kTC], tr[kTR]
-    uint32_t ti = 0, tj = 0;  // tile anchor: rows (ti - kTR, ti], columns (tj - kTC, tj]
-    bool have_tile = false;
-    const int32_t gp = sc.g;
-    int32_t h = hv_at(i, j);
-    U4 rec = rec_at(i);
-    uint32_t n = 0;
-    bool bad = false;
-    while (true) {
-      if (SW) {
-        if (h == 0) break;
-      } else {
-        if (i == 0 && j == 0) break;
-      }
-      const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
-      const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;  // no in-edges: the virtual row 0 is the predecessor
-      const uint32_t ncand = 2 * npp + 1;
-      const int32_t mc = (i != 0 && j != 0) ? (meta_code(rec.x) == seq_codes[j - 1] ? sc.m : sc.x) : 0;
-      uint32_t first = kNone, pr_next = 0;
-      int32_t hv_next = 0;
-      U4 rec_next = rec;
-      bool retile = false;
-      for (uint32_t c0 = 0; c0 < ncand; c0 += W) {
-        const uint32_t c = c0 + L;
-        // this lane's candidate: row pr, column cj; kind 0 diagonal, 1 vertical, 2 horizontal, 3 none
-        uint32_t pr = i, cj = j, kind = 3;
-        if (c < 2 * npp) {
-          const uint32_t p = c < npp ? c : c - npp;
-          if (np == 0) pr = 0;
-          else if (p == 0) pr = rec.y;
-          else if (p == 1) pr = rec.z;
-          else if (np == 3) pr = rec.w;
-          else pr = sl.ovf[rec.w + p - 2];
-          if (c < npp) {
-            if (j != 0) {
-              kind = 0;
-              cj = j - 1;
-            }
-          } else {
-            kind = 1;
-          }
-        } else if (c == 2 * npp && j != 0) {
-          kind = 2;
-          cj = j - 1;
-        }
-        const bool in_tile = have_tile && pr <= ti && pr + kTR > ti && cj <= tj && cj + kTC > tj;
-        const bool direct = have_tile && ti == i && tj == j;  // just anchored here: what is still outside is far away
-        if (!direct) {
-          // all candidates of this chunk must be in the tile, else fetch a tile anchored at the current cell
-          const uint32_t miss = ex.reduce_max((kind != 3 && !in_tile) ? 1u : 0u);
-          if (miss) {
-            retile = true;
-            break;
-          }
-        }
-        bool ok = false;
-        int32_t hv = 0;
-        U4 nr = rec;
-        if (kind != 3) {
-          if (in_tile) {
-            hv = th[(ti - pr) * kTC + (tj - cj)];
-            if (kind != 2) nr = tr[ti - pr];
-          } else {
-            hv = hv_at(pr, cj);
-            if (kind != 2) nr = rec_at(pr);
-          }
-          ok = h == hv + (kind == 0 ? mc : gp);
-        }
-        const uint32_t f = ex.reduce_min(ok ? c : kNone);
-        if (f != kNone) {
-          const uint32_t src = f - c0;
-          first = f;
-          hv_next = static_cast<int32_t>(ex.bcast(static_cast<uint32_t>(hv), src));
-          pr_next = ex.bcast(pr, src);
-          rec_next.x = ex.bcast(nr.x, src);
-          rec_next.y = ex.bcast(nr.y, src);
-          rec_next.z = ex.bcast(nr.z, src);
-          rec_next.w = ex.bcast(nr.w, src);
-          break;
-        }
-      }
-      if (retile) {
-        ex.sync();
-        ti = i;
-        tj = j;
-        for (uint32_t t = L; t < static_cast<uint32_t>(kTR * kTC); t += W) {
-          const uint32_t rr = t / kTC, cc = t % kTC;
-          if (rr <= ti && cc <= tj) th[t] = static_cast<int16_t>(hv_at(ti - rr, tj - cc));
-        }
-        for (uint32_t t = L; t < static_cast<uint32_t>(kTR); t += W) {
-          if (t <= ti) tr[t] = rec_at(ti - t);
-        }
-        have_tile = true;
-        ex.sync();
-        continue;
-      }
-      if (first == kNone || n >= sl.aln_cap) {
-        bad = true;
-        break;
-      }
-      const uint32_t pi = pr_next;
-      const uint32_t pj = (first >= npp && first < 2 * npp) ? j : j - 1;
-      if (ex.leader()) {
-        sl.aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(nodes[i - 1]);
-        sl.aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
-      }
-      ++n;
-      i = pi;
-      j = pj;
-      h = hv_next;
-      rec = rec_next;
-    }
+  VGC_HD void traceback(uint32_t layer, uint32_t mode) {
     if (ex.leader()) {
-      if (bad) fail(kStInternal);
-      ws.aln_len = n;
+      if (ws.best_row == 0 && ws.best_col == 0) {
+        ws.aln_len = 0;
+      } else {
+        TraceWalker t;
+        uint32_t* th;
+        U4* tr;
+        ex.trace_tile(&th, &tr);
+        init_walker(t, layer, mode, th, tr);
+        int st;
+        while ((st = t.step()) < kWalkDone) {
+          if (st == kWalkMiss) t.refill();
+        }
+        if (st == kWalkBad) fail(kStInternal);
+        ws.aln_len = t.n;
+      }
     }
     ex.sync();
   }
@@ -1091,9 +1146,7 @@ struct Poa {
     if (ws.need != kNeedTrace) return;
     ex.sync();
     if (ex.leader()) ws.t_last = ex.clock();
-    const uint32_t l = ws.fill_layer, mode = ws.fill_mode;
-    uint8_t* codes = stage_codes(l);
-    traceback(codes, mode, mode == kModeNW ? nw : sw);
+    traceback(ws.fill_layer, ws.fill_mode);
     tick(kPhTrace);
     if (ws.status != kStOk) return finish();
     if (ex.leader()) ws.need = kNeedUpdate;

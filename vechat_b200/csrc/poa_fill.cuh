@@ -39,10 +39,10 @@ __device__ __forceinline__ int32_t hi16(uint32_t w) { return static_cast<int16_t
 
 template <int K>
 __device__ __forceinline__ void row_load(const uint32_t* __restrict__ row, int lane, uint32_t (&u)[K]) {
-  const uint2* p = reinterpret_cast<const uint2*>(row) + lane;
+  const uint2* p = reinterpret_cast<const uint2*>(row + lane * K);  // lane-major: K consecutive words per lane
 #pragma unroll
   for (int k = 0; k < K; k += 2) {
-    uint2 t = p[(k >> 1) * 32];
+    uint2 t = p[k >> 1];
     u[k] = t.x;
     u[k + 1] = t.y;
   }
@@ -50,9 +50,9 @@ __device__ __forceinline__ void row_load(const uint32_t* __restrict__ row, int l
 
 template <int K>
 __device__ __forceinline__ void row_store(uint32_t* __restrict__ row, int lane, const uint32_t (&h)[K]) {
-  uint2* p = reinterpret_cast<uint2*>(row) + lane;
+  uint2* p = reinterpret_cast<uint2*>(row + lane * K);
 #pragma unroll
-  for (int k = 0; k < K; k += 2) p[(k >> 1) * 32] = make_uint2(h[k], h[k + 1]);
+  for (int k = 0; k < K; k += 2) p[k >> 1] = make_uint2(h[k], h[k + 1]);
 }
 
 // prof : shared memory, num_codes * 32*K words;  stage: shared memory, 32 uint4
@@ -137,10 +137,10 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       const uint32_t np = meta_npred(meta);
       uint32_t pr[K];
       {
-        const uint2* pp = reinterpret_cast<const uint2*>(prof + meta_code(meta) * RM::kWords) + lane;
+        const uint2* pp = reinterpret_cast<const uint2*>(prof + meta_code(meta) * RM::kWords + lane * K);
 #pragma unroll
         for (int k = 0; k < K; k += 2) {
-          uint2 t = pp[(k >> 1) * 32];
+          uint2 t = pp[k >> 1];
           pr[k] = t.x;
           pr[k + 1] = t.y;
         }

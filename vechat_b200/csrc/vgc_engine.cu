@@ -53,7 +53,6 @@ struct WarpEx {
   uint32_t max_len;
   int lane_;          // lane inside the group
   uint32_t mask_;     // the group's lanes inside the warp
-  const uint16_t* lut_ = nullptr;
 
   __device__ __forceinline__ unsigned long long clock() const { return clock64(); }
   __device__ __forceinline__ int lane() const { return lane_; }
@@ -62,11 +61,10 @@ struct WarpEx {
   __device__ __forceinline__ void sync() { __syncwarp(mask_); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(mask_, v, src, G); }
-  __device__ __forceinline__ const uint16_t* col_lut() const { return lut_; }
-  // traceback tile (poa_core.h kTR x kTC cells + kTR records) at the start of the arena
-  __device__ __forceinline__ void trace_tile(int16_t** th, U4** tr) {
-    *tr = reinterpret_cast<U4*>(arena());
-    *th = reinterpret_cast<int16_t*>(arena() + 16 * sizeof(U4));
+  // never used on the device: the traceback runs in trace_kernel, one thread per window
+  __device__ __forceinline__ void trace_tile(uint32_t** th, U4** tr) {
+    *th = nullptr;
+    *tr = nullptr;
   }
   __device__ __forceinline__ uint32_t reduce_min(uint32_t v) {
     if constexpr (G == 32) {
@@ -203,46 +201,87 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
   return ex;
 }
 
-// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback).  A step of the
-// walk compares at most 2 * in-degree + 1 candidate cells, so 8 lanes per window are plenty: a warp walks four
-// windows at once and a 128-thread block sixteen.  shared memory: column table (RowMap::lut_entry per column) |
-// per window: Slot/WinState header + codes[max_len].
-constexpr int kTraceLanes = 8;
-constexpr int kTraceWins = 16;   // windows per block
+// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback): ONE THREAD per
+// window, 32 windows per warp (poa_core.h TraceWalker).  Every lane owns a tile of its window's DP matrix in
+// shared memory; the warp alternates between a refill phase (the lanes whose walk left their tile fetch a new
+// one, all loads in flight together) and a walk phase of up to kTraceRound steps out of shared memory.
+// shared memory: coder[256] | 32 x { tile cells kTR x kTW words | tile records kTR x 16 B | pad }
+constexpr uint32_t kTraceLaneWords = kTR * kTW + kTR * 4 + 4;  // = 4 mod 32: 16-byte aligned, banks spread
+constexpr uint32_t kTraceSmem = 256 + 32 * kTraceLaneWords * 4;
+constexpr int kTraceRound = 8;
 
 template <int K>
-__host__ __device__ constexpr uint32_t trace_lut_bytes() {
-  return (RowMap<K>::kCols * 2u + 255u) & ~255u;
-}
-// header | codes[max_len] | tile records 16 x 16 B | tile cells 16 x 8 x 2 B
-__host__ __device__ inline uint32_t trace_win_bytes(uint32_t max_len) { return kSmemHeader + ((max_len + 15u) & ~15u) + 512; }
-
-template <int K>
-__global__ void __launch_bounds__(kTraceLanes * kTraceWins, 4) trace_kernel(const KernelArgs a, uint32_t base,
-                                                                          uint32_t count, uint32_t max_len) {
+__global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
   extern __shared__ __align__(16) uint8_t smem[];
-  uint16_t* lut = reinterpret_cast<uint16_t*>(smem);
-  for (uint32_t c = threadIdx.x; c < static_cast<uint32_t>(RowMap<K>::kCols); c += blockDim.x)
-    lut[c] = static_cast<uint16_t>(RowMap<K>::lut_entry(c));
-  __syncthreads();
-  const uint32_t slot = threadIdx.x / kTraceLanes;
-  const uint32_t i = blockIdx.x * kTraceWins + slot;
-  if (i >= count) return;
-  const int gl = threadIdx.x % kTraceLanes;
-  const uint32_t mask = ((1u << kTraceLanes) - 1u) << ((threadIdx.x & 31) / kTraceLanes * kTraceLanes);
-  uint8_t* mine = smem + trace_lut_bytes<K>() + slot * trace_win_bytes(max_len);
-  WinCtx c;
-  if (!win_enter(a, base + i, kNeedTrace, mine, &c, gl, kTraceLanes, mask)) return;
-  WarpEx<K, kTraceLanes> ex;
-  ex.sm = mine + kSmemHeader;
-  ex.sm_bytes = trace_win_bytes(max_len) - kSmemHeader;
-  ex.max_len = max_len;
-  ex.lane_ = gl;
-  ex.mask_ = mask;
-  ex.lut_ = lut;
-  Poa<WarpEx<K, kTraceLanes>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
-  poa.step_trace();
-  win_leave(a, c);
+  const unsigned long long t0 = clock64();
+  uint8_t* coder = smem;
+  for (uint32_t c = threadIdx.x; c < 256; c += 32) coder[c] = a.bv.coder[c];
+  __syncwarp();
+  const uint32_t idx = blockIdx.x * 32 + threadIdx.x;
+  bool active = idx < count;
+  WinState* gws = a.wstates + base + (active ? idx : 0);
+  if (active && (gws->pc == kPcDone || gws->need != kNeedTrace)) active = false;
+  TraceWalker t;
+  uint32_t w = 0;
+  if (active) {
+    const Slot* sl = a.slots + base + idx;
+    w = a.work[base + idx];
+    const uint32_t layer = gws->fill_layer, mode = gws->fill_mode;
+    t.H = sl->H;
+    t.fc = sl->fc;
+    t.rp = reinterpret_cast<const U4*>(sl->rowprog);
+    t.ovf = sl->ovf;
+    t.nodes = gws->sub ? sl->order : sl->r2n;
+    t.seq = a.bv.bases + a.bv.seq_off[layer];
+    t.coder = coder;
+    t.aln_node = sl->aln_node;
+    t.aln_pos = sl->aln_pos;
+    t.aln_cap = sl->aln_cap;
+    t.rw = sl->row_words;
+    t.half_words = RowMap<K>::kWords;
+    t.m = mode == kModeNW ? a.nw.m : 3;   // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
+    t.x = mode == kModeNW ? a.nw.x : -5;
+    t.g = mode == kModeNW ? a.nw.g : -4;
+    t.sw = mode == kModeSW;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(smem + 256) + threadIdx.x * kTraceLaneWords;
+    t.th = mine;
+    t.tr = reinterpret_cast<U4*>(mine + kTR * kTW);
+    t.start(gws->best_row, gws->best_col);
+    if (t.i == 0 && t.j == 0) {
+      gws->aln_len = 0;
+      gws->need = kNeedUpdate;
+      active = false;
+    }
+  }
+  bool need_refill = false;
+  while (__any_sync(0xFFFFFFFFu, active)) {
+    if (active && need_refill) {
+      t.refill();
+      need_refill = false;
+    }
+    __syncwarp();
+    for (int s = 0; s < kTraceRound; ++s) {
+      if (active && !need_refill) {
+        const int st = t.step();
+        if (st == kWalkMiss) {
+          need_refill = true;
+        } else if (st >= kWalkDone) {
+          gws->aln_len = t.n;
+          gws->phase[kPhTrace] += clock64() - t0;
+          if (st == kWalkBad) {
+            gws->status = kStInternal;
+            gws->pc = kPcDone;
+            gws->need = kNeedNone;
+            a.status[w] = kStInternal;
+          } else {
+            gws->need = kNeedUpdate;
+          }
+          active = false;
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, active && !need_refill)) break;
+    }
+  }
 }
 
 // U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, AddWeights,
@@ -376,10 +415,10 @@ struct vgc_engine {
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
-  int groups = 8;                 // streams of a lockstep pass
-  int group_mode = 1;             // 1: contiguous blocks of the depth-sorted window list, 0: round-robin
-  cudaStream_t gstream[32] = {};
-  cudaEvent_t gev[32] = {};
+  int groups = 48;                // streams of a lockstep pass (upper bound)
+  int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
+  cudaStream_t gstream[64] = {};
+  cudaEvent_t gev[64] = {};
   uint32_t smem_trace = 0, smem_update = 0, smem_sort = 0, smem_fill = 0;
   size_t mem_budget = 0;
   // device copies of the batch
@@ -475,7 +514,7 @@ BatchView make_view(vgc_engine* h) {
   return v;
 }
 
-constexpr int kMaxGroups = 32;
+constexpr int kMaxGroups = 64;
 
 template <int K>
 int set_kernel_attrs(const vgc_engine* h) {
@@ -484,7 +523,7 @@ int set_kernel_attrs(const vgc_engine* h) {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   };
-  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), trace_lut_bytes<K>() + kTraceWins * trace_win_bytes(1024)));
+  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), kTraceSmem));
   VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), h->smem_update));
   VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
   VGC_CUDA(set(reinterpret_cast<const void*>(fill_kernel<K>), h->smem_fill));
@@ -498,9 +537,8 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
   KernelArgs k = a;
   uint32_t n = 0;
   if (nru && !first) {
-    const uint32_t ml = std::max<uint32_t>(h->prep.max_len, 16);
-    k.smem_bytes = trace_lut_bytes<K>() + kTraceWins * trace_win_bytes(ml);
-    trace_kernel<K><<<(nru + kTraceWins - 1) / kTraceWins, kTraceLanes * kTraceWins, k.smem_bytes, st>>>(k, base, nru, ml);
+    k.smem_bytes = kTraceSmem;
+    trace_kernel<K><<<(nru + 31) / 32, 32, kTraceSmem, st>>>(k, base, nru);
     ++n;
   }
   if (nru) {
@@ -573,7 +611,27 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     // ---- deal the chunk's windows to groups.  VGC_GROUP_MODE=0: group g takes sorted positions g, g+G, ... (every
     // group sees the whole depth range); 1 (default): contiguous blocks of the sorted list (a group's windows run
     // the same program in step: the serial phase transitions of a cycle do not stall the other windows)
-    const int G = std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)));
+    // group_mode 2 (default): one group per distinct number of fills (windows of a group then run the very same
+    // program, so the heavy serial steps — PruneGraph + LargestSubgraph, three times per window — coincide instead
+    // of stalling some cycle of every group); sparse values at the tails are merged until a group has >= 64 windows.
+    std::vector<uint32_t> gstart;  // positions in the chunk (sorted by decreasing fills) where a group starts
+    if (h->group_mode == 2) {
+      uint32_t min_group = 64;
+      while (true) {
+        gstart.assign(1, 0);
+        for (uint32_t i = 1; i < n; ++i) {
+          if (pr.win_nfill[wins[pos + i]] != pr.win_nfill[wins[pos + i - 1]] && i - gstart.back() >= min_group)
+            gstart.push_back(i);
+        }
+        if (gstart.size() <= static_cast<size_t>(h->groups)) break;
+        min_group *= 2;
+      }
+    } else {
+      const int G0 = std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)));
+      for (int g = 0; g < G0; ++g) gstart.push_back(static_cast<uint32_t>(static_cast<uint64_t>(n) * g / G0));
+    }
+    const int G = h->group_mode == 0 ? std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)))
+                                     : static_cast<int>(gstart.size());
     std::vector<uint32_t> work(n);
     std::vector<Slot> slots(n);
     std::vector<uint32_t> gbase(G + 1, 0);
@@ -581,8 +639,8 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     uint32_t k = 0;
     for (int g = 0; g < G; ++g) {
       gbase[g] = k;
-      const uint32_t b0 = h->group_mode ? static_cast<uint32_t>(static_cast<uint64_t>(n) * g / G) : g;
-      const uint32_t b1 = h->group_mode ? static_cast<uint32_t>(static_cast<uint64_t>(n) * (g + 1) / G) : n;
+      const uint32_t b0 = h->group_mode ? gstart[g] : g;
+      const uint32_t b1 = h->group_mode ? (g + 1 < G ? gstart[g + 1] : n) : n;
       for (uint32_t i = b0; i < b1; i += h->group_mode ? 1 : G) {
         work[k] = wins[pos + i];
         slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
@@ -817,7 +875,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
   h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
-  if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::atoi(s) ? 1 : 0;
+  if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -841,7 +899,7 @@ int vgc_destroy(vgc_handle h) {
   for (auto& ev : h->ev) {
     if (ev) cudaEventDestroy(ev);
   }
-  for (int g = 0; g < 32; ++g) {
+  for (int g = 0; g < 64; ++g) {
     if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
     if (h->gev[g]) cudaEventDestroy(h->gev[g]);
   }
