@@ -19,8 +19,8 @@ namespace {
 using namespace vgc;
 
 struct HostEx {
-  std::vector<uint8_t> fl;
-  std::vector<uint16_t> off16, tail16, stk16;
+  std::vector<uint32_t> rec32;
+  std::vector<uint16_t> tail16, stk16;
   std::vector<uint8_t> codes;
   bool allow_fast = true;
   uint32_t small_stack = 0;  // test hook: tiny fast stack to force the overflow path
@@ -49,17 +49,31 @@ struct HostEx {
     *total = v;
     return 0;
   }
-  bool stage_fast(uint32_t nV, uint32_t nE, uint8_t** f, uint16_t** o, uint16_t** t, uint16_t** s, uint32_t* cap) {
-    if (!allow_fast || nV >= 65535 || nE >= 65535) return false;
-    fl.assign(nV + 1, 0);
-    off16.assign(nV + 2, 0);
-    tail16.assign(nE + 1, 0);
+  bool stage_fast(uint32_t nV, uint32_t nA, uint32_t** r, uint16_t** t, uint16_t** s, uint32_t* cap) {
+    if (!allow_fast || nV >= 65535 || nA >= 65535) return false;
+    rec32.assign(nV + 1, 0);
+    tail16.assign(nA + 1, 0);
     uint32_t c = small_stack ? small_stack : 1024;
     stk16.assign(c, 0);
-    *f = fl.data();
-    *o = off16.data();
+    *r = rec32.data();
     *t = tail16.data();
     *s = stk16.data();
+    *cap = c;
+    return true;
+  }
+  std::vector<uint16_t> l_off, l_adj, l_stk;
+  std::vector<uint8_t> l_vis;
+  bool stage_lsg(uint32_t nV, uint32_t nA, uint16_t** o, uint16_t** t, uint8_t** vis, uint16_t** s, uint32_t* cap) {
+    if (!allow_fast || nV >= 65535 || nA >= 65535) return false;
+    l_off.assign(nV + 2, 0);
+    l_adj.assign(nA + 1, 0);
+    l_vis.assign(nV + 1, 0);
+    uint32_t c = small_stack ? small_stack : 1024;
+    l_stk.assign(c, 0);
+    *o = l_off.data();
+    *t = l_adj.data();
+    *vis = l_vis.data();
+    *s = l_stk.data();
     *cap = c;
     return true;
   }

@@ -71,7 +71,7 @@ enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRealignPost = 2, kPcFinalPos
 // step a window waits for (WinState::need); a zeroed WinState starts at kPcInit / kNeedUpdate
 enum : uint32_t { kNeedUpdate = 0, kNeedPrepare = 1, kNeedFill = 2, kNeedTrace = 3, kNeedNone = 4 };
 // what step_prepare must do (WinState::prep)
-enum : uint32_t { kPrepMainSort = 1, kPrepSubSort = 2, kPrepRowprog = 4, kPrepFill = 8 };
+enum : uint32_t { kPrepMainSort = 1, kPrepSubSort = 2, kPrepRowprog = 4, kPrepFill = 8, kPrepLargest = 16 };
 
 // flags byte per node used by the sorts
 enum : uint8_t {
@@ -149,13 +149,16 @@ struct Slot {
   uint32_t aln_cap;
 };
 
-// rowprog meta word
-constexpr uint32_t kMetaSink = 1u << 31;
-VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink) {
-  return code | (npred << 8) | (sink ? kMetaSink : 0u);
+// rowprog meta word: code (bits 0-3) | sink (bit 4) | number of predecessors (bits 5-15) | node id (bits 16-31,
+// meaningful while the slot holds fewer than 65536 nodes; the traceback reads it instead of a table in HBM)
+constexpr uint32_t kMetaSink = 1u << 4;
+constexpr uint32_t kMetaMaxPred = 2047;
+VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, uint32_t node) {
+  return code | (sink ? kMetaSink : 0u) | (npred << 5) | (node << 16);
 }
-VGC_HD VGC_INL uint32_t meta_code(uint32_t m) { return m & 0xFFu; }
-VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 8) & 0x7FFFFFu; }
+VGC_HD VGC_INL uint32_t meta_code(uint32_t m) { return m & 0xFu; }
+VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 5) & 0x7FFu; }
+VGC_HD VGC_INL uint32_t meta_node(uint32_t m) { return m >> 16; }
 
 // Shared per-window state (shared memory on the device).
 struct WinState {
@@ -227,9 +230,9 @@ struct TraceWalker {
   const int16_t* fc;
   const U4* rp;
   const uint32_t* ovf;
-  const uint32_t* nodes;   // rank -> node id
+  const uint32_t* nodes;   // rank -> node id; nullptr: the id is in the row record (slots below 65536 nodes)
   const uint8_t* seq;      // the sequence's bases
-  const uint8_t* coder;    // byte -> code
+  uint64_t dec64;          // code -> base byte, 8 codes packed (byte c = decoder[c])
   int32_t* aln_node;
   int32_t* aln_pos;
   uint32_t aln_cap, rw, half_words;
@@ -242,8 +245,19 @@ struct TraceWalker {
   uint32_t i, j, n;
   int32_t h;
   U4 rec;
+  uint32_t sb;             // seq[j - 1] (the base of DP column j), valid while j >= 1
   uint32_t ti, wb;
   bool have, fresh, started;
+
+  VGC_HD VGC_INL static uint64_t pack_decoder(const uint8_t* decoder) {
+    uint64_t d = 0;
+    for (int c = 0; c < kMaxCodes; ++c) d |= static_cast<uint64_t>(decoder[c]) << (8 * c);
+    return d;
+  }
+  VGC_HD VGC_INL uint32_t base_of(uint32_t code) const { return static_cast<uint32_t>(dec64 >> (8 * code)) & 0xFFu; }
+  VGC_HD VGC_INL static int32_t half_of(uint32_t v, uint32_t hi) {
+    return static_cast<int16_t>(hi ? (v >> 16) : (v & 0xFFFFu));
+  }
 
   VGC_HD VGC_INL void start(uint32_t row, uint32_t col) {
     i = row;
@@ -251,6 +265,7 @@ struct TraceWalker {
     n = 0;
     h = 0;
     rec = U4{0, 0, 0, 0};
+    sb = col ? seq[col - 1] : 0u;
     ti = wb = 0;
     have = fresh = started = false;
   }
@@ -340,9 +355,50 @@ struct TraceWalker {
       if (i == 0 && j == 0) return kWalkDone;
     }
     const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
+    if (i != 0 && j >= 2 && np <= 2) {
+      // ---- fast path (at most two predecessors, away from the borders): all five candidate cells and both
+      //      predecessor records are read from the tile at once and the first match in priority order is
+      //      selected without branching, so the 32 walks of a warp stay converged
+      const uint32_t nb = seq[j - 2];  // base of DP column j - 1, consumed when the move changes the column
+      const uint32_t p0 = np ? rec.y : 0u;
+      const uint32_t p1 = np == 2 ? rec.z : p0;
+      const uint32_t c1 = j - 1, c0 = j - 2;
+      const uint32_t hi1 = c1 >= half_words ? 1u : 0u, hi0 = c0 >= half_words ? 1u : 0u;
+      const uint32_t dq1 = (hi1 ? c1 - half_words : c1) - wb, dq0 = (hi0 ? c0 - half_words : c0) - wb;
+      const uint32_t dr0 = ti - p0, dr1 = ti - p1, dri = ti - i;
+      const uint32_t TRu = static_cast<uint32_t>(kTR), TWu = static_cast<uint32_t>(kTW);
+      if (dq1 < TWu && dq0 < TWu && dr0 < TRu && dr1 < TRu && dri < TRu) {
+        const uint32_t* r0 = th + dr0 * kTW;
+        const uint32_t* r1 = th + dr1 * kTW;
+        const uint32_t a00 = r0[dq0], a01 = r0[dq1], a10 = r1[dq0], a11 = r1[dq1], ai0 = th[dri * kTW + dq0];
+        const U4 n0 = tr[dr0], n1 = tr[dr1];
+        const int32_t mcf = base_of(meta_code(rec.x)) == sb ? m : x;
+        const int32_t D0 = half_of(a00, hi0), V0 = half_of(a01, hi1), D1 = half_of(a10, hi0), V1 = half_of(a11, hi1),
+                      HH = half_of(ai0, hi0);
+        const bool d0 = h == D0 + mcf, d1 = h == D1 + mcf, v0 = h == V0 + g, v1 = h == V1 + g, hh = h == HH + g;
+        if (!(d0 || d1 || v0 || v1 || hh) || n >= aln_cap) return kWalkBad;
+        const bool diag = d0 || d1, vert = !diag && (v0 || v1);
+        const bool first = d0 || (!d1 && v0);  // the winning move goes to p0 (else p1, unless horizontal)
+        const uint32_t pi = (diag || vert) ? (first ? p0 : p1) : i;
+        const int32_t hn = d0 ? D0 : d1 ? D1 : v0 ? V0 : v1 ? V1 : HH;
+        aln_node[n] = (diag || vert) ? static_cast<int32_t>(nodes ? nodes[i - 1] : meta_node(rec.x)) : -1;
+        aln_pos[n] = vert ? -1 : static_cast<int32_t>(j - 1);
+        ++n;
+        if (diag || vert) rec = first ? n0 : n1;
+        i = pi;
+        if (!vert) {
+          j = j - 1;
+          sb = nb;
+        }
+        h = hn;
+        fresh = false;
+        return kWalkStep;
+      }
+      if (!fresh) return kWalkMiss;
+    }
     const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;
     int32_t mc = 0;
-    if (i != 0 && j != 0) mc = (meta_code(rec.x) == coder[seq[j - 1]]) ? m : x;
+    if (i != 0 && j != 0) mc = (base_of(meta_code(rec.x)) == sb) ? m : x;
     uint32_t pi = i, pj = j;
     int32_t hn = 0;
     bool found = false;
@@ -383,10 +439,11 @@ struct TraceWalker {
       }
     }
     if (!found || n >= aln_cap) return kWalkBad;
-    aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(nodes[i - 1]);
+    aln_node[n] = (i == pi) ? -1 : static_cast<int32_t>(nodes ? nodes[i - 1] : meta_node(rec.x));
     aln_pos[n] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
     ++n;
     if (pi != i) rec = rec_of(pi);
+    if (pj != j) sb = pj ? seq[pj - 1] : 0u;
     i = pi;
     j = pj;
     h = hn;
@@ -535,6 +592,95 @@ struct Poa {
     }
   }
 
+  // ---- the same sort over the staged graph of the executor's fast storage.  One 32-bit record per node:
+  //      adjacency offset (bits 0-15) | in-degree (16-21) | aligned count (22-24) | expanded (25) | done (26) |
+  //      ignored (27) | member (28).  A node is scanned once: the first visit pushes what is not done yet and
+  //      marks it expanded; when it surfaces again everything it pushed is done (the graph is a DAG), so the second
+  //      visit only emits — the reference re-scans and finds exactly that (graph.cpp:318-352).
+  static constexpr uint32_t kRExpanded = 1u << 25, kRDone = 1u << 26, kRIgnored = 1u << 27, kRMember = 1u << 28;
+  VGC_HD VGC_INL static uint32_t rec_pack(uint32_t off, uint32_t nin, uint32_t nal) { return off | (nin << 16) | (nal << 22); }
+
+  template <bool SUB, class StkT>
+  VGC_HD uint32_t toposort_fast(uint32_t* rec, const uint16_t* adj, StkT* stack, uint32_t stack_cap, uint32_t* dst,
+                                bool* overflow) {
+    const uint32_t nV = G().nV;
+    uint32_t n = 0, sp = 0;
+    *overflow = false;
+    for (uint32_t root = 0; root < nV; ++root) {
+      const uint32_t rr = rec[root];
+      if (rr & (kRDone | kRExpanded)) continue;
+      if (SUB && !(rr & kRMember)) continue;
+      stack[sp++] = static_cast<StkT>(root);
+      while (sp > 0) {
+        const uint32_t curr = stack[sp - 1];
+        const uint32_t r = rec[curr];
+        if (r & kRDone) {
+          --sp;
+          continue;
+        }
+        const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 7u;
+        const bool primary = !(r & kRIgnored);
+        bool valid = true;
+        if (!(r & kRExpanded)) {
+          if (sp + nin + nal + 1 > stack_cap) {
+            *overflow = true;
+            return 0;
+          }
+          for (uint32_t i = 0; i < nin; ++i) {
+            const uint32_t t = adj[off + i];
+            const uint32_t rt = rec[t];
+            if (SUB && !(rt & kRMember)) continue;
+            if (!(rt & kRDone)) {
+              stack[sp++] = static_cast<StkT>(t);
+              valid = false;
+            }
+          }
+          if (primary) {
+            for (uint32_t i = 0; i < nal; ++i) {
+              const uint32_t a = adj[off + nin + i];
+              const uint32_t ra = rec[a];
+              if (SUB && !(ra & kRMember)) continue;
+              if (!(ra & kRDone)) {
+                stack[sp++] = static_cast<StkT>(a);
+                rec[a] = ra | kRIgnored;
+                valid = false;
+              }
+            }
+          }
+        }
+        if (valid) {
+          rec[curr] = r | kRDone;
+          if (primary) {
+            dst[n++] = curr;
+            for (uint32_t i = 0; i < nal; ++i) {
+              const uint32_t a = adj[off + nin + i];
+              if (SUB && !(rec[a] & kRMember)) continue;
+              dst[n++] = a;
+            }
+          }
+          --sp;
+        } else {
+          rec[curr] = r | kRExpanded;
+        }
+      }
+    }
+    return n;
+  }
+
+  VGC_HD void extract_fast(uint32_t* rec, const uint16_t* adj, uint32_t* stack, uint32_t from, uint32_t floor_id) {
+    uint32_t sp = 0;
+    stack[sp++] = from;
+    while (sp > 0) {
+      const uint32_t curr = stack[--sp];
+      const uint32_t r = rec[curr];
+      if (!(r & kRMember) && curr >= floor_id) {
+        const uint32_t off = r & 0xFFFFu, cnt = ((r >> 16) & 63u) + ((r >> 22) & 7u);
+        for (uint32_t i = 0; i < cnt; ++i) stack[sp++] = adj[off + i];
+        rec[curr] = r | kRMember;
+      }
+    }
+  }
+
   // Topological order of the live graph (or of the Subgraph view begin..end) into dst.  Builds the adjacency
   // view in the executor's fast storage (16-bit ids) when it fits, else in the H scratch (32-bit ids).
   // H scratch layout (words): [0, nV] offsets | [nV+1, nV+1+nA) adjacency | big stack after that.
@@ -556,25 +702,27 @@ struct Poa {
     const uint32_t nA = carry;
     if (ex.leader()) goff[nV] = nA;
     ex.sync();
-    uint8_t* fl;
-    uint16_t *off16, *adj16, *stk16;
+    uint32_t* rec;
+    uint16_t *adj16, *stk16;
     uint32_t stk_cap;
-    const bool fast = ex.stage_fast(nV, nA, &fl, &off16, &adj16, &stk16, &stk_cap);
+    uint32_t max_in = 0;
+    for (uint32_t v = L; v < nV; v += W) max_in = g.nin[v] > max_in ? g.nin[v] : max_in;
+    max_in = ex.reduce_max(max_in);
+    const bool fast = max_in < 64u && ex.stage_fast(nV, nA, &rec, &adj16, &stk16, &stk_cap);
+    uint8_t* fl = sl.flags;
     uint32_t* gadj = sl.H + nV + 1;
     uint32_t* gstack = gadj + nA;
-    if (!fast) fl = sl.flags;
     for (uint32_t v = L; v < nV; v += W) {
       const uint32_t na = g.nal[v];
-      fl[v] = static_cast<uint8_t>((na ? kFHasAligned : 0) | (na << kFNalShift));
       const uint32_t o = goff[v] + g.nin[v];
       for (uint32_t i = 0; i < na; ++i) {
         const uint32_t a = g.al[v * kAlStride + i];
         if (fast) adj16[o + i] = static_cast<uint16_t>(a);
         else gadj[o + i] = a;
       }
-      if (fast) off16[v] = static_cast<uint16_t>(goff[v]);
+      if (fast) rec[v] = rec_pack(goff[v], g.nin[v], na);
+      else fl[v] = static_cast<uint8_t>((na ? kFHasAligned : 0) | (na << kFNalShift));
     }
-    if (fast && L == 0) off16[nV] = static_cast<uint16_t>(nA);
     for (uint32_t e = L; e < nE; e += W) {
       const uint32_t pos = goff[g.ehead[e]] + g.ein_ord[e];
       if (fast) adj16[pos] = static_cast<uint16_t>(g.etail[e]);
@@ -585,13 +733,17 @@ struct Poa {
       uint32_t n = 0;
       bool ovf = false;
       if (fast) {
-        if (sub) extract_impl<uint16_t>(fl, off16, adj16, gstack, sub_end, sub_begin);
-        n = toposort_impl<uint16_t, uint16_t>(fl, off16, adj16, stk16, stk_cap, sub, dst, &ovf);
+        if (sub) {
+          extract_fast(rec, adj16, gstack, sub_end, sub_begin);
+          n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, &ovf);
+        } else {
+          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, &ovf);
+        }
         if (ovf) {
-          // deep recursion: redo with the big stack in HBM (flags: clear marks/ignored, keep member + counts);
-          // 16-bit ids in a 32-bit stack
-          for (uint32_t v = 0; v < nV; ++v) fl[v] &= static_cast<uint8_t>(kFHasAligned | kFMember | (7u << kFNalShift));
-          n = toposort_impl<uint16_t, uint32_t>(fl, off16, adj16, gstack, 0xFFFFFFFFu, sub, dst, &ovf);
+          // deep recursion: redo with the big stack in HBM (records: clear the marks, keep membership)
+          for (uint32_t v = 0; v < nV; ++v) rec[v] &= ~(kRExpanded | kRDone | kRIgnored);
+          if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, &ovf);
+          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, &ovf);
         }
       } else {
         if (sub) extract_impl<uint32_t>(fl, goff, gadj, gstack, sub_end, sub_begin);
@@ -603,7 +755,7 @@ struct Poa {
     const uint32_t n = ws.scratch[0];
     if (sub) {
       // keep the membership where the row-program builder can see it
-      for (uint32_t v = L; v < nV; v += W) sl.flags[v] = fl[v] & kFMember;
+      for (uint32_t v = L; v < nV; v += W) sl.flags[v] = fast ? ((rec[v] & kRMember) ? kFMember : 0) : (fl[v] & kFMember);
       ex.sync();
     }
     return n;
@@ -657,7 +809,8 @@ struct Poa {
         p2 = o;  // predecessor p (>= 2) is ovf[p2 + p - 2]
       }
       const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
-      U4 rec = {meta_pack(g.code[v], np, sink), p0, p1, p2};
+      if (np > kMetaMaxPred) fail(kStDegreeOverflow);
+      U4 rec = {meta_pack(g.code[v], np, sink, v), p0, p1, p2};
       *reinterpret_cast<U4*>(sl.rowprog + 4 * static_cast<size_t>(r)) = rec;
     }
     ex.sync();
@@ -671,9 +824,9 @@ struct Poa {
     t.fc = sl.fc;
     t.rp = reinterpret_cast<const U4*>(sl.rowprog);
     t.ovf = sl.ovf;
-    t.nodes = ws.sub ? sl.order : sl.r2n;
+    t.nodes = sl.max_nodes < 65536u ? nullptr : (ws.sub ? sl.order : sl.r2n);
     t.seq = bv.bases + bv.seq_off[layer];
-    t.coder = bv.coder;
+    t.dec64 = TraceWalker::pack_decoder(bv.decoder);
     t.aln_node = sl.aln_node;
     t.aln_pos = sl.aln_pos;
     t.aln_cap = sl.aln_cap;
@@ -944,100 +1097,182 @@ struct Poa {
     ex.sync();
   }
 
-  // ---- graph.cpp:984-1089 (leader): components by recursive pre-order over [live in-tails, live
-  //      out-heads]; last largest wins; rebuild with DFS-order ids, zero weights, no aligned links ----
+  // ---- graph.cpp:984-1089.  Components of the pruned graph by the reference's recursive pre-order (DfsUtil:
+  //      a node's neighbours are its live in-edge tails in in-list order, then its live out-edge heads in
+  //      out-list order; `visited` is tested when the loop reaches a neighbour); the LAST largest component wins
+  //      (`>=`, :1049); the graph is rebuilt with ids = pre-order positions, edges in (new tail id, out-list
+  //      position) order with weight 0, and no aligned links.
+  //      Parallel: live adjacency (staged in the executor's fast storage when it fits) and the whole rebuild.
+  //      Serial (leader): only the pre-order walk itself, over the compact adjacency.
+  template <class OffT, class AdjT, class StkT>
+  VGC_HD bool components(const OffT* off, const AdjT* adj, uint8_t* visited, StkT* stk, uint32_t cap, uint32_t* comp,
+                         uint32_t* best_start_out, uint32_t* best_size_out) {
+    const uint32_t nV = G().nV;
+    uint32_t ncomp = 0, best_start = 0, best_size = 0;
+    for (uint32_t v0 = 0; v0 < nV; ++v0) {
+      if (visited[v0]) continue;
+      const uint32_t start = ncomp;
+      visited[v0] = 1;
+      comp[ncomp++] = v0;
+      if (off[v0] != off[v0 + 1]) {
+        uint32_t sp = 0;
+        stk[sp++] = static_cast<StkT>(v0);
+        while (sp > 0) {
+          // re-scan from the first neighbour: everything before the one taken last time is visited by now
+          const uint32_t v = stk[sp - 1];
+          uint32_t next = kNone;
+          for (uint32_t c = off[v], e = off[v + 1]; c < e; ++c) {
+            const uint32_t u = adj[c];
+            if (!visited[u]) {
+              next = u;
+              break;
+            }
+          }
+          if (next == kNone) {
+            --sp;
+          } else {
+            if (sp >= cap) return false;
+            visited[next] = 1;
+            comp[ncomp++] = next;
+            stk[sp++] = static_cast<StkT>(next);
+          }
+        }
+      }
+      if (ncomp - start >= best_size) {
+        best_size = ncomp - start;
+        best_start = start;
+      }
+    }
+    *best_start_out = best_start;
+    *best_size_out = best_size;
+    return true;
+  }
+
   VGC_HD void largest_subgraph() {
     build_out_csr();
     Graph& g = G();
     const uint32_t S = sl.in_stride;
     Graph& h = sl.g[ws.cur ^ 1];
     const uint32_t nV = g.nV;
-    uint32_t* comp = sl.tmp0;             // all components back to back
+    const int W = ex.width(), L = ex.lane();
+    uint32_t* comp = sl.tmp0;   // all components back to back
     uint32_t* newid = sl.tmp1;
-    uint8_t* visited = sl.flags;
-    uint32_t* stk = sl.H;                 // frames: {node, cursor}
-    for (uint32_t v = ex.lane(); v < nV; v += ex.width()) visited[v] = 0;
+    uint32_t* goff = sl.H;      // [nV + 1] offsets of the live adjacency
+    // live degree and offsets
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nV; base += W) {
+      const uint32_t v = base + L;
+      uint32_t c = 0;
+      if (v < nV) {
+        for (uint32_t i = 0; i < g.nin[v]; ++i) c += g.edead[g.ieid[v * S + i]] ? 0u : 1u;
+        for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) c += g.edead[sl.out_eid[k]] ? 0u : 1u;
+      }
+      uint32_t tot;
+      const uint32_t q = ex.excl_scan(c, &tot);
+      if (v < nV) goff[v] = carry + q;
+      carry += tot;
+    }
+    const uint32_t nA = carry;
+    if (ex.leader()) goff[nV] = nA;
+    ex.sync();
+    uint16_t *off16, *adj16, *stk16;
+    uint8_t* vis;
+    uint32_t cap16;
+    const bool fast = ex.stage_lsg(nV, nA, &off16, &adj16, &vis, &stk16, &cap16);
+    uint32_t* gadj = sl.H + nV + 1;
+    uint32_t* gstk = gadj + nA;
+    if (!fast) vis = sl.flags;
+    for (uint32_t v = L; v < nV; v += W) {
+      uint32_t o = goff[v];
+      for (uint32_t i = 0; i < g.nin[v]; ++i) {
+        const uint32_t e = g.ieid[v * S + i];
+        if (g.edead[e]) continue;
+        if (fast) adj16[o] = static_cast<uint16_t>(g.etail[e]);
+        else gadj[o] = g.etail[e];
+        ++o;
+      }
+      for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) {
+        const uint32_t e = sl.out_eid[k];
+        if (g.edead[e]) continue;
+        if (fast) adj16[o] = static_cast<uint16_t>(g.ehead[e]);
+        else gadj[o] = g.ehead[e];
+        ++o;
+      }
+      vis[v] = 0;
+      if (fast) off16[v] = static_cast<uint16_t>(goff[v]);
+    }
+    if (fast && L == 0) off16[nV] = static_cast<uint16_t>(nA);
     ex.sync();
     if (ex.leader()) {
-      uint32_t ncomp = 0, best_start = 0, best_size = 0;
-      for (uint32_t v0 = 0; v0 < nV; ++v0) {
-        if (visited[v0]) continue;
-        const uint32_t start = ncomp;
-        uint32_t sp = 0;
-        visited[v0] = 1;
-        comp[ncomp++] = v0;
-        stk[0] = v0;
-        stk[1] = 0;
-        sp = 1;
-        while (sp > 0) {
-          const uint32_t v = stk[2 * (sp - 1)];
-          uint32_t c = stk[2 * (sp - 1) + 1];
-          const uint32_t nin = g.nin[v];
-          const uint32_t nout = sl.out_off[v + 1] - sl.out_off[v];
-          uint32_t next = kNone;
-          while (c < nin + nout) {
-            uint32_t e, u;
-            if (c < nin) {
-              e = g.ieid[v * S + c];
-              u = g.etail[e];
-            } else {
-              e = sl.out_eid[sl.out_off[v] + (c - nin)];
-              u = g.ehead[e];
-            }
-            ++c;
-            if (g.edead[e]) continue;
-            if (!visited[u]) {
-              next = u;
-              break;
-            }
-          }
-          stk[2 * (sp - 1) + 1] = c;
-          if (next == kNone) {
-            --sp;
-          } else {
-            visited[next] = 1;
-            comp[ncomp++] = next;
-            stk[2 * sp] = next;
-            stk[2 * sp + 1] = 0;
-            ++sp;
-          }
+      uint32_t bs = 0, bn = 0;
+      bool ok = false;
+      if (fast) {
+        ok = components<uint16_t, uint16_t, uint16_t>(off16, adj16, vis, stk16, cap16, comp, &bs, &bn);
+        if (!ok) {
+          for (uint32_t v = 0; v < nV; ++v) vis[v] = 0;  // deep recursion: redo with the big stack in HBM
+          ok = components<uint16_t, uint16_t, uint32_t>(off16, adj16, vis, gstk, 0xFFFFFFFFu, comp, &bs, &bn);
         }
-        if (ncomp - start >= best_size) {
-          best_size = ncomp - start;
-          best_start = start;
-        }
+      } else {
+        ok = components<uint32_t, uint32_t, uint32_t>(goff, gadj, vis, gstk, 0xFFFFFFFFu, comp, &bs, &bn);
       }
-      // rebuild
-      h.nV = best_size;
-      for (uint32_t i = 0; i < best_size; ++i) {
+      ws.scratch[0] = bs;
+      ws.scratch[1] = bn;
+    }
+    ex.sync();
+    const uint32_t best_start = ws.scratch[0], best_size = ws.scratch[1];
+    // ---- rebuild (all lanes).  Node i of the new graph = comp[best_start + i].
+    uint32_t* eoff = sl.rank_of;  // first new edge id of each new node (scratch: the next sort rewrites rank_of)
+    uint32_t ecarry = 0;
+    for (uint32_t base = 0; base < best_size; base += W) {
+      const uint32_t i = base + L;
+      uint32_t lout = 0;
+      if (i < best_size) {
         const uint32_t v = comp[best_start + i];
         newid[v] = i;
+        uint32_t lin = 0;
+        for (uint32_t q = 0; q < g.nin[v]; ++q) lin += g.edead[g.ieid[v * S + q]] ? 0u : 1u;
+        for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) lout += g.edead[sl.out_eid[k]] ? 0u : 1u;
         h.code[i] = g.code[v];
         h.nal[i] = 0;
-        h.nin[i] = 0;
-        h.nout[i] = 0;
         h.cov[i] = 0;
+        h.nin[i] = lin;
+        h.nout[i] = lout;
       }
-      uint32_t ne = 0;
-      for (uint32_t i = 0; i < best_size; ++i) {
-        const uint32_t v = comp[best_start + i];
-        for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) {
-          const uint32_t e = sl.out_eid[k];
-          if (g.edead[e]) continue;
-          const uint32_t hd = newid[g.ehead[e]];
-          h.etail[ne] = i;
-          h.ehead[ne] = hd;
-          h.ew[ne] = 0;
-          h.edead[ne] = 0;
-          const uint32_t slot = h.nin[hd]++;  // <= the node's in-degree in g, which fits the stride
-          h.itail[hd * S + slot] = i;
-          h.ieid[hd * S + slot] = ne;
-          h.ein_ord[ne] = slot;
-          h.eout_ord[ne] = h.nout[i]++;
-          ++ne;
+      uint32_t tot;
+      const uint32_t q = ex.excl_scan(lout, &tot);
+      if (i < best_size) eoff[i] = ecarry + q;
+      ecarry += tot;
+    }
+    ex.sync();
+    for (uint32_t i = L; i < best_size; i += W) {
+      const uint32_t v = comp[best_start + i];
+      uint32_t t = 0;
+      for (uint32_t k = sl.out_off[v]; k < sl.out_off[v + 1]; ++k) {
+        const uint32_t e = sl.out_eid[k];
+        if (g.edead[e]) continue;
+        const uint32_t ne = eoff[i] + t;
+        const uint32_t ho = g.ehead[e];
+        const uint32_t hd = newid[ho];
+        // position in the head's new in-list: edges are created in increasing new tail id
+        uint32_t slot = 0;
+        for (uint32_t q = 0; q < g.nin[ho]; ++q) {
+          const uint32_t e2 = g.ieid[ho * S + q];
+          if (!g.edead[e2] && newid[g.etail[e2]] < i) ++slot;
         }
+        h.etail[ne] = i;
+        h.ehead[ne] = hd;
+        h.ew[ne] = 0;
+        h.edead[ne] = 0;
+        h.itail[hd * S + slot] = i;
+        h.ieid[hd * S + slot] = ne;
+        h.ein_ord[ne] = slot;
+        h.eout_ord[ne] = t;
+        ++t;
       }
-      h.nE = ne;
+    }
+    if (ex.leader()) {
+      h.nV = best_size;
+      h.nE = ecarry;
       ws.cur ^= 1;
     }
     ex.sync();
@@ -1159,6 +1394,10 @@ struct Poa {
     if (ex.leader()) ws.t_last = ex.clock();
     const uint32_t prep = ws.prep;
     uint32_t nMain = ws.nMain;
+    if (prep & kPrepLargest) {
+      largest_subgraph();
+      tick(kPhLargest);
+    }
     if (prep & kPrepMainSort) {
       nMain = sort_graph(false, 0, 0, sl.r2n);
       tick(kPhSort);
@@ -1213,6 +1452,7 @@ struct Poa {
     Act act = kBuildNext;
     uint32_t j = ws.j, k = ws.k;
     bool changed = false;  // graph changed since the last sort
+    bool largest = false;  // PruneGraph ran: LargestSubgraph is pending
     ex.sync();
     if (ex.leader()) ws.t_last = ex.clock();
     // plan: make the next alignment (or sort-only step) pending
@@ -1221,7 +1461,7 @@ struct Poa {
         ws.pc = next_pc;
         ws.j = j;
         ws.k = k;
-        ws.prep = prep | (changed ? kPrepMainSort : 0u);
+        ws.prep = prep | (changed ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
         ws.fill_layer = layer;
         ws.fill_mode = mode;
         ws.need = (ws.prep == kPrepFill) ? kNeedFill : kNeedPrepare;
@@ -1345,8 +1585,7 @@ struct Poa {
         // haplotype mode: prune (window.cpp:300-319); LargestSubgraph rebuilds the CSR it needs
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
-        largest_subgraph();
-        tick(kPhLargest);
+        largest = true;  // LargestSubgraph runs in step_prepare, next to the sort (same staged-graph storage)
         changed = true;
         k = 0;
         act = kRoundStart;
@@ -1367,8 +1606,7 @@ struct Poa {
         }
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
-        largest_subgraph();
-        tick(kPhLargest);
+        largest = true;
         changed = true;
         ++k;
         act = kRoundStart;

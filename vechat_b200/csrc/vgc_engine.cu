@@ -95,22 +95,36 @@ struct WarpEx {
     return x - v;
   }
   // layout: codes[max_len] | arena.  The arena holds the sort's staged graph:
-  //   flags[nV] | off16[nV+1] | adj16[nA] | stack16[>=256]
+  //   rec32[nV] | adj16[nA] | stack16[>= 256]
   __device__ __forceinline__ uint8_t* seq_codes() { return sm; }
   __device__ __forceinline__ uint8_t* arena() { return sm + ((max_len + 15u) & ~15u); }
   __device__ __forceinline__ uint32_t arena_bytes() { return sm_bytes - ((max_len + 15u) & ~15u); }
-  __device__ bool stage_fast(uint32_t nV, uint32_t nE, uint8_t** f, uint16_t** o, uint16_t** t, uint16_t** s,
-                             uint32_t* cap) {
-    if (nV >= 65535u || nE >= 65535u) return false;
-    const uint32_t oo = (nV + 3u) & ~3u;
-    const uint32_t to = oo + (((nV + 1u) * 2u + 3u) & ~3u);
-    const uint32_t so = to + ((nE * 2u + 3u) & ~3u);
+  __device__ bool stage_fast(uint32_t nV, uint32_t nA, uint32_t** r, uint16_t** t, uint16_t** s, uint32_t* cap) {
+    if (nV >= 65535u || nA >= 65535u) return false;
+    const uint32_t to = nV * 4u;
+    const uint32_t so = to + ((nA * 2u + 3u) & ~3u);
     const uint32_t avail = arena_bytes();
     if (so + 512u > avail) return false;
     uint8_t* base = arena();
-    *f = base;
-    *o = reinterpret_cast<uint16_t*>(base + oo);
+    *r = reinterpret_cast<uint32_t*>(base);
     *t = reinterpret_cast<uint16_t*>(base + to);
+    *s = reinterpret_cast<uint16_t*>(base + so);
+    *cap = (avail - so) / 2u;
+    return true;
+  }
+  // LargestSubgraph's staged live adjacency: off16[nV+1] | adj16[nA] | visited[nV] | stack16[>= 256]
+  __device__ bool stage_lsg(uint32_t nV, uint32_t nA, uint16_t** o, uint16_t** t, uint8_t** vis, uint16_t** s,
+                            uint32_t* cap) {
+    if (nV >= 65535u || nA >= 65535u) return false;
+    const uint32_t to = ((nV + 1u) * 2u + 3u) & ~3u;
+    const uint32_t vo = to + ((nA * 2u + 3u) & ~3u);
+    const uint32_t so = vo + ((nV + 3u) & ~3u);
+    const uint32_t avail = arena_bytes();
+    if (so + 512u > avail) return false;
+    uint8_t* base = arena();
+    *o = reinterpret_cast<uint16_t*>(base);
+    *t = reinterpret_cast<uint16_t*>(base + to);
+    *vis = base + vo;
     *s = reinterpret_cast<uint16_t*>(base + so);
     *cap = (avail - so) / 2u;
     return true;
@@ -214,9 +228,8 @@ template <int K>
 __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
   extern __shared__ __align__(16) uint8_t smem[];
   const unsigned long long t0 = clock64();
-  uint8_t* coder = smem;
-  for (uint32_t c = threadIdx.x; c < 256; c += 32) coder[c] = a.bv.coder[c];
-  __syncwarp();
+  uint64_t dec64 = 0;
+  for (int c = 0; c < kMaxCodes; ++c) dec64 |= static_cast<uint64_t>(a.bv.decoder[c]) << (8 * c);
   const uint32_t idx = blockIdx.x * 32 + threadIdx.x;
   bool active = idx < count;
   WinState* gws = a.wstates + base + (active ? idx : 0);
@@ -231,9 +244,9 @@ __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t 
     t.fc = sl->fc;
     t.rp = reinterpret_cast<const U4*>(sl->rowprog);
     t.ovf = sl->ovf;
-    t.nodes = gws->sub ? sl->order : sl->r2n;
+    t.nodes = sl->max_nodes < 65536u ? nullptr : (gws->sub ? sl->order : sl->r2n);
     t.seq = a.bv.bases + a.bv.seq_off[layer];
-    t.coder = coder;
+    t.dec64 = dec64;
     t.aln_node = sl->aln_node;
     t.aln_pos = sl->aln_pos;
     t.aln_cap = sl->aln_cap;
@@ -864,8 +877,13 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->sm_count = prop.multiProcessorCount;
   VGC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) VGC_CUDA(cudaEventCreate(&ev));
+  // groups are ordered deepest windows first: their chain of cycles is the critical path of a pass, so their
+  // streams get the higher priorities
+  int prio_least = 0, prio_greatest = 0;
+  VGC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   for (int g = 0; g < kMaxGroups; ++g) {
-    VGC_CUDA(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    const int prio = std::min(prio_least, prio_greatest + g / 4);
+    VGC_CUDA(cudaStreamCreateWithPriority(&h->gstream[g], cudaStreamNonBlocking, prio));
     VGC_CUDA(cudaEventCreateWithFlags(&h->gev[g], cudaEventDisableTiming));
   }
   // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
