@@ -53,6 +53,19 @@ def build_engine(force=False, verbose=False):
     return out
 
 
+def build_host(force=False):
+    """libvgchost.so: the C++ host side above the C-ABI (csrc/host/vgc_host.hpp: createWindow / add_layer /
+    B200Polisher::polish) behind a flat C test entry; links libvgc.so."""
+    out = os.path.join(LIB_DIR, "libvgchost.so")
+    hdir = os.path.join(CSRC, "host")
+    srcs = [os.path.join(hdir, "vgc_host_capi.cpp")]
+    deps = srcs + [os.path.join(hdir, "vgc_host.hpp"), os.path.join(INC, "vgc.h")]
+    if force or _stale(out, deps):
+        _run([CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", INC, "-I", hdir, "-o", out] + srcs +
+             ["-L", LIB_DIR, "-lvgc", "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
 def build_sim(force=False):
     """libvgcsim.so: synthetic reads / ground-truth overlaps / windowizer (host only)."""
     os.makedirs(LIB_DIR, exist_ok=True)
@@ -74,6 +87,7 @@ def build_oracle():
 def build_all(force=False):
     build_sim(force)
     build_engine(force)
+    build_host(force)
     build_oracle()
 
 
