@@ -8,7 +8,7 @@
 Workload ("step" = one pass of the hot path over one batch): synthetic PacBio CLR of SURVEY.md §8(d) config 2
 (10k reads x 10 kb over a 3.33 Mb genome, 15 % error 9:4.5:1.5, Q~N(12,2), ground-truth overlaps, 500 bp
 windows, m=3 x=-5 g=-4 -p -d 0.2 -s 0.2 -k 3).  One batch = all windows of `--targets` consecutive target reads
-(default 400 reads = 8000 windows, depth ~30) per GPU; rank r takes targets [r*T, (r+1)*T) (weak scaling, no
+(default 1600 reads = 32000 windows, depth ~30, ~100 GB of DP scratch) per GPU; rank r takes targets [r*T, (r+1)*T) (weak scaling, no
 data-path collective; the gather of corrected reads to rank 0 is part of the e2e leg).
 
 Legs of our arm:
@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--targets", type=int, default=400, help="target reads per GPU per step (20 windows each)")
+    ap.add_argument("--targets", type=int, default=1600, help="target reads per GPU per step (20 windows each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     return ap.parse_args()
@@ -53,7 +53,7 @@ def workload_config(args, world):
                         "per step" % (WORKLOAD, args.targets),
             "targets_per_gpu": args.targets, "window_length": 500, "ranks": world,
             "sharding": "whole target reads per rank, no data-path collective; gather of corrected reads in e2e",
-            "l2": "inputs per step (~240 MB) and DP scratch (GBs) exceed the 126 MB L2; no explicit flush"}
+            "l2": "inputs per step (~1 GB at 1600 targets) and DP scratch (~100 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 def make_batch(args, rank):
@@ -268,17 +268,23 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # roofline of the dominant (only) kernel: algorithmic bytes = 2 B x sum over alignments of (R_a+1) x L_a
-        # of THIS rank's launch / its average launch duration (CUDA events on the launch stream, in the library)
-        k_launches = sum(s["kernel_launches"] for s in res_stats)
-        alg_bytes_per_launch = 2.0 * cells * len(res_stats) / max(k_launches, 1)
+        # roofline of the dominant kernel (fill_kernel: it alone writes the DP cells).  A pass is thousands of small
+        # launches of four kernels on dozens of streams, so the unit here is one PASS (= one step): algorithmic bytes
+        # = 2 B x sum over the pass's alignments of (R_a+1) x L_a of THIS rank, divided by the device time of the
+        # whole pass (CUDA events on the launch stream, in the library) — i.e. the fill is charged with the traceback /
+        # update / sort kernels it waits for.  The fill kernel's own figure (ncu launch list) is in profiles/.
+        k_launches = len(res_stats)
+        alg_bytes_per_launch = 2.0 * cells
         k_avg_s = kern_ms / 1e3 / max(k_launches, 1)
         achieved = alg_bytes_per_launch / k_avg_s / 1e9
+        # DRAM traffic of the fill kernel per pass: bytes per DP cell measured once with `ncu --set full`
+        # (dram__bytes_read.sum + dram__bytes_write.sum of one fill_kernel launch / the cells that launch filled,
+        # profiles/traffic.json) x the cells of this pass
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                traffic = float(json.load(open(tpath))["fill_dram_bytes_per_cell"]) * cells
             except Exception:
                 traffic = None
         line = {
@@ -297,7 +303,9 @@ def main():
                     "kernel_ms": e2e_stats[-1]["kernel_ms"], "d2h_ms": e2e_stats[-1]["d2h_ms"]},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "poa_window_kernel",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fill_kernel, charged with the whole lockstep pass (trace/update/sort/fill)",
+                         "launch_unit": "one pass = one step (all kernel launches of a vgc_polish_resident call)",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "dp_cells_per_launch": cells, "kernel_ms_per_launch": k_avg_s * 1e3,
                          "gcups": cells / k_avg_s / 1e9},

@@ -111,11 +111,9 @@ struct HostEx {
       for (uint32_t j = 1; j <= len; ++j) row[j] = INT32_MIN;
       for (uint32_t p = 0; p < np; ++p) {
         uint32_t pr;
+        const U4 er = {sl.rowprog[4 * r], sl.rowprog[4 * r + 1], sl.rowprog[4 * r + 2], sl.rowprog[4 * r + 3]};
         if (npred == 0) pr = 0;
-        else if (p == 0) pr = sl.rowprog[4 * r + 1];
-        else if (p == 1) pr = sl.rowprog[4 * r + 2];
-        else if (npred == 3) pr = sl.rowprog[4 * r + 3];
-        else pr = sl.ovf[sl.rowprog[4 * r + 3] + p - 2];
+        else pr = rec_pred(er, r + 1, p, sl.ovf);
         fcv = std::max(fcv, H(pr, 0));
         for (uint32_t j = 1; j <= len; ++j) {
           const int32_t s = codes_[j - 1] == code ? sc.m : sc.x;

@@ -28,7 +28,7 @@ def lib():
         if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)
             subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", csrc,
-                            "-o", OUT, SRC], check=True)
+                            "-o", OUT, SRC, "-lpthread"], check=True)
         _lib = C.CDLL(OUT)
         _lib.hm_polish.restype = C.c_int
         _lib.hm_polish.argtypes = [C.POINTER(VgcBatch), C.POINTER(VgcParams), C.POINTER(VgcResult), C.c_int, C.c_int,

@@ -46,7 +46,7 @@ def build_engine(force=False, verbose=False):
     out = os.path.join(LIB_DIR, "libvgc.so")
     srcs = [os.path.join(CSRC, "vgc_engine.cu")]
     if force or _stale(out, engine_sources()):
-        cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", out] + srcs + ["-lcudart"]
+        cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", out] + srcs + ["-lcudart", "-lpthread"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         _run(cmd)

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "poa_core.h"
@@ -65,7 +66,8 @@ struct Prepared {
   uint64_t out_total = 0;
 };
 
-// Returns VGC_OK or VGC_ERR_INVALID / VGC_ERR_CAPACITY with a message.
+// Returns VGC_OK or VGC_ERR_INVALID / VGC_ERR_CAPACITY with a message.  Windows are independent, so the
+// per-window part runs on a few host threads (the reference does the same work inside its per-window tasks).
 inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out, std::string* err) {
   const uint32_t nw = b->n_windows, nl = b->n_layers;
   if (p->gap > 0 || (p->num_prune == 0 && p->haplotype)) {
@@ -91,124 +93,149 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
   out->win_max_len.assign(nw, 0);
   out->win_nfill.assign(nw, 0);
   out->device_windows.clear();
+  out->max_len = 0;
+  out->max_nodes_ub = 0;
+  const double* qv = quality_value_lut();  // initialise the table before the threads start
+
+  struct Part {
+    int rc = VGC_OK;
+    uint32_t bad_window = 0xFFFFFFFFu;
+    std::string err;
+    bool seen[256] = {false};
+  };
+  auto run_range = [&](uint32_t w0, uint32_t w1, Part* part) {
+    std::vector<uint32_t> rank;
+    auto bail = [&](uint32_t w, int rc, const char* msg) {
+      part->rc = rc;
+      part->bad_window = w;
+      part->err = msg;
+    };
+    for (uint32_t w = w0; w < w1; ++w) {
+      const uint32_t f = b->win_first[w], l = b->win_first[w + 1];
+      if (l <= f) return bail(w, VGC_ERR_INVALID, "window without a backbone");
+      const uint64_t blen64 = b->seq_off[f + 1] - b->seq_off[f];
+      if (blen64 == 0 || blen64 > 65535)  // createWindow (window.cpp:22-27); uint16 loop counters (:216,:232)
+        return bail(w, VGC_ERR_INVALID, "empty or oversized backbone");
+      const uint32_t blen = static_cast<uint32_t>(blen64);
+      if (!b->has_qual[f] || !b->quals) return bail(w, VGC_ERR_INVALID, "backbone must carry a quality (real or dummy)");
+      rank.clear();
+      rank.push_back(f);
+      uint64_t sum_len = blen;
+      uint32_t max_len = blen;
+      for (uint32_t i = f + 1; i < l; ++i) {
+        const uint64_t len = b->seq_off[i + 1] - b->seq_off[i];
+        const uint32_t bg = b->begin[i], en = b->end[i];
+        if (len == 0 || bg == en) continue;  // add_layer returns silently (window.cpp:51-54)
+        if (bg >= en || bg > blen || en > blen)
+          return bail(w, VGC_ERR_INVALID, "layer begin and end positions are invalid");  // window.cpp:62-67
+        if (len > 65535) return bail(w, VGC_ERR_INVALID, "layer longer than 65535");
+        if (b->has_qual[i] && !b->quals) return bail(w, VGC_ERR_INVALID, "has_qual set but quals is NULL");
+        rank.push_back(i);
+        sum_len += len;
+        max_len = std::max<uint32_t>(max_len, static_cast<uint32_t>(len));
+      }
+      const uint32_t nseq = static_cast<uint32_t>(rank.size());
+      out->win_nseq[w] = nseq;
+      std::sort(rank.begin() + 1, rank.end(),
+                [&](uint32_t lhs, uint32_t rhs) { return b->begin[lhs] < b->begin[rhs]; });
+      std::copy(rank.begin(), rank.end(), out->layer_rank.begin() + f);
+      // alphabet: which bytes occur
+      for (uint32_t j = 0; j < nseq; ++j) {
+        const uint8_t* s = b->bases + b->seq_off[rank[j]];
+        const uint64_t len = b->seq_off[rank[j] + 1] - b->seq_off[rank[j]];
+        for (uint64_t k = 0; k < len; ++k) part->seen[s[k]] = true;
+      }
+      // output capacity: < 3 sequences -> the backbone itself; otherwise nodes touched by an alignment
+      if (nseq < 3) {
+        out->out_cap[w] = blen;
+      } else {
+        out->out_cap[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 2ull * max_len + 2ull * blen + 64));
+        out->win_work[w] = sum_len * static_cast<uint64_t>(blen) * (p->haplotype ? 3 : 1) * nseq / 8 + 1;
+        out->win_sum_len[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 0xFFFFFFFFu));
+        out->win_max_len[w] = max_len;
+        // fills of the window program (poa_core.h step_update): build + realign rounds + final, or build only
+        out->win_nfill[w] = p->haplotype ? (nseq - 1) + (p->num_prune - 1) * nseq + 1 : (nseq - 1);
+      }
+      // average_weight (haplotype mode only): fp64 sum in rank order (window.cpp:215-309).  The addend
+      // 1 - pow(10, (33 - q) / 10.0) is a pure function of the quality byte: tabulate it once (same libm, same
+      // expression) and add the tabulated doubles in the reference's order — bit-identical, ~100x fewer pow calls.
+      if (p->haplotype && nseq >= 3) {
+        double total = 0.0;
+        bool if_fasta = false;
+        const uint16_t window_len = static_cast<uint16_t>(blen);
+        if (b->win_flags[w] & VGC_WIN_DUMMY_QUAL) {
+          total += blen;
+          if_fasta = true;
+        } else {
+          const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[f]);
+          for (uint16_t k = 0; k < blen; ++k) total += qv[static_cast<uint8_t>(q[k])];
+        }
+        for (uint32_t j = 1; j < nseq; ++j) {
+          const uint32_t i = rank[j];
+          const uint32_t len = static_cast<uint32_t>(b->seq_off[i + 1] - b->seq_off[i]);
+          if (!b->has_qual[i]) {
+            total += len;
+          } else {
+            const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[i]);
+            for (uint16_t k = 0; k < len; ++k) total += qv[static_cast<uint8_t>(q[k])];
+          }
+        }
+        out->win_avgw[w] = if_fasta ? 2.0 * total / window_len : 2.0 * total / window_len * 1000;
+      }
+    }
+  };
+  unsigned nt = nw >= 1024 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  std::vector<Part> parts(nt);
+  if (nt == 1) {
+    run_range(0, nw, &parts[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+      const uint32_t w0 = static_cast<uint32_t>(static_cast<uint64_t>(nw) * t / nt);
+      const uint32_t w1 = static_cast<uint32_t>(static_cast<uint64_t>(nw) * (t + 1) / nt);
+      th.emplace_back(run_range, w0, w1, &parts[t]);
+    }
+    for (auto& x : th) x.join();
+  }
+  for (const Part& part : parts) {  // ranges are in window order: the first failing window reports
+    if (part.rc != VGC_OK) {
+      *err = part.err;
+      return part.rc;
+    }
+  }
+  // alphabet: A C G T fixed, then every other byte that occurs, in byte order (the numbering is internal: codes are
+  // only compared for equality and decoded back, so it does not need the reference's first-seen order)
   std::memset(out->coder, 0xFF, sizeof(out->coder));
   std::memset(out->decoder, 0, sizeof(out->decoder));
-  // fixed part of the alphabet, then first-seen order for anything else
   const char* acgt = "ACGT";
   for (int i = 0; i < 4; ++i) {
     out->coder[static_cast<uint8_t>(acgt[i])] = static_cast<uint8_t>(i);
     out->decoder[i] = static_cast<uint8_t>(acgt[i]);
   }
   out->num_codes = 4;
+  for (int c = 0; c < 256; ++c) {
+    bool seen = false;
+    for (const Part& part : parts) seen = seen || part.seen[c];
+    if (!seen || out->coder[c] != 0xFF) continue;
+    if (c >= 128) {
+      *err = "base byte >= 128";
+      return VGC_ERR_INVALID;
+    }
+    if (out->num_codes >= static_cast<uint32_t>(kMaxCodes)) {
+      *err = "more than 8 distinct base bytes in one batch";
+      return VGC_ERR_CAPACITY;
+    }
+    out->coder[c] = static_cast<uint8_t>(out->num_codes);
+    out->decoder[out->num_codes++] = static_cast<uint8_t>(c);
+  }
   uint64_t out_total = 0;
-  std::vector<uint32_t> rank;
   for (uint32_t w = 0; w < nw; ++w) {
-    const uint32_t f = b->win_first[w], l = b->win_first[w + 1];
-    if (l <= f) {
-      *err = "window without a backbone";
-      return VGC_ERR_INVALID;
-    }
-    const uint64_t blen64 = b->seq_off[f + 1] - b->seq_off[f];
-    if (blen64 == 0 || blen64 > 65535) {  // createWindow (window.cpp:22-27); uint16 loop counters (:216,:232)
-      *err = "empty or oversized backbone";
-      return VGC_ERR_INVALID;
-    }
-    const uint32_t blen = static_cast<uint32_t>(blen64);
-    if (!b->has_qual[f] || !b->quals) {
-      *err = "backbone must carry a quality (real or dummy)";
-      return VGC_ERR_INVALID;
-    }
-    rank.clear();
-    rank.push_back(f);
-    uint64_t sum_len = blen;
-    uint32_t max_len = blen;
-    for (uint32_t i = f + 1; i < l; ++i) {
-      const uint64_t len = b->seq_off[i + 1] - b->seq_off[i];
-      const uint32_t bg = b->begin[i], en = b->end[i];
-      if (len == 0 || bg == en) continue;  // add_layer returns silently (window.cpp:51-54)
-      if (bg >= en || bg > blen || en > blen) {
-        *err = "layer begin and end positions are invalid";  // window.cpp:62-67
-        return VGC_ERR_INVALID;
-      }
-      if (len > 65535) {
-        *err = "layer longer than 65535";
-        return VGC_ERR_INVALID;
-      }
-      if (b->has_qual[i] && !b->quals) {
-        *err = "has_qual set but quals is NULL";
-        return VGC_ERR_INVALID;
-      }
-      rank.push_back(i);
-      sum_len += len;
-      max_len = std::max<uint32_t>(max_len, static_cast<uint32_t>(len));
-    }
-    const uint32_t nseq = static_cast<uint32_t>(rank.size());
-    out->win_nseq[w] = nseq;
-    std::sort(rank.begin() + 1, rank.end(),
-              [&](uint32_t lhs, uint32_t rhs) { return b->begin[lhs] < b->begin[rhs]; });
-    std::copy(rank.begin(), rank.end(), out->layer_rank.begin() + f);
-    // alphabet
-    for (uint32_t j = 0; j < nseq; ++j) {
-      const uint8_t* s = b->bases + b->seq_off[rank[j]];
-      const uint64_t len = b->seq_off[rank[j] + 1] - b->seq_off[rank[j]];
-      for (uint64_t k = 0; k < len; ++k) {
-        const uint8_t c = s[k];
-        if (out->coder[c] == 0xFF) {
-          if (c >= 128) {
-            *err = "base byte >= 128";
-            return VGC_ERR_INVALID;
-          }
-          if (out->num_codes >= static_cast<uint32_t>(kMaxCodes)) {
-            *err = "more than 8 distinct base bytes in one batch";
-            return VGC_ERR_CAPACITY;
-          }
-          out->coder[c] = static_cast<uint8_t>(out->num_codes);
-          out->decoder[out->num_codes++] = c;
-        }
-      }
-    }
-    // output capacity: < 3 sequences -> the backbone itself; otherwise nodes touched by an alignment
     out->out_off[w] = out_total;
-    if (nseq < 3) {
-      out->out_cap[w] = blen;
-    } else {
-      out->out_cap[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 2ull * max_len + 2ull * blen + 64));
-      out->device_windows.push_back(w);
-      out->max_len = std::max(out->max_len, max_len);
-      out->max_nodes_ub = std::max(out->max_nodes_ub, sum_len);
-      out->win_work[w] = sum_len * static_cast<uint64_t>(blen) * (p->haplotype ? 3 : 1) * nseq / 8 + 1;
-      out->win_sum_len[w] = static_cast<uint32_t>(std::min<uint64_t>(sum_len, 0xFFFFFFFFu));
-      out->win_max_len[w] = max_len;
-      // fills of the window program (poa_core.h advance()): build + realign rounds + final, or build only
-      out->win_nfill[w] = p->haplotype ? (nseq - 1) + (p->num_prune - 1) * nseq + 1 : (nseq - 1);
-    }
     out_total += out->out_cap[w];
-    // average_weight (haplotype mode only): fp64 sum in rank order (window.cpp:215-309).  The addend
-    // 1 - pow(10, (33 - q) / 10.0) is a pure function of the quality byte: tabulate it once (same libm, same
-    // expression) and add the tabulated doubles in the reference's order — bit-identical, ~100x fewer pow calls.
-    if (p->haplotype && nseq >= 3) {
-      const double* qv = quality_value_lut();
-      double total = 0.0;
-      bool if_fasta = false;
-      const uint16_t window_len = static_cast<uint16_t>(blen);
-      if (b->win_flags[w] & VGC_WIN_DUMMY_QUAL) {
-        total += blen;
-        if_fasta = true;
-      } else {
-        const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[f]);
-        for (uint16_t k = 0; k < blen; ++k) total += qv[static_cast<uint8_t>(q[k])];
-      }
-      for (uint32_t j = 1; j < nseq; ++j) {
-        const uint32_t i = rank[j];
-        const uint32_t len = static_cast<uint32_t>(b->seq_off[i + 1] - b->seq_off[i]);
-        if (!b->has_qual[i]) {
-          total += len;
-        } else {
-          const char* q = reinterpret_cast<const char*>(b->quals + b->seq_off[i]);
-          for (uint16_t k = 0; k < len; ++k) total += qv[static_cast<uint8_t>(q[k])];
-        }
-      }
-      out->win_avgw[w] = if_fasta ? 2.0 * total / window_len : 2.0 * total / window_len * 1000;
+    if (out->win_nseq[w] >= 3) {
+      out->device_windows.push_back(w);
+      out->max_len = std::max(out->max_len, out->win_max_len[w]);
+      out->max_nodes_ub = std::max<uint64_t>(out->max_nodes_ub, out->win_sum_len[w]);
     }
   }
   out->out_total = out_total;

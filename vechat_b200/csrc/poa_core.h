@@ -149,16 +149,32 @@ struct Slot {
   uint32_t aln_cap;
 };
 
-// rowprog meta word: code (bits 0-3) | sink (bit 4) | number of predecessors (bits 5-15) | node id (bits 16-31,
-// meaningful while the slot holds fewer than 65536 nodes; the traceback reads it instead of a table in HBM)
+// Row program record (16 B per DP row, rank order):
+//   x = meta: code (bits 0-3) | sink (4) | inline (5) | number of predecessors (6-15) | node id (16-31; meaningful
+//       while the slot holds fewer than 65536 nodes — the traceback reads it instead of a table in HBM)
+//   inline (<= 6 predecessors, every one within 65535 rows): y, z, w = six 16-bit row DISTANCES d_p (predecessor
+//       p is row - d_p), in-edge order; a node without in-edges has the virtual row 0 as its only predecessor
+//       (np = 0, d_0 = its own row)
+//   otherwise: w = offset into ovf[] holding the np predecessor rows
 constexpr uint32_t kMetaSink = 1u << 4;
-constexpr uint32_t kMetaMaxPred = 2047;
-VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, uint32_t node) {
-  return code | (sink ? kMetaSink : 0u) | (npred << 5) | (node << 16);
+constexpr uint32_t kMetaInline = 1u << 5;
+constexpr uint32_t kMetaMaxPred = 1023;
+constexpr uint32_t kInlinePreds = 6;
+VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, bool inl, uint32_t node) {
+  return code | (sink ? kMetaSink : 0u) | (inl ? kMetaInline : 0u) | (npred << 6) | (node << 16);
 }
 VGC_HD VGC_INL uint32_t meta_code(uint32_t m) { return m & 0xFu; }
-VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 5) & 0x7FFu; }
+VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 6) & 0x3FFu; }
 VGC_HD VGC_INL uint32_t meta_node(uint32_t m) { return m >> 16; }
+// predecessor p of the row `row` whose record is `e`
+VGC_HD VGC_INL uint32_t rec_delta(const U4& e, uint32_t p) {
+  const uint32_t wd = p < 2 ? e.y : (p < 4 ? e.z : e.w);
+  return (p & 1u) ? (wd >> 16) : (wd & 0xFFFFu);
+}
+VGC_HD VGC_INL uint32_t rec_pred(const U4& e, uint32_t row, uint32_t p, const uint32_t* ovf) {
+  if (e.x & kMetaInline) return row - rec_delta(e, p);
+  return ovf[e.w + p];
+}
 
 // Shared per-window state (shared memory on the device).
 struct WinState {
@@ -220,7 +236,7 @@ struct RowMap {
 // matrix (kTR consecutive rows in rank space x kTW consecutive words of the lane-major row) that the thread
 // fetches with 16-byte loads whenever the walk leaves it: DRAM latency is paid once per tile, not once per step.
 // Pairs are appended in reverse (end of the alignment first).
-constexpr int kTR = 32;  // tile rows (ranks ti, ti-1, ..)
+constexpr int kTR = 24;  // tile rows (ranks ti, ti-1, ..)
 constexpr int kTW = 16;  // tile words per row
 enum : int { kWalkStep = 0, kWalkMiss = 1, kWalkDone = 2, kWalkBad = 3 };
 
@@ -246,7 +262,7 @@ struct TraceWalker {
   int32_t h;
   U4 rec;
   uint32_t sb;             // seq[j - 1] (the base of DP column j), valid while j >= 1
-  uint32_t ti, wb;
+  uint32_t ti, wb, rec_base;  // tile anchor row, first word, row of tr[0]
   bool have, fresh, started;
 
   VGC_HD VGC_INL static uint64_t pack_decoder(const uint8_t* decoder) {
@@ -267,6 +283,7 @@ struct TraceWalker {
     rec = U4{0, 0, 0, 0};
     sb = col ? seq[col - 1] : 0u;
     ti = wb = 0;
+    rec_base = 1;
     have = fresh = started = false;
   }
 
@@ -280,20 +297,32 @@ struct TraceWalker {
     if (b + kTW > half_words) b = half_words - kTW;
     wb = b;
 #ifdef __CUDA_ARCH__
-    // asynchronous 16-byte copies global -> shared (LDGSTS): no registers are tied up, so every load of the tile
-    // is in flight at once and the refill costs one DRAM round trip
-    for (uint32_t r = 0; r < static_cast<uint32_t>(kTR); ++r) {
-      if (r > ti) break;
-      const uint32_t row = ti - r;
-      const uint32_t* src = H + static_cast<uint64_t>(row) * rw + wb;
-      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(th + r * kTW));
+    // asynchronous 16-byte copies global -> shared (cp.async, SASS LDGSTS): no registers are tied up, so every
+    // load of the tile is in flight at once and the refill costs one DRAM round trip.  (Per-thread TMA bulk copies
+    // were measured 2x slower here: a tile is ~30 small pieces and the bulk-copy unit serialises them.)
+    const uint32_t nrows = ti + 1 < static_cast<uint32_t>(kTR) ? ti + 1 : static_cast<uint32_t>(kTR);
+    const uint32_t nrec = ti < static_cast<uint32_t>(kTR) ? ti : static_cast<uint32_t>(kTR);  // rows >= 1 have a record
+    {
+      const uint32_t* src = H + static_cast<uint64_t>(ti) * rw + wb;
+      uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(th));
+#pragma unroll 2
+      for (uint32_t r = 0; r < nrows; ++r) {
 #pragma unroll
-      for (int q = 0; q < kTW / 4; ++q)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 4) : "memory");
-      const uint32_t rdst = static_cast<uint32_t>(__cvta_generic_to_shared(tr + r));
-      if (row) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rdst), "l"(rp + (row - 1)) : "memory");
-      else tr[r] = U4{0, 0, 0, 0};
+        for (int q = 0; q < kTW / 4; ++q)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 4) : "memory");
+        src -= rw;
+        dst += kTW * 4;
+      }
+      // records of rows ti - nrec + 1 .. ti (record of row r is rp[r - 1]); tr[q] = record of row ti - nrec + 1 + q
+      const U4* rsrc = rp + (ti - nrec);
+      uint32_t rdst = static_cast<uint32_t>(__cvta_generic_to_shared(tr));
+      for (uint32_t q = 0; q < nrec; ++q) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rdst), "l"(rsrc) : "memory");
+        rsrc += 1;
+        rdst += 16;
+      }
     }
+    rec_base = ti - nrec + 1;
     asm volatile("cp.async.wait_all;" ::: "memory");
 #else
     for (uint32_t r = 0; r < static_cast<uint32_t>(kTR); ++r) {
@@ -302,7 +331,11 @@ struct TraceWalker {
       const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(row) * rw + wb);
       U4* dst = reinterpret_cast<U4*>(th + r * kTW);
       for (int q = 0; q < kTW / 4; ++q) dst[q] = src[q];
-      tr[r] = row ? rp[row - 1] : U4{0, 0, 0, 0};
+    }
+    {
+      const uint32_t nrec = ti < static_cast<uint32_t>(kTR) ? ti : static_cast<uint32_t>(kTR);
+      rec_base = ti - nrec + 1;
+      for (uint32_t q = 0; q < nrec; ++q) tr[q] = rp[rec_base + q - 1];
     }
 #endif
     have = true;
@@ -328,16 +361,13 @@ struct TraceWalker {
   }
   VGC_HD VGC_INL U4 rec_of(uint32_t row) const {
     if (row == 0) return U4{0, 0, 0, 0};
-    const uint32_t dr = ti - row;
-    if (have && dr < static_cast<uint32_t>(kTR)) return tr[dr];
+    const uint32_t q = row - rec_base;
+    if (have && row <= ti && q < static_cast<uint32_t>(kTR)) return tr[q];
     return rp[row - 1];
   }
   VGC_HD VGC_INL uint32_t pred(uint32_t np, uint32_t p) const {
     if (np == 0) return 0u;  // no in-edges: the virtual row 0 is the predecessor
-    if (p == 0) return rec.y;
-    if (p == 1) return rec.z;
-    if (np == 3) return rec.w;
-    return ovf[rec.w + p - 2];
+    return rec_pred(rec, i, p, ovf);
   }
 
   VGC_HD VGC_INL int step() {
@@ -355,36 +385,62 @@ struct TraceWalker {
       if (i == 0 && j == 0) return kWalkDone;
     }
     const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
-    if (i != 0 && j >= 2 && np <= 2) {
-      // ---- fast path (at most two predecessors, away from the borders): all five candidate cells and both
-      //      predecessor records are read from the tile at once and the first match in priority order is
-      //      selected without branching, so the 32 walks of a warp stay converged
+    if (i != 0 && j >= 2 && (rec.x & kMetaInline)) {
+      // ---- fast path (<= 6 predecessors inline, away from the borders): every candidate cell is read from the
+      //      tile at once and the first match in the reference's priority order (diagonals in in-edge order,
+      //      verticals in in-edge order, horizontal) is selected without branching, so the 32 walks of a warp
+      //      stay converged
       const uint32_t nb = seq[j - 2];  // base of DP column j - 1, consumed when the move changes the column
-      const uint32_t p0 = np ? rec.y : 0u;
-      const uint32_t p1 = np == 2 ? rec.z : p0;
+      const uint32_t npp = np ? np : 1u;
+      uint32_t dl[kInlinePreds];
+#pragma unroll
+      for (uint32_t p = 0; p < kInlinePreds; ++p) dl[p] = rec_delta(rec, p);
+      uint32_t maxd = dl[0];
+#pragma unroll
+      for (uint32_t p = 1; p < kInlinePreds; ++p) maxd = dl[p] > maxd ? dl[p] : maxd;
       const uint32_t c1 = j - 1, c0 = j - 2;
       const uint32_t hi1 = c1 >= half_words ? 1u : 0u, hi0 = c0 >= half_words ? 1u : 0u;
       const uint32_t dq1 = (hi1 ? c1 - half_words : c1) - wb, dq0 = (hi0 ? c0 - half_words : c0) - wb;
-      const uint32_t dr0 = ti - p0, dr1 = ti - p1, dri = ti - i;
+      const uint32_t dri = ti - i;
       const uint32_t TRu = static_cast<uint32_t>(kTR), TWu = static_cast<uint32_t>(kTW);
-      if (dq1 < TWu && dq0 < TWu && dr0 < TRu && dr1 < TRu && dri < TRu) {
-        const uint32_t* r0 = th + dr0 * kTW;
-        const uint32_t* r1 = th + dr1 * kTW;
-        const uint32_t a00 = r0[dq0], a01 = r0[dq1], a10 = r1[dq0], a11 = r1[dq1], ai0 = th[dri * kTW + dq0];
-        const U4 n0 = tr[dr0], n1 = tr[dr1];
+      if (dq1 < TWu && dq0 < TWu && dri < TRu && dri + maxd < TRu) {
+        const uint32_t* base = th + dri * kTW;
         const int32_t mcf = base_of(meta_code(rec.x)) == sb ? m : x;
-        const int32_t D0 = half_of(a00, hi0), V0 = half_of(a01, hi1), D1 = half_of(a10, hi0), V1 = half_of(a11, hi1),
-                      HH = half_of(ai0, hi0);
-        const bool d0 = h == D0 + mcf, d1 = h == D1 + mcf, v0 = h == V0 + g, v1 = h == V1 + g, hh = h == HH + g;
-        if (!(d0 || d1 || v0 || v1 || hh) || n >= aln_cap) return kWalkBad;
-        const bool diag = d0 || d1, vert = !diag && (v0 || v1);
-        const bool first = d0 || (!d1 && v0);  // the winning move goes to p0 (else p1, unless horizontal)
-        const uint32_t pi = (diag || vert) ? (first ? p0 : p1) : i;
-        const int32_t hn = d0 ? D0 : d1 ? D1 : v0 ? V0 : v1 ? V1 : HH;
-        aln_node[n] = (diag || vert) ? static_cast<int32_t>(nodes ? nodes[i - 1] : meta_node(rec.x)) : -1;
+        const int32_t HH = half_of(base[dq0], hi0);
+        int32_t D[kInlinePreds], V[kInlinePreds];
+#pragma unroll
+        for (uint32_t p = 0; p < kInlinePreds; ++p) {
+          const uint32_t* rowp = base + dl[p] * kTW;
+          D[p] = half_of(rowp[dq0], hi0);
+          V[p] = half_of(rowp[dq1], hi1);
+        }
+        // lowest candidate index wins: scan from the back
+        int32_t sel = (h == HH + g) ? 12 : 13;
+        int32_t hn = HH;
+#pragma unroll
+        for (int p = static_cast<int>(kInlinePreds) - 1; p >= 0; --p) {
+          if (static_cast<uint32_t>(p) < npp && h == V[p] + g) {
+            sel = 6 + p;
+            hn = V[p];
+          }
+        }
+#pragma unroll
+        for (int p = static_cast<int>(kInlinePreds) - 1; p >= 0; --p) {
+          if (static_cast<uint32_t>(p) < npp && h == D[p] + mcf) {
+            sel = p;
+            hn = D[p];
+          }
+        }
+        if (sel == 13 || n >= aln_cap) return kWalkBad;
+        const bool horiz = sel == 12, vert = sel >= 6 && sel < 12;
+        uint32_t dsel = 0;
+#pragma unroll
+        for (uint32_t p = 0; p < kInlinePreds; ++p) dsel = (static_cast<uint32_t>(sel) == p || static_cast<uint32_t>(sel) == 6 + p) ? dl[p] : dsel;
+        const uint32_t pi = i - dsel;  // horizontal: dsel = 0
+        aln_node[n] = horiz ? -1 : static_cast<int32_t>(nodes ? nodes[i - 1] : meta_node(rec.x));
         aln_pos[n] = vert ? -1 : static_cast<int32_t>(j - 1);
         ++n;
-        if (diag || vert) rec = first ? n0 : n1;
+        if (!horiz) rec = pi ? tr[pi - rec_base] : U4{0, 0, 0, 0};
         i = pi;
         if (!vert) {
           j = j - 1;
@@ -464,6 +520,10 @@ struct Poa {
   Scores nw;      // NW engine scores (params)
   Scores sw;      // SW engine: 3/-5/-4 hard-wired (window.cpp:326)
   using RM = RowMap<K>;
+  // staged graph of the last sort_graph() of this step (executor fast storage): records + 16-bit adjacency
+  bool staged = false;
+  const uint32_t* st_rec = nullptr;
+  const uint16_t* st_adj = nullptr;
 
   VGC_HD Poa(Ex& e, const BatchView& b, Slot& s, WinState& w, Scores nw_) : ex(e), bv(b), sl(s), ws(w), nw(nw_) {
     sw.m = 3;
@@ -602,7 +662,7 @@ struct Poa {
 
   template <bool SUB, class StkT>
   VGC_HD uint32_t toposort_fast(uint32_t* rec, const uint16_t* adj, StkT* stack, uint32_t stack_cap, uint32_t* dst,
-                                bool* overflow) {
+                                uint32_t* rank_of, bool* overflow) {
     const uint32_t nV = G().nV;
     uint32_t n = 0, sp = 0;
     *overflow = false;
@@ -651,10 +711,12 @@ struct Poa {
         if (valid) {
           rec[curr] = r | kRDone;
           if (primary) {
+            rank_of[curr] = n;
             dst[n++] = curr;
             for (uint32_t i = 0; i < nal; ++i) {
               const uint32_t a = adj[off + nin + i];
               if (SUB && !(rec[a] & kRMember)) continue;
+              rank_of[a] = n;
               dst[n++] = a;
             }
           }
@@ -735,15 +797,15 @@ struct Poa {
       if (fast) {
         if (sub) {
           extract_fast(rec, adj16, gstack, sub_end, sub_begin);
-          n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, &ovf);
+          n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf);
         } else {
-          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, &ovf);
+          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf);
         }
         if (ovf) {
           // deep recursion: redo with the big stack in HBM (records: clear the marks, keep membership)
           for (uint32_t v = 0; v < nV; ++v) rec[v] &= ~(kRExpanded | kRDone | kRIgnored);
-          if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, &ovf);
-          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, &ovf);
+          if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf);
+          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf);
         }
       } else {
         if (sub) extract_impl<uint32_t>(fl, goff, gadj, gstack, sub_end, sub_begin);
@@ -753,6 +815,9 @@ struct Poa {
     }
     ex.sync();
     const uint32_t n = ws.scratch[0];
+    staged = fast;  // the row-program builder reads the adjacency (and the ranks the sort wrote) from here
+    st_rec = rec;
+    st_adj = adj16;
     if (sub) {
       // keep the membership where the row-program builder can see it
       for (uint32_t v = L; v < nV; v += W) sl.flags[v] = fast ? ((rec[v] & kRMember) ? kFMember : 0) : (fl[v] & kFMember);
@@ -782,35 +847,51 @@ struct Poa {
         }
       }
     }
-    for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.rank_of[order[r]] = r;
+    // with a staged sort the DFS wrote rank_of itself and the in-tails are in the staged adjacency (same order)
+    const bool st = staged;
+    if (!st) {
+      for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.rank_of[order[r]] = r;
+    }
     ex.sync();
-    // DP rows live in rank space: row = rank + 1 (0 = the virtual row), predecessors are given as rows
+    // DP rows live in rank space: row = rank + 1 (0 = the virtual row)
     for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
       const uint32_t v = order[r];
-      uint32_t np = 0, p0 = 0, p1 = 0, p2 = 0;
-      const uint32_t b = v * S, e = v * S + g.nin[v];
+      const uint32_t row = r + 1;
+      uint32_t np = 0, far = 0;
+      uint32_t d[kInlinePreds] = {row, row, row, row, row, row};  // np == 0: the virtual row, d_0 = row
+      const uint32_t rv = st ? st_rec[v] : 0u;
+      const uint32_t b = st ? (rv & 0xFFFFu) : v * S;
+      const uint32_t e = b + (st ? ((rv >> 16) & 63u) : g.nin[v]);
       for (uint32_t i = b; i < e; ++i) {
-        const uint32_t t = g.itail[i];
-        if (sub && !(sl.flags[t] & kFMember)) continue;
-        const uint32_t row = sl.rank_of[t] + 1;
-        if (np == 0) p0 = row;
-        if (np == 1) p1 = row;
-        if (np == 2) p2 = row;
+        const uint32_t t = st ? static_cast<uint32_t>(st_adj[i]) : g.itail[i];
+        if (sub && !(st ? (st_rec[t] & kRMember) != 0 : (sl.flags[t] & kFMember) != 0)) continue;
+        const uint32_t dist = row - (sl.rank_of[t] + 1);
+        if (np < kInlinePreds) d[np] = dist;
+        far |= dist > 0xFFFFu ? 1u : 0u;
         ++np;
       }
-      if (np > 3) {
-        const uint32_t o = ex.atomic_add(&ws.ovf_n, np - 2);
-        uint32_t k = 0, q = 0;
-        for (uint32_t i = b; i < e; ++i) {
+      const bool inl = np <= kInlinePreds && !far && row <= 0xFFFFu;
+      U4 rec;
+      if (inl) {
+        const uint32_t fill_d = d[0];  // unused slots repeat the first predecessor (harmless duplicates)
+        for (uint32_t q = np ? np : 1u; q < kInlinePreds; ++q) d[q] = fill_d;
+        rec.y = d[0] | (d[1] << 16);
+        rec.z = d[2] | (d[3] << 16);
+        rec.w = d[4] | (d[5] << 16);
+      } else {
+        const uint32_t o = ex.atomic_add(&ws.ovf_n, np);
+        uint32_t k = 0;
+        for (uint32_t i = v * S; i < v * S + g.nin[v]; ++i) {
           const uint32_t t = g.itail[i];
           if (sub && !(sl.flags[t] & kFMember)) continue;
-          if (q++ > 1) sl.ovf[o + k++] = sl.rank_of[t] + 1;
+          sl.ovf[o + k++] = sl.rank_of[t] + 1;
         }
-        p2 = o;  // predecessor p (>= 2) is ovf[p2 + p - 2]
+        rec.y = rec.z = 0;
+        rec.w = o;
       }
       const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
       if (np > kMetaMaxPred) fail(kStDegreeOverflow);
-      U4 rec = {meta_pack(g.code[v], np, sink, v), p0, p1, p2};
+      rec.x = meta_pack(g.code[v], np, sink, inl, v);
       *reinterpret_cast<U4*>(sl.rowprog + 4 * static_cast<size_t>(r)) = rec;
     }
     ex.sync();
@@ -1394,6 +1475,7 @@ struct Poa {
     if (ex.leader()) ws.t_last = ex.clock();
     const uint32_t prep = ws.prep;
     uint32_t nMain = ws.nMain;
+    staged = false;
     if (prep & kPrepLargest) {
       largest_subgraph();
       tick(kPhLargest);

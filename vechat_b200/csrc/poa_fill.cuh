@@ -145,7 +145,8 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
           pr[k + 1] = t.y;
         }
       }
-      const uint32_t p0 = np == 0 ? 0u : e.y;
+      const U4 er = {e.x, e.y, e.z, e.w};
+      const uint32_t p0 = np == 0 ? 0u : rec_pred(er, row, 0, sl.ovf);
       int32_t fcmax;
       if (np <= 1 && p0 == prev_row) {
         // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
@@ -164,9 +165,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
         for (uint32_t p = 0; p < npp; ++p) {
           uint32_t prow;
           if (p == 0) prow = p0;
-          else if (p == 1) prow = e.z;
-          else if (np == 3) prow = e.w;
-          else prow = sl.ovf[e.w + p - 2];
+          else prow = rec_pred(er, row, p, sl.ovf);
           uint32_t u[K];
           int32_t fcp;
           int hit = -1;

@@ -220,7 +220,7 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
 // shared memory; the warp alternates between a refill phase (the lanes whose walk left their tile fetch a new
 // one, all loads in flight together) and a walk phase of up to kTraceRound steps out of shared memory.
 // shared memory: coder[256] | 32 x { tile cells kTR x kTW words | tile records kTR x 16 B | pad }
-constexpr uint32_t kTraceLaneWords = kTR * kTW + kTR * 4 + 4;  // = 4 mod 32: 16-byte aligned, banks spread
+constexpr uint32_t kTraceLaneWords = kTR * kTW + kTR * 4 + 4;  // 16-byte aligned, lanes' banks spread
 constexpr uint32_t kTraceSmem = 256 + 32 * kTraceLaneWords * 4;
 constexpr int kTraceRound = 8;
 
