@@ -312,8 +312,12 @@ def main():
             "clocks": sampler.summary(),
         }
         ph = eng.phase_profile()
-        tot_ph = sum(ph.values()) or 1.0
-        line["phase_share"] = {k: round(v / tot_ph, 4) for k, v in ph.items()}
+        # per-window latency shares (leader-lane / walker cycles summed over windows): diagnostics, not device time.
+        # trace_refill is a sub-interval of traceback and trace_refills a count: both are left out of the total
+        tot_ph = sum(v for k, v in ph.items() if k not in ("trace_refill", "trace_refills")) or 1.0
+        line["phase_share"] = {k: round(v / tot_ph, 4) for k, v in ph.items() if k != "trace_refills"}
+        line["phase_raw"] = {k: float(v) for k, v in ph.items()}
+        line["alignments"] = int(res_stats[-1]["alignments"])
         if world == 1 and not args.no_cpu_baseline:
             kind, cores, sb, fn = cpu_leg(batch, params, args.cpu_seconds)
             t0 = time.perf_counter()

@@ -120,8 +120,9 @@ int vgc_upload(vgc_handle h, const vgc_batch* batch);
 int vgc_polish_resident(vgc_handle h, vgc_result* result, vgc_stats* stats);
 
 /* Diagnostics: cycles the window leader lane spent per phase in the last polish call, summed over windows.
- * Index: 0 csr, 1 toposort, 2 row program, 3 DP fill, 4 traceback, 5 AddAlignment, 6 AddWeights, 7 PruneGraph,
- * 8 LargestSubgraph, 9 emit/consensus, 10 other. */
+ * Index: 0 traceback cycles spent in tile-refill phases (part of 4), 1 toposort, 2 row program, 3 DP fill,
+ * 4 traceback, 5 AddAlignment, 6 AddWeights, 7 PruneGraph, 8 LargestSubgraph, 9 emit/consensus,
+ * 10 number of traceback tile refills (a count, not cycles). */
 int vgc_phase_profile(vgc_handle h, double out[16]);
 
 const char* vgc_last_error(void);

@@ -73,3 +73,13 @@ def test_host_model_fuzz_vs_oracle(seed):
     batch = fuzz_batch(seed, **kw)
     p = make_params(**pkw)
     assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d %r %r" % (seed, kw, pkw))
+
+
+def test_threaded_host_prep_matches_oracle():
+    """>= 1024 windows: prepare_batch (rank sort, average weights, alphabet) runs on several host threads; the
+    result must not depend on the split."""
+    batch = fuzz_batch(311, n_windows=1100, length=24, depth=4, n_frac=0.02)
+    p = make_params()
+    got = hm_polish(batch, p)
+    want = checker.oracle_polish(batch, p, threads=8)
+    assert_same(got, want, "threaded prep")

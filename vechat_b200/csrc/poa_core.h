@@ -406,47 +406,42 @@ struct TraceWalker {
       if (dq1 < TWu && dq0 < TWu && dri < TRu && dri + maxd < TRu) {
         const uint32_t* base = th + dri * kTW;
         const int32_t mcf = base_of(meta_code(rec.x)) == sb ? m : x;
-        const int32_t HH = half_of(base[dq0], hi0);
-        int32_t D[kInlinePreds], V[kInlinePreds];
+        // a candidate matches iff its 16-bit cell equals h - (its move's score): compare raw halves, no sign extension
+        const uint32_t tD = static_cast<uint32_t>(h - mcf) & 0xFFFFu, tV = static_cast<uint32_t>(h - g) & 0xFFFFu;
+        const uint32_t sh0 = hi0 * 16u, sh1 = hi1 * 16u;
+        // bit p: diagonal over predecessor p, bit 6 + p: vertical, bit 12: horizontal — the reference's priority
+        // order is the bit order, so the winner is the lowest set bit
+        uint32_t mask = (((base[dq0] >> sh0) & 0xFFFFu) == tV) ? (1u << 12) : 0u;
 #pragma unroll
         for (uint32_t p = 0; p < kInlinePreds; ++p) {
           const uint32_t* rowp = base + dl[p] * kTW;
-          D[p] = half_of(rowp[dq0], hi0);
-          V[p] = half_of(rowp[dq1], hi1);
+          mask |= (((rowp[dq0] >> sh0) & 0xFFFFu) == tD) ? (1u << p) : 0u;
+          mask |= (((rowp[dq1] >> sh1) & 0xFFFFu) == tV) ? (64u << p) : 0u;
         }
-        // lowest candidate index wins: scan from the back
-        int32_t sel = (h == HH + g) ? 12 : 13;
-        int32_t hn = HH;
-#pragma unroll
-        for (int p = static_cast<int>(kInlinePreds) - 1; p >= 0; --p) {
-          if (static_cast<uint32_t>(p) < npp && h == V[p] + g) {
-            sel = 6 + p;
-            hn = V[p];
-          }
-        }
-#pragma unroll
-        for (int p = static_cast<int>(kInlinePreds) - 1; p >= 0; --p) {
-          if (static_cast<uint32_t>(p) < npp && h == D[p] + mcf) {
-            sel = p;
-            hn = D[p];
-          }
-        }
-        if (sel == 13 || n >= aln_cap) return kWalkBad;
+        const uint32_t live = (1u << npp) - 1u;
+        mask &= live | (live << 6) | (1u << 12);
+        if (mask == 0 || n >= aln_cap) return kWalkBad;
+#ifdef __CUDA_ARCH__
+        const uint32_t sel = static_cast<uint32_t>(__ffs(static_cast<int>(mask))) - 1u;
+#else
+        uint32_t sel = 0;
+        while (!((mask >> sel) & 1u)) ++sel;
+#endif
         const bool horiz = sel == 12, vert = sel >= 6 && sel < 12;
-        uint32_t dsel = 0;
-#pragma unroll
-        for (uint32_t p = 0; p < kInlinePreds; ++p) dsel = (static_cast<uint32_t>(sel) == p || static_cast<uint32_t>(sel) == 6 + p) ? dl[p] : dsel;
-        const uint32_t pi = i - dsel;  // horizontal: dsel = 0
+        const uint32_t psel = sel >= 6 ? sel - 6 : sel;
+        const uint32_t dsel = horiz ? 0u : rec_delta(rec, psel);
+        const uint32_t pi = i - dsel;
         aln_node[n] = horiz ? -1 : static_cast<int32_t>(nodes ? nodes[i - 1] : meta_node(rec.x));
         aln_pos[n] = vert ? -1 : static_cast<int32_t>(j - 1);
         ++n;
+        // the score of the cell moved to: the compare above proved it equals h minus the move's score
+        h = (horiz || vert) ? h - g : h - mcf;
         if (!horiz) rec = pi ? tr[pi - rec_base] : U4{0, 0, 0, 0};
         i = pi;
         if (!vert) {
           j = j - 1;
           sb = nb;
         }
-        h = hn;
         fresh = false;
         return kWalkStep;
       }
@@ -686,7 +681,8 @@ struct Poa {
             *overflow = true;
             return 0;
           }
-          for (uint32_t i = 0; i < nin; ++i) {
+#pragma unroll 1
+          for (uint32_t i = 0; i < nin; ++i) {  // degrees are 1-3: an unrolled body would mostly run predicated off
             const uint32_t t = adj[off + i];
             const uint32_t rt = rec[t];
             if (SUB && !(rt & kRMember)) continue;
@@ -696,6 +692,7 @@ struct Poa {
             }
           }
           if (primary) {
+#pragma unroll 1
             for (uint32_t i = 0; i < nal; ++i) {
               const uint32_t a = adj[off + nin + i];
               const uint32_t ra = rec[a];
@@ -713,6 +710,7 @@ struct Poa {
           if (primary) {
             rank_of[curr] = n;
             dst[n++] = curr;
+#pragma unroll 1
             for (uint32_t i = 0; i < nal; ++i) {
               const uint32_t a = adj[off + nin + i];
               if (SUB && !(rec[a] & kRMember)) continue;
@@ -737,6 +735,7 @@ struct Poa {
       const uint32_t r = rec[curr];
       if (!(r & kRMember) && curr >= floor_id) {
         const uint32_t off = r & 0xFFFFu, cnt = ((r >> 16) & 63u) + ((r >> 22) & 7u);
+#pragma unroll 1
         for (uint32_t i = 0; i < cnt; ++i) stack[sp++] = adj[off + i];
         rec[curr] = r | kRMember;
       }
@@ -1202,6 +1201,7 @@ struct Poa {
           // re-scan from the first neighbour: everything before the one taken last time is visited by now
           const uint32_t v = stk[sp - 1];
           uint32_t next = kNone;
+#pragma unroll 1
           for (uint32_t c = off[v], e = off[v + 1]; c < e; ++c) {
             const uint32_t u = adj[c];
             if (!visited[u]) {

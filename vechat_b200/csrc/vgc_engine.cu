@@ -267,12 +267,16 @@ __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t 
     }
   }
   bool need_refill = false;
+  unsigned long long t_refill = 0, n_refill = 0;  // diagnostics: cycles this walk spent in refill phases / refills
   while (__any_sync(0xFFFFFFFFu, active)) {
+    const unsigned long long r0 = clock64();
     if (active && need_refill) {
       t.refill();
       need_refill = false;
+      ++n_refill;
     }
     __syncwarp();
+    if (active) t_refill += clock64() - r0;
     for (int s = 0; s < kTraceRound; ++s) {
       if (active && !need_refill) {
         const int st = t.step();
@@ -281,6 +285,8 @@ __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t 
         } else if (st >= kWalkDone) {
           gws->aln_len = t.n;
           gws->phase[kPhTrace] += clock64() - t0;
+          gws->phase[kPhCsr] += t_refill;        // (slot reused: the CSR phase no longer exists as a timed phase)
+          gws->phase[kPhOther] += n_refill;      // (count, not cycles)
           if (st == kWalkBad) {
             gws->status = kStInternal;
             gws->pc = kPcDone;

@@ -103,8 +103,8 @@ class Engine:
         return None, _stats(st)
 
 
-PHASES = ["csr", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
-          "largest_subgraph", "emit", "other"]
+PHASES = ["trace_refill", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
+          "largest_subgraph", "emit", "trace_refills"]
 
 
 def _phase_profile(engine):
