@@ -122,7 +122,8 @@ int vgc_polish_resident(vgc_handle h, vgc_result* result, vgc_stats* stats);
 /* Diagnostics: cycles the window leader lane spent per phase in the last polish call, summed over windows.
  * Index: 0 traceback cycles spent in tile-refill phases (part of 4), 1 toposort, 2 row program, 3 DP fill,
  * 4 traceback, 5 AddAlignment, 6 AddWeights, 7 PruneGraph, 8 LargestSubgraph, 9 emit/consensus,
- * 10 number of traceback tile refills (a count, not cycles). */
+ * 10 number of traceback tile refills (a count, not cycles), 11 host wall-clock milliseconds spent enqueueing the
+ * kernel launches. */
 int vgc_phase_profile(vgc_handle h, double out[16]);
 
 const char* vgc_last_error(void);

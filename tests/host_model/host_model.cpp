@@ -161,7 +161,7 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   const int K = k_regs;
   SlotDims d;
   d.max_nodes = static_cast<uint32_t>(std::max<uint64_t>(prep.max_nodes_ub, 16));
-  d.max_edges = d.max_nodes;
+  d.max_edges = 2 * d.max_nodes + 64;
   d.max_len = std::max<uint32_t>(prep.max_len, 16);
   d.row_words = 32 * K;
   d.in_stride = 8;

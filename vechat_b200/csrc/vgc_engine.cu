@@ -16,6 +16,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_prep.h"
@@ -432,9 +433,11 @@ struct vgc_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
+  double launch_ms = 0.0;       // host wall time spent enqueueing the kernel launches of the current call
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int groups = 48;                // streams of a lockstep pass (upper bound)
+  int launch_threads = 1;         // host threads enqueueing the launches of a pass (measured: the enqueue is not the limit)
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
   cudaStream_t gstream[64] = {};
   cudaEvent_t gev[64] = {};
@@ -605,7 +608,7 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       const uint32_t f = win_first[w];
       SlotDims d;
       d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact), 64);
-      d.max_edges = d.max_nodes;
+      d.max_edges = 2 * d.max_nodes + 64;  // ~2 edges per node in practice; AddAlignment wants room for a whole layer
       d.max_len = std::max<uint32_t>(pr.max_len, 16);
       d.row_words = row_words;
       // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
@@ -698,16 +701,33 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     std::vector<uint32_t> liveA(G), liveB(G);
     for (int g = 0; g < G; ++g) liveA[g] = liveB[g] = static_cast<uint32_t>(gfill[g].size());
     const uint32_t max_fill = pr.win_nfill[wins[pos]] + extra;
-    for (uint32_t c = 0; c <= max_fill; ++c) {
-      for (int g = 0; g < G; ++g) {
-        const std::vector<uint32_t>& nf = gfill[g];
-        if (nf.empty() || nf[0] + extra < c) continue;
-        while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
-        while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
-        if (K == 10) *launches += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
-        else *launches += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
+    const auto tl0 = std::chrono::steady_clock::now();
+    // Enqueue with a few host threads, each owning every T-th group (= its streams): a pass is tens of thousands of
+    // launches and one thread issues only ~100-150 k launches/s, which would otherwise pace the light groups.
+    const int T = std::max(1, std::min(h->launch_threads, G));
+    std::vector<uint32_t> tl(T, 0);
+    auto enqueue = [&](int t) {
+      cudaSetDevice(h->device);
+      for (uint32_t c = 0; c <= max_fill; ++c) {
+        for (int g = t; g < G; g += T) {
+          const std::vector<uint32_t>& nf = gfill[g];
+          if (nf.empty() || nf[0] + extra < c) continue;
+          while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
+          while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
+          if (K == 10) tl[t] += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
+          else tl[t] += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
+        }
       }
+    };
+    if (T == 1) {
+      enqueue(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; ++t) th.emplace_back(enqueue, t);
+      for (auto& x : th) x.join();
     }
+    for (int t = 0; t < T; ++t) *launches += tl[t];
+    h->launch_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
     VGC_CUDA(cudaGetLastError());
     for (int g = 0; g < G; ++g) {
       VGC_CUDA(cudaEventRecord(h->gev[g], h->gstream[g]));
@@ -748,6 +768,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   unsigned long long totals[2 + vgc::kPhCount] = {0};
   float kernel_ms = 0.f, d2h_ms = 0.f;
   h->pass_kernel_ms = 0.0;
+  h->launch_ms = 0.0;
   VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 256, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_out_len.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
@@ -825,6 +846,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   }
   if (stats) {
     for (int i = 0; i < vgc::kPhCount; ++i) h->phase_cycles[i] = static_cast<double>(totals[2 + i]);
+    h->phase_cycles[11] = h->launch_ms;
     stats->cells = totals[0];
     stats->alignments = totals[1];
     stats->input_bytes = input_bytes;
@@ -900,6 +922,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
+  if (const char* s = std::getenv("VGC_LAUNCH_THREADS")) h->launch_threads = std::max(1, std::min(16, std::atoi(s)));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
