@@ -162,3 +162,26 @@ def test_properties_at_scale(pb_batch):
     clen = np.diff(r1.cons_off.astype(np.int64))[:pb_batch.n_windows]
     assert np.all(clen[nseq >= 3] > 0.5 * blen[nseq >= 3]) and np.all(clen < 2.0 * blen + 64)
     assert st1["alignments"] == sum(3 * (int(n) - 1) + 3 for n in nseq if n >= 3)    # 3*depth+3
+
+
+@pytest.mark.parametrize("config,kw,n_targets,step", [
+    ("ont_10k_x_20kb", dict(n_reads=400, genome_len=260_000), 2, 4),      # BASELINE configs[2]: ONT, 20 kb, 10 % error
+    ("hap2_50k_x_12kb", dict(n_reads=900, genome_len=180_000), 3, 5),     # configs[3]: 2 haplotypes 50:50, depth ~60
+])
+def test_other_baseline_configs_sample(config, kw, n_targets, step):
+    """Scaled-down instances of BASELINE.json's other workloads (same error model, read length, windowing; smaller
+    genome so the depth matches) against the reference, every `step`-th window."""
+    sim = Simulator(config, **kw)
+    b = sim.windows(0, n_targets)
+    sub = b.select(range(0, b.n_windows, step))
+    st = check(sub, dict(), config)
+    assert st["relaunched_windows"] == 0 or st["relaunched_windows"] < sub.n_windows
+
+
+def test_large_batch_many_groups():
+    """A batch wide enough to be dealt into many stream groups (one per number of alignments) and to exercise the
+    lockstep schedule's prefix logic with windows of very different depth."""
+    rng = np.random.default_rng(77)
+    wins = [fuzz_window(rng, length=int(rng.integers(30, 120)), depth=int(rng.integers(0, 40))) for _ in range(1500)]
+    check(WindowBatch.from_windows(wins), dict(), "many groups")
+    check(WindowBatch.from_windows(wins[:700]), dict(haplotype=0, trim=0), "many groups linear")

@@ -29,7 +29,7 @@
 
 namespace vgc {
 
-constexpr int kRingRows = 4;  // recent rows kept in shared memory (when the space is there)
+constexpr int kRingRows = 4;  // recent rows kept in shared memory (power of two; row r lives in slot r % kRingRows)
 
 __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) {
   return (static_cast<uint32_t>(lo) & 0xFFFFu) | (static_cast<uint32_t>(hi) << 16);
@@ -99,18 +99,16 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
   for (int k = 0; k < K; ++k) hp[k] = SW ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
   row_store<K>(sl.H, lane, hp);
   if (lane == 0) sl.fc[0] = 0;
-  uint32_t prev_row = 0;
   int32_t fc_prev = 0;
 
-  // ring of recent rows: tags (row ids) and first-column values live in registers (uniform across the warp)
-  uint32_t tag[kRingRows];
-  int32_t rfc[kRingRows];
-#pragma unroll
-  for (int r = 0; r < kRingRows; ++r) {
-    tag[r] = 0xFFFFFFFFu;
-    rfc[r] = 0;
+  // ring of the most recent rows in shared memory: row r lives in slot r % kRingRows (with its first-column value
+  // in ring_fc), so "is predecessor row - d in the ring" is just d <= kRingRows — no tags to search or maintain
+  const bool use_ring = ring_rows == kRingRows;
+  int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * RM::kWords);
+  if (use_ring) {
+    row_store<K>(ring, lane, hp);
+    if (lane == 0) ring_fc[0] = 0;
   }
-  int rpos = 0;
 
   // ---- best-cell tracking
   uint32_t bestv = 0;                   // SW: per-lane packed running max (scores >= 0)
@@ -146,9 +144,11 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
         }
       }
       const U4 er = {e.x, e.y, e.z, e.w};
-      const uint32_t p0 = np == 0 ? 0u : rec_pred(er, row, 0, sl.ovf);
+      const bool inl = (meta & kMetaInline) != 0;
+      // distance to predecessor p (rows are processed in rank order: distance 1 = the row in registers)
+      const uint32_t d0 = np == 0 ? row : (inl ? rec_delta(er, 0) : row - sl.ovf[e.w]);
       int32_t fcmax;
-      if (np <= 1 && p0 == prev_row) {
+      if (np <= 1 && d0 == 1) {
         // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
         uint32_t x = __shfl_up_sync(0xFFFFFFFFu, hp[K - 1], 1);
         const uint32_t y = __shfl_sync(0xFFFFFFFFu, hp[K - 1], 31);
@@ -163,34 +163,21 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
         fcmax = INT32_MIN;
         const uint32_t npp = np == 0 ? 1 : np;
         for (uint32_t p = 0; p < npp; ++p) {
-          uint32_t prow;
-          if (p == 0) prow = p0;
-          else prow = rec_pred(er, row, p, sl.ovf);
+          const uint32_t d = p == 0 ? d0 : (inl ? rec_delta(er, p) : row - sl.ovf[e.w + p]);
           uint32_t u[K];
           int32_t fcp;
-          int hit = -1;
-#pragma unroll
-          for (int r = 0; r < kRingRows; ++r) {
-            if (tag[r] == prow) hit = r;
-          }
-          if (prow == prev_row) {
+          if (d == 1) {
 #pragma unroll
             for (int k = 0; k < K; ++k) u[k] = hp[k];
             fcp = fc_prev;
-          } else if (hit >= 0) {
-            row_load<K>(ring + hit * RM::kWords, lane, u);
-            fcp = rfc[0];
-#pragma unroll
-            for (int r = 1; r < kRingRows; ++r) {
-              if (hit == r) fcp = rfc[r];
-            }
+          } else if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
+            const uint32_t slot = (row - d) & (kRingRows - 1);
+            row_load<K>(ring + slot * RM::kWords, lane, u);
+            fcp = ring_fc[slot];
           } else {
+            const uint32_t prow = row - d;
             row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
-            fcp = 0;
-            if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
-              if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
-              fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
-            }
+            fcp = SW ? 0 : static_cast<int32_t>(sl.fc[prow]);  // same address in every lane: one broadcast load
           }
           fcmax = fcp > fcmax ? fcp : fcmax;
           // diagonal of this lane's first cells: the previous lane's last cells
@@ -236,16 +223,10 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       // ---- write the row once (HBM) and keep it in the ring
       row_store<K>(sl.H + static_cast<uint64_t>(row) * sl.row_words, lane, hp);
       if (!SW && lane == 0) sl.fc[row] = static_cast<int16_t>(fci);
-      if (ring_rows > 0) {
-        row_store<K>(ring + rpos * RM::kWords, lane, hp);
-#pragma unroll
-        for (int r = 0; r < kRingRows; ++r) {
-          if (r == rpos) {
-            tag[r] = row;
-            rfc[r] = fci;
-          }
-        }
-        rpos = rpos + 1 == ring_rows ? 0 : rpos + 1;
+      if (use_ring) {
+        const uint32_t slot = row & (kRingRows - 1);
+        row_store<K>(ring + slot * RM::kWords, lane, hp);
+        if (lane == 0) ring_fc[slot] = fci;
       }
       // ---- best cell
       if (SW) {
@@ -270,7 +251,6 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
           nw_row = row;
         }
       }
-      prev_row = row;
       fc_prev = fci;
     }
   }

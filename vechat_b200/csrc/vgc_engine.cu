@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArg
   // the rest of the shared memory is the ring of recent rows
   uint32_t* ring = prof + a.bv.num_codes * RowMap<K>::kWords;
   const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
-  int ring_rows = used < a.smem_bytes ? static_cast<int>((a.smem_bytes - used) / (RowMap<K>::kWords * 4)) : 0;
-  if (ring_rows > kRingRows) ring_rows = kRingRows;
+  // all kRingRows rows + their first-column values (16 B) or no ring at all
+  const int ring_rows = used + kRingRows * RowMap<K>::kWords * 4 + 16 <= a.smem_bytes ? kRingRows : 0;
   warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage, ring,
                ring_rows);
   if (lane == 0) {
