@@ -437,6 +437,7 @@ struct vgc_engine {
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int groups = 48;                // streams of a lockstep pass (upper bound)
+  double sort_growth = 0.07;      // new graph nodes per base added, upper estimate (sizes the sort kernel's shared memory)
   int launch_threads = 1;         // host threads enqueueing the launches of a pass (measured: the enqueue is not the limit)
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
   cudaStream_t gstream[64] = {};
@@ -555,7 +556,7 @@ int set_kernel_attrs(const vgc_engine* h) {
 // one lockstep cycle for the first `nru` (trace, update) / `ntf` (sort, fill) windows of a group
 template <int K>
 uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, uint32_t nru, uint32_t ntf, bool first,
-                      cudaStream_t st) {
+                      cudaStream_t st, uint32_t sort_smem) {
   KernelArgs k = a;
   uint32_t n = 0;
   if (nru && !first) {
@@ -569,7 +570,7 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
     ++n;
   }
   if (ntf) {
-    k.smem_bytes = h->smem_sort;
+    k.smem_bytes = sort_smem;
     sort_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
     k.smem_bytes = h->smem_fill;
     fill_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
@@ -658,6 +659,9 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     std::vector<Slot> slots(n);
     std::vector<uint32_t> gbase(G + 1, 0);
     std::vector<std::vector<uint32_t>> gfill(G);  // fills of each window of the group, in list order
+    std::vector<uint32_t> gmin_nseq(G, 0xFFFFFFFFu);
+    std::vector<double> gblen(G, 0.0), gavglen(G, 0.0);  // per group: longest backbone, largest mean layer length
+    const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
     uint32_t k = 0;
     for (int g = 0; g < G; ++g) {
       gbase[g] = k;
@@ -667,6 +671,14 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
         work[k] = wins[pos + i];
         slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
         gfill[g].push_back(pr.win_nfill[wins[pos + i]]);
+        {
+          const uint32_t w = wins[pos + i];
+          const uint32_t f = win_first[w];
+          const double bl = static_cast<double>(seq_off[f + 1] - seq_off[f]);
+          gmin_nseq[g] = std::min(gmin_nseq[g], pr.win_nseq[w]);
+          gblen[g] = std::max(gblen[g], bl);
+          gavglen[g] = std::max(gavglen[g], (pr.win_sum_len[w] - bl) / std::max(1.0, pr.win_nseq[w] - 1.0));
+        }
         ++k;
       }
     }
@@ -714,8 +726,17 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
           if (nf.empty() || nf[0] + extra < c) continue;
           while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
           while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
-          if (K == 10) tl[t] += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
-          else tl[t] += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g]);
+          // shared memory of the sort kernel: sized for the graph this cycle can have reached (build phase: the
+          // backbone + a share of the bases added so far), so early cycles run more CTAs per SM; a graph that
+          // outgrows it sorts out of HBM instead (slower, same result)
+          uint32_t ss = h->smem_sort;
+          if (c + 1 < gmin_nseq[g]) {
+            const double nvb = gblen[g] + h->sort_growth * c * gavglen[g] + 64.0;
+            const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
+            ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
+          }
+          if (K == 10) tl[t] += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g], ss);
+          else tl[t] += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g], ss);
         }
       }
     };
@@ -922,6 +943,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
+  if (const char* s = std::getenv("VGC_SORT_GROWTH")) h->sort_growth = std::atof(s);
   if (const char* s = std::getenv("VGC_LAUNCH_THREADS")) h->launch_threads = std::max(1, std::min(16, std::atoi(s)));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
   size_t free_b = 0, total_b = 0;
