@@ -47,6 +47,7 @@ def build_engine(force=False, verbose=False):
     srcs = [os.path.join(CSRC, "vgc_engine.cu")]
     if force or _stale(out, engine_sources()):
         cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", out] + srcs + ["-lcudart", "-lpthread"]
+        cmd += os.environ.get("VGC_NVCC_EXTRA", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         _run(cmd)

@@ -29,7 +29,10 @@
 
 namespace vgc {
 
-constexpr int kRingRows = 4;  // recent rows kept in shared memory (power of two; row r lives in slot r % kRingRows)
+#ifndef VGC_RING_ROWS
+#define VGC_RING_ROWS 4
+#endif
+constexpr int kRingRows = VGC_RING_ROWS;  // recent rows kept in shared memory (power of two; row r lives in slot r % kRingRows)
 
 __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) {
   return (static_cast<uint32_t>(lo) & 0xFFFFu) | (static_cast<uint32_t>(hi) << 16);

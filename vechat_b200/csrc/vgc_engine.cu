@@ -155,7 +155,9 @@ __device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t 
 #ifndef VGC_SORT_CTAS
 #define VGC_SORT_CTAS 12
 #endif
+#ifndef VGC_FILL_CTAS
 #define VGC_FILL_CTAS 16
+#endif
 
 struct WinCtx {
   Slot* sl;
@@ -937,7 +939,9 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   }
   // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
   auto smem_for = [](int ctas) { return static_cast<uint32_t>(((228 * 1024 - ctas * 1024) / ctas) & ~255); };
-  h->smem_fill = 13568;
+  // what VGC_FILL_CTAS one-warp CTAs per SM leave each (16 -> 13.5 KB: profile + a 4-row ring for 640-column rows)
+  h->smem_fill = smem_for(VGC_FILL_CTAS);
+  if (h->smem_fill > 13568) h->smem_fill = 13568;
   h->smem_sort = smem_for(VGC_SORT_CTAS);
   h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
   h->smem_trace = 2048;
