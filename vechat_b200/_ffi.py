@@ -227,7 +227,7 @@ class PolishResult:
 
 def alloc_result(batch):
     cap = batch.result_bound()
-    cons = np.zeros(cap, dtype=np.uint8)
+    cons = np.empty(cap, dtype=np.uint8)   # written by the engine up to cons_off[n_windows]
     cons_off = np.zeros(batch.n_windows + 1, dtype=np.uint64)
     polished = np.zeros(max(batch.n_windows, 1), dtype=np.uint8)
     r = VgcResult()

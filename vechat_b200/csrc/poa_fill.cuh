@@ -107,10 +107,12 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
   // ring of the most recent rows in shared memory: row r lives in slot r % kRingRows (with its first-column value
   // in ring_fc), so "is predecessor row - d in the ring" is just d <= kRingRows — no tags to search or maintain
   const bool use_ring = ring_rows == kRingRows;
-  int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * RM::kWords);
+  // (every lane keeps its own copy of the first-column values: a lane only ever reads what it wrote itself, rows
+  //  and first columns alike, so the ring needs no warp synchronisation)
+  int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * RM::kWords) + lane;
   if (use_ring) {
     row_store<K>(ring, lane, hp);
-    if (lane == 0) ring_fc[0] = 0;
+    ring_fc[0] = 0;
   }
 
   // ---- best-cell tracking
@@ -176,11 +178,15 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
           } else if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
             const uint32_t slot = (row - d) & (kRingRows - 1);
             row_load<K>(ring + slot * RM::kWords, lane, u);
-            fcp = ring_fc[slot];
+            fcp = ring_fc[slot * 32];
           } else {
             const uint32_t prow = row - d;
             row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
-            fcp = SW ? 0 : static_cast<int32_t>(sl.fc[prow]);  // same address in every lane: one broadcast load
+            fcp = 0;
+            if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
+              if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
+              fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
+            }
           }
           fcmax = fcp > fcmax ? fcp : fcmax;
           // diagonal of this lane's first cells: the previous lane's last cells
@@ -229,7 +235,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       if (use_ring) {
         const uint32_t slot = row & (kRingRows - 1);
         row_store<K>(ring + slot * RM::kWords, lane, hp);
-        if (lane == 0) ring_fc[slot] = fci;
+        ring_fc[slot * 32] = fci;
       }
       // ---- best cell
       if (SW) {

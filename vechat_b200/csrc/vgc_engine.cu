@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArg
   // the rest of the shared memory is the ring of recent rows
   uint32_t* ring = prof + a.bv.num_codes * RowMap<K>::kWords;
   const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
-  // all kRingRows rows + their first-column values (16 B) or no ring at all
-  const int ring_rows = used + kRingRows * RowMap<K>::kWords * 4 + 16 <= a.smem_bytes ? kRingRows : 0;
+  // all kRingRows rows + their first-column values (one copy per lane) or no ring at all
+  const int ring_rows = used + kRingRows * (RowMap<K>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
   warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage, ring,
                ring_rows);
   if (lane == 0) {

@@ -48,26 +48,31 @@ def shard_targets(win_target, work, world):
 def stitch(result, win_target, win_rank, names, coverages, fragment_correction=True, drop_unpolished=False,
            w0=0):
     """src/polisher.cpp:520-546 for windows [w0, w0 + n) of a shard whose results are in `result` (local index).
-    Returns [(header, sequence bytes)]."""
-    out = []
+    Returns [(header, sequence bytes)].  The windows of a target are consecutive and so are their corrected bytes
+    in `result.cons`, so a target's sequence is one slice (no per-window concatenation)."""
     n = len(result.polished)
-    data, num_polished = [], 0
-    for i in range(n):
-        g = w0 + i
-        num_polished += int(result.polished[i])
-        data.append(result.window(i))
-        last = (i == n - 1) or (win_rank[g + 1] == 0)
-        if last:
-            ratio = num_polished / float(int(win_rank[g]) + 1)
-            if (not drop_unpolished) or ratio > 0:
-                seq = b"".join(data)
-                t = int(win_target[g])
-                tags = "r" if fragment_correction else ""
-                tags += " LN:i:%d" % len(seq)
-                tags += " RC:i:%d" % int(coverages.get(t, 0) if hasattr(coverages, "get") else coverages[t])
-                tags += " XC:f:%f" % ratio
-                out.append((names(t) + tags if callable(names) else names[t] + tags, seq))
-            data, num_polished = [], 0
+    if n == 0:
+        return []
+    rank = np.asarray(win_rank[w0:w0 + n])
+    # a target ends at the last window or where the next window has rank 0 (polisher.cpp:530)
+    last = np.flatnonzero(np.concatenate([rank[1:] == 0, [True]]))
+    first = np.concatenate([[0], last[:-1] + 1])
+    csum = np.concatenate([[0], np.cumsum(np.asarray(result.polished, dtype=np.int64))])
+    off = np.asarray(result.cons_off, dtype=np.int64)
+    cons = result.cons
+    tags0 = "r" if fragment_correction else ""
+    get_cov = coverages.get if hasattr(coverages, "get") else None
+    out = []
+    for f, l in zip(first.tolist(), last.tolist()):
+        num_polished = int(csum[l + 1] - csum[f])
+        ratio = num_polished / float(int(rank[l]) + 1)
+        if drop_unpolished and not ratio > 0:
+            continue
+        seq = cons[off[f]:off[l + 1]].tobytes()
+        t = int(win_target[w0 + l])
+        cov = get_cov(t, 0) if get_cov else coverages[t]
+        tags = "%s LN:i:%d RC:i:%d XC:f:%f" % (tags0, len(seq), int(cov), ratio)
+        out.append(((names(t) if callable(names) else names[t]) + tags, seq))
     return out
 
 
