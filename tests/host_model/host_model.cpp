@@ -85,11 +85,12 @@ struct HostEx {
   template <int K>
   void fill(Slot& sl, WinState& ws, const uint8_t* codes_, uint32_t len, uint32_t mode, const Scores& sc,
             uint32_t /*num_codes*/) {
-    using RM = RowMap<K>;
     const uint32_t nR = ws.nR;
+    const uint32_t half = 32u * fill_width(K, len);  // the device's per-alignment row width
+    ws.fill_k = half / 32u;
     auto cell = [&](uint32_t row, uint32_t c) -> int16_t* {  // lane-major words: low half = column w, high = 32K + w
-      const uint32_t h = c >= static_cast<uint32_t>(RM::kWords) ? 1u : 0u;
-      return reinterpret_cast<int16_t*>(sl.H + static_cast<uint64_t>(row) * sl.row_words + (h ? c - RM::kWords : c)) + h;
+      const uint32_t h = c >= half ? 1u : 0u;
+      return reinterpret_cast<int16_t*>(sl.H + static_cast<uint64_t>(row) * sl.row_words + (h ? c - half : c)) + h;
     };
     auto H = [&](uint32_t row, uint32_t j) -> int32_t {  // j = DP column, 0 = first column
       if (j == 0) return mode == kModeSW ? 0 : sl.fc[row];

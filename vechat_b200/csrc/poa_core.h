@@ -196,6 +196,7 @@ struct WinState {
   uint32_t fill_layer;   // pending alignment: layer id, mode, sub-graph flag
   uint32_t fill_mode;
   uint32_t sub;          // the pending alignment runs on a Subgraph view (rank -> node through sl.order)
+  uint32_t fill_k;       // words per lane the fill used for the pending alignment (row layout: 32 * fill_k words per half)
   uint32_t need;         // kNeed*
   uint32_t prep;         // kPrep* flags for step_prepare
   unsigned long long cells;
@@ -226,6 +227,15 @@ struct RowMap {
     return static_cast<int16_t>(h ? (w >> 16) : (w & 0xFFFFu));
   }
 };
+
+// Words per lane the fill uses for an alignment of `len` columns when the slot's rows hold K words per lane: the
+// smallest supported width that fits (512-, 640- or 1024-column rows).  Narrow layers cost fewer DPX operations and
+// fewer bytes per row; the row stride in HBM stays the slot's.
+VGC_HD VGC_INL uint32_t fill_width(uint32_t K, uint32_t len) {
+  if (K > 8 && len <= 512u) return 8u;
+  if (K > 10 && len <= 640u) return 10u;
+  return K;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Traceback walker: ONE thread per alignment (the device runs 32 alignments per warp, the host model one).
@@ -659,68 +669,78 @@ struct Poa {
   VGC_HD uint32_t toposort_fast(uint32_t* rec, const uint16_t* adj, StkT* stack, uint32_t stack_cap, uint32_t* dst,
                                 uint32_t* rank_of, bool* overflow) {
     const uint32_t nV = G().nV;
-    uint32_t n = 0, sp = 0;
+    uint32_t n = 0;
     *overflow = false;
     for (uint32_t root = 0; root < nV; ++root) {
       const uint32_t rr = rec[root];
       if (rr & (kRDone | kRExpanded)) continue;
       if (SUB && !(rr & kRMember)) continue;
-      stack[sp++] = static_cast<StkT>(root);
-      while (sp > 0) {
-        const uint32_t curr = stack[sp - 1];
-        const uint32_t r = rec[curr];
-        if (r & kRDone) {
-          --sp;
-          continue;
-        }
-        const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 7u;
-        const bool primary = !(r & kRIgnored);
-        bool valid = true;
-        if (!(r & kRExpanded)) {
-          if (sp + nin + nal + 1 > stack_cap) {
-            *overflow = true;
-            return 0;
-          }
-#pragma unroll 1
-          for (uint32_t i = 0; i < nin; ++i) {  // degrees are 1-3: an unrolled body would mostly run predicated off
-            const uint32_t t = adj[off + i];
-            const uint32_t rt = rec[t];
-            if (SUB && !(rt & kRMember)) continue;
-            if (!(rt & kRDone)) {
-              stack[sp++] = static_cast<StkT>(t);
-              valid = false;
+      // (curr, r) = the top of the stack, kept in registers: after a node pushes its pending tails the next node to
+      // look at is the last one pushed, whose record was just read — no reload on the way down
+      uint32_t sp = 1, curr = root, r = rr;
+      stack[0] = static_cast<StkT>(root);
+      while (true) {
+        bool pop = (r & kRDone) != 0;
+        if (!pop) {
+          const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 7u;
+          const bool primary = !(r & kRIgnored);
+          uint32_t last = kNone, last_r = 0;
+          if (!(r & kRExpanded)) {
+            if (sp + nin + nal + 1 > stack_cap) {
+              *overflow = true;
+              return 0;
             }
-          }
-          if (primary) {
 #pragma unroll 1
-            for (uint32_t i = 0; i < nal; ++i) {
-              const uint32_t a = adj[off + nin + i];
-              const uint32_t ra = rec[a];
-              if (SUB && !(ra & kRMember)) continue;
-              if (!(ra & kRDone)) {
-                stack[sp++] = static_cast<StkT>(a);
-                rec[a] = ra | kRIgnored;
-                valid = false;
+            for (uint32_t i = 0; i < nin; ++i) {  // degrees are 1-3: an unrolled body would mostly run predicated off
+              const uint32_t t = adj[off + i];
+              const uint32_t rt = rec[t];
+              if (SUB && !(rt & kRMember)) continue;
+              if (!(rt & kRDone)) {
+                stack[sp++] = static_cast<StkT>(t);
+                last = t;
+                last_r = rt;
+              }
+            }
+            if (primary) {
+#pragma unroll 1
+              for (uint32_t i = 0; i < nal; ++i) {
+                const uint32_t a = adj[off + nin + i];
+                const uint32_t ra = rec[a];
+                if (SUB && !(ra & kRMember)) continue;
+                if (!(ra & kRDone)) {
+                  stack[sp++] = static_cast<StkT>(a);
+                  rec[a] = ra | kRIgnored;
+                  last = a;
+                  last_r = ra | kRIgnored;
+                }
               }
             }
           }
-        }
-        if (valid) {
-          rec[curr] = r | kRDone;
-          if (primary) {
-            rank_of[curr] = n;
-            dst[n++] = curr;
+          if (last == kNone) {
+            // nothing pending below: emit (second visit, or a first visit whose tails were all done)
+            rec[curr] = r | kRDone;
+            if (primary) {
+              rank_of[curr] = n;
+              dst[n++] = curr;
 #pragma unroll 1
-            for (uint32_t i = 0; i < nal; ++i) {
-              const uint32_t a = adj[off + nin + i];
-              if (SUB && !(rec[a] & kRMember)) continue;
-              rank_of[a] = n;
-              dst[n++] = a;
+              for (uint32_t i = 0; i < nal; ++i) {
+                const uint32_t a = adj[off + nin + i];
+                if (SUB && !(rec[a] & kRMember)) continue;
+                rank_of[a] = n;
+                dst[n++] = a;
+              }
             }
+            pop = true;
+          } else {
+            rec[curr] = r | kRExpanded;
+            curr = last;
+            r = last_r;  // nothing was written to that record after it was read (the last push is the last write)
           }
-          --sp;
-        } else {
-          rec[curr] = r | kRExpanded;
+        }
+        if (pop) {
+          if (--sp == 0) break;
+          curr = stack[sp - 1];
+          r = rec[curr];
         }
       }
     }
@@ -911,7 +931,7 @@ struct Poa {
     t.aln_pos = sl.aln_pos;
     t.aln_cap = sl.aln_cap;
     t.rw = sl.row_words;
-    t.half_words = RM::kWords;
+    t.half_words = 32u * ws.fill_k;
     t.m = sc.m;
     t.x = sc.x;
     t.g = sc.g;

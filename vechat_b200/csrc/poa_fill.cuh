@@ -213,8 +213,8 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       uint32_t V = __vadd2(hp[K - 1], voff);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, V, d);
-        if (lane >= d) V = __vmaxs2(V, t);
+        // lanes below d get their own value back from shfl_up: the max is a no-op there, no predicate needed
+        V = __vmaxs2(V, __shfl_up_sync(0xFFFFFFFFu, V, d));
       }
       const int32_t lowtot = lo16(__shfl_sync(0xFFFFFFFFu, V, 31));
       const int32_t vfc = fci + g;

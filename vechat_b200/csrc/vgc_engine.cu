@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t 
     t.aln_pos = sl->aln_pos;
     t.aln_cap = sl->aln_cap;
     t.rw = sl->row_words;
-    t.half_words = RowMap<K>::kWords;
+    t.half_words = 32u * gws->fill_k;
     t.m = mode == kModeNW ? a.nw.m : 3;   // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
     t.x = mode == kModeNW ? a.nw.x : -5;
     t.g = mode == kModeNW ? a.nw.g : -4;
@@ -333,6 +333,17 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
   win_leave(a, c);
 }
 
+// shared memory after the profile: the ring of recent rows (all kRingRows rows + one first-column value per lane and
+// row, or no ring at all)
+template <int KR>
+__device__ __forceinline__ void run_fill(const KernelArgs& a, WinCtx& c, const uint8_t* codes, uint32_t len, uint32_t mode,
+                                         const Scores& sc, uint32_t* prof, uint4* stage, const uint8_t* smem) {
+  uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
+  const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
+  const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
+  warp_fill<KR>(*c.sl, *c.ws, codes, len, mode, sc, a.bv.num_codes, prof, stage, ring, ring_rows);
+}
+
 // F: the DP fill of the pending alignment (poa_fill.cuh; replaces SimdAlignmentEngine::Linear's fill).
 // shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words] | ring
 template <int K>
@@ -357,17 +368,17 @@ __global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArg
   sw.x = -5;
   sw.g = -4;
   const uint32_t mode = c.ws->fill_mode;
-  // the rest of the shared memory is the ring of recent rows
-  uint32_t* ring = prof + a.bv.num_codes * RowMap<K>::kWords;
-  const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
-  // all kRingRows rows + their first-column values (one copy per lane) or no ring at all
-  const int ring_rows = used + kRingRows * (RowMap<K>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
-  warp_fill<K>(*c.sl, *c.ws, codes, len, mode, mode == kModeNW ? a.nw : sw, a.bv.num_codes, prof, stage, ring,
-               ring_rows);
+  // row width for this alignment (fill_width): narrow layers run the 512-column variant
+  const uint32_t kr = fill_width(K, len);
+  const Scores sc = mode == kModeNW ? a.nw : sw;
+  if (kr == 8) run_fill<8>(a, c, codes, len, mode, sc, prof, stage, smem);
+  else if (kr == 10) run_fill<10>(a, c, codes, len, mode, sc, prof, stage, smem);
+  else run_fill<K>(a, c, codes, len, mode, sc, prof, stage, smem);
   if (lane == 0) {
     c.gws->best_row = c.ws->best_row;
     c.gws->best_col = c.ws->best_col;
     c.gws->best_score = c.ws->best_score;
+    c.gws->fill_k = kr;
     c.gws->need = kNeedTrace;
     c.gws->phase[kPhFill] += clock64() - t0;
   }
