@@ -213,7 +213,7 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
   ex.sm = smem + kSmemHeader;
   ex.sm_bytes = a.smem_bytes - kSmemHeader;
   ex.max_len = sl->max_len;
-  ex.lane_ = threadIdx.x;
+  ex.lane_ = threadIdx.x & 31;
   ex.mask_ = 0xFFFFFFFFu;
   return ex;
 }
@@ -309,11 +309,16 @@ __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t 
 // U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, AddWeights,
 // PruneGraph, LargestSubgraph, GenerateCorrectedSequence / GenerateConsensus, and Window::generate_consensus'
 // control flow).
+constexpr int kUpdateWins = 4;  // windows (= warps) per CTA: the SM's 32-CTA limit must not cap the light kernel
 template <int K>
-__global__ void __launch_bounds__(32, VGC_UPDATE_CTAS) update_kernel(const KernelArgs a, uint32_t base) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(32 * kUpdateWins) update_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
+  extern __shared__ __align__(16) uint8_t smem_all[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * kUpdateWins + warp;
+  if (i >= count) return;
+  uint8_t* smem = smem_all + warp * a.smem_bytes;
   WinCtx c;
-  if (!win_enter(a, base + blockIdx.x, kNeedUpdate, smem, &c)) return;
+  if (!win_enter(a, base + i, kNeedUpdate, smem, &c, threadIdx.x & 31)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_update(c.w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
@@ -560,7 +565,7 @@ int set_kernel_attrs(const vgc_engine* h) {
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   };
   VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), kTraceSmem));
-  VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), h->smem_update));
+  VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * h->smem_update));
   VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
   VGC_CUDA(set(reinterpret_cast<const void*>(fill_kernel<K>), h->smem_fill));
   return VGC_OK;
@@ -578,8 +583,8 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
     ++n;
   }
   if (nru) {
-    k.smem_bytes = h->smem_update;
-    update_kernel<K><<<nru, 32, k.smem_bytes, st>>>(k, base);
+    k.smem_bytes = h->smem_update;  // per window (warp)
+    update_kernel<K><<<(nru + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * k.smem_bytes, st>>>(k, base, nru);
     ++n;
   }
   if (ntf) {
