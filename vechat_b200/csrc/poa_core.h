@@ -246,7 +246,7 @@ VGC_HD VGC_INL uint32_t fill_width(uint32_t K, uint32_t len) {
 // matrix (kTR consecutive rows in rank space x kTW consecutive words of the lane-major row) that the thread
 // fetches with 16-byte loads whenever the walk leaves it: DRAM latency is paid once per tile, not once per step.
 // Pairs are appended in reverse (end of the alignment first).
-constexpr int kTR = 24;  // tile rows (ranks ti, ti-1, ..)
+constexpr int kTR = 16;  // tile rows (ranks ti, ti-1, ..)
 constexpr int kTW = 16;  // tile words per row
 enum : int { kWalkStep = 0, kWalkMiss = 1, kWalkDone = 2, kWalkBad = 3 };
 

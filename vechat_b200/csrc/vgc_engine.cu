@@ -455,7 +455,7 @@ struct vgc_engine {
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int groups = 48;                // streams of a lockstep pass (upper bound)
-  double sort_growth = 0.07;      // new graph nodes per base added, upper estimate (sizes the sort kernel's shared memory)
+  double sort_growth = 0.055;     // new graph nodes per base added, upper estimate (sizes the sort kernel's shared memory)
   int launch_threads = 1;         // host threads enqueueing the launches of a pass (measured: the enqueue is not the limit)
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
   cudaStream_t gstream[64] = {};
