@@ -130,6 +130,33 @@ def test_scratch_regrow_path(monkeypatch):
     e.close()
 
 
+def test_retry_pass_with_exact_capacities(monkeypatch):
+    """First-pass slots far too small for the graphs (node estimate = backbone + 1/200 of the layer bases): the
+    windows overflow, report it, and are re-run in a second pass sized by the exact upper bound."""
+    monkeypatch.setenv("VGC_NODE_SHARE_DIV", "200")
+    e = Engine(0)
+    b = fuzz_batch(421, n_windows=12, depth=30, length=300, err=0.3)
+    got, st = e.polish(b)
+    assert st["relaunched_windows"] > 0
+    assert_same(got, checker.oracle_polish(b, make_params(), threads=8), "retry pass")
+    e.close()
+
+
+@pytest.mark.parametrize("env", [dict(VGC_SORT_SMEM="3072"), dict(VGC_SORT_GROWTH="0.0005")])
+def test_sort_out_of_hbm_when_shared_memory_is_short(monkeypatch, env):
+    """The staged (shared-memory) TopologicalSort / LargestSubgraph fall back to their HBM twins when the graph does
+    not fit the kernel's shared memory: same results, slower."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for pkw, seed, kw in ((dict(), 422, dict(n_windows=10, depth=20, length=250, partial=0.4)),
+                          (dict(haplotype=0), 423, dict(n_windows=10, depth=20, length=250, partial=0.4))):
+        e = Engine(0, **pkw)
+        b = fuzz_batch(seed, **kw)
+        got, _ = e.polish(b)
+        assert_same(got, checker.oracle_polish(b, make_params(**pkw), threads=8), "hbm sort %s" % (env,))
+        e.close()
+
+
 @pytest.fixture(scope="module")
 def pb_batch():
     sim = Simulator("pb_clr_10k_x_10kb", n_reads=1500, genome_len=500_000)

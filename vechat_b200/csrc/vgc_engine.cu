@@ -455,6 +455,7 @@ struct vgc_engine {
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int groups = 48;                // streams of a lockstep pass (upper bound)
+  uint32_t node_share_div = 6;    // first-pass node capacity = backbone + (sum of layer lengths) / this + one layer
   double sort_growth = 0.055;     // new graph nodes per base added, upper estimate (sizes the sort kernel's shared memory)
   int launch_threads = 1;         // host threads enqueueing the launches of a pass (measured: the enqueue is not the limit)
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
@@ -600,10 +601,10 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
 // Node capacity of a window's slot on the first pass: backbone + a share of the layer bases (a read adds a node
 // only where it disagrees with the graph) + one layer of head-room for AddAlignment's conservative check.  Windows
 // that outgrow it are re-run with the exact upper bound (sum of layer lengths).
-uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exact) {
+uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exact, uint32_t share_div) {
   const uint64_t ub = static_cast<uint64_t>(pr.win_sum_len[w]) + 64;
   if (exact) return static_cast<uint32_t>(ub);
-  const uint64_t est = blen + pr.win_sum_len[w] / 6 + pr.win_max_len[w] + 64;
+  const uint64_t est = blen + pr.win_sum_len[w] / share_div + pr.win_max_len[w] + 64;
   return static_cast<uint32_t>(std::min(ub, est));
 }
 
@@ -626,7 +627,7 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       const uint32_t w = wins[e];
       const uint32_t f = win_first[w];
       SlotDims d;
-      d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact), 64);
+      d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div), 64);
       d.max_edges = 2 * d.max_nodes + 64;  // ~2 edges per node in practice; AddAlignment wants room for a whole layer
       d.max_len = std::max<uint32_t>(pr.max_len, 16);
       d.row_words = row_words;
@@ -963,6 +964,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
+  if (const char* s = std::getenv("VGC_NODE_SHARE_DIV")) h->node_share_div = static_cast<uint32_t>(std::max(1, std::atoi(s)));
   if (const char* s = std::getenv("VGC_SORT_GROWTH")) h->sort_growth = std::atof(s);
   if (const char* s = std::getenv("VGC_LAUNCH_THREADS")) h->launch_threads = std::max(1, std::min(16, std::atoi(s)));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
