@@ -1,8 +1,9 @@
 // poa_core.h — the window-correction algorithm on flat arrays, written once.
 //
 // The same template code is instantiated
-//   * in the CUDA engine (vgc_engine.cu) with a warp executor: one window per warp/CTA, 32 lanes,
-//     warp shuffles, shared memory, the packed int16x2 DP fill of poa_fill.cuh; and
+//   * in the CUDA engine (vgc_engine.cu) with a warp executor (one window per warp, 32 lanes, warp shuffles,
+//     shared memory) for the update / sort steps, the packed int16x2 DP fill of poa_fill.cuh, and the
+//     one-thread-per-window TraceWalker below; and
 //   * in tests/host_model (g++, one "lane") so that the serial graph logic can be checked against the
 //     oracle on a machine without a GPU.  The host build is test-only: the product library never
 //     contains a CPU path.
@@ -11,15 +12,15 @@
 //   Window::generate_consensus haplotype  src/window.cpp:176-428      -> run_window()
 //   Window::generate_consensus linear     src/window.cpp:74-174       -> run_window() (haplotype == 0)
 //   Graph::AddAlignment / AddSequence     vendor/spoa/src/graph.cpp:109-130,182-299 -> add_alignment()
-//   Graph::TopologicalSort                graph.cpp:301-371           -> toposort()
-//   Graph::Subgraph / ExtractSubgraph     graph.cpp:640-732           -> extract_subgraph() + filtered toposort
+//   Graph::TopologicalSort                graph.cpp:301-371           -> toposort_fast() (staged) / toposort_impl()
+//   Graph::Subgraph / ExtractSubgraph     graph.cpp:640-732           -> extract_fast() / extract_impl() + member-only sort
 //   Graph::PruneGraph                     graph.cpp:811-982           -> prune()
 //   Graph::LargestSubgraph / DfsUtil      graph.cpp:984-1089          -> largest_subgraph()
 //   Graph::AddWeights                     graph.cpp:1104-1165         -> add_weights()
-//   Graph::GenerateCorrectedSequence      graph.cpp:1167-1179         -> emit_corrected()
+//   Graph::GenerateCorrectedSequence      graph.cpp:1167-1179         -> step_update(), kPcFinalPost
 //   Graph::GenerateConsensus (+coverage)  graph.cpp:450-485,534-638   -> heaviest_bundle()
 //   Linear-gap NW/SW traceback            simd_alignment_engine_implementation.hpp:908-1105
-//                                         (scalar twin sisd_alignment_engine.cpp:362-460) -> traceback()
+//                                         (scalar twin sisd_alignment_engine.cpp:362-460) -> TraceWalker
 //
 // Data layout (per window "slot", all in HBM unless noted):
 //   nodes : code u8, nin/nout u32, aligned list (<= kMaxAligned ids), coverage u32
@@ -28,7 +29,8 @@
 //           off[node] + ord), dead u8 (pruned hole)
 //   in-lists: per node a fixed-stride row of (tail, edge id) in creation order — appended in place, never
 //           rebuilt; out_off/out_eid: CSR of out-edges, built only where a pass needs it
-//   H     : one row of packed int16 score cells per graph node (+ virtual row 0), row = node id + 1
+//   rowprog: 16 B per DP row in rank order: code, sink, node id, up to six predecessors as 16-bit row distances
+//   H     : one row of packed int16 score cells per DP row (row = rank + 1; row 0 = the virtual row), lane-major
 //   fc    : int16 first-column value per row (NW border)
 #ifndef VGC_POA_CORE_H_
 #define VGC_POA_CORE_H_

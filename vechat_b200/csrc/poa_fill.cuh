@@ -15,10 +15,11 @@
 //   diagonal   : register k-1 of the predecessor row (lane boundary: one shuffle)
 //   horizontal : in-register running max over the lane's K cells, then a 5-step warp-shuffle max-scan of
 //                (segment end value - g * column) across the 64 segments, then one fused add-max per register
-// Rows are written once to HBM (2 B per cell, coalesced 8-byte stores) because the traceback re-reads
-// them.  Predecessor rows come, in order of preference, from registers (the row just computed: the
-// common case along chains, updated in place), from a small ring of the most recent rows in shared
-// memory, or from HBM/L2.
+// Rows are written once to HBM (2 B per cell, lane-major: lane l stores its K words at [l*K, l*K + K), so a run
+// of columns is a run of words for the traceback's tiles) because the traceback re-reads them.  The row width is
+// chosen per alignment (fill_width: K = 8 for layers up to 512 columns).  Predecessor rows come, in order of
+// preference, from registers (distance 1: the row just computed, the common case along chains, updated in place),
+// from a ring of the four most recent rows in shared memory (slot = row mod 4), or from HBM/L2.
 #ifndef VGC_POA_FILL_CUH_
 #define VGC_POA_FILL_CUH_
 

@@ -1,9 +1,13 @@
-// vgc_engine.cu — C-ABI (include/vgc.h) + the persistent sm_100a POA kernel.
+// vgc_engine.cu — C-ABI (include/vgc.h) + the four sm_100a kernels of the lockstep POA engine.
 //
-// One window per CTA, one warp per CTA (32 lanes): the DP rows are register-resident across the warp
-// (poa_fill.cuh), the graph lives in a per-CTA scratch slot in HBM with its sort-time working set staged in
-// shared memory, and the window algorithm itself is the template of poa_core.h.  CTAs are persistent: the
-// grid is (#SMs x resident CTAs per SM) and each CTA pulls windows, heaviest first, from an atomic cursor.
+// A window is a resumable program (poa_core.h: WinState + Poa::step_*) whose state lives in HBM; one lockstep
+// cycle advances every live window of a stream group by one sequence-to-graph alignment:
+//   trace_kernel   traceback of the alignment just filled            one THREAD per window (TraceWalker)
+//   update_kernel  AddAlignment / AddWeights / prune / emit + plan   one warp per window, 4 windows per CTA
+//   sort_kernel    LargestSubgraph, TopologicalSort, row program     one warp per window, graph staged in smem
+//   fill_kernel    DP fill of the next alignment (poa_fill.cuh)      one warp per window, rows in registers
+// The host (run_pass) deals the windows of a batch into stream groups (one per number of alignments), gives every
+// window a scratch slot in HBM and enqueues the cycles; groups overlap freely on the device.
 //
 // Replaces Polisher::polish's per-window lambda (reference src/polisher.cpp:498-516) for a whole batch.
 // No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
