@@ -123,7 +123,8 @@ int vgc_polish_resident(vgc_handle h, vgc_result* result, vgc_stats* stats);
  * Index: 0 traceback cycles spent in tile-refill phases (part of 4), 1 toposort, 2 row program, 3 DP fill,
  * 4 traceback, 5 AddAlignment, 6 AddWeights, 7 PruneGraph, 8 LargestSubgraph, 9 emit/consensus,
  * 10 number of traceback tile refills (a count, not cycles), 11 host wall-clock milliseconds spent enqueueing the
- * kernel launches. */
+ * kernel launches, 12 TopologicalSort runs, 13 how many of them sorted out of HBM because the staged graph did not fit
+ * the kernel's shared memory. */
 int vgc_phase_profile(vgc_handle h, double out[16]);
 
 const char* vgc_last_error(void);

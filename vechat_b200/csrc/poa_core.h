@@ -203,6 +203,7 @@ struct WinState {
   uint32_t prep;         // kPrep* flags for step_prepare
   unsigned long long cells;
   uint32_t alignments;
+  uint32_t sorts, sorts_hbm;   // TopologicalSort runs of this window / how many had to sort out of HBM (staging did not fit)
   // per-phase cycle counters (leader lane, clock64): see kPh*
   unsigned long long t_last;
   unsigned long long phase[12];
@@ -836,6 +837,10 @@ struct Poa {
     }
     ex.sync();
     const uint32_t n = ws.scratch[0];
+    if (ex.leader()) {
+      ws.sorts += 1;
+      ws.sorts_hbm += fast ? 0u : 1u;
+    }
     staged = fast;  // the row-program builder reads the adjacency (and the ranks the sort wrote) from here
     st_rec = rec;
     st_adj = adj16;
@@ -1584,6 +1589,7 @@ struct Poa {
         ws.aln_len = 0;
         ws.cells = 0;
         ws.alignments = 0;
+        ws.sorts = ws.sorts_hbm = 0;
         ws.nMain = 0;
         sl.g[0].nV = 0;
         sl.g[0].nE = 0;

@@ -42,7 +42,7 @@ struct KernelArgs {
   uint8_t* out;            // output bytes (bv.out_off / out_cap index into it)
   uint32_t* out_len;       // [n_windows]
   uint32_t* status;        // [n_windows]
-  unsigned long long* totals;  // [2 + kPhCount]: cells, alignments, per-phase cycles
+  unsigned long long* totals;  // [2 + kPhCount + 2]: cells, alignments, per-phase cycles, sorts, sorts out of HBM
   Scores nw;
   uint32_t haplotype, trim, num_prune;
   double min_confidence, min_support;
@@ -208,6 +208,8 @@ __device__ __forceinline__ void win_leave(const KernelArgs& a, const WinCtx& c) 
     atomicAdd(a.totals, c.ws->cells);
     atomicAdd(a.totals + 1, static_cast<unsigned long long>(c.ws->alignments));
     for (int i = 0; i < kPhCount; ++i) atomicAdd(a.totals + 2 + i, c.ws->phase[i]);
+    atomicAdd(a.totals + 2 + kPhCount, static_cast<unsigned long long>(c.ws->sorts));
+    atomicAdd(a.totals + 3 + kPhCount, static_cast<unsigned long long>(c.ws->sorts_hbm));
   }
 }
 
@@ -809,7 +811,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   }
   const uint32_t n_dev = static_cast<uint32_t>(pr.device_windows.size());
   uint32_t launches = 0, relaunched = 0;
-  unsigned long long totals[2 + vgc::kPhCount] = {0};
+  unsigned long long totals[4 + vgc::kPhCount] = {0};
   float kernel_ms = 0.f, d2h_ms = 0.f;
   h->pass_kernel_ms = 0.0;
   h->launch_ms = 0.0;
@@ -888,9 +890,18 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     }
     result->cons_off[nw] = off;
   }
+  // feedback for the next call: if more than 2 % of the sorts did not fit the shared memory the growth bound gave
+  // them, the data grows its graphs faster than assumed — raise the bound (sticky per engine)
+  {
+    const double sorts = static_cast<double>(totals[2 + vgc::kPhCount]);
+    const double hbm = static_cast<double>(totals[3 + vgc::kPhCount]);
+    if (sorts > 0 && hbm > 0.02 * sorts && h->sort_growth < 1.0) h->sort_growth *= 1.3;
+  }
   if (stats) {
     for (int i = 0; i < vgc::kPhCount; ++i) h->phase_cycles[i] = static_cast<double>(totals[2 + i]);
     h->phase_cycles[11] = h->launch_ms;
+    h->phase_cycles[12] = static_cast<double>(totals[2 + vgc::kPhCount]);
+    h->phase_cycles[13] = static_cast<double>(totals[3 + vgc::kPhCount]);
     stats->cells = totals[0];
     stats->alignments = totals[1];
     stats->input_bytes = input_bytes;

@@ -104,7 +104,7 @@ class Engine:
 
 
 PHASES = ["trace_refill", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
-          "largest_subgraph", "emit", "trace_refills", "host_launch_ms"]
+          "largest_subgraph", "emit", "trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm"]
 
 
 def _phase_profile(engine):
