@@ -146,6 +146,7 @@ def cpu_leg(batch, params, seconds, threads=None):
     n = int(max(cores, min(nw, rate * seconds)))
     idx = np.linspace(0, nw - 1, num=n).astype(int)
     sb = batch.select(idx)
+    sb.sample_index = idx
     return kind, cores, sb, fn
 
 
@@ -335,6 +336,11 @@ def main():
                 "corrected_bases_per_sec": r.total_bases() / dt,
                 "sample": "%d of the batch's %d windows (every k-th) in %.1f s on %d host threads" % (
                     sb.n_windows, batch.n_windows, dt, cores)}
+            # the checker's windows against the engine's (last e2e step), byte for byte: parity at the bench's size
+            bad = sum(1 for i, w in enumerate(sb.sample_index)
+                      if result.window(int(w)) != r.window(i) or int(result.polished[int(w)]) != int(r.polished[i]))
+            line["parity"] = {"windows_checked": int(sb.n_windows), "mismatches": int(bad),
+                              "against": "compiled reference" if kind == "reference" else "oracle port"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
