@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--targets", type=int, default=1600, help="target reads per GPU per step (20 windows each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--num-prune", type=int, default=3, help="diagnostics only: -k of the haplotype path (3 = the benchmark)")
     return ap.parse_args()
 
 
@@ -205,8 +206,8 @@ def main():
 
     sim, batch = make_batch(args, rank, world)
     batch = pin_batch(batch)
-    params = make_params()
-    eng = Engine(local)
+    params = make_params(num_prune=args.num_prune)
+    eng = Engine(local, num_prune=args.num_prune)
     pol = Polisher(local, rank=rank, world=world, engine=eng)
     dev = torch.device("cuda", local)
     names = lambda t: "read%d" % t  # noqa: E731
