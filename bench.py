@@ -44,14 +44,24 @@ def parse():
     ap.add_argument("--targets", type=int, default=1600, help="target reads per GPU per step (20 windows each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--workload", default="pb", choices=["pb", "ont", "hap2"],
+                    help="pb = BASELINE configs[1] (the benchmark); ont / hap2 = configs[2] / configs[3], extra evidence only")
     ap.add_argument("--num-prune", type=int, default=3, help="diagnostics only: -k of the haplotype path (3 = the benchmark)")
     return ap.parse_args()
 
 
+WORKLOADS = {
+    "pb": ("pb_clr_10k_x_10kb", "synthetic PacBio CLR 10k reads x 10 kb, 15% error"),
+    "ont": ("ont_10k_x_20kb", "synthetic ONT 10k reads x 20 kb, 10% error"),
+    "hap2": ("hap2_50k_x_12kb", "2-haplotype 50:50 mix, 50k reads x 12 kb, 15% error"),
+}
+
+
 def workload_config(args, world):
-    return {"workload": "%s: synthetic PacBio CLR 10k reads x 10 kb, 15%% error, 500 bp windows, haplotype mode "
+    name, text = WORKLOADS[args.workload]
+    return {"workload": "%s: %s, 500 bp windows, haplotype mode "
                         "(-p -d 0.2 -s 0.2 -k 3, m=3 x=-5 g=-4); batch = all windows of %d target reads per GPU "
-                        "per step" % (WORKLOAD, args.targets),
+                        "per step" % (name, text, args.targets),
             "targets_per_gpu": args.targets, "window_length": 500, "ranks": world,
             "sharding": "whole target reads per rank, no data-path collective; gather of corrected reads in e2e",
             "l2": "inputs per step (~1 GB at 1600 targets) and DP scratch (~100 GB) exceed the 126 MB L2; no explicit flush"}
@@ -62,7 +72,7 @@ def make_batch(args, rank, world=1):
     ranges while world * T fits the config's 10k reads, overlapping ones beyond that (8 x 1600 > 10k); either way
     every rank carries the same amount of work (weak scaling)."""
     from vechat_b200.sim import Simulator
-    sim = Simulator(WORKLOAD)
+    sim = Simulator(WORKLOADS[args.workload][0])
     T = min(args.targets, sim.n_reads)
     stride = min(T, sim.n_reads // max(world, 1))
     t0 = min(rank * stride, sim.n_reads - T)
