@@ -610,7 +610,11 @@ uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, u
 uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exact, uint32_t share_div) {
   const uint64_t ub = static_cast<uint64_t>(pr.win_sum_len[w]) + 64;
   if (exact) return static_cast<uint32_t>(ub);
-  const uint64_t est = blen + pr.win_sum_len[w] / share_div + pr.win_max_len[w] + 64;
+  // new nodes per read shrink as the graph saturates (measured: ~1 300 extra nodes at depth 30, ~1 550 at depth
+  // 100 for 520-base layers at 15 % error): cap the share at five mean layer lengths
+  const uint64_t nlay = pr.win_nseq[w] > 1 ? pr.win_nseq[w] - 1 : 1;
+  const uint64_t grow = std::min<uint64_t>(pr.win_sum_len[w] / share_div, 5 * ((pr.win_sum_len[w] - blen) / nlay + 1));
+  const uint64_t est = blen + grow + pr.win_max_len[w] + 64;
   return static_cast<uint32_t>(std::min(ub, est));
 }
 
