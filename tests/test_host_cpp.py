@@ -59,7 +59,8 @@ def ids_of(batch):
 
 
 @pytest.mark.parametrize("seed,kw", [(401, dict(n_windows=10)), (402, dict(n_windows=10, fastq=False)),
-                                     (403, dict(n_windows=10, n_frac=0.05, null_qual=0.5, partial=0.6))])
+                                     (403, dict(n_windows=10, n_frac=0.05, null_qual=0.5, partial=0.6)),
+                                     (405, dict(n_windows=300, length=20, depth=3, null_qual=0.3))])  # threaded copy
 def test_pack_matches_window_contents(seed, kw):
     batch = fuzz_batch(seed, **kw)
     wid, wrank = ids_of(batch)

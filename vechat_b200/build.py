@@ -63,7 +63,7 @@ def build_host(force=False):
     deps = srcs + [os.path.join(hdir, "vgc_host.hpp"), os.path.join(INC, "vgc.h")]
     if force or _stale(out, deps):
         _run([CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", INC, "-I", hdir, "-o", out] + srcs +
-             ["-L", LIB_DIR, "-lvgc", "-Wl,-rpath,$ORIGIN"])
+             ["-L", LIB_DIR, "-lvgc", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

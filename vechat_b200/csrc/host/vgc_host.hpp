@@ -16,7 +16,10 @@
 #include <cstdlib>
 #include <functional>
 #include <memory>
+#include <algorithm>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -124,8 +127,19 @@ class BatchPacker {
  public:
   // Copies the bytes the windows borrow (Window does not own them; the reference frees them when polish ends,
   // polisher.cpp:560-561).
-  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, PackedBatch* p) {
+  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, PackedBatch* p,
+                   unsigned num_threads = 0) {
     *p = PackedBatch();
+    // pass 1 (serial, metadata only): layer table and byte offsets
+    size_t n_layers = 0;
+    for (size_t i = first; i < last; ++i) n_layers += w[i]->sequences_.size();
+    p->win_first.reserve(last - first + 1);
+    p->win_flags.reserve(last - first);
+    p->seq_off.reserve(n_layers + 1);
+    p->has_qual.reserve(n_layers);
+    p->begin.reserve(n_layers);
+    p->end.reserve(n_layers);
+    uint64_t bytes = 0;
     for (size_t i = first; i < last; ++i) {
       const Window& win = *w[i];
       p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
@@ -135,19 +149,42 @@ class BatchPacker {
       p->win_flags.push_back(static_cast<uint8_t>((win.type_ == WindowType::kTGS ? VGC_WIN_TGS : 0u) |
                                                   (dummy ? VGC_WIN_DUMMY_QUAL : 0u)));
       for (size_t l = 0; l < win.sequences_.size(); ++l) {
-        const uint32_t len = win.sequences_[l].second;
-        p->seq_off.push_back(p->bases.size());
-        p->bases.insert(p->bases.end(), win.sequences_[l].first, win.sequences_[l].first + len);
-        const char* q = win.qualities_[l].first;
-        p->has_qual.push_back(q != nullptr ? 1 : 0);
-        if (q != nullptr) p->quals.insert(p->quals.end(), q, q + len);
-        else p->quals.resize(p->bases.size(), static_cast<uint8_t>('!'));
+        p->seq_off.push_back(bytes);
+        bytes += win.sequences_[l].second;
+        p->has_qual.push_back(win.qualities_[l].first != nullptr ? 1 : 0);
         p->begin.push_back(win.positions_[l].first);
         p->end.push_back(win.positions_[l].second);
       }
     }
     p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
-    p->seq_off.push_back(p->bases.size());
+    p->seq_off.push_back(bytes);
+    // pass 2 (threads over window ranges): copy the bytes the windows borrow
+    p->bases.resize(bytes);
+    p->quals.resize(bytes);
+    const size_t nw = last - first;
+    unsigned nt = num_threads ? num_threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nw < 256) nt = 1;
+    auto copy_range = [&](size_t a, size_t b) {
+      for (size_t i = a; i < b; ++i) {
+        const Window& win = *w[first + i];
+        size_t layer = p->win_first[i];
+        for (size_t l = 0; l < win.sequences_.size(); ++l, ++layer) {
+          const uint32_t len = win.sequences_[l].second;
+          const uint64_t o = p->seq_off[layer];
+          std::memcpy(p->bases.data() + o, win.sequences_[l].first, len);
+          const char* q = win.qualities_[l].first;
+          if (q != nullptr) std::memcpy(p->quals.data() + o, q, len);
+          else std::memset(p->quals.data() + o, '!', len);
+        }
+      }
+    };
+    if (nt == 1) {
+      copy_range(0, nw);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(copy_range, nw * t / nt, nw * (t + 1) / nt);
+      for (auto& x : th) x.join();
+    }
   }
   static void store(Window& win, const uint8_t* s, uint64_t n, bool polished) {
     win.consensus_.assign(reinterpret_cast<const char*>(s), n);
