@@ -30,7 +30,7 @@ def main():
                   partial=float(rng.choice([0.0, 0.3, 0.8])), fastq=bool(rng.random() < 0.7),
                   null_qual=float(rng.choice([0.0, 0.0, 0.4])), n_frac=float(rng.choice([0.0, 0.0, 0.03])))
         if rng.random() < 0.5:
-            kw["length"] = int(rng.integers(8, 700))
+            kw["length"] = int(rng.integers(8, 950 if rng.random() < 0.15 else 700))
         if rng.random() < 0.5:
             kw["depth"] = int(rng.integers(0, 60))
         key = tuple(sorted(pkw.items()))
