@@ -1570,7 +1570,9 @@ struct Poa {
         ws.pc = next_pc;
         ws.j = j;
         ws.k = k;
-        ws.prep = prep | (changed ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
+        // an alignment against a Subgraph view sorts that view itself and the graph changes again before anything
+        // could use the main order, so the main sort is skipped then (the reference sorts both, with the same result)
+        ws.prep = prep | ((changed && !(prep & kPrepSubSort)) ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
         ws.fill_layer = layer;
         ws.fill_mode = mode;
         ws.need = (ws.prep == kPrepFill) ? kNeedFill : kNeedPrepare;
