@@ -96,7 +96,7 @@ typedef struct {
   uint64_t input_bytes;    /* bytes copied host -> device                                        */
   uint64_t output_bytes;   /* bytes copied device -> host                                        */
   double   kernel_ms;      /* device time of the POA kernel(s), CUDA events on the launch stream  */
-  double   h2d_ms;
+  double   h2d_ms;         /* first H2D copy -> last (the bulk copies overlap the host preparation)             */
   double   d2h_ms;
   double   device_ms;      /* first device op of the call -> last (H2D if any + kernels + D2H), CUDA events   */
   double   host_prep_ms;   /* host-side batch preparation (rank sort, average weights), wall clock          */

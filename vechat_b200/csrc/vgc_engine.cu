@@ -493,7 +493,9 @@ namespace {
 
 using namespace vgc;
 
-int upload(vgc_engine* h, const vgc_batch* b, uint64_t* bytes_out) {
+// Host -> device copies of a batch, in two parts so that the bulk (bases, qualities, layer tables: everything the
+// caller owns) is already in flight on the copy stream while the host prepares the rest (prepare_batch).
+int upload_part(vgc_engine* h, const vgc_batch* b, bool raw, uint64_t* bytes_io) {
   const uint32_t nw = b->n_windows, nl = b->n_layers;
   const uint64_t nb = nl ? b->seq_off[nl] : 0;
   Prepared& pr = h->prep;
@@ -512,14 +514,18 @@ int upload(vgc_engine* h, const vgc_batch* b, uint64_t* bytes_out) {
     return VGC_OK;
   };
   int rc;
-  if ((rc = put(h->d_bases, b->bases, nb))) return rc;
-  if ((rc = put(h->d_quals, b->quals, b->quals ? nb : 0))) return rc;
-  if ((rc = put(h->d_seq_off, b->seq_off, (nl + 1) * sizeof(uint64_t)))) return rc;
-  if ((rc = put(h->d_has_qual, b->has_qual, nl))) return rc;
-  if ((rc = put(h->d_begin, b->begin, nl * 4ull))) return rc;
-  if ((rc = put(h->d_end, b->end, nl * 4ull))) return rc;
-  if ((rc = put(h->d_win_first, b->win_first, (nw + 1) * 4ull))) return rc;
-  if ((rc = put(h->d_win_flags, b->win_flags, nw))) return rc;
+  if (raw) {
+    if ((rc = put(h->d_bases, b->bases, nb))) return rc;
+    if ((rc = put(h->d_quals, b->quals, b->quals ? nb : 0))) return rc;
+    if ((rc = put(h->d_seq_off, b->seq_off, (nl + 1) * sizeof(uint64_t)))) return rc;
+    if ((rc = put(h->d_has_qual, b->has_qual, nl))) return rc;
+    if ((rc = put(h->d_begin, b->begin, nl * 4ull))) return rc;
+    if ((rc = put(h->d_end, b->end, nl * 4ull))) return rc;
+    if ((rc = put(h->d_win_first, b->win_first, (nw + 1) * 4ull))) return rc;
+    if ((rc = put(h->d_win_flags, b->win_flags, nw))) return rc;
+    *bytes_io += bytes;
+    return VGC_OK;
+  }
   if ((rc = put(h->d_rank, pr.layer_rank.data(), nl * 4ull))) return rc;
   if ((rc = put(h->d_nseq, pr.win_nseq.data(), nw * 4ull))) return rc;
   if ((rc = put(h->d_avgw, pr.win_avgw.data(), nw * 8ull))) return rc;
@@ -536,8 +542,16 @@ int upload(vgc_engine* h, const vgc_batch* b, uint64_t* bytes_out) {
     set_err(std::string("H2D sync failed: ") + cudaGetErrorString(e));
     return VGC_ERR_CUDA;
   }
-  *bytes_out = bytes;
+  *bytes_io += bytes;
   return VGC_OK;
+}
+
+// basic shape checks needed before anything is read from the batch's arrays (prepare_batch repeats them)
+bool batch_shape_ok(const vgc_batch* b) {
+  const uint32_t nw = b->n_windows;
+  if (!nw) return true;
+  return b->win_first && b->seq_off && b->bases && b->begin && b->end && b->has_qual && b->win_flags &&
+         b->win_first[nw] == b->n_layers;
 }
 
 BatchView make_view(vgc_engine* h) {
@@ -1031,17 +1045,23 @@ int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_sta
   VGC_CUDA(cudaSetDevice(h->device));
   h->resident = false;
   std::string err;
+  uint64_t in_bytes = 0;
+  float h2d_ms = 0.f;
+  int rc;
+  // the bulk copies start first and overlap the host-side preparation
+  VGC_CUDA(cudaEventRecord(h->ev[4], h->stream));
+  const bool early = batch_shape_ok(batch);
+  if (early && (rc = upload_part(h, batch, true, &in_bytes))) return rc;
   const auto t0 = std::chrono::steady_clock::now();
-  int rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
+  rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
   const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (rc != VGC_OK) {
+    cudaStreamSynchronize(h->stream);  // the caller may free its buffers as soon as we return
     set_err(err);
     return rc;
   }
-  uint64_t in_bytes = 0;
-  float h2d_ms = 0.f;
-  VGC_CUDA(cudaEventRecord(h->ev[4], h->stream));
-  if ((rc = upload(h, batch, &in_bytes))) return rc;
+  if (!early && (rc = upload_part(h, batch, true, &in_bytes))) return rc;
+  if ((rc = upload_part(h, batch, false, &in_bytes))) return rc;
   VGC_CUDA(cudaEventRecord(h->ev[5], h->stream));
   rc = polish_device(h, result, stats, in_bytes, batch->bases, batch->seq_off, batch->win_first, batch->n_windows);
   if (rc != VGC_OK) return rc;
@@ -1069,7 +1089,9 @@ int vgc_upload(vgc_handle h, const vgc_batch* batch) {
     set_err(err);
     return rc;
   }
-  if ((rc = upload(h, batch, &h->r_input_bytes))) return rc;
+  h->r_input_bytes = 0;
+  if ((rc = upload_part(h, batch, true, &h->r_input_bytes))) return rc;
+  if ((rc = upload_part(h, batch, false, &h->r_input_bytes))) return rc;
   // keep what the stitcher needs from the host batch
   h->r_n_windows = batch->n_windows;
   h->r_n_layers = batch->n_layers;
