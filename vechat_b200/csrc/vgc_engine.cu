@@ -231,7 +231,7 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
 // shared memory: coder[256] | 32 x { tile cells kTR x kTW words | tile records kTR x 16 B | pad }
 constexpr uint32_t kTraceLaneWords = kTR * kTW + kTR * 4 + 4;  // 16-byte aligned, lanes' banks spread
 constexpr uint32_t kTraceSmem = 256 + 32 * kTraceLaneWords * 4;
-constexpr int kTraceRound = 8;
+constexpr int kTraceRound = 16;
 
 template <int K>
 __global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
