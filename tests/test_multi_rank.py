@@ -77,3 +77,42 @@ def test_shard_targets_properties():
             if w0 < len(win_target) and w0 > 0:
                 assert win_target[w0] != win_target[w0 - 1]  # cut only between targets
     assert shard_targets(np.zeros(0, dtype=np.int64), np.zeros(0), 4) == [(0, 0)] * 4
+
+
+def _stitch_literal(result, win_target, win_rank, names, coverages, fragment_correction, drop_unpolished):
+    """src/polisher.cpp:520-546 transcribed statement by statement (the check for polisher.stitch)."""
+    out, data, num_polished = [], b"", 0
+    n = len(result.polished)
+    for i in range(n):
+        num_polished += 1 if result.polished[i] else 0
+        data += result.window(i)
+        if i == n - 1 or win_rank[i + 1] == 0:
+            ratio = num_polished / float(win_rank[i] + 1)
+            if (not drop_unpolished) or ratio > 0:
+                tags = "r" if fragment_correction else ""
+                tags += " LN:i:" + str(len(data))
+                tags += " RC:i:" + str(coverages[int(win_target[i])])
+                tags += " XC:f:" + "%f" % ratio
+                out.append((names[int(win_target[i])] + tags, data))
+            num_polished, data = 0, b""
+    return out
+
+
+def test_stitch_matches_the_reference_loop():
+    from vechat_b200._ffi import PolishResult
+    rng = np.random.default_rng(9)
+    for trial in range(20):
+        counts = rng.integers(1, 9, size=int(rng.integers(1, 30)))
+        win_target = np.repeat(np.arange(len(counts)), counts)
+        win_rank = np.concatenate([np.arange(c) for c in counts])
+        lens = rng.integers(0, 40, size=len(win_target))
+        cons = rng.integers(65, 70, size=int(lens.sum())).astype(np.uint8)
+        cons_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        polished = (rng.random(len(win_target)) < (0.0 if trial % 5 == 0 else 0.6)).astype(np.uint8)
+        res = PolishResult(cons, cons_off, polished)
+        names = ["t%d" % t for t in range(len(counts))]
+        cov = [int(x) for x in rng.integers(0, 50, size=len(counts))]
+        for frag in (True, False):
+            for drop in (True, False):
+                got = stitch(res, win_target, win_rank, names, cov, fragment_correction=frag, drop_unpolished=drop)
+                assert got == _stitch_literal(res, win_target, win_rank, names, cov, frag, drop)
