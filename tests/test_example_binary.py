@@ -1,0 +1,246 @@
+"""Config 1 plumbing: the reference PROGRAM with the B200 engine dropped in.
+
+* oracle/_ref/vechat_racon        — the unmodified reference (main.cpp, Polisher::initialize/polish, window.cpp, spoa)
+                                    compiled by oracle/Makefile `racon`; the authority here.
+* vechat_b200/lib/vechat_racon_b200 — the same objects + csrc/racon_binding/b200polisher.cpp (racon::B200Polisher,
+                                    overrides polish() only) + libvgc.so.
+
+Both read the same reads / overlaps / targets, so the window tilings are identical by construction (initialize() is
+inherited) and the corrected FASTA must be identical byte for byte, headers (LN/RC/XC tags) included.
+
+Fixture: tests/golden/example/ = a cluster of 10 neighbouring reads of the reference's example/reads.fq.gz as targets,
+the 89 reads overlapping them, overlaps from tools/example_overlaps.py (minimap2 is not in this image), and the
+reference binary's outputs (corrected.hap.fa: `-f -p -d 0.2 -s 0.2`, the vechat driver's first pass,
+scripts/vechat:69-72; corrected.lin.fa: `-f`, its second pass, :90-93).  One of the 10 targets has no polished
+window and is dropped by both (polisher.cpp:529).
+"""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+EX = os.path.join(GOLDEN, "example")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "vechat_racon")
+B200_BIN = os.path.join(ROOT, "vechat_b200", "lib", "vechat_racon_b200")
+HAP = ["-f", "-p", "-d", "0.2", "-s", "0.2"]
+LIN = ["-f"]
+
+need_ref = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/vechat_racon not built (needs /root/reference)")
+need_b200 = pytest.mark.skipif(not os.path.exists(B200_BIN), reason="vechat_racon_b200 not built (needs /root/reference)")
+
+
+def run(binary, opts, reads="reads.fq.gz", paf="overlaps.paf", targets="targets.fq.gz", cwd=EX, devices=None, threads=8):
+    env = dict(os.environ)
+    env.pop("VECHAT_B200_DEVICES", None)
+    if devices is not None:
+        env["VECHAT_B200_DEVICES"] = devices
+    return subprocess.run([binary] + opts + ["-t", str(threads), reads, paf, targets], cwd=cwd, env=env,
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+
+
+def golden(name):
+    with open(os.path.join(EX, name), "rb") as f:
+        return f.read()
+
+
+# ---------------------------------------------------------------- CPU: the authority and the seam
+
+@need_ref
+@pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN, "corrected.lin.fa")])
+def test_reference_binary_reproduces_committed_fasta(opts, want):
+    r = run(REF_BIN, opts)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert r.stdout == golden(want)
+    assert r.stdout.count(b">") == 9  # 10 targets, one without a polished window
+
+
+@need_ref
+def test_reference_binary_thread_count_is_not_a_parity_variable():
+    assert run(REF_BIN, HAP, threads=1).stdout == golden("corrected.hap.fa")
+
+
+@need_b200
+def test_b200_binary_without_devices_is_the_reference():
+    """No VECHAT_B200_DEVICES and no -c: createPolisherB200 forwards to the reference's own factory."""
+    r = run(B200_BIN, HAP)
+    assert r.returncode == 0
+    assert r.stdout == golden("corrected.hap.fa")
+
+
+@need_b200
+def test_b200_binary_fails_loudly_without_gpu():
+    """The engine has no CPU path: asking for a device that is not there ends like the reference's error sites
+    (stderr message + exit(1)), after initialize() and before any output."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = run(B200_BIN, HAP, devices="0")
+    assert r.returncode == 1
+    assert r.stdout == b""
+    assert b"[racon::B200Polisher::polish] error:" in r.stderr and b"no usable CUDA device" in r.stderr
+
+
+@need_b200
+def test_b200_binary_rejects_bad_device_list():
+    r = run(B200_BIN, HAP, devices="zero")
+    assert r.returncode == 1 and b"VECHAT_B200_DEVICES" in r.stderr
+
+
+# ---------------------------------------------------------------- the edlib stand-in both binaries are built on
+
+def _edlib():
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libedlib_standin.so"))
+
+    class Cfg(C.Structure):
+        _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int), ("eq", C.c_void_p), ("neq", C.c_int)]
+
+    class Res(C.Structure):
+        _fields_ = [("status", C.c_int), ("editDistance", C.c_int), ("endLocations", C.POINTER(C.c_int)),
+                    ("startLocations", C.POINTER(C.c_int)), ("numLocations", C.c_int),
+                    ("alignment", C.POINTER(C.c_ubyte)), ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+    lib.edlibNewAlignConfig.restype = Cfg
+    lib.edlibNewAlignConfig.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.edlibAlign.restype = Res
+    lib.edlibAlign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, Cfg]
+    lib.edlibAlignmentToCigar.restype = C.c_void_p
+    lib.edlibAlignmentToCigar.argtypes = [C.POINTER(C.c_ubyte), C.c_int, C.c_int]
+    lib.edlibFreeAlignResult.argtypes = [Res]
+    return lib
+
+
+def _edit_distance(a, b):
+    prev = np.arange(len(b) + 1)
+    for i, ca in enumerate(a, 1):
+        cur = np.empty_like(prev)
+        cur[0] = i
+        sub = prev[:-1] + (np.frombuffer(b, np.uint8) != ca)
+        best = np.minimum(sub, prev[1:] + 1)
+        # horizontal moves: cur[j] = min(best[j], cur[j-1] + 1)  -> prefix scan on (value - index)
+        row = np.concatenate(([i], best))
+        row = np.minimum.accumulate(row - np.arange(len(row))) + np.arange(len(row))
+        cur = row
+        prev = cur
+    return int(prev[-1])
+
+
+def test_edlib_standin_is_an_exact_global_aligner():
+    """edit distance == textbook DP; the path consumes both strings, its edits == the distance, M columns agree
+    with match/mismatch, and the standard CIGAR is the run-length form overlap.cpp:225-292 parses."""
+    lib = _edlib()
+    rng = np.random.default_rng(7)
+    cases = [(b"", b"ACGT"), (b"ACGT", b""), (b"A", b"A"), (b"A", b"C"), (b"ACGT" * 5, b"ACGT" * 5)]
+    for _ in range(60):
+        n = int(rng.integers(1, 400))
+        t = rng.integers(0, 4, n)
+        q = []
+        for x in t:  # noisy copy: 10 % sub, 8 % ins, 6 % del
+            u = rng.random()
+            if u < 0.06:
+                continue
+            q.append(int(rng.integers(0, 4)) if u < 0.16 else int(x))
+            if rng.random() < 0.08:
+                q.append(int(rng.integers(0, 4)))
+        cases.append((bytes(b"ACGT"[x] for x in q), bytes(b"ACGT"[x] for x in t)))
+    for q, t in cases:
+        cfg = lib.edlibNewAlignConfig(-1, 0, 2, None, 0)  # EDLIB_MODE_NW, EDLIB_TASK_PATH
+        r = lib.edlibAlign(q, len(q), t, len(t), cfg)
+        assert r.status == 0
+        assert r.editDistance == _edit_distance(q, t), (q, t)
+        ops = [r.alignment[i] for i in range(r.alignmentLength)]
+        i = j = edits = 0
+        for op in ops:
+            if op in (0, 3):
+                assert (q[i] == t[j]) == (op == 0)
+                i, j, edits = i + 1, j + 1, edits + (op == 3)
+            elif op == 1:
+                i, edits = i + 1, edits + 1
+            else:
+                j, edits = j + 1, edits + 1
+        assert (i, j, edits) == (len(q), len(t), r.editDistance)
+        p = lib.edlibAlignmentToCigar(r.alignment, r.alignmentLength, 0)
+        cigar = C.string_at(p).decode()
+        C.CDLL(None).free(C.c_void_p(p))
+        runs, k = [], 0
+        while k < len(cigar):
+            m = k
+            while cigar[m].isdigit():
+                m += 1
+            runs.append((int(cigar[k:m]), cigar[m]))
+            k = m + 1
+        assert sum(n for n, c in runs if c in "MI") == len(q) and sum(n for n, c in runs if c in "MD") == len(t)
+        assert all(a[1] != b[1] for a, b in zip(runs, runs[1:]))
+        lib.edlibFreeAlignResult(r)
+
+
+# ---------------------------------------------------------------- GPU: byte-for-byte FASTA parity
+
+def _b200(opts, **kw):
+    assert os.path.exists(B200_BIN), "vechat_racon_b200 is missing: build it in the development container " \
+                                     "(python -m vechat_b200.build) so that it travels with the snapshot"
+    r = run(B200_BIN, opts, devices="0", **kw)
+    assert r.returncode == 0, r.stderr[-600:]
+    assert b"[racon::B200Polisher::polish] generated consensus" in r.stderr  # the GPU polisher ran, not the CPU one
+    return r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN, "corrected.lin.fa")])
+def test_gpu_binary_matches_committed_reference_fasta(opts, want):
+    assert _b200(opts) == golden(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [
+    HAP + ["-u"],                               # keep unpolished targets (drop_unpolished_sequences = false)
+    HAP + ["-k", "1"], HAP + ["-k", "2", "-d", "0.3", "-s", "0.1"],
+    HAP + ["-w", "300"], HAP + ["-w", "640"],   # other window lengths (tilings change with them)
+    HAP + ["-q", "-1"],                         # no quality filter: every layer kept, deepest windows
+    HAP + ["-m", "5", "-x", "-4", "-g", "-8"],  # racon's own default scores
+    LIN + ["--no-trimming"], LIN + ["-u", "-w", "300"],
+], ids=lambda o: " ".join(o))
+def test_gpu_binary_matches_reference_binary_live(opts):
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/vechat_racon not built")
+    want = run(REF_BIN, opts)
+    assert want.returncode == 0
+    assert _b200(opts) == want.stdout
+
+
+@pytest.mark.gpu
+def test_gpu_binary_fasta_input(tmp_path):
+    """Second-pass shape (scripts/vechat:372-397): reads and targets are FASTA, every window takes the dummy-quality
+    branch of window.cpp:223 except each target's last, shorter window."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/vechat_racon not built")
+    for src, dst in (("reads.fq.gz", "reads.fa"), ("targets.fq.gz", "targets.fa")):
+        with gzip.open(os.path.join(EX, src), "rt") as f, open(tmp_path / dst, "w") as g:
+            lines = f.read().split("\n")
+            for i in range(0, len(lines) - 3, 4):
+                g.write(">" + lines[i][1:] + "\n" + lines[i + 1] + "\n")
+    paf = os.path.join(EX, "overlaps.paf")
+    for opts in (HAP, LIN):
+        want = run(REF_BIN, opts, "reads.fa", paf, "targets.fa", cwd=str(tmp_path))
+        got = run(B200_BIN, opts, "reads.fa", paf, "targets.fa", cwd=str(tmp_path), devices="0")
+        assert want.returncode == 0 and got.returncode == 0, got.stderr[-400:]
+        assert got.stdout == want.stdout and got.stdout.count(b">") >= 9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("VGC_FULL_EXAMPLE"), reason="opt-in (VGC_FULL_EXAMPLE=1): whole example, minutes")
+def test_gpu_binary_whole_example():
+    """All 2 802 reads of example/reads.fq.gz against themselves (oracle/_ref/example/, generated by
+    tools/example_overlaps.py; git-ignored, travels with the snapshot)."""
+    d = os.path.join(ROOT, "oracle", "_ref", "example")
+    want = os.path.join(d, "corrected.ref.fa")
+    if not os.path.exists(want):
+        pytest.skip("oracle/_ref/example not generated")
+    got = run(B200_BIN, HAP, cwd=d, devices="0", threads=os.cpu_count() or 8)
+    assert got.returncode == 0, got.stderr[-400:]
+    with open(want, "rb") as f:
+        assert got.stdout == f.read()

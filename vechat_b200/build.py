@@ -81,8 +81,21 @@ def build_oracle():
     """The checkers under oracle/ (test infrastructure): our CPU restatement and, when the reference
     tree is present, the compiled reference itself."""
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "edlib"])
     if os.path.isdir("/root/reference/src"):
         _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        _run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "racon"])
+
+
+def build_racon_binding():
+    """vechat_racon_b200: the UNMODIFIED reference program (main.cpp, Polisher::initialize, parsers, edlib step) linked
+    with csrc/racon_binding (racon::B200Polisher, the Polisher subclass a maintainer adds) and libvgc.so.  Needs the
+    reference tree for its sources and headers, so it is built in the development container only; the binary travels
+    to the GPU box with the snapshot like every other built file."""
+    out = os.path.join(LIB_DIR, "vechat_racon_b200")
+    if os.path.isdir("/root/reference/src"):
+        _run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "racon_b200"])
+    return out if os.path.exists(out) else None
 
 
 def build_all(force=False):
@@ -90,6 +103,7 @@ def build_all(force=False):
     build_engine(force)
     build_host(force)
     build_oracle()
+    build_racon_binding()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,283 @@
+// b200polisher.cpp — racon::B200Polisher: Polisher::polish (src/polisher.cpp:491-562) over the C-ABI of
+// include/vgc.h.  Compiled with -DCUDA_ENABLED *for this translation unit only*, which makes the reference's
+// own friend hook visible (src/window.hpp:61-63 `friend class CUDABatchProcessor;`): the class of that name below
+// is how the binding reads Window::sequences_/qualities_/positions_/type_ and writes Window::consensus_ without
+// touching a line of the reference.
+#include "b200polisher.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "bioparser/fasta_parser.hpp"
+#include "bioparser/fastq_parser.hpp"
+#include "bioparser/mhap_parser.hpp"
+#include "bioparser/paf_parser.hpp"
+#include "bioparser/sam_parser.hpp"
+
+#include "logger.hpp"
+#include "overlap.hpp"
+#include "sequence.hpp"
+#include "window.hpp"
+
+#include "vgc.h"
+
+namespace racon {
+
+namespace {
+
+[[noreturn]] void die(const char* where, const char* what) {
+  std::fprintf(stderr, "[racon::%s] error: %s\n", where, what);
+  std::exit(1);
+}
+
+// structure-of-arrays image of a run of windows (what vgc_batch points into)
+struct Packed {
+  std::vector<uint8_t> bases, quals, has_qual, win_flags;
+  std::vector<uint64_t> seq_off;
+  std::vector<uint32_t> begin, end, win_first;
+  vgc_batch view() const {
+    vgc_batch b;
+    b.n_windows = static_cast<uint32_t>(win_flags.size());
+    b.n_layers = static_cast<uint32_t>(begin.size());
+    b.bases = bases.data();
+    b.quals = quals.data();
+    b.seq_off = seq_off.data();
+    b.has_qual = has_qual.data();
+    b.begin = begin.data();
+    b.end = end.data();
+    b.win_first = win_first.data();
+    b.win_flags = win_flags.data();
+    return b;
+  }
+};
+
+}  // namespace
+
+class CUDABatchProcessor {
+ public:
+  static uint64_t bytes(const Window& w) {
+    uint64_t n = 0;
+    for (const auto& s : w.sequences_) n += s.second;
+    return n;
+  }
+  // Window only borrows pointers into Polisher::sequences_ (freed at polisher.cpp:560-561): copy the bytes once.
+  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p) {
+    uint64_t total = 0;
+    size_t layers = 0;
+    for (size_t i = first; i < last; ++i) total += bytes(*w[i]), layers += w[i]->sequences_.size();
+    p->bases.reserve(total);
+    p->quals.reserve(total);
+    p->seq_off.reserve(layers + 1);
+    for (size_t i = first; i < last; ++i) {
+      const Window& win = *w[i];
+      p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
+      // window.cpp:223 compares the backbone quality POINTER, as a C string, with a run of '!' of backbone length
+      const bool dummy = std::string(win.sequences_.front().second, '!') == win.qualities_.front().first;
+      p->win_flags.push_back(static_cast<uint8_t>((win.type_ == WindowType::kTGS ? VGC_WIN_TGS : 0u) |
+                                                  (dummy ? VGC_WIN_DUMMY_QUAL : 0u)));
+      for (size_t l = 0; l < win.sequences_.size(); ++l) {
+        const uint32_t len = win.sequences_[l].second;
+        p->seq_off.push_back(p->bases.size());
+        p->bases.insert(p->bases.end(), win.sequences_[l].first, win.sequences_[l].first + len);
+        const char* q = win.qualities_[l].first;
+        p->has_qual.push_back(q != nullptr ? 1 : 0);
+        if (q != nullptr) p->quals.insert(p->quals.end(), q, q + len);
+        else p->quals.resize(p->bases.size(), '!');
+        p->begin.push_back(win.positions_[l].first);
+        p->end.push_back(win.positions_[l].second);
+      }
+    }
+    p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
+    p->seq_off.push_back(p->bases.size());
+  }
+  static void store(Window& win, const uint8_t* s, uint64_t n) { win.consensus_.assign(reinterpret_cast<const char*>(s), n); }
+};
+
+B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
+                           std::unique_ptr<bioparser::Parser<Overlap>> oparser,
+                           std::unique_ptr<bioparser::Parser<Sequence>> tparser, PolisherType type, bool haplotype,
+                           double min_confidence, double min_support, uint32_t num_prune, uint32_t window_length,
+                           double quality_threshold, double error_threshold, bool trim, int8_t match, int8_t mismatch,
+                           int8_t gap, uint32_t num_threads, std::vector<int> devices)
+    : Polisher(std::move(sparser), std::move(oparser), std::move(tparser), type, haplotype, min_confidence, min_support,
+               num_prune, window_length, quality_threshold, error_threshold, trim, match, mismatch, gap, num_threads),
+      match_(match), mismatch_(mismatch), gap_(gap), num_threads_(num_threads), devices_(std::move(devices)) {
+  if (devices_.empty()) devices_.push_back(0);
+}
+
+B200Polisher::~B200Polisher() {}
+
+void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop_unpolished_sequences) {
+  logger_->log();
+
+  vgc_params prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.match = match_;
+  prm.mismatch = mismatch_;
+  prm.gap = gap_;
+  prm.haplotype = haplotype_ ? 1 : 0;
+  prm.trim = trim_ ? 1 : 0;
+  prm.num_prune = num_prune_;
+  prm.min_confidence = min_confidence_;
+  prm.min_support = min_support_;
+
+  const size_t n = windows_.size();
+  std::vector<uint8_t> polished(n, 0);
+
+  // One contiguous range of WHOLE targets per device (a target's windows are consecutive and start at rank 0,
+  // polisher.cpp:389-404), balanced by layer bytes.
+  const size_t nd = devices_.size();
+  std::vector<size_t> cut(nd + 1, n);
+  cut[0] = 0;
+  if (nd > 1) {
+    std::vector<uint64_t> acc(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) acc[i + 1] = acc[i] + CUDABatchProcessor::bytes(*windows_[i]);
+    size_t i = 0;
+    for (size_t d = 1; d < nd; ++d) {
+      const uint64_t want = acc[n] / nd * d;
+      while (i < n && (acc[i] < want || windows_[i]->rank() != 0)) ++i;
+      cut[d] = i;
+    }
+  }
+
+  // vgc_polish is re-entrant per handle and keeps no global state (vgc_last_error is thread-local): one host
+  // thread + one handle per device, the model of the legacy path (cudapolisher.cpp:229-241,255-277).
+  constexpr uint64_t kBatchBytes = 1ull << 30;  // bases per vgc_polish call
+  constexpr size_t kBatchWindows = 1u << 16;
+  std::vector<std::string> errors(nd);
+  auto run_device = [&](size_t d) {
+    vgc_handle h = nullptr;
+    if (vgc_create(&h, devices_[d], &prm) != VGC_OK) {
+      errors[d] = vgc_last_error();
+      return;
+    }
+    for (size_t first = cut[d]; first < cut[d + 1];) {
+      size_t last = first;
+      uint64_t b = 0;
+      while (last < cut[d + 1] && last - first < kBatchWindows && (last == first || b < kBatchBytes))
+        b += CUDABatchProcessor::bytes(*windows_[last++]);
+      Packed p;
+      CUDABatchProcessor::pack(windows_, first, last, &p);
+      const vgc_batch batch = p.view();
+      std::vector<uint8_t> cons(vgc_result_bound(&batch));
+      std::vector<uint64_t> off(batch.n_windows + 1);
+      vgc_result r = {cons.data(), cons.size(), off.data(), polished.data() + first};
+      if (vgc_polish(h, &batch, &r, nullptr) != VGC_OK) {  // no CPU fallback
+        errors[d] = vgc_last_error();
+        break;
+      }
+      for (size_t i = first; i < last; ++i)
+        CUDABatchProcessor::store(*windows_[i], cons.data() + off[i - first], off[i - first + 1] - off[i - first]);
+      first = last;
+    }
+    vgc_destroy(h);
+  };
+  if (nd == 1) {
+    run_device(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; ++d) th.emplace_back(run_device, d);
+    for (auto& t : th) t.join();
+  }
+  for (size_t d = 0; d < nd; ++d)
+    if (!errors[d].empty()) die("B200Polisher::polish", errors[d].c_str());
+
+  // In-order stitch per target with the reference's header tags (polisher.cpp:520-546): a target ends where the
+  // next window has rank 0.
+  size_t i = 0;
+  while (i < n) {
+    std::string data;
+    uint32_t good = 0;
+    size_t j = i;
+    do {
+      good += polished[j] ? 1 : 0;
+      data += windows_[j]->consensus();
+      ++j;
+    } while (j < n && windows_[j]->rank() != 0);
+    const Window& tail = *windows_[j - 1];
+    const double ratio = good / static_cast<double>(tail.rank() + 1);
+    if (!drop_unpolished_sequences || ratio > 0) {
+      std::string name = sequences_[tail.id()]->name();
+      if (type_ == PolisherType::kF) name += "r";
+      name += " LN:i:" + std::to_string(data.size());
+      name += " RC:i:" + std::to_string(targets_coverages_[tail.id()]);
+      name += " XC:f:" + std::to_string(ratio);
+      dst.emplace_back(createSequence(name, data));
+    }
+    for (; i < j; ++i) windows_[i].reset();
+  }
+  logger_->log("[racon::B200Polisher::polish] generated consensus");
+
+  std::vector<std::shared_ptr<Window>>().swap(windows_);
+  std::vector<std::unique_ptr<Sequence>>().swap(sequences_);
+}
+
+namespace {
+
+bool ends_with(const std::string& s, const char* suffix) {
+  const size_t k = std::strlen(suffix);
+  return s.size() >= k && s.compare(s.size() - k, k, suffix) == 0;
+}
+bool has_ext(const std::string& path, std::initializer_list<const char*> exts) {
+  for (const char* e : exts)
+    if (ends_with(path, e) || ends_with(path, (std::string(e) + ".gz").c_str())) return true;
+  return false;
+}
+// the extension rules of createPolisher (polisher.cpp:85-138), same messages
+std::unique_ptr<bioparser::Parser<Sequence>> sequence_parser(const std::string& path) {
+  if (has_ext(path, {".fasta", ".fna", ".fa"})) return bioparser::Parser<Sequence>::Create<bioparser::FastaParser>(path);
+  if (has_ext(path, {".fastq", ".fq"})) return bioparser::Parser<Sequence>::Create<bioparser::FastqParser>(path);
+  std::fprintf(stderr, "[racon::createPolisher] error: file %s has unsupported format extension (valid extensions: "
+               ".fasta, .fasta.gz, .fna, .fna.gz, .fa, .fa.gz, .fastq, .fastq.gz, .fq, .fq.gz)!\n", path.c_str());
+  std::exit(1);
+}
+std::unique_ptr<bioparser::Parser<Overlap>> overlap_parser(const std::string& path) {
+  if (has_ext(path, {".mhap"})) return bioparser::Parser<Overlap>::Create<bioparser::MhapParser>(path);
+  if (has_ext(path, {".paf"})) return bioparser::Parser<Overlap>::Create<bioparser::PafParser>(path);
+  if (has_ext(path, {".sam"})) return bioparser::Parser<Overlap>::Create<bioparser::SamParser>(path);
+  std::fprintf(stderr, "[racon::createPolisher] error: file %s has unsupported format extension (valid extensions: "
+               ".mhap, .mhap.gz, .paf, .paf.gz, .sam, .sam.gz)!\n", path.c_str());
+  std::exit(1);
+}
+
+}  // namespace
+
+std::unique_ptr<Polisher> createPolisherB200(const std::string& sequences_path, const std::string& overlaps_path,
+                                             const std::string& target_path, PolisherType type, bool haplotype,
+                                             double min_confidence, double min_support, uint32_t num_prune,
+                                             uint32_t window_length, double quality_threshold, double error_threshold,
+                                             bool trim, int8_t match, int8_t mismatch, int8_t gap, uint32_t num_threads,
+                                             uint32_t cuda_batches, bool cuda_banded_alignment,
+                                             uint32_t cudaaligner_batches, uint32_t cudaaligner_band_width) {
+  std::vector<int> devices;
+  if (const char* env = std::getenv("VECHAT_B200_DEVICES")) {
+    for (const char* p = env; *p;) {
+      char* e = nullptr;
+      const long v = std::strtol(p, &e, 10);
+      if (e == p) die("createPolisher", "VECHAT_B200_DEVICES must be a comma-separated list of device ordinals");
+      devices.push_back(static_cast<int>(v));
+      p = (*e == ',') ? e + 1 : e;
+    }
+  } else {
+    for (uint32_t d = 0; d < cuda_batches; ++d) devices.push_back(static_cast<int>(d));
+  }
+  if (devices.empty())  // CPU run requested: the reference's own factory, untouched
+    return createPolisher(sequences_path, overlaps_path, target_path, type, haplotype, min_confidence, min_support,
+                          num_prune, window_length, quality_threshold, error_threshold, trim, match, mismatch, gap,
+                          num_threads, 0, cuda_banded_alignment, cudaaligner_batches, cudaaligner_band_width);
+
+  if (type != PolisherType::kC && type != PolisherType::kF) die("createPolisher", "invalid polisher type!");
+  if (window_length == 0) die("createPolisher", "invalid window length!");
+  auto sparser = sequence_parser(sequences_path);
+  auto oparser = overlap_parser(overlaps_path);
+  auto tparser = sequence_parser(target_path);
+  return std::unique_ptr<Polisher>(new B200Polisher(std::move(sparser), std::move(oparser), std::move(tparser), type,
+                                                    haplotype, min_confidence, min_support, num_prune, window_length,
+                                                    quality_threshold, error_threshold, trim, match, mismatch, gap,
+                                                    num_threads, devices));
+}
+
+}  // namespace racon
