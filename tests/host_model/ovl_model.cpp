@@ -1,0 +1,29 @@
+// TEST-ONLY: vechat_b200/csrc/ovl_core.h (the arithmetic of the overlap-alignment kernel) driven on the host — the
+// loop over a wavefront's diagonals that the kernel spreads over a CTA's threads runs serially here (cells of one
+// wavefront only read the previous one).  Produces the CIGAR the kernel + vga_align would.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ovl_core.h"
+
+extern "C" int ovl_model_align(const uint8_t* q, int32_t m, const uint8_t* t, int32_t n, char* out, uint64_t cap,
+                               uint64_t* cells) {
+  std::vector<int32_t> arena;
+  int32_t D = -1;
+  for (int32_t d = 0; D < 0; ++d) {
+    arena.resize(ovl::wf_cells(d), 0x5a5a5a5a);  // poison: every cell read must have been written or range-checked
+    const int32_t lo = -d < -m ? -m : -d, hi = d < n ? d : n;
+    for (int32_t k = lo; k <= hi; ++k)
+      if (ovl::wf_cell(arena.data(), q, t, m, n, d, k) == m && k == n - m) D = d;
+  }
+  std::vector<uint32_t> runs(static_cast<size_t>(m) + n + 2);
+  const uint32_t nr = ovl::wf_traceback(arena.data(), m, n, D, runs.data());
+  std::string s;
+  for (uint32_t x = nr; x-- > 0;) s += std::to_string(runs[x] >> 2) + "MID?"[runs[x] & 3];
+  if (s.size() + 1 > cap) return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  if (cells) *cells = ovl::wf_cells(D);
+  return D;
+}

@@ -34,11 +34,15 @@ need_ref = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/v
 need_b200 = pytest.mark.skipif(not os.path.exists(B200_BIN), reason="vechat_racon_b200 not built (needs /root/reference)")
 
 
-def run(binary, opts, reads="reads.fq.gz", paf="overlaps.paf", targets="targets.fq.gz", cwd=EX, devices=None, threads=8):
+def run(binary, opts, reads="reads.fq.gz", paf="overlaps.paf", targets="targets.fq.gz", cwd=EX, devices=None, threads=8,
+        gpu_align=False):
     env = dict(os.environ)
     env.pop("VECHAT_B200_DEVICES", None)
+    env.pop("VECHAT_B200_ALIGN", None)
     if devices is not None:
         env["VECHAT_B200_DEVICES"] = devices
+    if gpu_align:
+        env["VECHAT_B200_ALIGN"] = "1"
     return subprocess.run([binary] + opts + ["-t", str(threads), reads, paf, targets], cwd=cwd, env=env,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
 
@@ -89,6 +93,16 @@ def test_b200_binary_fails_loudly_without_gpu():
 def test_b200_binary_rejects_bad_device_list():
     r = run(B200_BIN, HAP, devices="zero")
     assert r.returncode == 1 and b"VECHAT_B200_DEVICES" in r.stderr
+
+
+@need_b200
+def test_b200_binary_gpu_alignment_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = run(B200_BIN, HAP, devices="0", gpu_align=True)
+    assert r.returncode == 1 and r.stdout == b""
+    assert b"[racon::B200Polisher::find_overlap_breaking_points] error:" in r.stderr
 
 
 # ---------------------------------------------------------------- the edlib stand-in both binaries are built on
@@ -193,6 +207,17 @@ def _b200(opts, **kw):
 @pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN, "corrected.lin.fa")])
 def test_gpu_binary_matches_committed_reference_fasta(opts, want):
     assert _b200(opts) == golden(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN, "corrected.lin.fa")])
+def test_gpu_binary_with_gpu_overlap_alignment(opts, want):
+    """VECHAT_B200_ALIGN=1: the CIGARs come from vga_align (include/vga.h) instead of the host aligner; the tilings,
+    hence the FASTA, stay identical because the GPU aligner reproduces the host aligner's CIGARs exactly."""
+    r = run(B200_BIN, opts, devices="0", gpu_align=True)
+    assert r.returncode == 0, r.stderr[-600:]
+    assert b"aligned overlaps on the GPU" in r.stderr and b"[racon::B200Polisher::polish] generated consensus" in r.stderr
+    assert r.stdout == golden(want)
 
 
 @pytest.mark.gpu

@@ -1,0 +1,163 @@
+"""Overlap alignment -> CIGAR (include/vga.h, vechat_b200/csrc/ovl_align.cu + ovl_core.h).
+
+Oracle: oracle/shims/edlib_standin.cpp — an independent implementation (own containers, clipped wavefront layout)
+of the exact unit-cost global aligner both reference-program builds use in place of the absent edlib
+(tests/test_example_binary.py checks it against the textbook DP).  Bar: identical CIGAR strings (byte for byte) and
+edit distances.  Equality with the REAL edlib's tie-breaking is unpinned (edlib is not in this image).
+"""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+_model = None
+_standin = None
+
+
+def model():
+    global _model
+    if _model is None:
+        src = os.path.join(ROOT, "tests", "host_model", "ovl_model.cpp")
+        out = os.path.join(ROOT, "tests", "host_model", "_build", "libovlmodel.so")
+        core = os.path.join(ROOT, "vechat_b200", "csrc", "ovl_core.h")
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in (src, core)):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.dirname(core), "-o", out, src],
+                           check=True)
+        _model = C.CDLL(out)
+        _model.ovl_model_align.restype = C.c_int
+        _model.ovl_model_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_uint64,
+                                           C.POINTER(C.c_uint64)]
+    return _model
+
+
+def model_cigar(q, t):
+    buf = C.create_string_buffer(2 * (len(q) + len(t)) + 16)
+    cells = C.c_uint64()
+    d = model().ovl_model_align(q, len(q), t, len(t), buf, len(buf), C.byref(cells))
+    assert d >= 0 and cells.value == (d + 1) ** 2
+    return buf.value.decode(), d
+
+
+def standin_cigar(q, t):
+    global _standin
+    if _standin is None:
+        from test_example_binary import _edlib
+        _standin = _edlib()
+    lib = _standin
+    r = lib.edlibAlign(q, len(q), t, len(t), lib.edlibNewAlignConfig(-1, 0, 2, None, 0))
+    assert r.status == 0
+    p = lib.edlibAlignmentToCigar(r.alignment, r.alignmentLength, 0)
+    s = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    d = r.editDistance
+    lib.edlibFreeAlignResult(r)
+    return s, d
+
+
+def noisy_pairs(seed, count, max_len, sub=0.04, ins=0.10, dele=0.08):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        n = int(rng.integers(1, max_len))
+        t = rng.integers(0, 4, n)
+        u = rng.random(n)
+        q = []
+        for x, r in zip(t.tolist(), u.tolist()):
+            if r < dele:
+                continue
+            q.append(int(rng.integers(0, 4)) if r < dele + sub else x)
+            while rng.random() < ins:
+                q.append(int(rng.integers(0, 4)))
+        out.append((bytes(b"ACGT"[x] for x in q), bytes(b"ACGT"[x] for x in t)))
+    return out
+
+
+EDGE = [(b"", b""), (b"", b"ACGT"), (b"ACGT", b""), (b"A", b"A"), (b"A", b"C"), (b"AAAA", b"TTTTTTT"),
+        (b"ACGTACGT", b"ACGTACGT"), (b"ACGT" * 50, b"TGCA" * 40), (b"A" * 300, b"A" * 280), (b"AC" * 100, b"CA" * 100)]
+
+
+def test_host_model_matches_standin_cigars():
+    cases = EDGE + noisy_pairs(1, 150, 600) + noisy_pairs(2, 6, 6000) + noisy_pairs(3, 40, 300, 0.3, 0.3, 0.3)
+    for q, t in cases:
+        assert model_cigar(q, t) == standin_cigar(q, t), (q[:40], t[:40])
+
+
+def test_abi_exports_and_fails_loudly_without_gpu():
+    import re
+    import torch
+    from vechat_b200 import aligner, engine
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vga.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(vga_[a-z_]+)\s*\(", src)))
+    assert names == ["vga_align", "vga_create", "vga_destroy", "vga_last_error"]
+    lib = engine.load_library()
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert C.sizeof(aligner.VgaBatch) == 56 and C.sizeof(aligner.VgaResult) == 24 and C.sizeof(aligner.VgaStats) == 40
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError) as ei:
+            aligner.Aligner(0)
+        assert "no usable CUDA device" in str(ei.value)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+
+def pack(pairs):
+    blob, q_off, q_len, t_off, t_len = bytearray(), [], [], [], []
+    for q, t in pairs:
+        q_off.append(len(blob)); q_len.append(len(q)); blob += q
+        t_off.append(len(blob)); t_len.append(len(t)); blob += t
+    blob += b"\0"
+    return np.frombuffer(bytes(blob), np.uint8), q_off, q_len, t_off, t_len
+
+
+@pytest.mark.gpu
+def test_gpu_cigars_match_standin():
+    from vechat_b200.aligner import Aligner
+    pairs = EDGE + noisy_pairs(11, 400, 800) + noisy_pairs(12, 12, 9000) + noisy_pairs(13, 60, 400, 0.3, 0.3, 0.3)
+    a = Aligner(0)
+    cigars, edits, st = a.align(*pack(pairs))
+    for (q, t), c, d in zip(pairs, cigars, edits):
+        assert (c, d) == standin_cigar(q, t), (len(q), len(t))
+    assert st["kernel_launches"] >= 1 and st["cells"] == sum((d + 1) ** 2 for d in edits)
+    # same handle, second call, empty batch, and a batch that shares one sequence buffer between overlaps
+    assert a.align(np.zeros(1, np.uint8), [], [], [], [])[0] == []
+    seq = np.frombuffer(pairs[20][0] + pairs[20][1], np.uint8)
+    m, n = len(pairs[20][0]), len(pairs[20][1])
+    c2, _, _ = a.align(seq, [0, 0, 5], [m, m, m - 5], [m, m + 3, m], [n, n - 3, n])
+    assert c2[0] == cigars[20]
+    assert c2[1] == standin_cigar(pairs[20][0], pairs[20][1][3:])[0]
+    assert c2[2] == standin_cigar(pairs[20][0][5:], pairs[20][1])[0]
+    a.close()
+
+
+@pytest.mark.gpu
+def test_gpu_example_overlaps_match_standin():
+    """The overlaps of the committed example fixture (tests/golden/example): the substrings Overlap::
+    find_breaking_points hands to edlib (src/overlap.cpp:195-199)."""
+    from vechat_b200.aligner import Aligner
+    ex = os.path.join(GOLDEN, "example")
+    reads = {}
+    with gzip.open(os.path.join(ex, "reads.fq.gz"), "rb") as f:
+        lines = f.read().split(b"\n")
+    for i in range(0, len(lines) - 3, 4):
+        reads[lines[i][1:].decode()] = lines[i + 1]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    pairs = []
+    for line in open(os.path.join(ex, "overlaps.paf")):
+        f = line.split("\t")
+        q, t = reads[f[0]], reads[f[5]]
+        qb, qe, tb, te = int(f[2]), int(f[3]), int(f[7]), int(f[8])
+        qs = q[qb:qe] if f[4] == "+" else q.translate(comp)[::-1][len(q) - qe:len(q) - qb]
+        pairs.append((qs, t[tb:te]))
+    pairs = pairs[::3]
+    a = Aligner(0)
+    cigars, edits, st = a.align(*pack(pairs))
+    for (q, t), c, d in zip(pairs, cigars, edits):
+        assert (c, d) == standin_cigar(q, t)
+    a.close()

@@ -37,14 +37,14 @@ def _run(cmd):
 
 def engine_sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))
-            ] + [os.path.join(INC, "vgc.h")]
+            ] + [os.path.join(INC, "vgc.h"), os.path.join(INC, "vga.h")]
 
 
 def build_engine(force=False, verbose=False):
     """libvgc.so: the C-ABI + hand-written sm_100a kernels."""
     os.makedirs(LIB_DIR, exist_ok=True)
     out = os.path.join(LIB_DIR, "libvgc.so")
-    srcs = [os.path.join(CSRC, "vgc_engine.cu")]
+    srcs = [os.path.join(CSRC, "vgc_engine.cu"), os.path.join(CSRC, "ovl_align.cu")]
     if force or _stale(out, engine_sources()):
         cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", out] + srcs + ["-lcudart", "-lpthread"]
         cmd += os.environ.get("VGC_NVCC_EXTRA", "").split()

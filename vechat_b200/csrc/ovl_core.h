@@ -1,0 +1,121 @@
+// ovl_core.h — the arithmetic of the overlap aligner, shared by the sm_100a kernel (ovl_align.cu) and the host
+// model the CPU tests instantiate (tests/host_model/ovl_model.cpp): one wavefront cell, and the traceback.
+//
+// What it computes: Overlap::align_overlaps (src/overlap.cpp:205-224) asks edlib for a global unit-cost alignment
+// with path.  Here: furthest-reaching diagonals.  Wavefront d holds, for every diagonal k = j - i (i query, j
+// target characters consumed), the largest i reachable with exactly d edits; D = the first d whose diagonal n - m
+// reaches i = m.  All wavefronts stay in HBM for the traceback: wavefront d lives at arena[d*d, (d+1)*(d+1)),
+// diagonal k at d*d + d + k — D^2 cells instead of the m*n of a full matrix.
+#ifndef OVL_CORE_H_
+#define OVL_CORE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OVL_HD __host__ __device__ __forceinline__
+#else
+#define OVL_HD inline
+#endif
+
+namespace ovl {
+
+constexpr int32_t kNone = -(1 << 30);
+enum : uint32_t { kOpM = 0, kOpI = 1, kOpD = 2 };  // CIGAR letters M (match or mismatch), I (query only), D (target only)
+
+OVL_HD size_t wf_index(int32_t d, int32_t k) { return static_cast<size_t>(d) * d + static_cast<size_t>(d + k); }
+
+OVL_HD int32_t wf_get(const int32_t* arena, int32_t d, int32_t k, int32_t m, int32_t n) {
+  const int32_t lo = -d < -m ? -m : -d, hi = d < n ? d : n;
+  return (k < lo || k > hi) ? kNone : arena[wf_index(d, k)];
+}
+
+// The three ways into (d, k): a mismatch (from k), b insertion / query only (from k+1), c deletion / target only
+// (from k-1); kNone when the move does not exist or leaves the matrix.
+OVL_HD void wf_candidates(const int32_t* arena, int32_t d, int32_t k, int32_t m, int32_t n, int32_t* a, int32_t* b,
+                          int32_t* c) {
+  int32_t x = wf_get(arena, d - 1, k, m, n);
+  *a = (x == kNone || x + 1 > m || x + 1 + k > n) ? kNone : x + 1;
+  x = wf_get(arena, d - 1, k + 1, m, n);
+  *b = (x == kNone || x + 1 > m) ? kNone : x + 1;
+  x = wf_get(arena, d - 1, k - 1, m, n);
+  *c = (x == kNone || x + k > n) ? kNone : x;
+}
+
+OVL_HD int32_t max3(int32_t a, int32_t b, int32_t c) {
+  const int32_t ab = a > b ? a : b;
+  return ab > c ? ab : c;
+}
+
+// One cell of wavefront d (-d <= k <= d, inside the matrix): start point, then slide along the matches.
+OVL_HD int32_t wf_cell(int32_t* arena, const uint8_t* q, const uint8_t* t, int32_t m, int32_t n, int32_t d, int32_t k) {
+  int32_t i;
+  if (d == 0) {
+    i = 0;
+  } else {
+    int32_t a, b, c;
+    wf_candidates(arena, d, k, m, n, &a, &b, &c);
+    i = max3(a, b, c);
+  }
+  if (i != kNone) {
+    int32_t j = i + k;
+    while (i < m && j < n && q[i] == t[j]) ++i, ++j;
+  }
+  arena[wf_index(d, k)] = i;
+  return i;
+}
+
+// Run-length CIGAR writer; runs come out in traceback (reverse) order: run = length << 2 | op.
+struct RunWriter {
+  uint32_t* out;
+  uint32_t count, op, len;
+  OVL_HD void init(uint32_t* o) { out = o, count = 0, op = 3, len = 0; }
+  OVL_HD void add(uint32_t o, uint32_t l) {
+    if (l == 0) return;
+    if (o == op) {
+      len += l;
+    } else {
+      if (len) out[count++] = len << 2 | op;
+      op = o, len = l;
+    }
+  }
+  OVL_HD uint32_t finish() {
+    if (len) out[count++] = len << 2 | op;
+    len = 0;
+    return count;
+  }
+};
+
+// Walks back from (D, n - m, m).  Among equally far predecessors: mismatch, then deletion, then insertion.
+// `runs` needs room for m + n + 1 entries in the worst case.  Returns the number of runs (reverse order).
+OVL_HD uint32_t wf_traceback(const int32_t* arena, int32_t m, int32_t n, int32_t D, uint32_t* runs) {
+  RunWriter w;
+  w.init(runs);
+  int32_t k = n - m, i = m;
+  for (int32_t d = D; d > 0; --d) {
+    int32_t a, b, c;
+    wf_candidates(arena, d, k, m, n, &a, &b, &c);
+    const int32_t pre = max3(a, b, c);
+    w.add(kOpM, static_cast<uint32_t>(i - pre));
+    if (a == pre) {
+      w.add(kOpM, 1);
+      i = pre - 1;
+    } else if (c == pre) {
+      w.add(kOpD, 1);
+      i = pre;
+      k -= 1;
+    } else {
+      w.add(kOpI, 1);
+      i = pre - 1;
+      k += 1;
+    }
+  }
+  w.add(kOpM, static_cast<uint32_t>(i));
+  return w.finish();
+}
+
+// Cells of arena an alignment with edit distance D occupies.
+OVL_HD uint64_t wf_cells(uint64_t D) { return (D + 1) * (D + 1); }
+
+}  // namespace ovl
+#endif

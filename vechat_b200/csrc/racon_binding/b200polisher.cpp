@@ -22,6 +22,7 @@
 #include "sequence.hpp"
 #include "window.hpp"
 
+#include "vga.h"
 #include "vgc.h"
 
 namespace racon {
@@ -96,6 +97,61 @@ class CUDABatchProcessor {
   static void store(Window& win, const uint8_t* s, uint64_t n) { win.consensus_.assign(reinterpret_cast<const char*>(s), n); }
 };
 
+// The second friend hook of the reference (src/overlap.hpp:79-81 `friend class CUDABatchAligner;`): reads the overlap
+// coordinates, writes Overlap::cigar_.
+class CUDABatchAligner {
+ public:
+  static void align(std::vector<std::unique_ptr<Overlap>>& overlaps, const std::vector<std::unique_ptr<Sequence>>& sequences,
+                    int device) {
+    vga_handle h = nullptr;
+    if (vga_create(&h, device) != VGA_OK) die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+    constexpr size_t kChunk = 1u << 18;  // overlaps per vga_align call
+    for (size_t first = 0; first < overlaps.size(); first += kChunk) {
+      const size_t last = std::min(overlaps.size(), first + kChunk);
+      // every sequence (strand) the chunk touches goes into the byte buffer once
+      std::vector<uint8_t> seqs;
+      std::vector<uint64_t> where(2 * sequences.size(), ~0ull);
+      auto place = [&](uint64_t id, bool rc) -> uint64_t {
+        uint64_t& w = where[2 * id + (rc ? 1 : 0)];
+        if (w == ~0ull) {
+          const std::string& s = rc ? sequences[id]->reverse_complement() : sequences[id]->data();
+          w = seqs.size();
+          seqs.insert(seqs.end(), s.begin(), s.end());
+        }
+        return w;
+      };
+      std::vector<size_t> index;
+      std::vector<uint64_t> q_off, t_off;
+      std::vector<uint32_t> q_len, t_len;
+      for (size_t i = first; i < last; ++i) {
+        const Overlap& o = *overlaps[i];
+        if (!o.is_transmuted_) die("Overlap::find_breaking_points", "overlap is not transmuted!");
+        if (!o.cigar_.empty() || !o.breaking_points_.empty()) continue;  // SAM input / already done
+        index.push_back(i);
+        // the substrings of overlap.cpp:195-199
+        q_off.push_back(o.strand_ ? place(o.q_id_, true) + (o.q_length_ - o.q_end_) : place(o.q_id_, false) + o.q_begin_);
+        q_len.push_back(o.q_end_ - o.q_begin_);
+        t_off.push_back(place(o.t_id_, false) + o.t_begin_);
+        t_len.push_back(o.t_end_ - o.t_begin_);
+      }
+      if (index.empty()) continue;
+      vga_batch b;
+      b.seqs = seqs.data();
+      b.seqs_len = seqs.size();
+      b.n = static_cast<uint32_t>(index.size());
+      b.q_off = q_off.data();
+      b.q_len = q_len.data();
+      b.t_off = t_off.data();
+      b.t_len = t_len.data();
+      vga_result r;
+      if (vga_align(h, &b, &r, nullptr) != VGA_OK)  // no CPU fallback
+        die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+      for (size_t x = 0; x < index.size(); ++x) overlaps[index[x]]->cigar_ = r.cigar + r.cigar_off[x];
+    }
+    vga_destroy(h);
+  }
+};
+
 B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
                            std::unique_ptr<bioparser::Parser<Overlap>> oparser,
                            std::unique_ptr<bioparser::Parser<Sequence>> tparser, PolisherType type, bool haplotype,
@@ -104,11 +160,23 @@ B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
                            int8_t gap, uint32_t num_threads, std::vector<int> devices)
     : Polisher(std::move(sparser), std::move(oparser), std::move(tparser), type, haplotype, min_confidence, min_support,
                num_prune, window_length, quality_threshold, error_threshold, trim, match, mismatch, gap, num_threads),
-      match_(match), mismatch_(mismatch), gap_(gap), num_threads_(num_threads), devices_(std::move(devices)) {
+      match_(match), mismatch_(mismatch), gap_(gap), num_threads_(num_threads), devices_(std::move(devices)),
+      align_on_gpu_(false) {
   if (devices_.empty()) devices_.push_back(0);
+  const char* env = std::getenv("VECHAT_B200_ALIGN");
+  align_on_gpu_ = env != nullptr && env[0] != '\0' && env[0] != '0';
 }
 
 B200Polisher::~B200Polisher() {}
+
+void B200Polisher::find_overlap_breaking_points(std::vector<std::unique_ptr<Overlap>>& overlaps) {
+  if (align_on_gpu_) {
+    logger_->log();
+    CUDABatchAligner::align(overlaps, sequences_, devices_.front());
+    logger_->log("[racon::B200Polisher::find_overlap_breaking_points] aligned overlaps on the GPU");
+  }
+  Polisher::find_overlap_breaking_points(overlaps);  // cuts the breaking points; edlib only where cigar_ is empty
+}
 
 void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop_unpolished_sequences) {
   logger_->log();
