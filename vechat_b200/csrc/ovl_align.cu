@@ -270,7 +270,8 @@ int vga_align(vga_handle h, const vga_batch* b, vga_result* result, vga_stats* s
     });
 
     DevBuf d_seqs, d_tasks, d_work, d_meta, d_cursors, d_scratch;
-    VGA_CUDA(cudaMalloc(&d_seqs.p, std::max<uint64_t>(b->seqs_len, 1)));
+    VGA_CUDA(cudaMalloc(&d_seqs.p, b->seqs_len + 16));  // + padding for ovl::load4
+    VGA_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(d_seqs.p) + b->seqs_len, 0, 16, h->stream));
     VGA_CUDA(cudaMalloc(&d_tasks.p, sizeof(OvlTask) * n));
     VGA_CUDA(cudaMalloc(&d_work.p, sizeof(uint32_t) * n));
     VGA_CUDA(cudaMalloc(&d_meta.p, sizeof(OvlMeta) * n));

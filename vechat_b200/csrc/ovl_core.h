@@ -47,6 +47,35 @@ OVL_HD int32_t max3(int32_t a, int32_t b, int32_t c) {
   return ab > c ? ab : c;
 }
 
+#if defined(__CUDA_ARCH__)
+// 4 bytes from any address: two aligned words + a funnel shift (reads up to 7 bytes past p: the device copy of the
+// sequences is padded accordingly).
+__device__ __forceinline__ uint32_t load4(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), static_cast<uint32_t>(a & 3) * 8);
+}
+#endif
+
+// Length of the common prefix of q[i..m) and t[j..n).
+OVL_HD int32_t match_run(const uint8_t* q, const uint8_t* t, int32_t i, int32_t j, int32_t m, int32_t n) {
+  const int32_t i0 = i;
+#if defined(__CUDA_ARCH__)
+  for (;;) {  // four characters per step
+    const int32_t left = (m - i) < (n - j) ? (m - i) : (n - j);
+    if (left <= 0) break;
+    const uint32_t x = load4(q + i) ^ load4(t + j);
+    int32_t same = x ? (__ffs(static_cast<int>(x)) - 1) >> 3 : 4;
+    same = same < left ? same : left;
+    i += same, j += same;
+    if (same < 4) break;
+  }
+#else
+  while (i < m && j < n && q[i] == t[j]) ++i, ++j;
+#endif
+  return i - i0;
+}
+
 // One cell of wavefront d (-d <= k <= d, inside the matrix): start point, then slide along the matches.
 OVL_HD int32_t wf_cell(int32_t* arena, const uint8_t* q, const uint8_t* t, int32_t m, int32_t n, int32_t d, int32_t k) {
   int32_t i;
@@ -57,10 +86,7 @@ OVL_HD int32_t wf_cell(int32_t* arena, const uint8_t* q, const uint8_t* t, int32
     wf_candidates(arena, d, k, m, n, &a, &b, &c);
     i = max3(a, b, c);
   }
-  if (i != kNone) {
-    int32_t j = i + k;
-    while (i < m && j < n && q[i] == t[j]) ++i, ++j;
-  }
+  if (i != kNone) i += match_run(q, t, i, i + k, m, n);
   arena[wf_index(d, k)] = i;
   return i;
 }
