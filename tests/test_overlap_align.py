@@ -137,6 +137,26 @@ def test_gpu_cigars_match_standin():
 
 
 @pytest.mark.gpu
+def test_gpu_retry_rounds(monkeypatch):
+    """Overlaps that outgrow their wavefront arena or find the round's output buffer full are re-run by the host
+    loop with more room; results do not change."""
+    from vechat_b200.aligner import Aligner
+    pairs = noisy_pairs(21, 300, 700) + noisy_pairs(22, 4, 5000)
+    a = Aligner(0)
+    want, want_d, st0 = a.align(*pack(pairs))
+    assert st0["retried"] == 0 and st0["kernel_launches"] == 1
+    monkeypatch.setenv("VGA_ARENA_CELLS", "2500")   # edit distance <= 49 fits; the rest overflows, then x4 per round
+    got, got_d, st = a.align(*pack(pairs))
+    assert (got, got_d) == (want, want_d) and st["retried"] > 0 and st["kernel_launches"] >= 3
+    assert st["cells"] == st0["cells"]
+    monkeypatch.delenv("VGA_ARENA_CELLS")
+    monkeypatch.setenv("VGA_OUT_CAP_RUNS", "1")      # clamped to one worst-case alignment: many rounds
+    got, got_d, st = a.align(*pack(pairs))
+    assert (got, got_d) == (want, want_d) and st["retried"] > 0 and st["kernel_launches"] >= 2
+    a.close()
+
+
+@pytest.mark.gpu
 def test_gpu_example_overlaps_match_standin():
     """The overlaps of the committed example fixture (tests/golden/example): the substrings Overlap::
     find_breaking_points hands to edlib (src/overlap.cpp:195-199)."""

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -288,8 +289,12 @@ int vga_align(vga_handle h, const vga_batch* b, vga_result* result, vga_stats* s
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = static_cast<uint64_t>(free_b * 0.8);
     // output runs of one round: a fifth of the budget, at most 4 GiB, at least one worst-case alignment
-    const uint64_t out_cap = std::max<uint64_t>(std::min<uint64_t>(budget / 5, 4ull << 30) / sizeof(uint32_t),
-                                                scratch_stride);
+    uint64_t out_cap = std::min<uint64_t>(budget / 5, 4ull << 30) / sizeof(uint32_t);
+    uint64_t first_arena_cells = ~0ull;
+    // test hooks: start with a small output buffer / small arenas so that the retry rounds run
+    if (const char* e = std::getenv("VGA_OUT_CAP_RUNS")) out_cap = std::min<uint64_t>(out_cap, std::strtoull(e, nullptr, 10));
+    if (const char* e = std::getenv("VGA_ARENA_CELLS")) first_arena_cells = std::strtoull(e, nullptr, 10);
+    out_cap = std::max<uint64_t>(out_cap, scratch_stride);
     const uint64_t arena_budget = budget - std::min<uint64_t>(budget / 5, 4ull << 30);
     DevBuf d_out;
     VGA_CUDA(cudaMalloc(&d_out.p, out_cap * sizeof(uint32_t)));
@@ -303,6 +308,7 @@ int vga_align(vga_handle h, const vga_batch* b, vga_result* result, vga_stats* s
       const uint64_t cells_worst = ovl::wf_cells(worst);
       uint32_t ctas = static_cast<uint32_t>(std::min<uint64_t>(max_ctas, pending.size()));
       uint64_t arena_cells = std::min<uint64_t>(cells_worst, arena_budget / sizeof(int32_t) / ctas);
+      arena_cells = std::max<uint64_t>(std::min(arena_cells, first_arena_cells), 1);
       if (arena_cells < std::min(arena_floor, cells_worst)) {  // fewer, larger arenas
         arena_cells = std::min(arena_floor, cells_worst);
         ctas = static_cast<uint32_t>(std::min<uint64_t>(ctas, arena_budget / sizeof(int32_t) / arena_cells));
