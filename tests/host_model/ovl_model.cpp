@@ -14,9 +14,13 @@ extern "C" int ovl_model_align(const uint8_t* q, int32_t m, const uint8_t* t, in
   int32_t D = -1;
   for (int32_t d = 0; D < 0; ++d) {
     arena.resize(ovl::wf_cells(d), 0x5a5a5a5a);  // poison: every cell read must have been written or range-checked
-    const int32_t lo = -d < -m ? -m : -d, hi = d < n ? d : n;
-    for (int32_t k = lo; k <= hi; ++k)
-      if (ovl::wf_cell(arena.data(), q, t, m, n, d, k) == m && k == n - m) D = d;
+    const ovl::Front prev = ovl::wf_front(arena.data(), d > 0 ? d - 1 : 0, m, n);
+    const ovl::Front cur = ovl::wf_front(arena.data(), d, m, n);
+    for (int32_t k = cur.lo; k <= cur.hi; ++k) {
+      const int32_t i = ovl::wf_cell(prev, q, t, m, n, d, k);
+      arena[ovl::wf_index(d, k)] = i;
+      if (i == m && k == n - m) D = d;
+    }
   }
   std::vector<uint32_t> runs(static_cast<size_t>(m) + n + 2);
   const uint32_t nr = ovl::wf_traceback(arena.data(), m, n, D, runs.data());

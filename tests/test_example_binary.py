@@ -238,6 +238,24 @@ def test_gpu_binary_matches_reference_binary_live(opts):
 
 
 @pytest.mark.gpu
+def test_gpu_binary_two_handles(monkeypatch):
+    """The multi-device path of B200Polisher::polish: one host thread + one vgc_handle per listed device, each over
+    a contiguous range of whole targets.  Listing device 0 twice runs it on a single-GPU box (two handles on one
+    device, concurrent vgc_polish calls: the library keeps no global state); a second GPU is used when present."""
+    import torch
+    monkeypatch.setenv("VGC_MEM_BUDGET_MB", "12000")  # two engines share one device here
+    devices = "0,1" if torch.cuda.device_count() > 1 else "0,0"
+    r = run(B200_BIN, HAP, devices=devices)
+    assert r.returncode == 0, r.stderr[-600:]
+    assert r.stdout == golden("corrected.hap.fa")
+    r = run(B200_BIN, LIN + ["-u"], devices="0,0,0")
+    want = run(REF_BIN, LIN + ["-u"]) if os.path.exists(REF_BIN) else None
+    assert r.returncode == 0, r.stderr[-600:]
+    if want is not None:
+        assert r.stdout == want.stdout and r.stdout.count(b">") == 10
+
+
+@pytest.mark.gpu
 def test_gpu_binary_fasta_input(tmp_path):
     """Second-pass shape (scripts/vechat:372-397): reads and targets are FASTA, every window takes the dummy-quality
     branch of window.cpp:223 except each target's last, shorter window."""

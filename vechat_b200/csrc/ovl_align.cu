@@ -27,8 +27,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // CTA size of a full round: 8 CTAs per SM
 constexpr int kCtasPerSm = 8;
+constexpr int kThreadsFew = 1024;  // CTA size when a round has few overlaps (retries, small batches): the critical
+                                   // path is one alignment, and a wavefront is as wide as its edit distance
 
 struct OvlTask {
   uint64_t q_off, t_off;
@@ -43,13 +45,13 @@ struct OvlMeta {
   uint64_t run_off;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreadsFew)
 ovl_kernel(const uint8_t* __restrict__ seqs, const OvlTask* __restrict__ tasks, const uint32_t* __restrict__ work,
            uint32_t n_work, int32_t* arenas, uint64_t arena_cells, uint32_t* scratch, uint64_t scratch_stride,
            uint32_t* out_runs, uint64_t out_cap, unsigned long long* cursors, OvlMeta* meta) {
   __shared__ uint32_t s_item, s_status, s_nruns;
   __shared__ unsigned long long s_off;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   int32_t* arena = arenas + static_cast<size_t>(blockIdx.x) * arena_cells;
   uint32_t* runs = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
   for (;;) {
@@ -79,10 +81,13 @@ ovl_kernel(const uint8_t* __restrict__ seqs, const OvlTask* __restrict__ tasks, 
           status = kArenaFull;
           break;
         }
-        const int32_t lo = -d < -m ? -m : -d, hi = d < n ? d : n;
+        const ovl::Front prev = ovl::wf_front(arena, d > 0 ? d - 1 : 0, m, n);
+        const ovl::Front cur = ovl::wf_front(arena, d, m, n);
+        int32_t* out = arena + ovl::wf_index(d, 0);
         int reached = 0;
-        for (int32_t k = lo + tid; k <= hi; k += kThreads) {
-          const int32_t i = ovl::wf_cell(arena, q, t, m, n, d, k);
+        for (int32_t k = cur.lo + tid; k <= cur.hi; k += nthreads) {
+          const int32_t i = ovl::wf_cell(prev, q, t, m, n, d, k);
+          out[k] = i;
           reached |= (k == kf && i == m);
         }
         if (__syncthreads_or(reached)) {  // also orders wavefront d's stores before wavefront d+1's loads
@@ -104,7 +109,7 @@ ovl_kernel(const uint8_t* __restrict__ seqs, const OvlTask* __restrict__ tasks, 
       status = s_status;
       const uint32_t nr = s_nruns;
       if (status == kDone)
-        for (uint32_t x = tid; x < nr; x += kThreads) out_runs[s_off + x] = runs[nr - 1 - x];
+        for (uint32_t x = tid; x < nr; x += nthreads) out_runs[s_off + x] = runs[nr - 1 - x];
     }
     if (tid == 0) {
       OvlMeta mt;
@@ -306,7 +311,9 @@ int vga_align(vga_handle h, const vga_batch* b, vga_result* result, vga_stats* s
       uint32_t worst = 0;  // edit distance is at most max(m, n)
       for (uint32_t ov : pending) worst = std::max(worst, std::max(tasks[ov].m, tasks[ov].n));
       const uint64_t cells_worst = ovl::wf_cells(worst);
-      uint32_t ctas = static_cast<uint32_t>(std::min<uint64_t>(max_ctas, pending.size()));
+      const bool few = pending.size() * 4 <= max_ctas;
+      const int threads = few ? kThreadsFew : kThreads;
+      uint32_t ctas = static_cast<uint32_t>(std::min<uint64_t>(few ? max_ctas / 4 : max_ctas, pending.size()));
       uint64_t arena_cells = std::min<uint64_t>(cells_worst, arena_budget / sizeof(int32_t) / ctas);
       arena_cells = std::max<uint64_t>(std::min(arena_cells, first_arena_cells), 1);
       if (arena_cells < std::min(arena_floor, cells_worst)) {  // fewer, larger arenas
@@ -327,7 +334,7 @@ int vga_align(vga_handle h, const vga_batch* b, vga_result* result, vga_stats* s
                                h->stream));
       VGA_CUDA(cudaMemsetAsync(d_cursors.p, 0, sizeof(unsigned long long) * 4, h->stream));
       VGA_CUDA(cudaEventRecord(h->ev[0], h->stream));
-      ovl_kernel<<<ctas, kThreads, 0, h->stream>>>(
+      ovl_kernel<<<ctas, threads, 0, h->stream>>>(
           d_seqs.as<uint8_t>(), d_tasks.as<OvlTask>(), d_work.as<uint32_t>(), static_cast<uint32_t>(pending.size()),
           d_arena.as<int32_t>(), arena_cells, d_scratch.as<uint32_t>(), scratch_stride, d_out.as<uint32_t>(), out_cap,
           d_cursors.as<unsigned long long>(), d_meta.as<OvlMeta>());

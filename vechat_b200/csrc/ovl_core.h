@@ -25,20 +25,29 @@ enum : uint32_t { kOpM = 0, kOpI = 1, kOpD = 2 };  // CIGAR letters M (match or 
 
 OVL_HD size_t wf_index(int32_t d, int32_t k) { return static_cast<size_t>(d) * d + static_cast<size_t>(d + k); }
 
-OVL_HD int32_t wf_get(const int32_t* arena, int32_t d, int32_t k, int32_t m, int32_t n) {
-  const int32_t lo = -d < -m ? -m : -d, hi = d < n ? d : n;
-  return (k < lo || k > hi) ? kNone : arena[wf_index(d, k)];
+// One wavefront, addressed by diagonal: p[k] for lo <= k <= hi (the diagonals of wavefront d that lie inside the
+// m x n matrix); everything else reads as kNone.  Set up once per wavefront, not per cell.
+struct Front {
+  const int32_t* p;
+  int32_t lo, hi;
+  OVL_HD int32_t get(int32_t k) const { return (k < lo || k > hi) ? kNone : p[k]; }
+};
+OVL_HD Front wf_front(const int32_t* arena, int32_t d, int32_t m, int32_t n) {
+  Front f;
+  f.p = arena + wf_index(d, 0);
+  f.lo = -d < -m ? -m : -d;
+  f.hi = d < n ? d : n;
+  return f;
 }
 
-// The three ways into (d, k): a mismatch (from k), b insertion / query only (from k+1), c deletion / target only
-// (from k-1); kNone when the move does not exist or leaves the matrix.
-OVL_HD void wf_candidates(const int32_t* arena, int32_t d, int32_t k, int32_t m, int32_t n, int32_t* a, int32_t* b,
-                          int32_t* c) {
-  int32_t x = wf_get(arena, d - 1, k, m, n);
+// The three ways into diagonal k from the previous wavefront: a mismatch (from k), b insertion / query only (from
+// k+1), c deletion / target only (from k-1); kNone when the move does not exist or leaves the matrix.
+OVL_HD void wf_candidates(const Front& prev, int32_t k, int32_t m, int32_t n, int32_t* a, int32_t* b, int32_t* c) {
+  int32_t x = prev.get(k);
   *a = (x == kNone || x + 1 > m || x + 1 + k > n) ? kNone : x + 1;
-  x = wf_get(arena, d - 1, k + 1, m, n);
+  x = prev.get(k + 1);
   *b = (x == kNone || x + 1 > m) ? kNone : x + 1;
-  x = wf_get(arena, d - 1, k - 1, m, n);
+  x = prev.get(k - 1);
   *c = (x == kNone || x + k > n) ? kNone : x;
 }
 
@@ -76,18 +85,18 @@ OVL_HD int32_t match_run(const uint8_t* q, const uint8_t* t, int32_t i, int32_t 
   return i - i0;
 }
 
-// One cell of wavefront d (-d <= k <= d, inside the matrix): start point, then slide along the matches.
-OVL_HD int32_t wf_cell(int32_t* arena, const uint8_t* q, const uint8_t* t, int32_t m, int32_t n, int32_t d, int32_t k) {
+// One cell of wavefront d (diagonal k inside the matrix): start point from the previous wavefront (none for d = 0),
+// then slide along the matches.  The caller stores the result at arena[wf_index(d, k)].
+OVL_HD int32_t wf_cell(const Front& prev, const uint8_t* q, const uint8_t* t, int32_t m, int32_t n, int32_t d, int32_t k) {
   int32_t i;
   if (d == 0) {
     i = 0;
   } else {
     int32_t a, b, c;
-    wf_candidates(arena, d, k, m, n, &a, &b, &c);
+    wf_candidates(prev, k, m, n, &a, &b, &c);
     i = max3(a, b, c);
   }
   if (i != kNone) i += match_run(q, t, i, i + k, m, n);
-  arena[wf_index(d, k)] = i;
   return i;
 }
 
@@ -120,7 +129,7 @@ OVL_HD uint32_t wf_traceback(const int32_t* arena, int32_t m, int32_t n, int32_t
   int32_t k = n - m, i = m;
   for (int32_t d = D; d > 0; --d) {
     int32_t a, b, c;
-    wf_candidates(arena, d, k, m, n, &a, &b, &c);
+    wf_candidates(wf_front(arena, d - 1, m, n), k, m, n, &a, &b, &c);
     const int32_t pre = max3(a, b, c);
     w.add(kOpM, static_cast<uint32_t>(i - pre));
     if (a == pre) {
