@@ -88,6 +88,19 @@ def test_host_model_matches_standin_cigars():
         assert model_cigar(q, t) == standin_cigar(q, t), (q[:40], t[:40])
 
 
+def test_host_model_matrix_edges_fuzz():
+    """Short strings over two letters: most cells touch the matrix edge, where wf_cell leaves its fast path."""
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        q = bytes(rng.choice([65, 67], int(rng.integers(0, 11))).tolist())
+        t = bytes(rng.choice([65, 67], int(rng.integers(0, 11))).tolist())
+        assert model_cigar(q, t) == standin_cigar(q, t), (q, t)
+    for q, t in [(b"ACGT" * 10, b"ACGT" * 3), (b"A" * 5, b"A" * 50), (b"ACGTTGCA", b"TT"), (b"T" * 40, b"ACGT" * 10 + b"T"),
+                 (b"ACGT" * 30 + b"A", b"A")]:
+        assert model_cigar(q, t) == standin_cigar(q, t)
+        assert model_cigar(t, q) == standin_cigar(t, q)
+
+
 def test_abi_exports_and_fails_loudly_without_gpu():
     import re
     import torch
@@ -119,7 +132,10 @@ def pack(pairs):
 @pytest.mark.gpu
 def test_gpu_cigars_match_standin():
     from vechat_b200.aligner import Aligner
-    pairs = EDGE + noisy_pairs(11, 400, 800) + noisy_pairs(12, 12, 9000) + noisy_pairs(13, 60, 400, 0.3, 0.3, 0.3)
+    rng = np.random.default_rng(6)
+    tiny = [(bytes(rng.choice([65, 67], int(rng.integers(0, 11))).tolist()),
+             bytes(rng.choice([65, 67], int(rng.integers(0, 11))).tolist())) for _ in range(600)]
+    pairs = EDGE + tiny + noisy_pairs(11, 400, 800) + noisy_pairs(12, 12, 9000) + noisy_pairs(13, 60, 400, 0.3, 0.3, 0.3)
     a = Aligner(0)
     cigars, edits, st = a.align(*pack(pairs))
     for (q, t), c, d in zip(pairs, cigars, edits):
@@ -127,12 +143,15 @@ def test_gpu_cigars_match_standin():
     assert st["kernel_launches"] >= 1 and st["cells"] == sum((d + 1) ** 2 for d in edits)
     # same handle, second call, empty batch, and a batch that shares one sequence buffer between overlaps
     assert a.align(np.zeros(1, np.uint8), [], [], [], [])[0] == []
-    seq = np.frombuffer(pairs[20][0] + pairs[20][1], np.uint8)
-    m, n = len(pairs[20][0]), len(pairs[20][1])
+    pick = len(EDGE) + len(tiny) + 5
+    while min(len(pairs[pick][0]), len(pairs[pick][1])) < 20:
+        pick += 1
+    seq = np.frombuffer(pairs[pick][0] + pairs[pick][1], np.uint8)
+    m, n = len(pairs[pick][0]), len(pairs[pick][1])
     c2, _, _ = a.align(seq, [0, 0, 5], [m, m, m - 5], [m, m + 3, m], [n, n - 3, n])
-    assert c2[0] == cigars[20]
-    assert c2[1] == standin_cigar(pairs[20][0], pairs[20][1][3:])[0]
-    assert c2[2] == standin_cigar(pairs[20][0][5:], pairs[20][1])[0]
+    assert c2[0] == cigars[pick]
+    assert c2[1] == standin_cigar(pairs[pick][0], pairs[pick][1][3:])[0]
+    assert c2[2] == standin_cigar(pairs[pick][0][5:], pairs[pick][1])[0]
     a.close()
 
 

@@ -87,14 +87,30 @@ OVL_HD int32_t match_run(const uint8_t* q, const uint8_t* t, int32_t i, int32_t 
 
 // One cell of wavefront d (diagonal k inside the matrix): start point from the previous wavefront (none for d = 0),
 // then slide along the matches.  The caller stores the result at arena[wf_index(d, k)].
+//
+// Fast path: take the plain maximum of the three moves first.  A move that leaves the matrix (see wf_candidates)
+// always ends up being that maximum — an insertion can only leave through i > m, and a mismatch / deletion that
+// leaves through j > n lies beyond every move that stays inside on the same diagonal — so "maximum inside the
+// matrix" proves that no move had to be discarded, and the exact per-move checks run only next to the matrix edge.
 OVL_HD int32_t wf_cell(const Front& prev, const uint8_t* q, const uint8_t* t, int32_t m, int32_t n, int32_t d, int32_t k) {
   int32_t i;
   if (d == 0) {
     i = 0;
   } else {
-    int32_t a, b, c;
-    wf_candidates(prev, k, m, n, &a, &b, &c);
-    i = max3(a, b, c);
+    int32_t x0, x1, x2;
+    if (k - 1 >= prev.lo && k + 1 <= prev.hi) {  // interior diagonal: all three neighbours exist
+      x0 = prev.p[k], x1 = prev.p[k + 1], x2 = prev.p[k - 1];
+    } else {
+      x0 = prev.get(k), x1 = prev.get(k + 1), x2 = prev.get(k - 1);
+    }
+    i = max3(x0 + 1, x1 + 1, x2);  // kNone + 1 stays far below zero
+    if (i > m || i + k > n) {
+      int32_t a, b, c;
+      wf_candidates(prev, k, m, n, &a, &b, &c);
+      i = max3(a, b, c);
+    } else if (i < 0) {
+      i = kNone;
+    }
   }
   if (i != kNone) i += match_run(q, t, i, i + k, m, n);
   return i;

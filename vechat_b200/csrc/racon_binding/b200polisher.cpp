@@ -65,13 +65,18 @@ class CUDABatchProcessor {
     return n;
   }
   // Window only borrows pointers into Polisher::sequences_ (freed at polisher.cpp:560-561): copy the bytes once.
-  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p) {
-    uint64_t total = 0;
+  // Pass 1 (serial, metadata only) lays out the layer table and the byte offsets; pass 2 copies the bytes with
+  // `threads` host threads over window ranges.
+  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p, unsigned threads) {
     size_t layers = 0;
-    for (size_t i = first; i < last; ++i) total += bytes(*w[i]), layers += w[i]->sequences_.size();
-    p->bases.reserve(total);
-    p->quals.reserve(total);
+    for (size_t i = first; i < last; ++i) layers += w[i]->sequences_.size();
     p->seq_off.reserve(layers + 1);
+    p->has_qual.reserve(layers);
+    p->begin.reserve(layers);
+    p->end.reserve(layers);
+    p->win_first.reserve(last - first + 1);
+    p->win_flags.reserve(last - first);
+    uint64_t total = 0;
     for (size_t i = first; i < last; ++i) {
       const Window& win = *w[i];
       p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
@@ -80,19 +85,40 @@ class CUDABatchProcessor {
       p->win_flags.push_back(static_cast<uint8_t>((win.type_ == WindowType::kTGS ? VGC_WIN_TGS : 0u) |
                                                   (dummy ? VGC_WIN_DUMMY_QUAL : 0u)));
       for (size_t l = 0; l < win.sequences_.size(); ++l) {
-        const uint32_t len = win.sequences_[l].second;
-        p->seq_off.push_back(p->bases.size());
-        p->bases.insert(p->bases.end(), win.sequences_[l].first, win.sequences_[l].first + len);
-        const char* q = win.qualities_[l].first;
-        p->has_qual.push_back(q != nullptr ? 1 : 0);
-        if (q != nullptr) p->quals.insert(p->quals.end(), q, q + len);
-        else p->quals.resize(p->bases.size(), '!');
+        p->seq_off.push_back(total);
+        total += win.sequences_[l].second;
+        p->has_qual.push_back(win.qualities_[l].first != nullptr ? 1 : 0);
         p->begin.push_back(win.positions_[l].first);
         p->end.push_back(win.positions_[l].second);
       }
     }
     p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
-    p->seq_off.push_back(p->bases.size());
+    p->seq_off.push_back(total);
+    p->bases.resize(total);
+    p->quals.resize(total);
+    const size_t nw = last - first;
+    auto copy_range = [&](size_t a, size_t b) {
+      for (size_t i = a; i < b; ++i) {
+        const Window& win = *w[first + i];
+        size_t layer = p->win_first[i];
+        for (size_t l = 0; l < win.sequences_.size(); ++l, ++layer) {
+          const uint32_t len = win.sequences_[l].second;
+          const uint64_t o = p->seq_off[layer];
+          std::memcpy(p->bases.data() + o, win.sequences_[l].first, len);
+          const char* q = win.qualities_[l].first;
+          if (q != nullptr) std::memcpy(p->quals.data() + o, q, len);
+          else std::memset(p->quals.data() + o, '!', len);
+        }
+      }
+    };
+    const unsigned nt = nw < 512 ? 1u : std::max(1u, std::min(threads, 16u));
+    if (nt == 1) {
+      copy_range(0, nw);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(copy_range, nw * t / nt, nw * (t + 1) / nt);
+      for (auto& x : th) x.join();
+    }
   }
   static void store(Window& win, const uint8_t* s, uint64_t n) { win.consensus_.assign(reinterpret_cast<const char*>(s), n); }
 };
@@ -228,7 +254,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
       while (last < cut[d + 1] && last - first < kBatchWindows && (last == first || b < kBatchBytes))
         b += CUDABatchProcessor::bytes(*windows_[last++]);
       Packed p;
-      CUDABatchProcessor::pack(windows_, first, last, &p);
+      CUDABatchProcessor::pack(windows_, first, last, &p, std::max<unsigned>(1, num_threads_ / nd));
       const vgc_batch batch = p.view();
       std::vector<uint8_t> cons(vgc_result_bound(&batch));
       std::vector<uint64_t> off(batch.n_windows + 1);
