@@ -111,7 +111,7 @@ class CUDABatchProcessor {
         }
       }
     };
-    const unsigned nt = nw < 512 ? 1u : std::max(1u, std::min(threads, 16u));
+    const unsigned nt = nw < 64 ? 1u : std::max(1u, std::min(threads, 16u));
     if (nt == 1) {
       copy_range(0, nw);
     } else {
