@@ -105,6 +105,59 @@ def test_b200_binary_gpu_alignment_fails_loudly_without_gpu():
     assert b"[racon::B200Polisher::find_overlap_breaking_points] error:" in r.stderr
 
 
+# ---------------------------------------------------------------- CPU: the binding's host side behind a mock engine
+
+def _mock_env():
+    """LD_PRELOAD shim (tests/host_model/mock_vgc.cpp, test-only) that answers vgc_polish with the checker, so the
+    REAL vechat_racon_b200 binary runs here and its device ranges / batching / packing / store / stitch are checked
+    without a GPU."""
+    src = os.path.join(ROOT, "tests", "host_model", "mock_vgc.cpp")
+    out = os.path.join(ROOT, "tests", "host_model", "_build", "libmockvgc.so")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out, src,
+                        "-ldl"], check=True)
+    return {"LD_PRELOAD": out, "MOCK_VGC_REF_SO": os.path.join(ROOT, "oracle", "_ref", "libvechat_ref.so")}
+
+
+def _run_mock(opts, devices, batch_windows, cwd=EX, targets="targets.fq.gz"):
+    env = dict(os.environ, VECHAT_B200_DEVICES=devices, VECHAT_B200_BATCH_WINDOWS=str(batch_windows), **_mock_env())
+    env.pop("VECHAT_B200_ALIGN", None)
+    return subprocess.run([B200_BIN] + opts + ["-t", "8", "reads.fq.gz", "overlaps.paf", targets], cwd=cwd, env=env,
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+
+
+@need_b200
+@need_ref
+@pytest.mark.parametrize("opts,want,devices,batch", [
+    (HAP, "corrected.hap.fa", "0", 1 << 16), (HAP, "corrected.hap.fa", "0,1", 40), (LIN, "corrected.lin.fa", "0,1,2", 7),
+    (HAP, "corrected.hap.fa", "0,1,2,3,4,5,6,7,8,9,10,11", 1000),  # more devices than targets: empty ranges
+])
+def test_binding_host_side_behind_mock_engine(opts, want, devices, batch):
+    r = _run_mock(opts, devices, batch)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert r.stdout == golden(want)
+    calls = [l for l in r.stderr.decode().split("\n") if l.startswith("[mock_vgc]")]
+    windows = [int(l.split(":")[1].split()[0]) for l in calls]
+    assert sum(windows) == 168 and max(windows) <= batch  # every window exactly once, batches respected
+    nd, used = len(devices.split(",")), len({l.split()[4] for l in calls})
+    assert used == nd if nd <= 3 else 1 <= used <= 10  # contiguous ranges of whole targets (10 targets here)
+
+
+@need_b200
+@need_ref
+def test_binding_host_side_300_targets_behind_mock_engine():
+    """5 600 windows: the threaded packer, several batches per device, three device ranges."""
+    d = os.path.join(ROOT, "oracle", "_ref", "example_300")
+    want = os.path.join(d, "corrected.ref.fa")
+    if not os.path.exists(want):
+        pytest.skip("oracle/_ref/example_300 not generated (tools/example_overlaps.py --targets 300)")
+    r = _run_mock(HAP, "0,1,2", 700, cwd=d)
+    assert r.returncode == 0, r.stderr[-400:]
+    with open(want, "rb") as f:
+        assert r.stdout == f.read()
+
+
 # ---------------------------------------------------------------- the edlib stand-in both binaries are built on
 
 def _edlib():

@@ -239,8 +239,12 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
 
   // vgc_polish is re-entrant per handle and keeps no global state (vgc_last_error is thread-local): one host
   // thread + one handle per device, the model of the legacy path (cudapolisher.cpp:229-241,255-277).
-  constexpr uint64_t kBatchBytes = 1ull << 30;  // bases per vgc_polish call
-  constexpr size_t kBatchWindows = 1u << 16;
+  uint64_t kBatchBytes = 1ull << 30;  // bases per vgc_polish call
+  size_t kBatchWindows = 1u << 16;    // windows per vgc_polish call (VECHAT_B200_BATCH_WINDOWS: smaller batches)
+  if (const char* env = std::getenv("VECHAT_B200_BATCH_WINDOWS")) {
+    const long v = std::strtol(env, nullptr, 10);
+    if (v > 0) kBatchWindows = static_cast<size_t>(v);
+  }
   std::vector<std::string> errors(nd);
   auto run_device = [&](size_t d) {
     vgc_handle h = nullptr;
