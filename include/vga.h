@@ -12,6 +12,8 @@
  *                     the query / target substrings of src/overlap.cpp:195-199
  *   vga_result     <- Overlap::cigar_ (the caller then runs the reference's own find_breaking_points_from_cigar,
  *                     src/overlap.cpp:226-292)
+ *   vga_break      <- Overlap::find_breaking_points as a whole (src/overlap.cpp:179-203): alignment + the cut into
+ *                     per-window breaking points; vga_breaks <- Overlap::breaking_points_
  *
  * Result: an optimal unit-cost global alignment (edit distance == edlib's).  Among equally good paths the choice is
  * this library's (mismatch, then deletion, then insertion, on furthest-reaching diagonals), identical to
@@ -58,6 +60,23 @@ typedef struct {
   const int32_t*  edit_distance;   /* [n] */
 } vga_result;
 
+/* vga_break: per-overlap coordinates the breaking points are expressed in (src/overlap.cpp:238-239). */
+typedef struct {
+  const uint32_t* t_begin;        /* [n] Overlap::t_begin_ (the target substring starts there; t_end = t_begin + t_len) */
+  const uint32_t* q_start;        /* [n] query coordinate of the substring's first base:
+                                         strand ? q_length - q_end : q_begin */
+  uint32_t        window_length;  /* Polisher::window_length_ */
+} vga_cut;
+
+/* Filled by vga_break; buffers belong to the handle like vga_result's.  Overlap i owns the pairs
+ * [points_off[i], points_off[i + 1]); pair p = 4 words at points + 4 * p: first.t, first.q, last.t, last.q — two
+ * consecutive elements of Overlap::breaking_points_ (first match of a window stretch, one past its last match). */
+typedef struct {
+  const uint32_t* points;
+  const uint64_t* points_off;      /* [n + 1], in pairs */
+  const int32_t*  edit_distance;   /* [n] */
+} vga_breaks;
+
 typedef struct {
   uint64_t cells;            /* wavefront cells computed = sum over overlaps of (D+1)^2 */
   uint64_t wavefront_bytes;  /* 4 B x cells: the algorithmic bytes of the kernel (each cell written once) */
@@ -70,6 +89,9 @@ typedef struct {
 int vga_create(vga_handle* out, int device);
 int vga_destroy(vga_handle h);
 int vga_align(vga_handle h, const vga_batch* batch, vga_result* result, vga_stats* stats);
+/* Alignment + Overlap::find_breaking_points_from_cigar (src/overlap.cpp:226-292) on the device: only the breaking
+ * points come back (no CIGAR text crosses PCIe).  Same alignments as vga_align. */
+int vga_break(vga_handle h, const vga_batch* batch, const vga_cut* cut, vga_breaks* result, vga_stats* stats);
 const char* vga_last_error(void);
 
 #ifdef __cplusplus

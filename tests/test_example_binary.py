@@ -42,7 +42,7 @@ def run(binary, opts, reads="reads.fq.gz", paf="overlaps.paf", targets="targets.
     if devices is not None:
         env["VECHAT_B200_DEVICES"] = devices
     if gpu_align:
-        env["VECHAT_B200_ALIGN"] = "1"
+        env["VECHAT_B200_ALIGN"] = gpu_align if isinstance(gpu_align, str) else "1"
     return subprocess.run([binary] + opts + ["-t", str(threads), reads, paf, targets], cwd=cwd, env=env,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
 
@@ -113,16 +113,19 @@ def _mock_env():
     without a GPU."""
     src = os.path.join(ROOT, "tests", "host_model", "mock_vgc.cpp")
     out = os.path.join(ROOT, "tests", "host_model", "_build", "libmockvgc.so")
-    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+    core = os.path.join(ROOT, "vechat_b200", "csrc", "ovl_core.h")
+    if not os.path.exists(out) or max(os.path.getmtime(src), os.path.getmtime(core)) > os.path.getmtime(out):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out, src,
-                        "-ldl"], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "vechat_b200", "csrc"), "-o", out, src, "-ldl"], check=True)
     return {"LD_PRELOAD": out, "MOCK_VGC_REF_SO": os.path.join(ROOT, "oracle", "_ref", "libvechat_ref.so")}
 
 
-def _run_mock(opts, devices, batch_windows, cwd=EX, targets="targets.fq.gz"):
+def _run_mock(opts, devices, batch_windows, cwd=EX, targets="targets.fq.gz", align=None):
     env = dict(os.environ, VECHAT_B200_DEVICES=devices, VECHAT_B200_BATCH_WINDOWS=str(batch_windows), **_mock_env())
     env.pop("VECHAT_B200_ALIGN", None)
+    if align:
+        env["VECHAT_B200_ALIGN"] = align
     return subprocess.run([B200_BIN] + opts + ["-t", "8", "reads.fq.gz", "overlaps.paf", targets], cwd=cwd, env=env,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
 
@@ -142,6 +145,20 @@ def test_binding_host_side_behind_mock_engine(opts, want, devices, batch):
     assert sum(windows) == 168 and max(windows) <= batch  # every window exactly once, batches respected
     nd, used = len(devices.split(",")), len({l.split()[4] for l in calls})
     assert used == nd if nd <= 3 else 1 <= used <= 10  # contiguous ranges of whole targets (10 targets here)
+
+
+@need_b200
+@need_ref
+@pytest.mark.parametrize("align,call", [("1", "break"), ("cigar", "align")])
+@pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN + ["-w", "300"], None)])
+def test_binding_aligner_glue_behind_mock(align, call, opts, want):
+    """VECHAT_B200_ALIGN=1 / =cigar through the binding's CUDABatchAligner (substring offsets, strands, the hand-over
+    of breaking_points_ / cigar_) with the aligner core run on the host by the mock: FASTA = the reference program's,
+    i.e. the tilings did not move."""
+    r = _run_mock(opts, "0", 1 << 16, align=align)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert ("[mock_vga] %s: 422 overlaps" % call).encode() in r.stderr
+    assert r.stdout == (golden(want) if want else run(REF_BIN, opts).stdout)
 
 
 @need_b200
@@ -263,11 +280,13 @@ def test_gpu_binary_matches_committed_reference_fasta(opts, want):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["1", "cigar"])
 @pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN, "corrected.lin.fa")])
-def test_gpu_binary_with_gpu_overlap_alignment(opts, want):
-    """VECHAT_B200_ALIGN=1: the CIGARs come from vga_align (include/vga.h) instead of the host aligner; the tilings,
-    hence the FASTA, stay identical because the GPU aligner reproduces the host aligner's CIGARs exactly."""
-    r = run(B200_BIN, opts, devices="0", gpu_align=True)
+def test_gpu_binary_with_gpu_overlap_alignment(opts, want, mode):
+    """VECHAT_B200_ALIGN=1: overlaps aligned and cut into breaking points on the GPU (vga_break); =cigar: only the
+    CIGARs come from the GPU (vga_align).  The tilings, hence the FASTA, stay identical because the GPU aligner
+    reproduces the host aligner's alignments exactly."""
+    r = run(B200_BIN, opts, devices="0", gpu_align=mode)
     assert r.returncode == 0, r.stderr[-600:]
     assert b"aligned overlaps on the GPU" in r.stderr and b"[racon::B200Polisher::polish] generated consensus" in r.stderr
     assert r.stdout == golden(want)

@@ -101,17 +101,89 @@ def test_host_model_matrix_edges_fuzz():
         assert model_cigar(t, q) == standin_cigar(t, q)
 
 
+def breaking_points_from_cigar(cigar, t_begin, t_end, q_start, window_length):
+    """Checker: Overlap::find_breaking_points_from_cigar (src/overlap.cpp:226-292) restated base by base."""
+    window_ends = [i - 1 for i in range(0, t_end, window_length) if i > t_begin] + [t_end - 1]
+    out, w, found, first, last = [], 0, False, (0, 0), (0, 0)
+    q_ptr, t_ptr = q_start - 1, t_begin - 1
+    k = 0
+    while k < len(cigar):
+        j = k
+        while cigar[j].isdigit():
+            j += 1
+        num, op = int(cigar[k:j]), cigar[j]
+        k = j + 1
+        if op == "M":
+            for _ in range(num):
+                q_ptr += 1
+                t_ptr += 1
+                if not found:
+                    found, first = True, (t_ptr, q_ptr)
+                last = (t_ptr + 1, q_ptr + 1)
+                if t_ptr == window_ends[w]:
+                    if found:
+                        out += [first, last]
+                    found = False
+                    w += 1
+        elif op == "I":
+            q_ptr += num
+        else:
+            for _ in range(num):
+                t_ptr += 1
+                if t_ptr == window_ends[w]:
+                    if found:
+                        out += [first, last]
+                    found = False
+                    w += 1
+    return out
+
+
+def model_break(q, t, t_begin, q_start, wl):
+    lib = model()
+    cap = len(t) // wl + 4
+    out = (C.c_uint32 * (4 * cap))()
+    lib.ovl_model_break.restype = C.c_int
+    lib.ovl_model_break.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.c_uint32]
+    n = lib.ovl_model_break(q, len(q), t, len(t), t_begin, q_start, wl, out, cap)
+    assert 0 <= n <= cap
+    return [(out[4 * i + 2 * h], out[4 * i + 2 * h + 1]) for i in range(n) for h in range(2)]
+
+
+def cut_cases(seed, count, max_len):
+    rng = np.random.default_rng(seed)
+    out = []
+    for q, t in noisy_pairs(seed, count, max_len, 0.05, 0.12, 0.12):
+        if not t:
+            continue
+        wl = int(rng.choice([50, 100, 500, 640]))
+        t_begin = int(rng.choice([0, 1, wl - 1, wl, wl + 1, int(rng.integers(0, 3000))]))
+        out.append((q, t, t_begin, int(rng.integers(0, 2000)), wl))
+    return out
+
+
+def test_host_model_breaking_points_match_reference_loop():
+    cases = cut_cases(31, 250, 1500) + cut_cases(32, 4, 6000)
+    cases += [(b"ACGT" * 30, b"ACGT" * 30, 0, 0, 40), (b"A" * 100, b"A" * 100, 100, 7, 100), (b"C" * 20, b"A" * 20 + b"C" * 20, 90, 3, 10),
+              (b"AC" * 60, b"AC" * 10, 495, 0, 500), (b"G", b"ACGTACGT", 0, 0, 4)]
+    for q, t, t_begin, q_start, wl in cases:
+        cigar, _ = standin_cigar(q, t)
+        want = breaking_points_from_cigar(cigar, t_begin, t_begin + len(t), q_start, wl)
+        assert model_break(q, t, t_begin, q_start, wl) == want, (len(q), len(t), t_begin, q_start, wl)
+
+
 def test_abi_exports_and_fails_loudly_without_gpu():
     import re
     import torch
     from vechat_b200 import aligner, engine
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vga.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(vga_[a-z_]+)\s*\(", src)))
-    assert names == ["vga_align", "vga_create", "vga_destroy", "vga_last_error"]
+    assert names == ["vga_align", "vga_break", "vga_create", "vga_destroy", "vga_last_error"]
     lib = engine.load_library()
     for n in names:
         assert getattr(lib, n) is not None
     assert C.sizeof(aligner.VgaBatch) == 56 and C.sizeof(aligner.VgaResult) == 24 and C.sizeof(aligner.VgaStats) == 40
+    assert C.sizeof(aligner.VgaCut) == 24 and C.sizeof(aligner.VgaBreaks) == 24
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError) as ei:
             aligner.Aligner(0)
@@ -172,6 +244,29 @@ def test_gpu_retry_rounds(monkeypatch):
     monkeypatch.setenv("VGA_OUT_CAP_RUNS", "1")      # clamped to one worst-case alignment: many rounds
     got, got_d, st = a.align(*pack(pairs))
     assert (got, got_d) == (want, want_d) and st["retried"] > 0 and st["kernel_launches"] >= 2
+    a.close()
+
+
+@pytest.mark.gpu
+def test_gpu_breaking_points_match_reference_loop(monkeypatch):
+    """vga_break: alignment + the cut of src/overlap.cpp:226-292 on the device, against the base-by-base restatement
+    of the reference loop applied to the host aligner's CIGAR."""
+    from vechat_b200.aligner import Aligner
+    a = Aligner(0)
+    for wl in (100, 500):
+        cases = [c for c in cut_cases(41, 500, 1500) + cut_cases(42, 6, 7000)]
+        pairs = [(q, t) for q, t, _, _, _ in cases]
+        got, edits, st = a.breaks(*pack(pairs), [c[2] for c in cases], [c[3] for c in cases], wl)
+        for (q, t, t_begin, q_start, _), g, d in zip(cases, got, edits):
+            cigar, dist = standin_cigar(q, t)
+            assert d == dist
+            assert g == breaking_points_from_cigar(cigar, t_begin, t_begin + len(t), q_start, wl), (len(q), len(t), t_begin, wl)
+        assert st["retried"] == 0
+    # retry rounds in cut mode
+    monkeypatch.setenv("VGA_ARENA_CELLS", "2500")
+    monkeypatch.setenv("VGA_OUT_CAP_RUNS", "64")
+    got2, _, st = a.breaks(*pack(pairs), [c[2] for c in cases], [c[3] for c in cases], 500)
+    assert got2 == got and st["retried"] > 0
     a.close()
 
 

@@ -37,7 +37,7 @@ def run(binary, args, cwd, devices=None, gpu_align=False):
     if devices:
         env["VECHAT_B200_DEVICES"] = devices
     if gpu_align:
-        env["VECHAT_B200_ALIGN"] = "1"
+        env["VECHAT_B200_ALIGN"] = gpu_align if isinstance(gpu_align, str) else "1"
     t0 = time.time()
     r = subprocess.run([binary] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     wall = time.time() - t0
@@ -52,7 +52,8 @@ def main():
     ap.add_argument("--skip-ref", action="store_true")
     ap.add_argument("--devices", default="0")
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
-    ap.add_argument("--gpu-align", action="store_true", help="VECHAT_B200_ALIGN=1: overlap CIGARs from vga_align")
+    ap.add_argument("--gpu-align", nargs="?", const="1", default=None,
+                    help="VECHAT_B200_ALIGN: 1 = align + cut on the GPU (vga_break), cigar = CIGARs only (vga_align)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     targets = "targets.fq.gz" if os.path.exists(os.path.join(a.dir, "targets.fq.gz")) else "reads.fq.gz"
@@ -60,7 +61,7 @@ def main():
     args = ["-f", "-p", "-d", "0.2", "-s", "0.2", "-t", str(a.threads), "reads.fq.gz", paf, targets]
     rep = {"dir": os.path.relpath(a.dir, ROOT), "args": " ".join(args), "host_threads": a.threads}
     got, st, wall = run(B200_BIN, args, a.dir, a.devices, a.gpu_align)
-    rep["gpu_align"] = bool(a.gpu_align)
+    rep["gpu_align"] = a.gpu_align or False
     rep["b200"] = {"wall_s": round(wall, 2), "stages_s": st, "fasta_sha256": hashlib.sha256(got).hexdigest(),
                    "reads_out": got.count(b">"), "bases_out": sum(len(l) for l in got.split(b"\n") if not l.startswith(b">"))}
     if a.skip_ref:

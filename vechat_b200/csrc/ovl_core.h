@@ -165,6 +165,71 @@ OVL_HD uint32_t wf_traceback(const int32_t* arena, int32_t m, int32_t n, int32_t
   return w.finish();
 }
 
+// Breaking points of an alignment (Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-292): walk the
+// alignment forward over target windows of `window_length` bases; for every window the alignment touches with at
+// least one M column, emit (first M column of the stretch: target, query) and (one past its last M column: target + 1,
+// query + 1).  The reference walks base by base; here a run is cut arithmetically at the window ends it crosses.
+// Window ends (overlap.cpp:229-235): every multiple of window_length above t_begin, minus one, then t_end - 1.
+struct CutParams {
+  uint32_t t_begin, t_end;  // Overlap::t_begin_, t_end_ (target coordinates of the aligned substring)
+  uint32_t q_start;         // query coordinate of the substring's first base: strand ? q_length - q_end : q_begin
+  uint32_t window_length;
+};
+
+// `runs` as wf_traceback leaves them (reverse order, n_runs entries).  out: 4 words per breaking-point pair
+// (first.t, first.q, last.t, last.q); returns the number of pairs (never more than max_pairs are written).
+OVL_HD uint32_t wf_cut(const uint32_t* runs, uint32_t n_runs, const CutParams& c, uint32_t* out, uint32_t max_pairs) {
+  // positions of the last consumed base; wrap-around at -1 is intended (the reference uses int32 starting at begin - 1)
+  uint32_t q_ptr = c.q_start - 1, t_ptr = c.t_begin - 1;
+  // next window end: the smallest multiple of window_length above t_begin, minus one, capped by t_end - 1
+  uint32_t next_multiple = (c.t_begin / c.window_length + 1) * c.window_length;
+  uint32_t end = next_multiple < c.t_end ? next_multiple - 1 : c.t_end - 1;
+  bool found = false, ends_left = true;
+  uint32_t first_t = 0, first_q = 0, last_t = 0, last_q = 0, pairs = 0;
+  for (uint32_t x = n_runs; x-- > 0;) {
+    const uint32_t op = runs[x] & 3;
+    uint32_t len = runs[x] >> 2;
+    if (op == kOpI) {
+      q_ptr += len;
+      continue;
+    }
+    // M or D: consumes target; cut at every window end inside the run
+    while (ends_left && len > 0 && end - t_ptr <= len) {
+      const uint32_t step = end - t_ptr;  // >= 1 bases up to and including the window end
+      if (op == kOpM) {
+        if (!found) found = true, first_t = t_ptr + 1, first_q = q_ptr + 1;
+        q_ptr += step;
+        last_t = end + 1, last_q = q_ptr + 1;
+      }
+      t_ptr = end;
+      len -= step;
+      if (found) {
+        if (pairs < max_pairs) {
+          out[4 * pairs + 0] = first_t, out[4 * pairs + 1] = first_q;
+          out[4 * pairs + 2] = last_t, out[4 * pairs + 3] = last_q;
+        }
+        ++pairs;
+      }
+      found = false;
+      if (end + 1 >= c.t_end) {
+        ends_left = false;  // that was t_end - 1
+      } else {
+        next_multiple += c.window_length;
+        end = next_multiple < c.t_end ? next_multiple - 1 : c.t_end - 1;
+      }
+    }
+    if (len > 0) {
+      if (op == kOpM) {
+        if (!found) found = true, first_t = t_ptr + 1, first_q = q_ptr + 1;
+        q_ptr += len;
+        last_t = t_ptr + len + 1, last_q = q_ptr + 1;
+      }
+      t_ptr += len;
+    }
+  }
+  return pairs;
+}
+
 // Cells of arena an alignment with edit distance D occupies.
 OVL_HD uint64_t wf_cells(uint64_t D) { return (D + 1) * (D + 1); }
 

@@ -127,8 +127,10 @@ class CUDABatchProcessor {
 // coordinates, writes Overlap::cigar_.
 class CUDABatchAligner {
  public:
+  // cut_on_device: vga_break fills breaking_points_ directly (no CIGAR text crosses PCIe); otherwise vga_align fills
+  // cigar_ and the reference's find_breaking_points_from_cigar cuts it on the host.
   static void align(std::vector<std::unique_ptr<Overlap>>& overlaps, const std::vector<std::unique_ptr<Sequence>>& sequences,
-                    int device) {
+                    int device, uint32_t window_length, bool cut_on_device) {
     vga_handle h = nullptr;
     if (vga_create(&h, device) != VGA_OK) die("B200Polisher::find_overlap_breaking_points", vga_last_error());
     constexpr size_t kChunk = 1u << 18;  // overlaps per vga_align call
@@ -148,7 +150,7 @@ class CUDABatchAligner {
       };
       std::vector<size_t> index;
       std::vector<uint64_t> q_off, t_off;
-      std::vector<uint32_t> q_len, t_len;
+      std::vector<uint32_t> q_len, t_len, t_begin, q_start;
       for (size_t i = first; i < last; ++i) {
         const Overlap& o = *overlaps[i];
         if (!o.is_transmuted_) die("Overlap::find_breaking_points", "overlap is not transmuted!");
@@ -159,6 +161,8 @@ class CUDABatchAligner {
         q_len.push_back(o.q_end_ - o.q_begin_);
         t_off.push_back(place(o.t_id_, false) + o.t_begin_);
         t_len.push_back(o.t_end_ - o.t_begin_);
+        t_begin.push_back(o.t_begin_);
+        q_start.push_back(o.strand_ ? o.q_length_ - o.q_end_ : o.q_begin_);  // overlap.cpp:238
       }
       if (index.empty()) continue;
       vga_batch b;
@@ -169,10 +173,30 @@ class CUDABatchAligner {
       b.q_len = q_len.data();
       b.t_off = t_off.data();
       b.t_len = t_len.data();
-      vga_result r;
-      if (vga_align(h, &b, &r, nullptr) != VGA_OK)  // no CPU fallback
-        die("B200Polisher::find_overlap_breaking_points", vga_last_error());
-      for (size_t x = 0; x < index.size(); ++x) overlaps[index[x]]->cigar_ = r.cigar + r.cigar_off[x];
+      if (cut_on_device) {
+        vga_cut c;
+        c.t_begin = t_begin.data();
+        c.q_start = q_start.data();
+        c.window_length = window_length;
+        vga_breaks r;
+        if (vga_break(h, &b, &c, &r, nullptr) != VGA_OK)  // no CPU fallback
+          die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+        for (size_t x = 0; x < index.size(); ++x) {
+          Overlap& o = *overlaps[index[x]];
+          for (uint64_t p = r.points_off[x]; p < r.points_off[x + 1]; ++p) {
+            o.breaking_points_.emplace_back(r.points[4 * p], r.points[4 * p + 1]);
+            o.breaking_points_.emplace_back(r.points[4 * p + 2], r.points[4 * p + 3]);
+          }
+          // an alignment without a single match column has no breaking points: leave an empty alignment behind so
+          // that the reference's loop has nothing to align for it either
+          if (o.breaking_points_.empty()) o.cigar_ = "0M";
+        }
+      } else {
+        vga_result r;
+        if (vga_align(h, &b, &r, nullptr) != VGA_OK)  // no CPU fallback
+          die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+        for (size_t x = 0; x < index.size(); ++x) overlaps[index[x]]->cigar_ = r.cigar + r.cigar_off[x];
+      }
     }
     vga_destroy(h);
   }
@@ -187,10 +211,11 @@ B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
     : Polisher(std::move(sparser), std::move(oparser), std::move(tparser), type, haplotype, min_confidence, min_support,
                num_prune, window_length, quality_threshold, error_threshold, trim, match, mismatch, gap, num_threads),
       match_(match), mismatch_(mismatch), gap_(gap), num_threads_(num_threads), devices_(std::move(devices)),
-      align_on_gpu_(false) {
+      align_on_gpu_(false), cut_on_gpu_(false) {
   if (devices_.empty()) devices_.push_back(0);
   const char* env = std::getenv("VECHAT_B200_ALIGN");
   align_on_gpu_ = env != nullptr && env[0] != '\0' && env[0] != '0';
+  cut_on_gpu_ = align_on_gpu_ && std::strcmp(env, "cigar") != 0;
 }
 
 B200Polisher::~B200Polisher() {}
@@ -198,7 +223,7 @@ B200Polisher::~B200Polisher() {}
 void B200Polisher::find_overlap_breaking_points(std::vector<std::unique_ptr<Overlap>>& overlaps) {
   if (align_on_gpu_) {
     logger_->log();
-    CUDABatchAligner::align(overlaps, sequences_, devices_.front());
+    CUDABatchAligner::align(overlaps, sequences_, devices_.front(), window_length_, cut_on_gpu_);
     logger_->log("[racon::B200Polisher::find_overlap_breaking_points] aligned overlaps on the GPU");
   }
   Polisher::find_overlap_breaking_points(overlaps);  // cuts the breaking points; edlib only where cigar_ is empty

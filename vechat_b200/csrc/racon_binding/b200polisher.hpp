@@ -31,16 +31,18 @@ class B200Polisher : public Polisher {
   void polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop_unpolished_sequences) override;
 
  protected:
-  // Opt-in (VECHAT_B200_ALIGN=1): the overlaps' CIGARs come from the GPU aligner (include/vga.h) before the
-  // reference's own loop runs, which then skips edlib for them (src/overlap.cpp:191-199) and only cuts breaking
-  // points.  Off by default because the aligner's choice among equally good alignments is not edlib's.
+  // Opt-in (VECHAT_B200_ALIGN=1): the overlaps are aligned AND cut into breaking points on the GPU (vga_break,
+  // include/vga.h) before the reference's own loop runs, which then finds breaking_points_ filled and returns at
+  // src/overlap.cpp:187-189.  VECHAT_B200_ALIGN=cigar: only the CIGARs come from the GPU (vga_align) and the
+  // reference cuts them itself (overlap.cpp:191-203).  Off by default because the aligner's choice among equally
+  // good alignments is not edlib's.
   void find_overlap_breaking_points(std::vector<std::unique_ptr<Overlap>>& overlaps) override;
 
  private:
   int8_t match_, mismatch_, gap_;  // the base class hands them to spoa and forgets them (polisher.cpp:186-190)
   uint32_t num_threads_;
   std::vector<int> devices_;
-  bool align_on_gpu_;
+  bool align_on_gpu_, cut_on_gpu_;
 };
 
 // Drop-in for racon::createPolisher (same signature, src/polisher.hpp:42-49).  Returns a B200Polisher when the
