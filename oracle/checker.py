@@ -108,3 +108,51 @@ def ref_align_probe(type_, m, x, g, seqs, query):
 
 def oracle_align_probe(type_, m, x, g, seqs, query):
     return _probe(_load_oracle().oracle_align_probe, type_, m, x, g, seqs, query)
+
+
+# ---- the host aligner both reference-program builds use in place of edlib (oracle/shims/edlib_standin.cpp): the
+# checker of the overlap aligner (include/vga.h).
+
+EDLIB_SO = os.path.join(HERE, "_build", "libedlib_standin.so")
+_edlib = None
+
+
+class _EdlibConfig(C.Structure):
+    _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int), ("eq", C.c_void_p), ("neq", C.c_int)]
+
+
+class _EdlibResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("editDistance", C.c_int), ("endLocations", C.POINTER(C.c_int)),
+                ("startLocations", C.POINTER(C.c_int)), ("numLocations", C.c_int),
+                ("alignment", C.POINTER(C.c_ubyte)), ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+
+def edlib_standin():
+    global _edlib
+    if _edlib is None:
+        if not os.path.exists(EDLIB_SO):
+            subprocess.run(["make", "-s", "-C", HERE, "edlib"], check=True)
+        lib = C.CDLL(EDLIB_SO)
+        lib.edlibNewAlignConfig.restype = _EdlibConfig
+        lib.edlibNewAlignConfig.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.edlibAlign.restype = _EdlibResult
+        lib.edlibAlign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, _EdlibConfig]
+        lib.edlibAlignmentToCigar.restype = C.c_void_p
+        lib.edlibAlignmentToCigar.argtypes = [C.POINTER(C.c_ubyte), C.c_int, C.c_int]
+        lib.edlibFreeAlignResult.argtypes = [_EdlibResult]
+        _edlib = lib
+    return _edlib
+
+
+def standin_cigar(q, t):
+    """(standard CIGAR, edit distance) of the global alignment of bytes q against bytes t."""
+    lib = edlib_standin()
+    r = lib.edlibAlign(q, len(q), t, len(t), lib.edlibNewAlignConfig(-1, 0, 2, None, 0))  # EDLIB_MODE_NW, TASK_PATH
+    if r.status != 0:
+        raise RuntimeError("edlib stand-in failed")
+    p = lib.edlibAlignmentToCigar(r.alignment, r.alignmentLength, 0)
+    s = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    d = r.editDistance
+    lib.edlibFreeAlignResult(r)
+    return s, d
