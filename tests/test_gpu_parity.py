@@ -73,6 +73,15 @@ def test_fuzz(seed, kw, pkw):
     check(fuzz_batch(seed, **kw), pkw, "seed %d" % seed)
 
 
+@pytest.mark.parametrize("pkw", [dict(haplotype=0, trim=1), dict()])
+def test_ngs_windows(pkw):
+    """WindowType::kNGS windows (mean read length <= 1000, src/polisher.cpp:289-290) are never trimmed
+    (src/window.cpp:141)."""
+    b = fuzz_batch(77, n_windows=24, partial=0.7)
+    b.win_flags[1::2] &= np.uint8(~VGC_WIN_TGS & 0xFF)
+    check(b, pkw, "NGS windows")
+
+
 def test_empty_batch():
     b = WindowBatch.from_windows([])
     r, st = eng().polish(b)

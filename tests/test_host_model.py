@@ -75,6 +75,27 @@ def test_host_model_fuzz_vs_oracle(seed):
     assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d %r %r" % (seed, kw, pkw))
 
 
+def ngs_batch(seed, **kw):
+    """fuzz batch whose odd windows are WindowType::kNGS (flag cleared): never trimmed (src/window.cpp:141)."""
+    from vechat_b200._ffi import VGC_WIN_TGS
+    b = fuzz_batch(seed, **kw)
+    b.win_flags[1::2] &= np.uint8(~VGC_WIN_TGS & 0xFF)
+    return b
+
+
+@pytest.mark.parametrize("pkw", [dict(haplotype=0, trim=1), dict(haplotype=0, trim=0), dict()])
+def test_ngs_windows(pkw):
+    batch = ngs_batch(77, n_windows=24, partial=0.7)
+    p = make_params(**pkw)
+    want = checker.ref_polish(batch, p, threads=4) if checker.have_ref() else checker.oracle_polish(batch, p, threads=4)
+    assert_same(checker.oracle_polish(batch, p, threads=4), want, "oracle, NGS windows %r" % pkw)
+    assert_same(hm_polish(batch, p), want, "host model, NGS windows %r" % pkw)
+    if pkw.get("haplotype", 1) == 0 and pkw.get("trim", 1) == 1:
+        # the flag matters: with every window TGS some of these consensuses are trimmed
+        tgs = checker.oracle_polish(fuzz_batch(77, n_windows=24, partial=0.7), p, threads=4)
+        assert any(tgs.window(w) != want.window(w) for w in range(1, 24, 2))
+
+
 def test_threaded_host_prep_matches_oracle():
     """>= 1024 windows: prepare_batch (rank sort, average weights, alphabet) runs on several host threads; the
     result must not depend on the split."""
