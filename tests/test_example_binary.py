@@ -161,6 +161,50 @@ def test_binding_aligner_glue_behind_mock(align, call, opts, want):
     assert r.stdout == (golden(want) if want else run(REF_BIN, opts).stdout)
 
 
+def _write_sam(path):
+    """The fixture's overlaps as SAM records whose CIGARs are the host aligner's (soft clips for the unaligned ends;
+    for a reverse-strand record the CIGAR runs along the reverse complement, as SAM has it)."""
+    from oracle import checker
+    reads = {}
+    with gzip.open(os.path.join(EX, "reads.fq.gz"), "rb") as f:
+        lines = f.read().split(b"\n")
+    for i in range(0, len(lines) - 3, 4):
+        reads[lines[i][1:].decode()] = lines[i + 1]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    with open(path, "w") as out:
+        out.write("@HD\tVN:1.6\n")
+        for line in open(os.path.join(EX, "overlaps.paf")):
+            f = line.split("\t")
+            q, t = reads[f[0]], reads[f[5]]
+            ql, qb, qe, tb, te = int(f[1]), int(f[2]), int(f[3]), int(f[7]), int(f[8])
+            rev = f[4] == "-"
+            qs = q.translate(comp)[::-1][ql - qe:ql - qb] if rev else q[qb:qe]
+            cigar, _ = checker.standin_cigar(qs, t[tb:te])
+            left, right = (ql - qe, qb) if rev else (qb, ql - qe)
+            cigar = ("%dS" % left if left else "") + cigar + ("%dS" % right if right else "")
+            out.write("\t".join([f[0], "16" if rev else "0", f[5], str(tb + 1), "255", cigar, "*", "0", "0", "*", "*"]) + "\n")
+
+
+@need_b200
+@need_ref
+def test_sam_input_carries_its_own_alignments(tmp_path):
+    """SAM overlaps come with CIGARs: the reference skips edlib for them (overlap.cpp:191) and the binding's GPU
+    aligner must skip them too.  With the host aligner's CIGARs in the file the tilings equal the PAF run's, so the
+    FASTA equals the committed one — which also pins the I / D orientation of the aligner against the reference's
+    own CIGAR reading (overlap.cpp:71-93, 240-290)."""
+    sam = str(tmp_path / "overlaps.sam")
+    _write_sam(sam)
+    r = run(REF_BIN, HAP, paf=sam)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert r.stdout == golden("corrected.hap.fa")
+    env = dict(os.environ, VECHAT_B200_DEVICES="0", VECHAT_B200_ALIGN="1", **_mock_env())
+    m = subprocess.run([B200_BIN] + HAP + ["-t", "8", "reads.fq.gz", sam, "targets.fq.gz"], cwd=EX, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert m.returncode == 0, m.stderr[-400:]
+    assert m.stdout == golden("corrected.hap.fa")
+    assert b"[mock_vga]" not in m.stderr  # nothing left to align
+
+
 @need_b200
 @need_ref
 def test_binding_host_side_300_targets_behind_mock_engine():
