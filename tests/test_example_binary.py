@@ -149,15 +149,16 @@ def test_binding_host_side_behind_mock_engine(opts, want, devices, batch):
 
 @need_b200
 @need_ref
-@pytest.mark.parametrize("align,call", [("1", "break"), ("cigar", "align")])
+@pytest.mark.parametrize("align,call,devices", [("1", "break", "0"), ("cigar", "align", "0"), ("1", "break", "0,1,2")])
 @pytest.mark.parametrize("opts,want", [(HAP, "corrected.hap.fa"), (LIN + ["-w", "300"], None)])
-def test_binding_aligner_glue_behind_mock(align, call, opts, want):
+def test_binding_aligner_glue_behind_mock(align, call, devices, opts, want):
     """VECHAT_B200_ALIGN=1 / =cigar through the binding's CUDABatchAligner (substring offsets, strands, the hand-over
     of breaking_points_ / cigar_) with the aligner core run on the host by the mock: FASTA = the reference program's,
     i.e. the tilings did not move."""
-    r = _run_mock(opts, "0", 1 << 16, align=align)
+    r = _run_mock(opts, devices, 1 << 16, align=align)
     assert r.returncode == 0, r.stderr[-400:]
-    assert ("[mock_vga] %s: 422 overlaps" % call).encode() in r.stderr
+    calls = [l.split() for l in r.stderr.decode().split("\n") if l.startswith("[mock_vga] %s:" % call)]
+    assert len(calls) == len(devices.split(",")) and sum(int(c[2]) for c in calls) == 422  # one range per device
     assert r.stdout == (golden(want) if want else run(REF_BIN, opts).stdout)
 
 

@@ -129,13 +129,41 @@ class CUDABatchAligner {
  public:
   // cut_on_device: vga_break fills breaking_points_ directly (no CIGAR text crosses PCIe); otherwise vga_align fills
   // cigar_ and the reference's find_breaking_points_from_cigar cuts it on the host.
+  // One host thread + one vga_handle per device, each over a contiguous range of the overlaps (they are independent;
+  // vga_* keeps no global state).
   static void align(std::vector<std::unique_ptr<Overlap>>& overlaps, const std::vector<std::unique_ptr<Sequence>>& sequences,
-                    int device, uint32_t window_length, bool cut_on_device) {
+                    const std::vector<int>& devices, uint32_t window_length, bool cut_on_device) {
+    for (const auto& o : overlaps)
+      if (!o->is_transmuted_) die("Overlap::find_breaking_points", "overlap is not transmuted!");
+    const size_t nd = devices.size(), n = overlaps.size();
+    std::vector<std::string> errors(nd);
+    auto run_device = [&](size_t d) {
+      align_range(overlaps, sequences, n * d / nd, n * (d + 1) / nd, devices[d], window_length, cut_on_device, &errors[d]);
+    };
+    if (nd == 1) {
+      run_device(0);
+    } else {
+      std::vector<std::thread> th;
+      for (size_t d = 0; d < nd; ++d) th.emplace_back(run_device, d);
+      for (auto& t : th) t.join();
+    }
+    for (const std::string& e : errors)
+      if (!e.empty()) die("B200Polisher::find_overlap_breaking_points", e.c_str());  // no CPU fallback
+  }
+
+ private:
+  static void align_range(std::vector<std::unique_ptr<Overlap>>& overlaps,
+                          const std::vector<std::unique_ptr<Sequence>>& sequences, size_t range_first, size_t range_last,
+                          int device, uint32_t window_length, bool cut_on_device, std::string* error) {
+    if (range_first >= range_last) return;
     vga_handle h = nullptr;
-    if (vga_create(&h, device) != VGA_OK) die("B200Polisher::find_overlap_breaking_points", vga_last_error());
-    constexpr size_t kChunk = 1u << 18;  // overlaps per vga_align call
-    for (size_t first = 0; first < overlaps.size(); first += kChunk) {
-      const size_t last = std::min(overlaps.size(), first + kChunk);
+    if (vga_create(&h, device) != VGA_OK) {
+      *error = vga_last_error();
+      return;
+    }
+    constexpr size_t kChunk = 1u << 18;  // overlaps per vga_align / vga_break call
+    for (size_t first = range_first; first < range_last && error->empty(); first += kChunk) {
+      const size_t last = std::min(range_last, first + kChunk);
       // every sequence (strand) the chunk touches goes into the byte buffer once
       std::vector<uint8_t> seqs;
       std::vector<uint64_t> where(2 * sequences.size(), ~0ull);
@@ -153,7 +181,6 @@ class CUDABatchAligner {
       std::vector<uint32_t> q_len, t_len, t_begin, q_start;
       for (size_t i = first; i < last; ++i) {
         const Overlap& o = *overlaps[i];
-        if (!o.is_transmuted_) die("Overlap::find_breaking_points", "overlap is not transmuted!");
         if (!o.cigar_.empty() || !o.breaking_points_.empty()) continue;  // SAM input / already done
         index.push_back(i);
         // the substrings of overlap.cpp:195-199
@@ -179,8 +206,10 @@ class CUDABatchAligner {
         c.q_start = q_start.data();
         c.window_length = window_length;
         vga_breaks r;
-        if (vga_break(h, &b, &c, &r, nullptr) != VGA_OK)  // no CPU fallback
-          die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+        if (vga_break(h, &b, &c, &r, nullptr) != VGA_OK) {
+          *error = vga_last_error();
+          break;
+        }
         for (size_t x = 0; x < index.size(); ++x) {
           Overlap& o = *overlaps[index[x]];
           for (uint64_t p = r.points_off[x]; p < r.points_off[x + 1]; ++p) {
@@ -193,8 +222,10 @@ class CUDABatchAligner {
         }
       } else {
         vga_result r;
-        if (vga_align(h, &b, &r, nullptr) != VGA_OK)  // no CPU fallback
-          die("B200Polisher::find_overlap_breaking_points", vga_last_error());
+        if (vga_align(h, &b, &r, nullptr) != VGA_OK) {
+          *error = vga_last_error();
+          break;
+        }
         for (size_t x = 0; x < index.size(); ++x) overlaps[index[x]]->cigar_ = r.cigar + r.cigar_off[x];
       }
     }
@@ -223,7 +254,7 @@ B200Polisher::~B200Polisher() {}
 void B200Polisher::find_overlap_breaking_points(std::vector<std::unique_ptr<Overlap>>& overlaps) {
   if (align_on_gpu_) {
     logger_->log();
-    CUDABatchAligner::align(overlaps, sequences_, devices_.front(), window_length_, cut_on_gpu_);
+    CUDABatchAligner::align(overlaps, sequences_, devices_, window_length_, cut_on_gpu_);
     logger_->log("[racon::B200Polisher::find_overlap_breaking_points] aligned overlaps on the GPU");
   }
   Polisher::find_overlap_breaking_points(overlaps);  // cuts the breaking points; edlib only where cigar_ is empty
