@@ -308,24 +308,42 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
       errors[d] = vgc_last_error();
       return;
     }
+    // batches of this device's range, then a two-deep pipeline: while vgc_polish works on batch i, a helper thread
+    // packs batch i + 1 (the windows only borrow their bytes, so packing is a pure read of Polisher::sequences_)
+    std::vector<std::pair<size_t, size_t>> batches;
     for (size_t first = cut[d]; first < cut[d + 1];) {
       size_t last = first;
       uint64_t b = 0;
       while (last < cut[d + 1] && last - first < kBatchWindows && (last == first || b < kBatchBytes))
         b += CUDABatchProcessor::bytes(*windows_[last++]);
-      Packed p;
-      CUDABatchProcessor::pack(windows_, first, last, &p, std::max<unsigned>(1, num_threads_ / nd));
-      const vgc_batch batch = p.view();
+      batches.emplace_back(first, last);
+      first = last;
+    }
+    const unsigned pack_threads = std::max<unsigned>(1, num_threads_ / nd);
+    Packed cur, next;
+    if (!batches.empty()) CUDABatchProcessor::pack(windows_, batches[0].first, batches[0].second, &cur, pack_threads);
+    for (size_t x = 0; x < batches.size(); ++x) {
+      const size_t first = batches[x].first, last = batches[x].second;
+      std::thread packer;
+      if (x + 1 < batches.size()) {
+        next = Packed();
+        packer = std::thread([&, x] {
+          CUDABatchProcessor::pack(windows_, batches[x + 1].first, batches[x + 1].second, &next, pack_threads);
+        });
+      }
+      const vgc_batch batch = cur.view();
       std::vector<uint8_t> cons(vgc_result_bound(&batch));
       std::vector<uint64_t> off(batch.n_windows + 1);
       vgc_result r = {cons.data(), cons.size(), off.data(), polished.data() + first};
-      if (vgc_polish(h, &batch, &r, nullptr) != VGC_OK) {  // no CPU fallback
-        errors[d] = vgc_last_error();
-        break;
-      }
+      const int rc = vgc_polish(h, &batch, &r, nullptr);  // no CPU fallback
+      if (rc != VGC_OK) errors[d] = vgc_last_error();
+      if (packer.joinable()) packer.join();
+      if (rc != VGC_OK) break;
+      // consensus_ of batch x is written only after the packer of batch x + 1 is done: pack reads sequences_ of
+      // other windows only, but this keeps the two phases trivially disjoint
       for (size_t i = first; i < last; ++i)
         CUDABatchProcessor::store(*windows_[i], cons.data() + off[i - first], off[i - first + 1] - off[i - first]);
-      first = last;
+      std::swap(cur, next);
     }
     vgc_destroy(h);
   };
