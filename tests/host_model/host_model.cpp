@@ -43,6 +43,7 @@ struct HostEx {
     *th = reinterpret_cast<uint32_t*>(tile_h.data());
     *tr = tile_r.data();
   }
+  unsigned long long reduce_add64(unsigned long long v) { return v; }
   uint32_t reduce_min(uint32_t v) { return v; }
   uint32_t reduce_max(uint32_t v) { return v; }
   uint32_t excl_scan(uint32_t v, uint32_t* total) {
@@ -165,6 +166,7 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   d.max_edges = 2 * d.max_nodes + 64;
   d.max_len = std::max<uint32_t>(prep.max_len, 16);
   d.row_words = 32 * K;
+  d.h_words = (static_cast<uint64_t>(d.max_nodes) + 1) * d.row_words;  // the host model keeps whole DP matrices here
   d.in_stride = 8;
   for (uint32_t w = 0; w < b->n_windows; ++w) d.in_stride = std::max(d.in_stride, prep.win_nseq[w] + 1);
   std::vector<uint8_t> buf(slot_bytes(d));

@@ -251,7 +251,16 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
 struct SlotDims {
   uint32_t max_nodes, max_edges, max_len, row_words;
   uint32_t in_stride = 8;  // in-list capacity per node (exact bound: the number of sequences of the window)
+  uint64_t h_words = 0;    // words behind Slot::H; 0 = graph_scratch_words() (device: the DP rows live in the align pool)
 };
+
+// Scratch the graph passes carve out of Slot::H: sort_graph = offsets (nV + 1) + adjacency (nE + sum of aligned
+// counts) + DFS stack (<= adjacency + nV + 1); LargestSubgraph = offsets + live adjacency (2 nE) + stack (nV);
+// heaviest bundle = 5 nV.  Aligned lists hold at most kMaxAligned entries per node.
+inline uint64_t graph_scratch_words(const SlotDims& d) {
+  const uint64_t N = d.max_nodes, E = d.max_edges;
+  return 2 * E + (4 + 2 * static_cast<uint64_t>(kMaxAligned)) * N + 1024;
+}
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -293,9 +302,10 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
   t(N * 16);       // rowprog
   t(E * 4);        // ovf
   t((N + 1) * 2);  // fc
-  t((N + 1) * static_cast<uint64_t>(d.row_words) * 4);  // H
+  t((d.h_words ? d.h_words : graph_scratch_words(d)) * 4);  // H
   t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_node
   t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_pos
+  t(N * kInlinePreds * 4);                                // wacc
   return off;
 }
 
@@ -351,7 +361,9 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
   P(&s->H);
   P(&s->aln_node);
   P(&s->aln_pos);
+  P(&s->wacc);
   s->aln_cap = d.max_len + d.max_nodes + 2;
+  s->h_words = static_cast<uint32_t>(std::min<uint64_t>(d.h_words ? d.h_words : graph_scratch_words(d), 0xFFFFFFFFu));
 }
 
 }  // namespace vgc

@@ -69,7 +69,7 @@ enum : uint32_t {
 };
 
 enum : uint32_t { kModeNW = 0, kModeSW = 1 };
-enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRealignPost = 2, kPcFinalPost = 3, kPcDone = 4, kPcLinearFinal = 5 };
+enum : uint32_t { kPcInit = 0, kPcBuildPost = 1, kPcRoundPost = 2, kPcFinalPost = 3, kPcDone = 4, kPcLinearFinal = 5 };
 // step a window waits for (WinState::need); a zeroed WinState starts at kPcInit / kNeedUpdate
 enum : uint32_t { kNeedUpdate = 0, kNeedPrepare = 1, kNeedFill = 2, kNeedTrace = 3, kNeedNone = 4 };
 // what step_prepare must do (WinState::prep)
@@ -149,6 +149,10 @@ struct Slot {
   int32_t* aln_node;   // [max_len + max_nodes + 2]
   int32_t* aln_pos;
   uint32_t aln_cap;
+  uint32_t* wacc;      // [max_nodes * kInlinePreds] re-alignment round: weight added to in-edge p of the node at rank r
+                       // (index r * kInlinePreds + p) by the round's concurrent alignments; folded into ew by fold_weights()
+  uint32_t h_words;    // words behind H (the device keeps only the graph passes' scratch there; DP rows live in the
+                       // align kernel's per-SM pool)
 };
 
 // Row program record (16 B per DP row, rank order):
@@ -158,10 +162,10 @@ struct Slot {
 //       p is row - d_p), in-edge order; a node without in-edges has the virtual row 0 as its only predecessor
 //       (np = 0, d_0 = its own row)
 //   otherwise: w = offset into ovf[] holding the np predecessor rows
+constexpr uint32_t kInlinePreds = 6;
 constexpr uint32_t kMetaSink = 1u << 4;
 constexpr uint32_t kMetaInline = 1u << 5;
 constexpr uint32_t kMetaMaxPred = 1023;
-constexpr uint32_t kInlinePreds = 6;
 VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, bool inl, uint32_t node) {
   return code | (sink ? kMetaSink : 0u) | (inl ? kMetaInline : 0u) | (npred << 6) | (node << 16);
 }
@@ -201,6 +205,10 @@ struct WinState {
   uint32_t fill_k;       // words per lane the fill used for the pending alignment (row layout: 32 * fill_k words per half)
   uint32_t need;         // kNeed*
   uint32_t prep;         // kPrep* flags for step_prepare
+  uint32_t round;        // the pending fill is a whole re-alignment round: one alignment per sequence of the window,
+                         // all against the same frozen graph (AddWeights only adds to edge weights, so they commute)
+  uint32_t jobs_total;   // alignments of the pending step handed to the align kernel / how many of them are finished
+  uint32_t jobs_done;
   unsigned long long cells;
   uint32_t alignments;
   uint32_t sorts, sorts_hbm;   // TopologicalSort runs of this window / how many had to sort out of HBM (staging did not fit)
@@ -1496,7 +1504,7 @@ struct Poa {
     ex.sync();
   }
 
-  VGC_HD void step_prepare() {
+  VGC_HD void step_prepare(uint32_t win) {
     if (ws.need != kNeedPrepare) return;
     ex.sync();
     if (ex.leader()) ws.t_last = ex.clock();
@@ -1525,15 +1533,49 @@ struct Poa {
       tick(kPhRowprog);
     }
     if (prep & kPrepFill) {
-      // int16 range guard: every cell lies within +-(rows + columns + 2) * max|score|
+      // int16 range guard: every cell of the matrix (padding columns included) lies within
+      // +-(rows + columns + 2) * max|score|; the columns are those of the row width the fill will pick (fill_width).
+      // A round runs NW and SW alignments of every sequence of the window: both score sets, the longest layer.
       const uint32_t mode = ws.fill_mode;
-      const Scores& sc = mode == kModeNW ? nw : sw;
-      int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
-      if (-sc.g > a) a = -sc.g;
+      const bool round = ws.round != 0;
+      const uint32_t first = bv.win_first[win], nseq = bv.win_nseq[win];
+      const uint32_t* rank = bv.layer_rank + first;
+      auto maxabs = [](const Scores& sc) {
+        int32_t a = sc.m > -sc.x ? sc.m : -sc.x;
+        a = a > -sc.m ? a : -sc.m;
+        a = a > sc.x ? a : sc.x;
+        return -sc.g > a ? -sc.g : a;
+      };
+      int32_t a = maxabs(mode == kModeNW ? nw : sw);
+      uint32_t maxlen = layer_len(l);
+      unsigned long long cells = static_cast<unsigned long long>(ws.nR + 1) * layer_len(l);  // (R_a + 1) * L_a
+      uint32_t naln = 1;
+      if (round) {
+        const int32_t b = maxabs(sw), c = maxabs(nw);
+        a = b > c ? b : c;
+        cells = 0;
+        uint32_t ml = 0;
+        for (uint32_t j = ex.lane(); j < nseq; j += ex.width()) {
+          const uint32_t len = layer_len(rank[j]);
+          ml = len > ml ? len : ml;
+          cells += static_cast<unsigned long long>(ws.nR + 1) * len;
+        }
+        maxlen = ex.reduce_max(ml);
+        cells = ex.reduce_add64(cells);
+        naln = nseq;
+        // the round's alignments add their weights here (index rank * kInlinePreds + in-edge slot)
+        for (uint32_t i = ex.lane(); i < ws.nR * kInlinePreds; i += ex.width()) sl.wacc[i] = 0;
+      }
       if (ex.leader()) {
-        if (static_cast<int64_t>(ws.nR + RM::kCols + 8) * a > 30000) fail(kStScoreRange);
-        ws.alignments += 1;
-        ws.cells += static_cast<unsigned long long>(ws.nR + 1) * layer_len(l);  // (R_a + 1) * L_a
+        // (the row scan works on H - g * column, which is bounded by 2 * columns * max|score| from above and by
+        //  -rows * max|score| from below)
+        const int64_t cols = 64ll * fill_width(K, maxlen);
+        const int64_t rows = static_cast<int64_t>(ws.nR);
+        if (((rows > cols ? rows : cols) + cols + 2) * a > 32000) fail(kStScoreRange);
+        ws.alignments += naln;
+        ws.cells += cells;
+        ws.jobs_total = naln;
+        ws.jobs_done = 0;
       }
       ex.sync();
       if (ws.status != kStOk) return finish();
@@ -1557,15 +1599,16 @@ struct Poa {
     const uint32_t out_cap = bv.out_cap[w];
     const double avgw = bv.win_avgw[w];
     const uint32_t pc = ws.pc;
-    enum Act { kBuildNext, kRoundStart, kRealignNext, kFinalSchedule };
+    enum Act { kBuildNext, kRoundStart, kRoundEnd, kFinalSchedule };
     Act act = kBuildNext;
     uint32_t j = ws.j, k = ws.k;
     bool changed = false;  // graph changed since the last sort
     bool largest = false;  // PruneGraph ran: LargestSubgraph is pending
     ex.sync();
     if (ex.leader()) ws.t_last = ex.clock();
-    // plan: make the next alignment (or sort-only step) pending
-    auto plan = [&](uint32_t next_pc, uint32_t prep, uint32_t layer, uint32_t mode) {
+    // plan: make the next alignment (or a whole re-alignment round, or a sort-only step) pending.  Every fill is
+    // preceded by a prepare step (sort / row program), which also does the per-alignment accounting.
+    auto plan = [&](uint32_t next_pc, uint32_t prep, uint32_t layer, uint32_t mode, bool round) {
       if (ex.leader()) {
         ws.pc = next_pc;
         ws.j = j;
@@ -1575,11 +1618,8 @@ struct Poa {
         ws.prep = prep | ((changed && !(prep & kPrepSubSort)) ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
         ws.fill_layer = layer;
         ws.fill_mode = mode;
-        ws.need = (ws.prep == kPrepFill) ? kNeedFill : kNeedPrepare;
-        if (ws.prep == kPrepFill) {
-          ws.alignments += 1;
-          ws.cells += static_cast<unsigned long long>(ws.nR + 1) * layer_len(layer);
-        }
+        ws.round = round ? 1u : 0u;
+        ws.need = kNeedPrepare;
       }
       ex.sync();
     };
@@ -1625,12 +1665,12 @@ struct Poa {
       changed = true;
       ++j;
       act = kBuildNext;
-    } else if (pc == kPcRealignPost) {
-      add_weights(ws.fill_layer);
+    } else if (pc == kPcRoundPost) {
+      // every alignment of the round has added its weights (window.cpp:329-386, graph.cpp:1104-1165)
+      fold_weights();
       tick(kPhAddW);
       if (ws.status != kStOk) return finish();
-      ++j;
-      act = kRealignNext;
+      act = kRoundEnd;
     } else if (pc == kPcFinalPost) {
       // graph.cpp:1167-1179
       if (ex.leader()) {
@@ -1691,9 +1731,9 @@ struct Poa {
           const uint32_t l = rank[j];
           const uint32_t lb = bv.begin[l], le = bv.end[l];
           const bool full = lb < offset && le > blen - offset;
-          return plan(kPcBuildPost, kPrepFill | kPrepRowprog | (full ? 0u : kPrepSubSort), l, kModeNW);
+          return plan(kPcBuildPost, kPrepFill | kPrepRowprog | (full ? 0u : kPrepSubSort), l, kModeNW, false);
         }
-        if (!haplotype) return plan(kPcLinearFinal, 0u, bb, kModeNW);
+        if (!haplotype) return plan(kPcLinearFinal, 0u, bb, kModeNW, false);
         // haplotype mode: prune (window.cpp:300-319); LargestSubgraph rebuilds the CSR it needs
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
@@ -1702,20 +1742,11 @@ struct Poa {
         k = 0;
         act = kRoundStart;
       } else if (act == kRoundStart) {
-        if (k + 1 < num_prune) {
-          j = 0;
-          act = kRealignNext;
-        } else {
-          act = kFinalSchedule;
-        }
-      } else if (act == kRealignNext) {
-        // re-align + re-weight rounds (window.cpp:329-386)
-        if (j < nseq) {
-          const uint32_t l = rank[j];
-          const uint32_t lb = bv.begin[l], le = bv.end[l];
-          const bool global = (j == 0) || (lb < offset && le > blen - offset);
-          return plan(kPcRealignPost, kPrepFill | (j == 0 ? kPrepRowprog : 0u), l, global ? kModeNW : kModeSW);
-        }
+        // re-align + re-weight rounds (window.cpp:329-386): the graph is frozen during a round, so its nseq
+        // alignments (backbone and full-span layers global, the others local) are independent of each other
+        if (k + 1 < num_prune) return plan(kPcRoundPost, kPrepFill | kPrepRowprog, bb, kModeNW, true);
+        act = kFinalSchedule;
+      } else if (act == kRoundEnd) {
         prune(min_confidence, min_support, avgw);
         tick(kPhPrune);
         largest = true;
@@ -1724,9 +1755,40 @@ struct Poa {
         act = kRoundStart;
       } else {
         // final local alignment of the backbone (window.cpp:391-394)
-        return plan(kPcFinalPost, kPrepFill | kPrepRowprog, bb, kModeSW);
+        return plan(kPcFinalPost, kPrepFill | kPrepRowprog, bb, kModeSW, false);
       }
     }
+  }
+
+  // mode of sequence j of a re-alignment round (window.cpp:338-352): the backbone and full-span layers are aligned
+  // globally, the others locally (SW engine, hard-wired 3/-5/-4)
+  VGC_HD VGC_INL uint32_t round_mode(uint32_t win, uint32_t jj) const {
+    if (jj == 0) return kModeNW;
+    const uint32_t first = bv.win_first[win];
+    const uint32_t* rank = bv.layer_rank + first;
+    const uint32_t blen = layer_len(rank[0]);
+    const uint32_t offset = static_cast<uint32_t>(0.01 * blen);
+    const uint32_t l = rank[jj];
+    return (bv.begin[l] < offset && bv.end[l] > blen - offset) ? kModeNW : kModeSW;
+  }
+
+  // ---- end of a round: the weights the round's alignments left in wacc[rank * kInlinePreds + in-edge slot] go to
+  //      the edges (rows beyond kInlinePreds in-edges were added to ew directly)
+  VGC_HD void fold_weights() {
+    Graph& g = G();
+    const uint32_t S = sl.in_stride;
+    const uint32_t nR = ws.nMain;
+    for (uint32_t i = ex.lane(); i < nR * kInlinePreds; i += ex.width()) {
+      const uint32_t w = sl.wacc[i];
+      if (w == 0) continue;
+      const uint32_t v = sl.r2n[i / kInlinePreds], p = i % kInlinePreds;
+      if (p >= g.nin[v]) {
+        fail(kStInternal);
+        continue;
+      }
+      g.ew[g.ieid[v * S + p]] += w;
+    }
+    ex.sync();
   }
 
   // Whole window in one go (host model).
@@ -1741,14 +1803,35 @@ struct Poa {
     while (ws.pc != kPcDone) {
       step_trace();
       step_update(w, haplotype, trim, min_confidence, min_support, num_prune, out, out_len);
-      step_prepare();
+      step_prepare(w);
       if (ws.pc != kPcDone && ws.need == kNeedFill) {
-        const uint32_t l = ws.fill_layer;
-        uint8_t* codes = stage_codes(l);
-        ex.template fill<K>(sl, ws, codes, layer_len(l), ws.fill_mode, ws.fill_mode == kModeNW ? nw : sw, bv.num_codes);
-        ex.sync();
-        if (ex.leader()) ws.need = kNeedTrace;
-        ex.sync();
+        if (ws.round) {
+          // the device runs these nseq alignments concurrently (align kernel); here one after the other
+          const uint32_t nseq = bv.win_nseq[w];
+          const uint32_t* rank = bv.layer_rank + bv.win_first[w];
+          for (uint32_t jj = 0; jj < nseq && ws.status == kStOk; ++jj) {
+            const uint32_t l = rank[jj], mode = round_mode(w, jj);
+            uint8_t* codes = stage_codes(l);
+            ex.template fill<K>(sl, ws, codes, layer_len(l), mode, mode == kModeNW ? nw : sw, bv.num_codes);
+            ex.sync();
+            traceback(l, mode);
+            if (ws.status != kStOk) break;
+            add_weights(l);
+          }
+          if (ws.status != kStOk) {
+            finish();
+          } else {
+            if (ex.leader()) ws.need = kNeedUpdate;
+            ex.sync();
+          }
+        } else {
+          const uint32_t l = ws.fill_layer;
+          uint8_t* codes = stage_codes(l);
+          ex.template fill<K>(sl, ws, codes, layer_len(l), ws.fill_mode, ws.fill_mode == kModeNW ? nw : sw, bv.num_codes);
+          ex.sync();
+          if (ex.leader()) ws.need = kNeedTrace;
+          ex.sync();
+        }
       }
     }
   }

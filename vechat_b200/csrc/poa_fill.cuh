@@ -59,16 +59,34 @@ __device__ __forceinline__ void row_store(uint32_t* __restrict__ row, int lane, 
   for (int k = 0; k < K; k += 2) p[k >> 1] = make_uint2(h[k], h[k + 1]);
 }
 
+// The matrix of one alignment: rows of 32*K words (row = rank + 1, row 0 = the virtual row) in the align kernel's
+// private scratch buffer, first-column values next to it; the row program and its overflow list come from the
+// window's slot.
+struct FillIo {
+  uint32_t* H;             // [(nR + 1) * 32*K] words
+  int16_t* fc;             // [nR + 1]
+  const uint32_t* rowprog; // [nR * 4]
+  const uint32_t* ovf;
+  uint32_t nR;
+  // where the traceback starts (out)
+  uint32_t best_row, best_col;
+  int32_t best_score;
+};
+
 // prof : shared memory, num_codes * 32*K words;  stage: shared memory, 32 uint4
 // ring : shared memory, ring_rows * 32*K words (ring_rows <= kRingRows, may be 0)
 template <int K, bool SW>
-__device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len, const Scores sc,
+__device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, const Scores sc,
                             uint32_t num_codes, uint32_t* prof, uint4* stage, uint32_t* ring, int ring_rows) {
   static_assert(K % 2 == 0, "K must be even");
   using RM = RowMap<K>;
   const int lane = threadIdx.x & 31;
-  const uint32_t nR = ws.nR;
+  const uint32_t nR = io.nR;
   const int32_t g = sc.g;
+  uint32_t* const Hm = io.H;
+  int16_t* const fcm = io.fc;
+  const uint32_t* const ovfm = io.ovf;
+  constexpr uint32_t rw = RM::kWords;
 
   // ---- query profile (Initialize, simd...:520-530): per code, match/mismatch per column, padding beyond len
   {
@@ -101,8 +119,8 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
   uint32_t hp[K];  // the row computed last (registers); chain rows are updated in place
 #pragma unroll
   for (int k = 0; k < K; ++k) hp[k] = SW ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
-  row_store<K>(sl.H, lane, hp);
-  if (lane == 0) sl.fc[0] = 0;
+  row_store<K>(Hm, lane, hp);
+  if (lane == 0) fcm[0] = 0;
   int32_t fc_prev = 0;
 
   // ring of the most recent rows in shared memory: row r lives in slot r % kRingRows (with its first-column value
@@ -124,7 +142,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
   const uint32_t lc = len - 1;
   const int lastH = lc / (32 * K), lastL = (lc % (32 * K)) / K, lastK = lc % K;
 
-  const uint4* rp = reinterpret_cast<const uint4*>(sl.rowprog);
+  const uint4* rp = reinterpret_cast<const uint4*>(io.rowprog);
   uint4 nxt = make_uint4(0, 0, 0, 0);
   if (static_cast<uint32_t>(lane) < nR) nxt = rp[lane];
 
@@ -152,7 +170,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       const U4 er = {e.x, e.y, e.z, e.w};
       const bool inl = (meta & kMetaInline) != 0;
       // distance to predecessor p (rows are processed in rank order: distance 1 = the row in registers)
-      const uint32_t d0 = np == 0 ? row : (inl ? rec_delta(er, 0) : row - sl.ovf[e.w]);
+      const uint32_t d0 = np == 0 ? row : (inl ? rec_delta(er, 0) : row - ovfm[e.w]);
       int32_t fcmax;
       if (np <= 1 && d0 == 1) {
         // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
@@ -169,7 +187,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
         fcmax = INT32_MIN;
         const uint32_t npp = np == 0 ? 1 : np;
         for (uint32_t p = 0; p < npp; ++p) {
-          const uint32_t d = p == 0 ? d0 : (inl ? rec_delta(er, p) : row - sl.ovf[e.w + p]);
+          const uint32_t d = p == 0 ? d0 : (inl ? rec_delta(er, p) : row - ovfm[e.w + p]);
           uint32_t u[K];
           int32_t fcp;
           if (d == 1) {
@@ -182,10 +200,10 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
             fcp = ring_fc[slot * 32];
           } else {
             const uint32_t prow = row - d;
-            row_load<K>(sl.H + static_cast<uint64_t>(prow) * sl.row_words, lane, u);
+            row_load<K>(Hm + static_cast<uint64_t>(prow) * rw, lane, u);
             fcp = 0;
             if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
-              if (lane == 0) fcp = static_cast<int32_t>(sl.fc[prow]);
+              if (lane == 0) fcp = static_cast<int32_t>(fcm[prow]);
               fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
             }
           }
@@ -231,8 +249,8 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
         for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2(base, pack16(g * k, g * k), hp[k]);
       }
       // ---- write the row once (HBM) and keep it in the ring
-      row_store<K>(sl.H + static_cast<uint64_t>(row) * sl.row_words, lane, hp);
-      if (!SW && lane == 0) sl.fc[row] = static_cast<int16_t>(fci);
+      row_store<K>(Hm + static_cast<uint64_t>(row) * rw, lane, hp);
+      if (!SW && lane == 0) fcm[row] = static_cast<int16_t>(fci);
       if (use_ring) {
         const uint32_t slot = row & (kRingRows - 1);
         row_store<K>(ring + slot * RM::kWords, lane, hp);
@@ -267,11 +285,9 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
 
   // ---- where the traceback starts
   if (!SW) {
-    if (lane == 0) {
-      ws.best_row = nw_row;
-      ws.best_col = nw_row ? len : 0;
-      ws.best_score = nw_best;
-    }
+    io.best_row = nw_row;
+    io.best_col = nw_row ? len : 0;
+    io.best_score = nw_best;
   } else {
     // global max, then the first row in rank order that reached it, then its first column
     int32_t mx = lo16(bestv) > hi16(bestv) ? lo16(bestv) : hi16(bestv);
@@ -295,7 +311,7 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       brow = br + 1;
       uint32_t u[K];
       __syncwarp();
-      row_load<K>(sl.H + static_cast<uint64_t>(brow) * sl.row_words, lane, u);
+      row_load<K>(Hm + static_cast<uint64_t>(brow) * rw, lane, u);
       uint32_t bc = 0xFFFFFFFFu;
 #pragma unroll
       for (int k = K - 1; k >= 0; --k) {
@@ -312,21 +328,19 @@ __device__ void warp_fill_t(const Slot& sl, WinState& ws, const uint8_t* codes, 
       }
       col = bc + 1;
     }
-    if (lane == 0) {
-      ws.best_row = brow;
-      ws.best_col = col;
-      ws.best_score = mx;
-    }
+    io.best_row = brow;
+    io.best_col = col;
+    io.best_score = mx;
   }
   __syncwarp();
 }
 
 template <int K>
-__device__ __forceinline__ void warp_fill(const Slot& sl, WinState& ws, const uint8_t* codes, uint32_t len,
+__device__ __forceinline__ void warp_fill(FillIo& io, const uint8_t* codes, uint32_t len,
                                           uint32_t mode, const Scores sc, uint32_t num_codes, uint32_t* prof,
                                           uint4* stage, uint32_t* ring, int ring_rows) {
-  if (mode == kModeSW) warp_fill_t<K, true>(sl, ws, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
-  else warp_fill_t<K, false>(sl, ws, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
+  if (mode == kModeSW) warp_fill_t<K, true>(io, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
+  else warp_fill_t<K, false>(io, codes, len, sc, num_codes, prof, stage, ring, ring_rows);
 }
 
 }  // namespace vgc

@@ -1,13 +1,16 @@
-// vgc_engine.cu — C-ABI (include/vgc.h) + the four sm_100a kernels of the lockstep POA engine.
+// vgc_engine.cu — C-ABI (include/vgc.h) + the sm_100a kernels of the lockstep POA engine.
 //
 // A window is a resumable program (poa_core.h: WinState + Poa::step_*) whose state lives in HBM; one lockstep
-// cycle advances every live window of a stream group by one sequence-to-graph alignment:
-//   trace_kernel   traceback of the alignment just filled            one THREAD per window (TraceWalker)
-//   update_kernel  AddAlignment / AddWeights / prune / emit + plan   one warp per window, 4 windows per CTA
-//   sort_kernel    LargestSubgraph, TopologicalSort, row program     one warp per window, graph staged in smem
-//   fill_kernel    DP fill of the next alignment (poa_fill.cuh)      one warp per window, rows in registers
-// The host (run_pass) deals the windows of a batch into stream groups (one per number of alignments), gives every
-// window a scratch slot in HBM and enqueues the cycles; groups overlap freely on the device.
+// cycle advances every live window of a stream group by one step of Window::generate_consensus:
+//   update_kernel  AddAlignment / round end (fold weights, prune) / emit + plan   one warp per window, 4 per CTA
+//   sort_kernel    LargestSubgraph, TopologicalSort, row program; hands the pending alignments to the job list
+//                                                                                one warp per window, graph staged in smem
+//   align_kernel   one CTA (one warp) per ALIGNMENT: DP fill (poa_fill.cuh, rows in registers) followed by the
+//                  warp-cooperative traceback (poa_trace.cuh) of the matrix it has just written
+// The DP matrix of an alignment never outlives its CTA, so it lives in a pool of scratch buffers sized by what can
+// be resident at once (a few per SM), not in per-window HBM.  In the build phase a window has one alignment per
+// cycle; in a re-alignment round (the graph is frozen, AddWeights only adds to edge weights) all nseq alignments of
+// the window run concurrently and add their weights atomically, so a depth-30 window takes ~35 cycles, not 93.
 //
 // Replaces Polisher::polish's per-window lambda (reference src/polisher.cpp:498-516) for a whole batch.
 // No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
@@ -26,14 +29,22 @@
 #include "host_prep.h"
 #include "poa_core.h"
 #include "poa_fill.cuh"
+#include "poa_trace.cuh"
 #include "vgc.h"
 
 namespace vgc {
 
-constexpr int kSmemHeader = 640;  // Slot + WinState copies
+constexpr int kSmemHeader = 768;  // Slot + WinState copies
 
-// Arguments shared by the two kernels of a lockstep pass.  `idx` below is the position of a window in the
-// pass's work list (windows ordered group by group, inside a group by decreasing number of fills).
+// One pending alignment: position of its window in the pass's work list, and layer | flags.
+struct Job {
+  uint32_t idx;
+  uint32_t layer;  // bits 0-29 layer id, bit 30 = part of a re-alignment round (AddWeights fused), bit 31 = SW mode
+};
+constexpr uint32_t kJobRound = 1u << 30, kJobSW = 1u << 31, kJobLayerMask = kJobRound - 1u;
+
+// Arguments shared by the kernels of a lockstep pass.  `idx` below is the position of a window in the
+// pass's work list (windows ordered group by group, inside a group by decreasing number of cycles).
 struct KernelArgs {
   BatchView bv;
   const uint32_t* work;    // [n] window ids
@@ -47,10 +58,15 @@ struct KernelArgs {
   uint32_t haplotype, trim, num_prune;
   double min_confidence, min_support;
   uint32_t smem_bytes;     // dynamic shared memory per CTA of the launched kernel
+  // align kernel: pool of DP-matrix buffers, pool_per_sm per SM
+  uint8_t* pool;
+  uint32_t* pool_busy;     // [sm_count * pool_per_sm] 0 = free
+  unsigned long long pool_buf_bytes;
+  uint32_t pool_rows;      // rows a buffer holds (at the widest row)
+  uint32_t pool_per_sm, sm_count;
 };
 
-// Executor: the device side of poa_core.h's `Ex` concept.  G lanes work on one window (G = 32: a whole warp;
-// G = 8: four windows per warp, used where a step keeps only a handful of lanes busy).
+// Executor: the device side of poa_core.h's `Ex` concept.  G lanes work on one window (G = 32: a whole warp).
 template <int K, int G = 32>
 struct WarpEx {
   uint8_t* sm;        // this window's shared memory after the header
@@ -66,7 +82,7 @@ struct WarpEx {
   __device__ __forceinline__ void sync() { __syncwarp(mask_); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(mask_, v, src, G); }
-  // never used on the device: the traceback runs in trace_kernel, one thread per window
+  // never used on the device: the traceback runs in align_kernel (poa_trace.cuh)
   __device__ __forceinline__ void trace_tile(uint32_t** th, U4** tr) {
     *th = nullptr;
     *tr = nullptr;
@@ -88,6 +104,11 @@ struct WarpEx {
       for (int d = G / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(mask_, v, d, G));
       return v;
     }
+  }
+  __device__ __forceinline__ unsigned long long reduce_add64(unsigned long long v) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask_, v, d, G);
+    return v;
   }
   __device__ __forceinline__ uint32_t excl_scan(uint32_t v, uint32_t* total) {
     uint32_t x = v;
@@ -134,7 +155,7 @@ struct WarpEx {
     *cap = (avail - so) / 2u;
     return true;
   }
-  // the fill runs in its own kernel (fill_kernel): never called through the executor on the device
+  // the fill runs in align_kernel: never called through the executor on the device
   template <int KK>
   __device__ __forceinline__ void fill(Slot&, WinState&, const uint8_t*, uint32_t, uint32_t, const Scores&, uint32_t) {}
 };
@@ -145,22 +166,18 @@ __device__ __forceinline__ void copy_words(void* dst, const void* src, uint32_t 
   for (uint32_t i = lane; i < bytes / 4; i += width) d[i] = s[i];
 }
 
-// ---- the four kernels of a lockstep cycle (one warp = one CTA = one window in each of them) -------------
+// ---- the kernels of a lockstep cycle ---------------------------------------------------------------------
 // CTAs per SM each kernel is compiled and sized for (registers via __launch_bounds__, shared memory via the
-// dynamic size the host passes): the traceback wants many warps (one DRAM round trip per step, no shared state
-// beyond the sequence), the update is parallel and light, the sort is a serial DFS over a graph staged in shared
-// memory, the fill is register-heavy.
-#ifndef VGC_TRACE_CTAS
-#define VGC_TRACE_CTAS 32
-#endif
+// dynamic size the host passes): the update is parallel and light, the sort is a serial DFS over a graph staged in
+// shared memory, the align kernel is register-heavy (a DP row lives in registers).
 #ifndef VGC_UPDATE_CTAS
 #define VGC_UPDATE_CTAS 24
 #endif
 #ifndef VGC_SORT_CTAS
 #define VGC_SORT_CTAS 12
 #endif
-#ifndef VGC_FILL_CTAS
-#define VGC_FILL_CTAS 16
+#ifndef VGC_ALIGN_CTAS
+#define VGC_ALIGN_CTAS 16
 #endif
 
 struct WinCtx {
@@ -224,96 +241,8 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
   return ex;
 }
 
-// R: traceback of the alignment just filled (replaces SimdAlignmentEngine::Linear's traceback): ONE THREAD per
-// window, 32 windows per warp (poa_core.h TraceWalker).  Every lane owns a tile of its window's DP matrix in
-// shared memory; the warp alternates between a refill phase (the lanes whose walk left their tile fetch a new
-// one, all loads in flight together) and a walk phase of up to kTraceRound steps out of shared memory.
-// shared memory: coder[256] | 32 x { tile cells kTR x kTW words | tile records kTR x 16 B | pad }
-constexpr uint32_t kTraceLaneWords = kTR * kTW + kTR * 4 + 4;  // 16-byte aligned, lanes' banks spread
-constexpr uint32_t kTraceSmem = 256 + 32 * kTraceLaneWords * 4;
-constexpr int kTraceRound = 16;
-
-template <int K>
-__global__ void __launch_bounds__(32) trace_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const unsigned long long t0 = clock64();
-  uint64_t dec64 = 0;
-  for (int c = 0; c < kMaxCodes; ++c) dec64 |= static_cast<uint64_t>(a.bv.decoder[c]) << (8 * c);
-  const uint32_t idx = blockIdx.x * 32 + threadIdx.x;
-  bool active = idx < count;
-  WinState* gws = a.wstates + base + (active ? idx : 0);
-  if (active && (gws->pc == kPcDone || gws->need != kNeedTrace)) active = false;
-  TraceWalker t;
-  uint32_t w = 0;
-  if (active) {
-    const Slot* sl = a.slots + base + idx;
-    w = a.work[base + idx];
-    const uint32_t layer = gws->fill_layer, mode = gws->fill_mode;
-    t.H = sl->H;
-    t.fc = sl->fc;
-    t.rp = reinterpret_cast<const U4*>(sl->rowprog);
-    t.ovf = sl->ovf;
-    t.nodes = sl->max_nodes < 65536u ? nullptr : (gws->sub ? sl->order : sl->r2n);
-    t.seq = a.bv.bases + a.bv.seq_off[layer];
-    t.dec64 = dec64;
-    t.aln_node = sl->aln_node;
-    t.aln_pos = sl->aln_pos;
-    t.aln_cap = sl->aln_cap;
-    t.rw = sl->row_words;
-    t.half_words = 32u * gws->fill_k;
-    t.m = mode == kModeNW ? a.nw.m : 3;   // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
-    t.x = mode == kModeNW ? a.nw.x : -5;
-    t.g = mode == kModeNW ? a.nw.g : -4;
-    t.sw = mode == kModeSW;
-    uint32_t* mine = reinterpret_cast<uint32_t*>(smem + 256) + threadIdx.x * kTraceLaneWords;
-    t.th = mine;
-    t.tr = reinterpret_cast<U4*>(mine + kTR * kTW);
-    t.start(gws->best_row, gws->best_col);
-    if (t.i == 0 && t.j == 0) {
-      gws->aln_len = 0;
-      gws->need = kNeedUpdate;
-      active = false;
-    }
-  }
-  bool need_refill = false;
-  unsigned long long t_refill = 0, n_refill = 0;  // diagnostics: cycles this walk spent in refill phases / refills
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    const unsigned long long r0 = clock64();
-    if (active && need_refill) {
-      t.refill();
-      need_refill = false;
-      ++n_refill;
-    }
-    __syncwarp();
-    if (active) t_refill += clock64() - r0;
-    for (int s = 0; s < kTraceRound; ++s) {
-      if (active && !need_refill) {
-        const int st = t.step();
-        if (st == kWalkMiss) {
-          need_refill = true;
-        } else if (st >= kWalkDone) {
-          gws->aln_len = t.n;
-          gws->phase[kPhTrace] += clock64() - t0;
-          gws->phase[kPhCsr] += t_refill;        // (slot reused: the CSR phase no longer exists as a timed phase)
-          gws->phase[kPhOther] += n_refill;      // (count, not cycles)
-          if (st == kWalkBad) {
-            gws->status = kStInternal;
-            gws->pc = kPcDone;
-            gws->need = kNeedNone;
-            a.status[w] = kStInternal;
-          } else {
-            gws->need = kNeedUpdate;
-          }
-          active = false;
-        }
-      }
-      if (!__any_sync(0xFFFFFFFFu, active && !need_refill)) break;
-    }
-  }
-}
-
-// U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, AddWeights,
-// PruneGraph, LargestSubgraph, GenerateCorrectedSequence / GenerateConsensus, and Window::generate_consensus'
+// U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, the end of a
+// re-alignment round, PruneGraph, GenerateCorrectedSequence / GenerateConsensus, and Window::generate_consensus'
 // control flow).
 constexpr int kUpdateWins = 4;  // windows (= warps) per CTA: the SM's 32-CTA limit must not cap the light kernel
 template <int K>
@@ -332,66 +261,189 @@ __global__ void __launch_bounds__(32 * kUpdateWins) update_kernel(const KernelAr
   win_leave(a, c);
 }
 
-// T: Graph::TopologicalSort (+ Subgraph view of a partial layer) and the row program of the next alignment.
+// T: Graph::TopologicalSort (+ Subgraph view of a partial layer, LargestSubgraph after a prune) and the row program
+// of the next alignment(s); then the pending alignments go to the group's job list for align_kernel.
 template <int K>
-__global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArgs a, uint32_t base) {
+__global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArgs a, uint32_t base, Job* jobs,
+                                                                 uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
   WinCtx c;
   if (!win_enter(a, base + blockIdx.x, kNeedPrepare, smem, &c)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
-  poa.step_prepare();
+  poa.step_prepare(c.w);
+  if (c.ws->pc != kPcDone && c.ws->need == kNeedFill) {
+    const int lane = threadIdx.x;
+    if (c.ws->round) {
+      const uint32_t nseq = a.bv.win_nseq[c.w];
+      const uint32_t* rank = a.bv.layer_rank + a.bv.win_first[c.w];
+      uint32_t at = 0;
+      if (lane == 0) at = atomicAdd(njobs, nseq);
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      for (uint32_t j = lane; j < nseq; j += 32) {
+        Job jb;
+        jb.idx = c.idx;
+        jb.layer = rank[j] | kJobRound | (poa.round_mode(c.w, j) == kModeSW ? kJobSW : 0u);
+        jobs[at + j] = jb;
+      }
+    } else if (lane == 0) {
+      Job jb;
+      jb.idx = c.idx;
+      jb.layer = c.ws->fill_layer | (c.ws->fill_mode == kModeSW ? kJobSW : 0u);
+      jobs[atomicAdd(njobs, 1u)] = jb;
+    }
+  }
   win_leave(a, c);
 }
 
-// shared memory after the profile: the ring of recent rows (all kRingRows rows + one first-column value per lane and
-// row, or no ring at all)
+// A: one alignment = DP fill (replaces SimdAlignmentEngine::Linear's fill) + traceback, by one warp.
+// shared memory: Slot header | codes[max_len] | stage[32 x uint4] | fill: prof[num_codes x 32K words] | ring
+//                                                                 | trace: tile | w2[len]   (overlays prof / ring)
 template <int KR>
-__device__ __forceinline__ void run_fill(const KernelArgs& a, WinCtx& c, const uint8_t* codes, uint32_t len, uint32_t mode,
+__device__ __forceinline__ void run_fill(const KernelArgs& a, FillIo& io, const uint8_t* codes, uint32_t len, uint32_t mode,
                                          const Scores& sc, uint32_t* prof, uint4* stage, const uint8_t* smem) {
   uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
   const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
   const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
-  warp_fill<KR>(*c.sl, *c.ws, codes, len, mode, sc, a.bv.num_codes, prof, stage, ring, ring_rows);
+  warp_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, stage, ring, ring_rows);
 }
 
-// F: the DP fill of the pending alignment (poa_fill.cuh; replaces SimdAlignmentEngine::Linear's fill).
-// shared memory: Slot/WinState header | codes[max_len] | stage[32 x uint4] | prof[num_codes x 32K words] | ring
+__device__ __forceinline__ void win_fail(const KernelArgs& a, WinState* gws, uint32_t w, uint32_t st) {
+  gws->status = st;
+  gws->pc = kPcDone;
+  gws->need = kNeedNone;
+  a.status[w] = st;
+}
+
 template <int K>
-__global__ void __launch_bounds__(32, VGC_FILL_CTAS) fill_kernel(const KernelArgs a, uint32_t base) {
+__global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelArgs a, const Job* jobs,
+                                                                   const uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
+  if (blockIdx.x >= *njobs) return;
   const unsigned long long t0 = clock64();
-  WinCtx c;
-  if (!win_enter(a, base + blockIdx.x, kNeedFill, smem, &c)) return;
   const int lane = threadIdx.x;
+  const Job jb = jobs[blockIdx.x];
+  const uint32_t idx = jb.idx, l = jb.layer & kJobLayerMask;
+  const bool round = (jb.layer & kJobRound) != 0;
+  const uint32_t mode = (jb.layer & kJobSW) ? kModeSW : kModeNW;
+  WinState* gws = a.wstates + idx;
+  if (gws->pc == kPcDone) return;  // another alignment of the round failed the window
+  Slot* sl = reinterpret_cast<Slot*>(smem);
+  copy_words(sl, a.slots + idx, sizeof(Slot), lane);
+  const uint32_t nR = gws->nR, sub = gws->sub, cur = gws->cur;
+  const uint32_t w = a.work[idx];
+  __syncwarp();
+  // ---- a DP-matrix buffer of this SM's share of the pool (never more CTAs resident than buffers: the host caps
+  //      the kernel's residency at pool_per_sm; should the bound ever be off, wait for a neighbour to finish)
+  uint32_t buf = 0;
+  if (lane == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const uint32_t b0 = (smid % a.sm_count) * a.pool_per_sm;
+    uint32_t k = blockIdx.x % a.pool_per_sm;
+    while (atomicCAS(a.pool_busy + b0 + k, 0u, 1u) != 0u) k = k + 1 == a.pool_per_sm ? 0u : k + 1;
+    buf = b0 + k;
+  }
+  buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
+  uint8_t* pb = a.pool + static_cast<unsigned long long>(buf) * a.pool_buf_bytes;
   uint8_t* sm = smem + kSmemHeader;
-  const uint32_t max_len = c.sl->max_len;
+  const uint32_t max_len = sl->max_len;
   uint8_t* codes = sm;
   uint4* stage = reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u));
   uint32_t* prof = reinterpret_cast<uint32_t*>(stage + 32);
-  const uint32_t l = c.ws->fill_layer;
   const uint64_t o = a.bv.seq_off[l];
   const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
   for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
   __syncwarp();
   Scores sw;
-  sw.m = 3;
+  sw.m = 3;  // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
   sw.x = -5;
   sw.g = -4;
-  const uint32_t mode = c.ws->fill_mode;
+  const Scores sc = mode == kModeNW ? a.nw : sw;
   // row width for this alignment (fill_width): narrow layers run the 512-column variant
   const uint32_t kr = fill_width(K, len);
-  const Scores sc = mode == kModeNW ? a.nw : sw;
-  if (kr == 8) run_fill<8>(a, c, codes, len, mode, sc, prof, stage, smem);
-  else if (kr == 10) run_fill<10>(a, c, codes, len, mode, sc, prof, stage, smem);
-  else run_fill<K>(a, c, codes, len, mode, sc, prof, stage, smem);
+  FillIo io;
+  io.H = reinterpret_cast<uint32_t*>(pb);
+  io.fc = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
+  io.rowprog = sl->rowprog;
+  io.ovf = sl->ovf;
+  io.nR = nR;
+  io.best_row = io.best_col = 0;
+  io.best_score = 0;
+  int st = kWalkDone;
+  uint32_t n = 0, refills = 0;
+  unsigned long long t1 = t0;
+  if (nR + 1 > a.pool_rows) {
+    st = kWalkBad;
+  } else {
+    if (kr == 8) run_fill<8>(a, io, codes, len, mode, sc, prof, stage, smem);
+    else if (kr == 10) run_fill<10>(a, io, codes, len, mode, sc, prof, stage, smem);
+    else run_fill<K>(a, io, codes, len, mode, sc, prof, stage, smem);
+    t1 = clock64();
+    // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
+    __syncwarp();
+    TraceIo t;
+    t.H = io.H;
+    t.fc = io.fc;
+    t.rw = 32u * kr;
+    t.half_words = 32u * kr;
+    t.rp = reinterpret_cast<const U4*>(sl->rowprog);
+    t.ovf = sl->ovf;
+    t.nodes = sl->max_nodes < 65536u ? nullptr : (sub ? sl->order : sl->r2n);
+    t.codes = codes;
+    t.m = sc.m;
+    t.x = sc.x;
+    t.g = sc.g;
+    t.sw = mode == kModeSW;
+    t.row = io.best_row;
+    t.col = io.best_col;
+    t.max_steps = nR + len + 2;
+    t.aln_node = sl->aln_node;
+    t.aln_pos = sl->aln_pos;
+    t.aln_cap = sl->aln_cap;
+    t.wacc = sl->wacc;
+    t.ew = sl->g[cur].ew;
+    t.ieid = sl->g[cur].ieid;
+    t.in_stride = sl->in_stride;
+    uint32_t* tile = prof;
+    uint32_t* w2 = tile + kTraceTileBytes / 4;
+    t.w2 = w2;
+    if (round) {
+      const bool hq = a.bv.has_qual[l] != 0;
+      for (uint32_t i = lane; i < len; i += 32) {
+        uint32_t v = 0;
+        if (i >= 1) v = hq ? a.bv.wlut[a.bv.quals[o + i - 1]] + a.bv.wlut[a.bv.quals[o + i]] : 2u;
+        w2[i] = v;
+      }
+      __syncwarp();
+      st = warp_trace<true>(t, tile, &n, &refills);
+    } else {
+      st = warp_trace<false>(t, tile, &n, &refills);
+    }
+  }
+  __syncwarp();
   if (lane == 0) {
-    c.gws->best_row = c.ws->best_row;
-    c.gws->best_col = c.ws->best_col;
-    c.gws->best_score = c.ws->best_score;
-    c.gws->fill_k = kr;
-    c.gws->need = kNeedTrace;
-    c.gws->phase[kPhFill] += clock64() - t0;
+    __threadfence();
+    atomicExch(a.pool_busy + buf, 0u);
+    const unsigned long long t2 = clock64();
+    if (st != kWalkDone) {
+      win_fail(a, gws, w, kStInternal);
+    } else if (round) {
+      atomicAdd(&gws->phase[kPhFill], t1 - t0);
+      atomicAdd(&gws->phase[kPhTrace], t2 - t1);
+      atomicAdd(&gws->phase[kPhOther], static_cast<unsigned long long>(refills));
+      __threadfence();
+      if (atomicAdd(&gws->jobs_done, 1u) + 1u == gws->jobs_total) gws->need = kNeedUpdate;
+    } else {
+      gws->aln_len = n;
+      gws->best_row = io.best_row;
+      gws->best_col = io.best_col;
+      gws->best_score = io.best_score;
+      gws->phase[kPhFill] += t1 - t0;
+      gws->phase[kPhTrace] += t2 - t1;
+      gws->phase[kPhOther] += refills;
+      gws->need = kNeedUpdate;
+    }
   }
 }
 
@@ -467,12 +519,13 @@ struct vgc_engine {
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
   cudaStream_t gstream[64] = {};
   cudaEvent_t gev[64] = {};
-  uint32_t smem_trace = 0, smem_update = 0, smem_sort = 0, smem_fill = 0;
+  uint32_t smem_update = 0, smem_sort = 0;
   size_t mem_budget = 0;
   // device copies of the batch
   DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
   DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
   DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem, d_wstates;
+  DevBuf d_pool, d_pool_busy, d_jobs, d_jobcnt;  // align kernel: DP-matrix pool, per-group job lists, per-cycle counters
   // host staging (pinned)
   uint8_t* h_out = nullptr;
   size_t h_out_cap = 0;
@@ -579,43 +632,49 @@ BatchView make_view(vgc_engine* h) {
 constexpr int kMaxGroups = 64;
 
 template <int K>
-int set_kernel_attrs(const vgc_engine* h) {
+int set_kernel_attrs(const vgc_engine* h, uint32_t smem_align) {
   auto set = [](const void* f, uint32_t smem) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   };
-  VGC_CUDA(set(reinterpret_cast<const void*>(trace_kernel<K>), kTraceSmem));
   VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * h->smem_update));
   VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
-  VGC_CUDA(set(reinterpret_cast<const void*>(fill_kernel<K>), h->smem_fill));
+  VGC_CUDA(set(reinterpret_cast<const void*>(align_kernel<K>), smem_align));
   return VGC_OK;
 }
 
-// one lockstep cycle for the first `nru` (trace, update) / `ntf` (sort, fill) windows of a group
 template <int K>
-uint32_t launch_cycle(const vgc_engine* h, const KernelArgs& a, uint32_t base, uint32_t nru, uint32_t ntf, bool first,
-                      cudaStream_t st, uint32_t sort_smem) {
-  KernelArgs k = a;
-  uint32_t n = 0;
-  if (nru && !first) {
-    k.smem_bytes = kTraceSmem;
-    trace_kernel<K><<<(nru + 31) / 32, 32, kTraceSmem, st>>>(k, base, nru);
-    ++n;
-  }
-  if (nru) {
-    k.smem_bytes = h->smem_update;  // per window (warp)
-    update_kernel<K><<<(nru + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * k.smem_bytes, st>>>(k, base, nru);
-    ++n;
-  }
-  if (ntf) {
-    k.smem_bytes = sort_smem;
-    sort_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
-    k.smem_bytes = h->smem_fill;
-    fill_kernel<K><<<ntf, 32, k.smem_bytes, st>>>(k, base);
-    n += 2;
-  }
-  return n;
+int align_occupancy(uint32_t smem_align, int* per_sm) {
+  VGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, align_kernel<K>, 32, smem_align));
+  return VGC_OK;
+}
+
+// Shared memory of one align_kernel CTA: header | codes | stage | max(fill: profile [+ ring], trace: tile + weights).
+// The ring of recent rows is dropped when it does not fit `budget` (what the CTAs-per-SM target leaves); a profile
+// that does not fit either (many codes x wide rows) takes what it needs and fewer CTAs run per SM.
+uint32_t align_smem(uint32_t K, uint32_t num_codes, uint32_t max_len, uint32_t budget) {
+  const uint32_t fixed = kSmemHeader + ((max_len + 15u) & ~15u) + 512u;
+  const uint32_t prof = num_codes * 128u * K;
+  const uint32_t ring = kRingRows * (128u * K + 128u);
+  const uint32_t trace = kTraceTileBytes + 4u * max_len + 16u;
+  uint32_t body = prof + ring;
+  if (fixed + body > budget) body = prof;
+  body = std::max(body, trace);
+  return (fixed + body + 255u) & ~255u;
+}
+
+// cycles (update launches) of a window's program and the alignments it hands to the align kernel in cycle c
+// (poa_core.h step_update): build alignments one per cycle, then one cycle per re-alignment round (nseq alignments
+// each), the final alignment, the emit; linear mode: build, consensus sort, emit.
+inline uint32_t win_cycles(uint32_t nseq, bool haplotype, uint32_t num_prune) {
+  return haplotype ? nseq + num_prune : nseq + 1;
+}
+inline uint32_t win_jobs(uint32_t nseq, bool haplotype, uint32_t num_prune, uint32_t c) {
+  if (c + 1 < nseq) return 1;
+  if (!haplotype) return 0;
+  if (c + 1 < nseq + num_prune - 1) return nseq;
+  return c + 2 == nseq + num_prune ? 1u : 0u;
 }
 
 // Node capacity of a window's slot on the first pass: backbone + a share of the layer bases (a read adds a node
@@ -632,20 +691,68 @@ uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exac
   return static_cast<uint32_t>(std::min(ub, est));
 }
 
-// One lockstep pass over `wins` (ordered by decreasing number of fills): every window gets its own scratch slot,
-// the windows are dealt round-robin to `groups` streams, and each stream alternates graph_kernel / fill_kernel
-// launches — step s resumes the program of every window that still has >= s fills to go.  Chunked by the memory
-// budget.  Windows are independent, so no synchronisation other than stream order is needed.
-int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K, const uint64_t* seq_off,
-             const uint32_t* win_first, uint32_t* launches) {
+// One lockstep pass over `wins` (ordered by decreasing number of cycles): every window gets its own scratch slot
+// (graph, orders, row program — no DP matrix), the windows are dealt to stream groups, and each group's stream runs
+// cycle after cycle: update_kernel, sort_kernel over the live prefix, then align_kernel over the alignments the sort
+// handed out.  Chunked by the memory budget.  Windows are independent, so no synchronisation other than stream order.
+template <int K>
+int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, const uint64_t* seq_off,
+               const uint32_t* win_first, uint32_t* launches) {
   const Prepared& pr = h->prep;
-  const uint32_t row_words = 32 * K;
+  const bool hap = h->params.haplotype != 0;
+  const uint32_t num_prune = h->params.num_prune;
+  const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
+  // ---- align kernel: shared memory, residency, pool geometry
+  const uint32_t smem_budget = static_cast<uint32_t>(((228 * 1024 - VGC_ALIGN_CTAS * 1024) / VGC_ALIGN_CTAS) & ~255);
+  uint32_t smem_align = align_smem(K, pr.num_codes, ml, smem_budget);
   size_t pos = 0;
   while (pos < wins.size()) {
-    // ---- chunk: as many windows as the budget holds
+    // ---- chunk: as many windows as the budget holds (the pool of DP buffers takes its share first)
+    uint32_t pool_rows = 0;
+    {
+      // rows of the largest graph any window of the rest of the pass may reach
+      for (size_t e = pos; e < wins.size(); ++e) {
+        const uint32_t w = wins[e];
+        const uint32_t f = win_first[w];
+        pool_rows = std::max(pool_rows, estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div));
+      }
+      pool_rows = std::max<uint32_t>(pool_rows, 64) + 1;
+    }
+    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 2ull * pool_rows + 64, 256);
+    int rc;
+    if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
+    int occ = 0;
+    if ((rc = align_occupancy<K>(smem_align, &occ))) return rc;
+    if (occ < 1) {
+      set_err("align kernel does not fit an SM (shared memory)");
+      return VGC_ERR_CAPACITY;
+    }
+    uint32_t per_sm = static_cast<uint32_t>(occ);
+    // the pool may take at most 40 % of the budget: fewer buffers per SM if rows are long (exact pass, deep windows)
+    const uint64_t pool_cap = h->mem_budget * 2 / 5;
+    while (per_sm > 1 && static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes > pool_cap) --per_sm;
+    if (static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes > h->mem_budget) {
+      set_err("a window's DP matrix needs more scratch than the device memory budget");
+      return VGC_ERR_CAPACITY;
+    }
+    if (per_sm < static_cast<uint32_t>(occ)) {
+      // cap the residency at the number of buffers by asking for more shared memory per CTA
+      uint32_t want = static_cast<uint32_t>((227u * 1024u / per_sm - 1024u) & ~255u);
+      want = std::min<uint32_t>(want, 200u * 1024u);
+      smem_align = std::max(smem_align, want);
+      if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
+      if ((rc = align_occupancy<K>(smem_align, &occ))) return rc;
+      per_sm = std::max<uint32_t>(1, std::min<uint32_t>(per_sm, static_cast<uint32_t>(occ)));
+    }
+    const uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
+    if ((rc = h->d_pool.reserve(pool_bytes))) return rc;
+    if ((rc = h->d_pool_busy.reserve(4ull * per_sm * h->sm_count))) return rc;
+    VGC_CUDA(cudaMemsetAsync(h->d_pool_busy.p, 0, 4ull * per_sm * h->sm_count, h->stream));
+
     std::vector<SlotDims> dims;
     std::vector<uint64_t> offs;
     uint64_t bytes = 0;
+    const uint64_t slot_budget = h->mem_budget - pool_bytes;
     size_t e = pos;
     while (e < wins.size()) {
       const uint32_t w = wins[e];
@@ -653,13 +760,13 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       SlotDims d;
       d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div), 64);
       d.max_edges = 2 * d.max_nodes + 64;  // ~2 edges per node in practice; AddAlignment wants room for a whole layer
-      d.max_len = std::max<uint32_t>(pr.max_len, 16);
-      d.row_words = row_words;
+      d.max_len = ml;
+      d.row_words = 32 * K;
       // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
       d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : std::min<uint32_t>(16, std::max<uint32_t>(8, pr.win_nseq[w] + 1));
       const uint64_t sb = slot_bytes(d);
-      if (bytes + sb > h->mem_budget && e > pos) break;
-      if (sb > h->mem_budget) {
+      if (bytes + sb > slot_budget && e > pos) break;
+      if (sb > slot_budget) {
         set_err("a window needs more scratch than the device memory budget");
         return VGC_ERR_CAPACITY;
       }
@@ -669,18 +776,15 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       ++e;
     }
     const uint32_t n = static_cast<uint32_t>(e - pos);
-    int rc;
     if ((rc = h->d_slot_mem.reserve(bytes))) return rc;
     if ((rc = h->d_slots.reserve(sizeof(Slot) * n))) return rc;
     if ((rc = h->d_wstates.reserve(sizeof(WinState) * n))) return rc;
     if ((rc = h->d_work.reserve(4ull * n))) return rc;
-    // ---- deal the chunk's windows to groups.  VGC_GROUP_MODE=0: group g takes sorted positions g, g+G, ... (every
-    // group sees the whole depth range); 1 (default): contiguous blocks of the sorted list (a group's windows run
-    // the same program in step: the serial phase transitions of a cycle do not stall the other windows)
-    // group_mode 2 (default): one group per distinct number of fills (windows of a group then run the very same
-    // program, so the heavy serial steps — PruneGraph + LargestSubgraph, three times per window — coincide instead
-    // of stalling some cycle of every group); sparse values at the tails are merged until a group has >= 64 windows.
-    std::vector<uint32_t> gstart;  // positions in the chunk (sorted by decreasing fills) where a group starts
+    // ---- deal the chunk's windows to groups: one group per distinct number of alignments (windows of a group then
+    // run the very same program, so the heavy serial steps — PruneGraph + LargestSubgraph — coincide instead of
+    // stalling some cycle of every group); sparse values at the tails are merged until a group has >= 64 windows.
+    // VGC_GROUP_MODE=1: equal contiguous blocks of the sorted list.
+    std::vector<uint32_t> gstart;  // positions in the chunk (sorted by decreasing cycles) where a group starts
     if (h->group_mode == 2) {
       uint32_t min_group = 64;
       while (true) {
@@ -696,36 +800,43 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
       const int G0 = std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)));
       for (int g = 0; g < G0; ++g) gstart.push_back(static_cast<uint32_t>(static_cast<uint64_t>(n) * g / G0));
     }
-    const int G = h->group_mode == 0 ? std::max(1, std::min<int>(h->groups, static_cast<int>((n + 255) / 256)))
-                                     : static_cast<int>(gstart.size());
+    const int G = static_cast<int>(gstart.size());
     std::vector<uint32_t> work(n);
     std::vector<Slot> slots(n);
     std::vector<uint32_t> gbase(G + 1, 0);
-    std::vector<std::vector<uint32_t>> gfill(G);  // fills of each window of the group, in list order
+    std::vector<std::vector<uint32_t>> gnseq(G);  // sequences of each window of the group, in list order (decreasing)
     std::vector<uint32_t> gmin_nseq(G, 0xFFFFFFFFu);
+    std::vector<uint64_t> gjobs_cap(G, 0);
     std::vector<double> gblen(G, 0.0), gavglen(G, 0.0);  // per group: longest backbone, largest mean layer length
-    const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
     uint32_t k = 0;
+    uint32_t max_cyc = 0;
     for (int g = 0; g < G; ++g) {
       gbase[g] = k;
-      const uint32_t b0 = h->group_mode ? gstart[g] : g;
-      const uint32_t b1 = h->group_mode ? (g + 1 < G ? gstart[g + 1] : n) : n;
-      for (uint32_t i = b0; i < b1; i += h->group_mode ? 1 : G) {
-        work[k] = wins[pos + i];
+      const uint32_t b0 = gstart[g];
+      const uint32_t b1 = g + 1 < G ? gstart[g + 1] : n;
+      for (uint32_t i = b0; i < b1; ++i) {
+        const uint32_t w = wins[pos + i];
+        work[k] = w;
         slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
-        gfill[g].push_back(pr.win_nfill[wins[pos + i]]);
-        {
-          const uint32_t w = wins[pos + i];
-          const uint32_t f = win_first[w];
-          const double bl = static_cast<double>(seq_off[f + 1] - seq_off[f]);
-          gmin_nseq[g] = std::min(gmin_nseq[g], pr.win_nseq[w]);
-          gblen[g] = std::max(gblen[g], bl);
-          gavglen[g] = std::max(gavglen[g], (pr.win_sum_len[w] - bl) / std::max(1.0, pr.win_nseq[w] - 1.0));
-        }
+        gnseq[g].push_back(pr.win_nseq[w]);
+        gjobs_cap[g] += pr.win_nseq[w];
+        max_cyc = std::max(max_cyc, win_cycles(pr.win_nseq[w], hap, num_prune));
+        const uint32_t f = win_first[w];
+        const double bl = static_cast<double>(seq_off[f + 1] - seq_off[f]);
+        gmin_nseq[g] = std::min(gmin_nseq[g], pr.win_nseq[w]);
+        gblen[g] = std::max(gblen[g], bl);
+        gavglen[g] = std::max(gavglen[g], (pr.win_sum_len[w] - bl) / std::max(1.0, pr.win_nseq[w] - 1.0));
         ++k;
       }
     }
     gbase[G] = k;
+    // job lists (one per group, reused every cycle) and their per-cycle counters
+    std::vector<uint64_t> gjob_off(G + 1, 0);
+    for (int g = 0; g < G; ++g) gjob_off[g + 1] = gjob_off[g] + gjobs_cap[g];
+    if ((rc = h->d_jobs.reserve(std::max<uint64_t>(gjob_off[G], 1) * sizeof(Job)))) return rc;
+    const size_t ncnt = static_cast<size_t>(G) * (max_cyc + 1);
+    if ((rc = h->d_jobcnt.reserve(4ull * ncnt))) return rc;
+    VGC_CUDA(cudaMemsetAsync(h->d_jobcnt.p, 0, 4ull * ncnt, h->stream));
     VGC_CUDA(cudaMemcpyAsync(h->d_work.p, work.data(), 4ull * n, cudaMemcpyHostToDevice, h->stream));
     VGC_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), sizeof(Slot) * n, cudaMemcpyHostToDevice, h->stream));
     VGC_CUDA(cudaMemsetAsync(h->d_wstates.p, 0, sizeof(WinState) * n, h->stream));
@@ -747,50 +858,59 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     a.min_confidence = h->params.min_confidence;
     a.min_support = h->params.min_support;
     a.smem_bytes = 0;
+    a.pool = h->d_pool.as<uint8_t>();
+    a.pool_busy = h->d_pool_busy.as<uint32_t>();
+    a.pool_buf_bytes = buf_bytes;
+    a.pool_rows = pool_rows;
+    a.pool_per_sm = per_sm;
+    a.sm_count = static_cast<uint32_t>(h->sm_count);
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
-    // ---- lockstep: the lists are sorted by decreasing fills, so the live windows of a cycle are a prefix.
-    // Cycle c runs trace + update for windows with fills + extra >= c (extra = 1 in linear mode: its consensus
-    // needs one more update after the last sort) and sort + fill for windows with fills + extra > c.
-    const uint32_t extra = h->params.haplotype ? 0u : 1u;
-    std::vector<uint32_t> liveA(G), liveB(G);
-    for (int g = 0; g < G; ++g) liveA[g] = liveB[g] = static_cast<uint32_t>(gfill[g].size());
-    const uint32_t max_fill = pr.win_nfill[wins[pos]] + extra;
+    // ---- lockstep: the lists are sorted by decreasing cycles, so the live windows of a cycle are a prefix
+    std::vector<uint32_t> live(G);
+    for (int g = 0; g < G; ++g) live[g] = static_cast<uint32_t>(gnseq[g].size());
     const auto tl0 = std::chrono::steady_clock::now();
-    // Enqueue with a few host threads, each owning every T-th group (= its streams): a pass is tens of thousands of
-    // launches and one thread issues only ~100-150 k launches/s, which would otherwise pace the light groups.
-    const int T = std::max(1, std::min(h->launch_threads, G));
-    std::vector<uint32_t> tl(T, 0);
-    auto enqueue = [&](int t) {
-      cudaSetDevice(h->device);
-      for (uint32_t c = 0; c <= max_fill; ++c) {
-        for (int g = t; g < G; g += T) {
-          const std::vector<uint32_t>& nf = gfill[g];
-          if (nf.empty() || nf[0] + extra < c) continue;
-          while (liveA[g] > 0 && nf[liveA[g] - 1] + extra < c) --liveA[g];
-          while (liveB[g] > 0 && nf[liveB[g] - 1] + extra <= c) --liveB[g];
-          // shared memory of the sort kernel: sized for the graph this cycle can have reached (build phase: the
-          // backbone + a share of the bases added so far), so early cycles run more CTAs per SM; a graph that
-          // outgrows it sorts out of HBM instead (slower, same result)
-          uint32_t ss = h->smem_sort;
-          if (c + 1 < gmin_nseq[g]) {
-            const double nvb = gblen[g] + h->sort_growth * c * gavglen[g] + 64.0;
-            const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
-            ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
-          }
-          if (K == 10) tl[t] += launch_cycle<10>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g], ss);
-          else tl[t] += launch_cycle<16>(h, a, gbase[g], liveA[g], liveB[g], c == 0, h->gstream[g], ss);
+    uint32_t nl = 0;
+    for (uint32_t c = 0; c < max_cyc; ++c) {
+      for (int g = 0; g < G; ++g) {
+        const std::vector<uint32_t>& ns = gnseq[g];
+        while (live[g] > 0 && win_cycles(ns[live[g] - 1], hap, num_prune) <= c) --live[g];
+        const uint32_t nlive = live[g];
+        if (!nlive) continue;
+        cudaStream_t st = h->gstream[g];
+        KernelArgs ka = a;
+        ka.smem_bytes = h->smem_update;  // per window (warp)
+        update_kernel<K><<<(nlive + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * ka.smem_bytes, st>>>(ka, gbase[g], nlive);
+        ++nl;
+        uint64_t njobs = 0;
+        uint32_t nprep = 0;  // windows that still have a prepare step in this cycle: all but those that just emitted
+        for (uint32_t i = 0; i < nlive; ++i) {
+          njobs += win_jobs(ns[i], hap, num_prune, c);
+          if (win_cycles(ns[i], hap, num_prune) > c + 1) nprep = i + 1;
+        }
+        if (!nprep) continue;
+        // shared memory of the sort kernel: sized for the graph this cycle can have reached (build phase: the
+        // backbone + a share of the bases added so far), so early cycles run more CTAs per SM; a graph that
+        // outgrows it sorts out of HBM instead (slower, same result)
+        uint32_t ss = h->smem_sort;
+        if (c + 1 < gmin_nseq[g]) {
+          const double nvb = gblen[g] + h->sort_growth * c * gavglen[g] + 64.0;
+          const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
+          ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
+        }
+        Job* jobs = h->d_jobs.as<Job>() + gjob_off[g];
+        uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + static_cast<size_t>(g) * (max_cyc + 1) + c;
+        ka.smem_bytes = ss;
+        sort_kernel<K><<<nprep, 32, ss, st>>>(ka, gbase[g], jobs, cnt);
+        ++nl;
+        if (njobs) {
+          ka.smem_bytes = smem_align;
+          align_kernel<K><<<static_cast<uint32_t>(njobs), 32, smem_align, st>>>(ka, jobs, cnt);
+          ++nl;
         }
       }
-    };
-    if (T == 1) {
-      enqueue(0);
-    } else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < T; ++t) th.emplace_back(enqueue, t);
-      for (auto& x : th) x.join();
     }
-    for (int t = 0; t < T; ++t) *launches += tl[t];
+    *launches += nl;
     h->launch_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
     VGC_CUDA(cudaGetLastError());
     for (int g = 0; g < G; ++g) {
@@ -805,6 +925,12 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
     pos = e;
   }
   return VGC_OK;
+}
+
+int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K, const uint64_t* seq_off,
+             const uint32_t* win_first, uint32_t* launches) {
+  if (K == 10) return run_pass_k<10>(h, wins, exact, seq_off, win_first, launches);
+  return run_pass_k<16>(h, wins, exact, seq_off, win_first, launches);
 }
 
 int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t input_bytes,
@@ -842,9 +968,6 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
       set_err("layer longer than 1024 bases: beyond the engine's row capacity");
       return VGC_ERR_CAPACITY;
     }
-    if (K == 10) rc = set_kernel_attrs<10>(h);
-    else rc = set_kernel_attrs<16>(h);
-    if (rc) return rc;
     VGC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = run_pass(h, pr.device_windows, false, K, seq_off, win_first, &launches))) return rc;
     VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
@@ -989,12 +1112,8 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   }
   // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
   auto smem_for = [](int ctas) { return static_cast<uint32_t>(((228 * 1024 - ctas * 1024) / ctas) & ~255); };
-  // what VGC_FILL_CTAS one-warp CTAs per SM leave each (16 -> 13.5 KB: profile + a 4-row ring for 640-column rows)
-  h->smem_fill = smem_for(VGC_FILL_CTAS);
-  if (h->smem_fill > 13568) h->smem_fill = 13568;
   h->smem_sort = smem_for(VGC_SORT_CTAS);
   h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
-  h->smem_trace = 2048;
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
   if (const char* s = std::getenv("VGC_NODE_SHARE_DIV")) h->node_share_div = static_cast<uint32_t>(std::max(1, std::atoi(s)));
@@ -1015,7 +1134,8 @@ int vgc_destroy(vgc_handle h) {
   for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
                     &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
                     &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
-                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates})
+                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs,
+                    &h->d_jobcnt})
     d->release();
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_out_len) cudaFreeHost(h->h_out_len);
