@@ -332,8 +332,9 @@ def main():
         ph = eng.phase_profile()
         # per-window latency shares (leader-lane / walker cycles summed over windows): diagnostics, not device time.
         # trace_refill is a sub-interval of traceback and trace_refills a count: both are left out of the total
-        tot_ph = sum(v for k, v in ph.items() if k not in ("trace_refill", "trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm")) or 1.0
-        line["phase_share"] = {k: round(v / tot_ph, 4) for k, v in ph.items() if k not in ("trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm")}
+        from vechat_b200.engine import PHASE_NOT_CYCLES
+        tot_ph = sum(v for k, v in ph.items() if k not in PHASE_NOT_CYCLES) or 1.0
+        line["phase_share"] = {k: round(v / tot_ph, 4) for k, v in ph.items() if k not in PHASE_NOT_CYCLES}
         line["phase_raw"] = {k: float(v) for k, v in ph.items()}
         line["alignments"] = int(res_stats[-1]["alignments"])
         line["relaunched_windows"] = int(res_stats[-1]["relaunched_windows"])

@@ -18,6 +18,10 @@ namespace {
 
 using namespace vgc;
 
+// diagnostics: histogram of predecessor row distances over every row of every fill (hm_dist_hist)
+unsigned long long g_dhist[4][66];
+unsigned long long g_npred[16];
+
 struct HostEx {
   std::vector<uint32_t> rec32;
   std::vector<uint16_t> tail16, stk16;
@@ -110,12 +114,17 @@ struct HostEx {
       const uint32_t npred = meta_npred(meta);
       const uint32_t np = npred == 0 ? 1 : npred;
       int32_t fcv = INT32_MIN;
+      g_npred[np < 15 ? np : 15] += 1;
       for (uint32_t j = 1; j <= len; ++j) row[j] = INT32_MIN;
       for (uint32_t p = 0; p < np; ++p) {
         uint32_t pr;
         const U4 er = {sl.rowprog[4 * r], sl.rowprog[4 * r + 1], sl.rowprog[4 * r + 2], sl.rowprog[4 * r + 3]};
         if (npred == 0) pr = 0;
         else pr = rec_pred(er, r + 1, p, sl.ovf);
+        {
+          const uint32_t dd = r + 1 - pr;
+          g_dhist[ws.round ? 1 : 0][dd < 65 ? dd : 65] += 1;
+        }
         fcv = std::max(fcv, H(pr, 0));
         for (uint32_t j = 1; j <= len; ++j) {
           const int32_t s = codes_[j - 1] == code ? sc.m : sc.x;
@@ -152,6 +161,11 @@ struct HostEx {
 }  // namespace
 
 extern "C" {
+
+void hm_dist_hist(unsigned long long* out, unsigned long long* np) {
+  for (int i = 0; i < 2 * 66; ++i) out[i] = (&g_dhist[0][0])[i];
+  for (int i = 0; i < 16; ++i) np[i] = g_npred[i];
+}
 
 // Same contract as ref_polish / oracle_polish.  flags: bit0 = disable the staged (16-bit) sort path,
 // bits 8.. = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).

@@ -18,9 +18,13 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", os.path.join(tmp, cubin)], capture_output=True,
-                         text=True).stdout.splitlines()
+    dis = []
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        out = subprocess.run(["nvdisasm", "--print-line-info", "-c", os.path.join(tmp, cubin)], capture_output=True,
+                             text=True).stdout
+        if kname in out:
+            dis = out.splitlines()
+            break
     # offset -> (file, line) for the chosen kernel
     loc, cur, inside = {}, ("?", 0), False
     for ln in dis:

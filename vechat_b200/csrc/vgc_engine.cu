@@ -297,15 +297,42 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
 }
 
 // A: one alignment = DP fill (replaces SimdAlignmentEngine::Linear's fill) + traceback, by one warp.
-// shared memory: Slot header | codes[max_len] | stage[32 x uint4] | fill: prof[num_codes x 32K words] | ring
+// shared memory: Slot header | codes[max_len] | recs[64 x 16 B] | fill: prof[num_codes x 32K words] | ring
 //                                                                 | trace: tile | w2[len]   (overlays prof / ring)
+// fill + traceback of one alignment with rows of KR words per lane
+struct AlignOut {
+  int st;
+  uint32_t n, refills, slow;
+  unsigned long long t_fill_end;
+};
 template <int KR>
-__device__ __forceinline__ void run_fill(const KernelArgs& a, FillIo& io, const uint8_t* codes, uint32_t len, uint32_t mode,
-                                         const Scores& sc, uint32_t* prof, uint4* stage, const uint8_t* smem) {
+__device__ __forceinline__ void align_one(const KernelArgs& a, FillIo& io, TraceIo& t, const uint8_t* codes, uint32_t len,
+                                          uint32_t mode, const Scores& sc, uint32_t* prof, U4* recs, const uint8_t* smem,
+                                          bool round, bool hq, const uint8_t* quals, AlignOut* out) {
   uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
   const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
   const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
-  warp_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, stage, ring, ring_rows);
+  wave_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, recs, ring, ring_rows);
+  out->t_fill_end = clock64();
+  // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
+  __syncwarp();
+  const int lane = threadIdx.x;
+  t.row = io.best_row;
+  t.col = io.best_col;
+  uint32_t* tile = prof;
+  uint32_t* w2 = tile + kTraceTileBytes / 4;
+  t.w2 = w2;
+  if (round) {
+    for (uint32_t i = lane; i < len; i += 32) {
+      uint32_t v = 0;
+      if (i >= 1) v = hq ? a.bv.wlut[quals[i - 1]] + a.bv.wlut[quals[i]] : 2u;
+      w2[i] = v;
+    }
+    __syncwarp();
+    out->st = warp_trace<KR, true>(t, tile, &out->n, &out->refills, &out->slow);
+  } else {
+    out->st = warp_trace<KR, false>(t, tile, &out->n, &out->refills, &out->slow);
+  }
 }
 
 __device__ __forceinline__ void win_fail(const KernelArgs& a, WinState* gws, uint32_t w, uint32_t st) {
@@ -335,13 +362,16 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   __syncwarp();
   // ---- a DP-matrix buffer of this SM's share of the pool (never more CTAs resident than buffers: the host caps
   //      the kernel's residency at pool_per_sm; should the bound ever be off, wait for a neighbour to finish)
-  uint32_t buf = 0;
+  uint32_t buf = 0, pool_spins = 0, slow_steps = 0;
   if (lane == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     const uint32_t b0 = (smid % a.sm_count) * a.pool_per_sm;
     uint32_t k = blockIdx.x % a.pool_per_sm;
-    while (atomicCAS(a.pool_busy + b0 + k, 0u, 1u) != 0u) k = k + 1 == a.pool_per_sm ? 0u : k + 1;
+    while (atomicCAS(a.pool_busy + b0 + k, 0u, 1u) != 0u) {
+      k = k + 1 == a.pool_per_sm ? 0u : k + 1;
+      ++pool_spins;
+    }
     buf = b0 + k;
   }
   buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
@@ -349,8 +379,8 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   uint8_t* sm = smem + kSmemHeader;
   const uint32_t max_len = sl->max_len;
   uint8_t* codes = sm;
-  uint4* stage = reinterpret_cast<uint4*>(sm + ((max_len + 15u) & ~15u));
-  uint32_t* prof = reinterpret_cast<uint32_t*>(stage + 32);
+  U4* recs = reinterpret_cast<U4*>(sm + ((max_len + 15u) & ~15u));
+  uint32_t* prof = reinterpret_cast<uint32_t*>(recs + kRecRing);
   const uint64_t o = a.bv.seq_off[l];
   const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
   for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
@@ -364,29 +394,22 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   const uint32_t kr = fill_width(K, len);
   FillIo io;
   io.H = reinterpret_cast<uint32_t*>(pb);
-  io.fc = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
+  io.left = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
   io.rowprog = sl->rowprog;
   io.ovf = sl->ovf;
   io.nR = nR;
   io.best_row = io.best_col = 0;
   io.best_score = 0;
-  int st = kWalkDone;
-  uint32_t n = 0, refills = 0;
-  unsigned long long t1 = t0;
-  if (nR + 1 > a.pool_rows) {
-    st = kWalkBad;
+  AlignOut ao;
+  ao.st = kWalkDone;
+  ao.n = ao.refills = ao.slow = 0;
+  ao.t_fill_end = t0;
+  if (nR + 1 + kSkewRows > a.pool_rows) {
+    ao.st = kWalkBad;
   } else {
-    if (kr == 8) run_fill<8>(a, io, codes, len, mode, sc, prof, stage, smem);
-    else if (kr == 10) run_fill<10>(a, io, codes, len, mode, sc, prof, stage, smem);
-    else run_fill<K>(a, io, codes, len, mode, sc, prof, stage, smem);
-    t1 = clock64();
-    // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
-    __syncwarp();
     TraceIo t;
     t.H = io.H;
-    t.fc = io.fc;
-    t.rw = 32u * kr;
-    t.half_words = 32u * kr;
+    t.left = io.left;
     t.rp = reinterpret_cast<const U4*>(sl->rowprog);
     t.ovf = sl->ovf;
     t.nodes = sl->max_nodes < 65536u ? nullptr : (sub ? sl->order : sl->r2n);
@@ -395,8 +418,6 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
     t.x = sc.x;
     t.g = sc.g;
     t.sw = mode == kModeSW;
-    t.row = io.best_row;
-    t.col = io.best_col;
     t.max_steps = nR + len + 2;
     t.aln_node = sl->aln_node;
     t.aln_pos = sl->aln_pos;
@@ -405,27 +426,26 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
     t.ew = sl->g[cur].ew;
     t.ieid = sl->g[cur].ieid;
     t.in_stride = sl->in_stride;
-    uint32_t* tile = prof;
-    uint32_t* w2 = tile + kTraceTileBytes / 4;
-    t.w2 = w2;
-    if (round) {
-      const bool hq = a.bv.has_qual[l] != 0;
-      for (uint32_t i = lane; i < len; i += 32) {
-        uint32_t v = 0;
-        if (i >= 1) v = hq ? a.bv.wlut[a.bv.quals[o + i - 1]] + a.bv.wlut[a.bv.quals[o + i]] : 2u;
-        w2[i] = v;
-      }
-      __syncwarp();
-      st = warp_trace<true>(t, tile, &n, &refills);
-    } else {
-      st = warp_trace<false>(t, tile, &n, &refills);
-    }
+    const bool hq = a.bv.has_qual[l] != 0;
+    const uint8_t* quals = a.bv.quals + o;
+    if (kr == 8) align_one<8>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
+    else if (kr == 10) align_one<10>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
+    else align_one<K>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
   }
+  const int st = ao.st;
+  const uint32_t n = ao.n, refills = ao.refills;
+  slow_steps = ao.slow;
+  const unsigned long long t1 = ao.t_fill_end;
   __syncwarp();
   if (lane == 0) {
     __threadfence();
     atomicExch(a.pool_busy + buf, 0u);
     const unsigned long long t2 = clock64();
+    // diagnostics: slowest fill / traceback of the call, pool waits
+    atomicMax(a.totals + 4 + kPhCount, t1 - t0);
+    atomicMax(a.totals + 5 + kPhCount, t2 - t1);
+    atomicAdd(a.totals + 6 + kPhCount, static_cast<unsigned long long>(slow_steps));
+    atomicAdd(a.totals + 7 + kPhCount, static_cast<unsigned long long>(pool_spins));
     if (st != kWalkDone) {
       win_fail(a, gws, w, kStInternal);
     } else if (round) {
@@ -509,6 +529,7 @@ struct vgc_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
+  double pool_spins = 0.0;      // last call: failed attempts to take a DP buffer (0 unless the residency bound is off)
   double launch_ms = 0.0;       // host wall time spent enqueueing the kernel launches of the current call
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
@@ -654,12 +675,12 @@ int align_occupancy(uint32_t smem_align, int* per_sm) {
 // The ring of recent rows is dropped when it does not fit `budget` (what the CTAs-per-SM target leaves); a profile
 // that does not fit either (many codes x wide rows) takes what it needs and fewer CTAs run per SM.
 uint32_t align_smem(uint32_t K, uint32_t num_codes, uint32_t max_len, uint32_t budget) {
-  const uint32_t fixed = kSmemHeader + ((max_len + 15u) & ~15u) + 512u;
+  const uint32_t fixed = kSmemHeader + ((max_len + 15u) & ~15u) + 16u * kRecRing;
   const uint32_t prof = num_codes * 128u * K;
   const uint32_t ring = kRingRows * (128u * K + 128u);
   const uint32_t trace = kTraceTileBytes + 4u * max_len + 16u;
+  (void)budget;  // the ring of recent rows is worth more than residency: 99 % of the predecessor rows are within 8 rows
   uint32_t body = prof + ring;
-  if (fixed + body > budget) body = prof;
   body = std::max(body, trace);
   return (fixed + body + 255u) & ~255u;
 }
@@ -716,9 +737,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         const uint32_t f = win_first[w];
         pool_rows = std::max(pool_rows, estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div));
       }
-      pool_rows = std::max<uint32_t>(pool_rows, 64) + 1;
+      pool_rows = std::max<uint32_t>(pool_rows, 64) + 1 + kSkewRows;
     }
-    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 2ull * pool_rows + 64, 256);
+    // a buffer = pool_rows rows of 32*K words + per row the 32 left values (int16) of the lanes
+    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 64ull * pool_rows + 64, 256);
     int rc;
     if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
     int occ = 0;
@@ -955,7 +977,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   }
   const uint32_t n_dev = static_cast<uint32_t>(pr.device_windows.size());
   uint32_t launches = 0, relaunched = 0;
-  unsigned long long totals[4 + vgc::kPhCount] = {0};
+  unsigned long long totals[8 + vgc::kPhCount] = {0};
   float kernel_ms = 0.f, d2h_ms = 0.f;
   h->pass_kernel_ms = 0.0;
   h->launch_ms = 0.0;
@@ -1043,6 +1065,13 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     h->phase_cycles[11] = h->launch_ms;
     h->phase_cycles[12] = static_cast<double>(totals[2 + vgc::kPhCount]);
     h->phase_cycles[13] = static_cast<double>(totals[3 + vgc::kPhCount]);
+    h->phase_cycles[14] = static_cast<double>(totals[4 + vgc::kPhCount]);
+    h->phase_cycles[15] = static_cast<double>(totals[5 + vgc::kPhCount]);
+    h->phase_cycles[0] = static_cast<double>(totals[6 + vgc::kPhCount]);
+    h->pool_spins = static_cast<double>(totals[7 + vgc::kPhCount]);
+    if (std::getenv("VGC_VERBOSE"))
+      std::fprintf(stderr, "[vgc] pass: %.1f ms kernels, %u launches, pool waits %.0f, slow trace steps %.0f, max fill %.0f / trace %.0f cycles\n",
+                   h->pass_kernel_ms, launches, h->pool_spins, h->phase_cycles[0], h->phase_cycles[14], h->phase_cycles[15]);
     stats->cells = totals[0];
     stats->alignments = totals[1];
     stats->input_bytes = input_bytes;

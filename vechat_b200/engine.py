@@ -103,8 +103,12 @@ class Engine:
         return None, _stats(st)
 
 
-PHASES = ["trace_refill", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
-          "largest_subgraph", "emit", "trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm"]
+PHASES = ["trace_slow_steps", "toposort", "rowprog", "fill", "traceback", "add_alignment", "add_weights", "prune",
+          "largest_subgraph", "emit", "trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm",
+          "max_fill_cycles", "max_trace_cycles"]
+# entries of the profile that are counts / maxima / host times, not per-window cycle sums
+PHASE_NOT_CYCLES = ("trace_slow_steps", "trace_refills", "host_launch_ms", "sorts", "sorts_out_of_hbm",
+                    "max_fill_cycles", "max_trace_cycles")
 
 
 def _phase_profile(engine):
