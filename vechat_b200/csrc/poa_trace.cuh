@@ -44,8 +44,8 @@ constexpr uint32_t kTraceTileBytes = kTileRows * kTilePitch * 4 + kTileRows * 16
 
 struct TraceIo {
   // the matrix (align kernel's scratch) and the row program it was filled from
-  const uint32_t* H;       // skewed: block l (words [K*l, K*l + K)) of row r lives in memory row r + l
-  const int16_t* left;     // left[row * 32]: first-column value of the row (NW border; lane 0 is not skewed)
+  const uint32_t* H;       // rows of 32*K words: word w holds column w (low half) and column 32*K + w (high half)
+  const int16_t* fc;       // first-column value of every row (NW border)
   const U4* rp;
   const uint32_t* ovf;
   const uint32_t* nodes;   // rank -> node id; nullptr: the id is in the row record (slots below 65536 nodes)
@@ -69,10 +69,9 @@ struct TraceIo {
 // cell column (0-based) -> word of the row and half of the word, for rows of K words per lane
 template <int K>
 __device__ __forceinline__ uint32_t col_word(uint32_t c, uint32_t* hi) {
-  const uint32_t q = c / (2u * K), rem = c % (2u * K);
-  const uint32_t h = rem >= static_cast<uint32_t>(K) ? 1u : 0u;
+  const uint32_t h = c >= 32u * K ? 1u : 0u;
   *hi = h;
-  return q * K + rem - h * K;
+  return c - h * (32u * K);
 }
 
 // returns kWalkDone or kWalkBad; *n_out = pairs written (WEIGHTS == false) or moves taken
@@ -94,10 +93,10 @@ __device__ int warp_trace(const TraceIo& t, uint32_t* tile, uint32_t* n_out, uin
 
   // H(row, jj) by direct load; jj = DP column (0 = first column).  Uniform across the warp.
   auto cell_g = [&](uint32_t row, uint32_t jj) -> int32_t {
-    if (jj == 0) return sw ? 0 : static_cast<int32_t>(t.left[static_cast<uint64_t>(row) * 32]);
+    if (jj == 0) return sw ? 0 : static_cast<int32_t>(t.fc[row]);
     uint32_t hi;
     const uint32_t w = col_word<K>(jj - 1, &hi);
-    const uint32_t v = t.H[static_cast<uint64_t>(row + w / K) * rw + w];
+    const uint32_t v = t.H[static_cast<uint64_t>(row) * rw + w];
     return static_cast<int16_t>(hi ? (v >> 16) : (v & 0xFFFFu));
   };
   auto node_of = [&](uint32_t row, uint32_t meta) -> int32_t {
@@ -119,19 +118,17 @@ __device__ int warp_trace(const TraceIo& t, uint32_t* tile, uint32_t* n_out, uin
   auto refill = [&]() {
     __syncwarp();
     ti = i;
-    // the tile ends with the lane block of the current column and extends to the left (lower columns = lower words)
-    const uint32_t endw = ((j - 1) / (2u * K) + 1u) * K;
-    wb = endw > TW ? (endw - TW + 3u) & ~3u : 0u;
+    // the tile ends just after the word of the current column and extends to the left (lower columns = lower words)
+    uint32_t hi1;
+    const uint32_t endw = (col_word<K>(j - 1, &hi1) & ~3u) + 4u;
+    wb = endw > TW ? endw - TW : 0u;
     if (static_cast<uint32_t>(lane) <= ti) {
       const uint32_t row = ti - lane;
       const uint32_t dst = tile_s + lane * (kTilePitch * 4);
-      // 8-byte pieces: a pair of words never straddles two lane blocks (K is even), and each block has its own skew
+      const uint32_t* src = t.H + static_cast<uint64_t>(row) * rw + wb;
 #pragma unroll
-      for (int q = 0; q < kTileWords / 2; ++q) {
-        const uint32_t w = wb + 2 * q;
-        const uint32_t* src = t.H + static_cast<uint64_t>(row + w / K) * rw + w;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + q * 8), "l"(src) : "memory");
-      }
+      for (int q = 0; q < kTileWords / 4; ++q)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 4) : "memory");
       if (row >= 1) {
         const uint32_t rdst = tile_s + kTileRows * kTilePitch * 4 + lane * 16;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rdst), "l"(t.rp + (row - 1)) : "memory");

@@ -41,6 +41,7 @@ struct Job {
   uint32_t idx;
   uint32_t layer;  // bits 0-29 layer id, bit 30 = part of a re-alignment round (AddWeights fused), bit 31 = SW mode
 };
+constexpr uint32_t kRecRing = 32;  // row records staged in shared memory by the fill
 constexpr uint32_t kJobRound = 1u << 30, kJobSW = 1u << 31, kJobLayerMask = kJobRound - 1u;
 
 // Arguments shared by the kernels of a lockstep pass.  `idx` below is the position of a window in the
@@ -60,10 +61,10 @@ struct KernelArgs {
   uint32_t smem_bytes;     // dynamic shared memory per CTA of the launched kernel
   // align kernel: pool of DP-matrix buffers, pool_per_sm per SM
   uint8_t* pool;
-  uint32_t* pool_busy;     // [sm_count * pool_per_sm] 0 = free
+  uint32_t* pool_free;     // [pool_n] ring of free buffer ids, then [pool_n] = take counter, [pool_n + 1] = give counter
   unsigned long long pool_buf_bytes;
   uint32_t pool_rows;      // rows a buffer holds (at the widest row)
-  uint32_t pool_per_sm, sm_count;
+  uint32_t pool_n;         // buffers = CTAs of align_kernel the device can hold at once
 };
 
 // Executor: the device side of poa_core.h's `Ex` concept.  G lanes work on one window (G = 32: a whole warp).
@@ -312,7 +313,7 @@ __device__ __forceinline__ void align_one(const KernelArgs& a, FillIo& io, Trace
   uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
   const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
   const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
-  wave_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, recs, ring, ring_rows);
+  warp_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, reinterpret_cast<uint4*>(recs), ring, ring_rows);
   out->t_fill_end = clock64();
   // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
   __syncwarp();
@@ -360,19 +361,14 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   const uint32_t nR = gws->nR, sub = gws->sub, cur = gws->cur;
   const uint32_t w = a.work[idx];
   __syncwarp();
-  // ---- a DP-matrix buffer of this SM's share of the pool (never more CTAs resident than buffers: the host caps
-  //      the kernel's residency at pool_per_sm; should the bound ever be off, wait for a neighbour to finish)
+  // ---- a DP-matrix buffer from the pool: a ring of free ids with take / give tickets.  There are as many buffers as
+  //      CTAs of this kernel can be resident on the device, so ticket h finds the id given back by ticket h - pool_n
+  //      (or the initial fill) in slot h % pool_n; it only ever waits for that store to land.
   uint32_t buf = 0, pool_spins = 0, slow_steps = 0;
   if (lane == 0) {
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const uint32_t b0 = (smid % a.sm_count) * a.pool_per_sm;
-    uint32_t k = blockIdx.x % a.pool_per_sm;
-    while (atomicCAS(a.pool_busy + b0 + k, 0u, 1u) != 0u) {
-      k = k + 1 == a.pool_per_sm ? 0u : k + 1;
-      ++pool_spins;
-    }
-    buf = b0 + k;
+    const uint32_t ticket = atomicAdd(a.pool_free + a.pool_n, 1u);
+    uint32_t* slot = a.pool_free + ticket % a.pool_n;
+    while ((buf = atomicExch(slot, kNone)) == kNone) ++pool_spins;
   }
   buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
   uint8_t* pb = a.pool + static_cast<unsigned long long>(buf) * a.pool_buf_bytes;
@@ -394,7 +390,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   const uint32_t kr = fill_width(K, len);
   FillIo io;
   io.H = reinterpret_cast<uint32_t*>(pb);
-  io.left = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
+  io.fc = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
   io.rowprog = sl->rowprog;
   io.ovf = sl->ovf;
   io.nR = nR;
@@ -404,12 +400,12 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   ao.st = kWalkDone;
   ao.n = ao.refills = ao.slow = 0;
   ao.t_fill_end = t0;
-  if (nR + 1 + kSkewRows > a.pool_rows) {
+  if (nR + 1 > a.pool_rows) {
     ao.st = kWalkBad;
   } else {
     TraceIo t;
     t.H = io.H;
-    t.left = io.left;
+    t.fc = io.fc;
     t.rp = reinterpret_cast<const U4*>(sl->rowprog);
     t.ovf = sl->ovf;
     t.nodes = sl->max_nodes < 65536u ? nullptr : (sub ? sl->order : sl->r2n);
@@ -439,7 +435,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   __syncwarp();
   if (lane == 0) {
     __threadfence();
-    atomicExch(a.pool_busy + buf, 0u);
+    atomicExch(a.pool_free + atomicAdd(a.pool_free + a.pool_n + 1, 1u) % a.pool_n, buf);
     const unsigned long long t2 = clock64();
     // diagnostics: slowest fill / traceback of the call, pool waits
     atomicMax(a.totals + 4 + kPhCount, t1 - t0);
@@ -679,8 +675,8 @@ uint32_t align_smem(uint32_t K, uint32_t num_codes, uint32_t max_len, uint32_t b
   const uint32_t prof = num_codes * 128u * K;
   const uint32_t ring = kRingRows * (128u * K + 128u);
   const uint32_t trace = kTraceTileBytes + 4u * max_len + 16u;
-  (void)budget;  // the ring of recent rows is worth more than residency: 99 % of the predecessor rows are within 8 rows
   uint32_t body = prof + ring;
+  if (fixed + body > budget) body = prof;
   body = std::max(body, trace);
   return (fixed + body + 255u) & ~255u;
 }
@@ -737,10 +733,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         const uint32_t f = win_first[w];
         pool_rows = std::max(pool_rows, estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div));
       }
-      pool_rows = std::max<uint32_t>(pool_rows, 64) + 1 + kSkewRows;
+      pool_rows = std::max<uint32_t>(pool_rows, 64) + 1;
     }
-    // a buffer = pool_rows rows of 32*K words + per row the 32 left values (int16) of the lanes
-    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 64ull * pool_rows + 64, 256);
+    // a buffer = pool_rows rows of 32*K words + the first-column value (int16) of every row
+    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 2ull * pool_rows + 64, 256);
     int rc;
     if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
     int occ = 0;
@@ -768,8 +764,13 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     }
     const uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
     if ((rc = h->d_pool.reserve(pool_bytes))) return rc;
-    if ((rc = h->d_pool_busy.reserve(4ull * per_sm * h->sm_count))) return rc;
-    VGC_CUDA(cudaMemsetAsync(h->d_pool_busy.p, 0, 4ull * per_sm * h->sm_count, h->stream));
+    const uint32_t pool_n = per_sm * static_cast<uint32_t>(h->sm_count);
+    if ((rc = h->d_pool_busy.reserve(4ull * (pool_n + 2)))) return rc;
+    std::vector<uint32_t> pool_init(pool_n + 2);
+    for (uint32_t i = 0; i < pool_n; ++i) pool_init[i] = i;
+    pool_init[pool_n] = 0;           // take tickets
+    pool_init[pool_n + 1] = pool_n;  // give tickets: the initial ids count as given back
+    VGC_CUDA(cudaMemcpyAsync(h->d_pool_busy.p, pool_init.data(), 4ull * (pool_n + 2), cudaMemcpyHostToDevice, h->stream));
 
     std::vector<SlotDims> dims;
     std::vector<uint64_t> offs;
@@ -881,11 +882,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     a.min_support = h->params.min_support;
     a.smem_bytes = 0;
     a.pool = h->d_pool.as<uint8_t>();
-    a.pool_busy = h->d_pool_busy.as<uint32_t>();
+    a.pool_free = h->d_pool_busy.as<uint32_t>();
     a.pool_buf_bytes = buf_bytes;
     a.pool_rows = pool_rows;
-    a.pool_per_sm = per_sm;
-    a.sm_count = static_cast<uint32_t>(h->sm_count);
+    a.pool_n = pool_n;
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
     // ---- lockstep: the lists are sorted by decreasing cycles, so the live windows of a cycle are a prefix
