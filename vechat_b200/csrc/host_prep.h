@@ -57,6 +57,7 @@ struct Prepared {
   std::vector<uint32_t> win_sum_len; // sum of layer lengths (upper bound of graph nodes)
   std::vector<uint32_t> win_max_len; // longest layer
   std::vector<uint32_t> win_nfill;   // alignments (DP fills) the window program runs
+  std::vector<uint8_t> layer_sw;     // [n_layers] 1: a re-alignment round aligns this layer locally (window.cpp:338-352)
   uint8_t coder[256];
   uint8_t decoder[kMaxCodes];
   uint32_t num_codes = 0;
@@ -92,6 +93,7 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
   out->win_sum_len.assign(nw, 0);
   out->win_max_len.assign(nw, 0);
   out->win_nfill.assign(nw, 0);
+  out->layer_sw.assign(nl, 0);
   out->device_windows.clear();
   out->max_len = 0;
   out->max_nodes_ub = 0;
@@ -136,6 +138,14 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
       }
       const uint32_t nseq = static_cast<uint32_t>(rank.size());
       out->win_nseq[w] = nseq;
+      {
+        // full-span layers (and the backbone) are re-aligned globally, the others locally (window.cpp:212,338-352)
+        const uint32_t offset = static_cast<uint32_t>(0.01 * blen);
+        for (uint32_t j = 1; j < nseq; ++j) {
+          const uint32_t i = rank[j];
+          out->layer_sw[i] = (b->begin[i] < offset && b->end[i] > blen - offset) ? 0 : 1;
+        }
+      }
       std::sort(rank.begin() + 1, rank.end(),
                 [&](uint32_t lhs, uint32_t rhs) { return b->begin[lhs] < b->begin[rhs]; });
       std::copy(rank.begin(), rank.end(), out->layer_rank.begin() + f);

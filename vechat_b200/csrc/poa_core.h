@@ -156,8 +156,9 @@ struct Slot {
 };
 
 // Row program record (16 B per DP row, rank order):
-//   x = meta: code (bits 0-3) | sink (4) | inline (5) | number of predecessors (6-15) | node id (16-31; meaningful
-//       while the slot holds fewer than 65536 nodes — the traceback reads it instead of a table in HBM)
+//   x = meta: code (bits 0-3) | sink (4) | inline (5) | number of predecessors (6-14) | chain (15: the only
+//       predecessor is the row just above — the fill's fast path) | node id (16-31; meaningful while the slot holds
+//       fewer than 65536 nodes — the traceback reads it instead of a table in HBM)
 //   inline (<= 6 predecessors, every one within 65535 rows): y, z, w = six 16-bit row DISTANCES d_p (predecessor
 //       p is row - d_p), in-edge order; a node without in-edges has the virtual row 0 as its only predecessor
 //       (np = 0, d_0 = its own row)
@@ -165,12 +166,13 @@ struct Slot {
 constexpr uint32_t kInlinePreds = 6;
 constexpr uint32_t kMetaSink = 1u << 4;
 constexpr uint32_t kMetaInline = 1u << 5;
-constexpr uint32_t kMetaMaxPred = 1023;
-VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, bool inl, uint32_t node) {
-  return code | (sink ? kMetaSink : 0u) | (inl ? kMetaInline : 0u) | (npred << 6) | (node << 16);
+constexpr uint32_t kMetaChain = 1u << 15;
+constexpr uint32_t kMetaMaxPred = 511;
+VGC_HD VGC_INL uint32_t meta_pack(uint32_t code, uint32_t npred, bool sink, bool inl, uint32_t node, bool chain) {
+  return code | (sink ? kMetaSink : 0u) | (inl ? kMetaInline : 0u) | (npred << 6) | (chain ? kMetaChain : 0u) | (node << 16);
 }
 VGC_HD VGC_INL uint32_t meta_code(uint32_t m) { return m & 0xFu; }
-VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 6) & 0x3FFu; }
+VGC_HD VGC_INL uint32_t meta_npred(uint32_t m) { return (m >> 6) & 0x1FFu; }
 VGC_HD VGC_INL uint32_t meta_node(uint32_t m) { return m >> 16; }
 // predecessor p of the row `row` whose record is `e`
 VGC_HD VGC_INL uint32_t rec_delta(const U4& e, uint32_t p) {
@@ -925,7 +927,7 @@ struct Poa {
       }
       const bool sink = sub ? (sl.tmp0[v] == 0) : (g.nout[v] == 0);
       if (np > kMetaMaxPred) fail(kStDegreeOverflow);
-      rec.x = meta_pack(g.code[v], np, sink, inl, v);
+      rec.x = meta_pack(g.code[v], np, sink, inl, v, inl && np <= 1 && d[0] == 1);
       *reinterpret_cast<U4*>(sl.rowprog + 4 * static_cast<size_t>(r)) = rec;
     }
     ex.sync();

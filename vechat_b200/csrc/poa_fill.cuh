@@ -41,22 +41,74 @@ __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) {
 __device__ __forceinline__ int32_t lo16(uint32_t w) { return static_cast<int16_t>(w & 0xFFFFu); }
 __device__ __forceinline__ int32_t hi16(uint32_t w) { return static_cast<int16_t>(w >> 16); }
 
+// keep a loop-invariant value in its register: without this ptxas recomputes the packed per-lane constants in every
+// row (cheaper in registers, ~40 extra instructions per row)
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
+// K words of this lane to global memory (`p` already offset to the lane's words), as st.global vectors
 template <int K>
-__device__ __forceinline__ void row_load(const uint32_t* __restrict__ row, int lane, uint32_t (&u)[K]) {
-  const uint2* p = reinterpret_cast<const uint2*>(row + lane * K);  // lane-major: K consecutive words per lane
+__device__ __forceinline__ void lane_store_global(uint32_t* p, const uint32_t (&h)[K]) {
+  if constexpr (K % 4 == 0) {
 #pragma unroll
-  for (int k = 0; k < K; k += 2) {
-    uint2 t = p[k >> 1];
-    u[k] = t.x;
-    u[k + 1] = t.y;
+    for (int k = 0; k < K; k += 4)
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + k), "r"(h[k]), "r"(h[k + 1]), "r"(h[k + 2]), "r"(h[k + 3]) : "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; k += 2)
+      asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p + k), "r"(h[k]), "r"(h[k + 1]) : "memory");
+  }
+}
+template <int K>
+__device__ __forceinline__ void lane_load_global(const uint32_t* p, uint32_t (&u)[K]) {
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4)
+      asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k]), "=r"(u[k + 1]), "=r"(u[k + 2]), "=r"(u[k + 3]) : "l"(p + k) : "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; k += 2)
+      asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(u[k]), "=r"(u[k + 1]) : "l"(p + k) : "memory");
+  }
+}
+
+// K words of this lane from / to `p` (already offset to the lane's words): 16-byte vectors when the lane stride allows
+template <int K>
+__device__ __forceinline__ void lane_load(const uint32_t* __restrict__ p, uint32_t (&u)[K]) {
+  if constexpr (K % 4 == 0) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+      uint4 t = q[k >> 2];
+      u[k] = t.x;
+      u[k + 1] = t.y;
+      u[k + 2] = t.z;
+      u[k + 3] = t.w;
+    }
+  } else {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+      uint2 t = q[k >> 1];
+      u[k] = t.x;
+      u[k + 1] = t.y;
+    }
   }
 }
 
 template <int K>
-__device__ __forceinline__ void row_store(uint32_t* __restrict__ row, int lane, const uint32_t (&h)[K]) {
-  uint2* p = reinterpret_cast<uint2*>(row + lane * K);
+__device__ __forceinline__ void lane_store(uint32_t* __restrict__ p, const uint32_t (&h)[K]) {
+  if constexpr (K % 4 == 0) {
+    uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
-  for (int k = 0; k < K; k += 2) p[k >> 1] = make_uint2(h[k], h[k + 1]);
+    for (int k = 0; k < K; k += 4) q[k >> 2] = make_uint4(h[k], h[k + 1], h[k + 2], h[k + 3]);
+  } else {
+    uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < K; k += 2) q[k >> 1] = make_uint2(h[k], h[k + 1]);
+  }
 }
 
 // The matrix of one alignment: rows of 32*K words (row = rank + 1, row 0 = the virtual row) in the align kernel's
@@ -76,7 +128,7 @@ struct FillIo {
 // prof : shared memory, num_codes * 32*K words;  stage: shared memory, 32 uint4
 // ring : shared memory, ring_rows * 32*K words (ring_rows <= kRingRows, may be 0)
 template <int K, bool SW>
-__device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, const Scores sc,
+__device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, const Scores sc,
                             uint32_t num_codes, uint32_t* prof, uint4* stage, uint32_t* ring, int ring_rows) {
   static_assert(K % 2 == 0, "K must be even");
   using RM = RowMap<K>;
@@ -110,16 +162,24 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
     }
   }
   // ---- per-lane constants
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int32_t c0l = lane * K, c0h = 32 * K + lane * K;
-  const uint32_t g2 = pack16(g, g);
-  const uint32_t voff = pack16(-g * (c0l + K - 1), -g * (c0h + K - 1));
-  const uint32_t gbase = pack16(g * c0l, g * c0h);
+  const uint32_t g2 = pinned(pack16(g, g));
+  const uint32_t voff = pinned(pack16(-g * (c0l + K - 1), -g * (c0h + K - 1)));
+  const uint32_t gbase = pinned(pack16(g * c0l, g * c0h));
+  uint32_t gk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) gk[k] = pinned(pack16(g * k, g * k));
+  const int rot = (lane + 31) & 31;              // the lane to my left (lane 0: lane 31, whose low half feeds my high half)
+  const uint32_t* const profl = prof + lane * K;  // my words of the profile rows / ring rows / matrix rows
+  uint32_t* const ringl = ring + lane * K;
+  uint32_t* hrow = Hm + lane * K;
 
   // ---- virtual row 0 (NW: j * g; SW: zeros) and its first column
   uint32_t hp[K];  // the row computed last (registers); chain rows are updated in place
 #pragma unroll
   for (int k = 0; k < K; ++k) hp[k] = SW ? 0u : pack16(g * (c0l + k + 1), g * (c0h + k + 1));
-  row_store<K>(Hm, lane, hp);
+  lane_store_global<K>(hrow, hp);
   if (lane == 0) fcm[0] = 0;
   int32_t fc_prev = 0;
 
@@ -128,9 +188,9 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
   const bool use_ring = ring_rows == kRingRows;
   // (every lane keeps its own copy of the first-column values: a lane only ever reads what it wrote itself, rows
   //  and first columns alike, so the ring needs no warp synchronisation)
-  int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * RM::kWords) + lane;
+  int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * rw) + lane;
   if (use_ring) {
-    row_store<K>(ring, lane, hp);
+    lane_store<K>(ringl, hp);
     ring_fc[0] = 0;
   }
 
@@ -146,48 +206,44 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
   uint4 nxt = make_uint4(0, 0, 0, 0);
   if (static_cast<uint32_t>(lane) < nR) nxt = rp[lane];
 
+  uint32_t row = 0;
   for (uint32_t r0 = 0; r0 < nR; r0 += 32) {
     __syncwarp();
     stage[lane] = nxt;
     if (r0 + 32 + lane < nR) nxt = rp[r0 + 32 + lane];
     __syncwarp();
     const uint32_t rn = nR - r0 < 32 ? nR - r0 : 32;
+#pragma unroll 1
     for (uint32_t rr = 0; rr < rn; ++rr) {
-      // rows live in rank space: this is row r0 + rr + 1; e = {meta, p0, p1, p2 | ovf offset}, predecessors as rows
+      // rows live in rank space: this is row r0 + rr + 1; e = {meta, p0p1, p2p3, p4p5 | ovf offset}, predecessors as
+      // row distances
       const uint4 e = stage[rr];
-      const uint32_t row = r0 + rr + 1, meta = e.x;
-      const uint32_t np = meta_npred(meta);
+      const uint32_t meta = e.x;
+      ++row;
+      hrow += rw;
       uint32_t pr[K];
-      {
-        const uint2* pp = reinterpret_cast<const uint2*>(prof + meta_code(meta) * RM::kWords + lane * K);
-#pragma unroll
-        for (int k = 0; k < K; k += 2) {
-          uint2 t = pp[k >> 1];
-          pr[k] = t.x;
-          pr[k + 1] = t.y;
-        }
-      }
-      const U4 er = {e.x, e.y, e.z, e.w};
-      const bool inl = (meta & kMetaInline) != 0;
-      // distance to predecessor p (rows are processed in rank order: distance 1 = the row in registers)
-      const uint32_t d0 = np == 0 ? row : (inl ? rec_delta(er, 0) : row - ovfm[e.w]);
+      lane_load<K>(profl + meta_code(meta) * rw, pr);
       int32_t fcmax;
-      if (np <= 1 && d0 == 1) {
+      if (meta & kMetaChain) {
         // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
-        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, hp[K - 1], 1);
-        const uint32_t y = __shfl_sync(0xFFFFFFFFu, hp[K - 1], 31);
-        if (lane == 0) x = pack16(fc_prev, lo16(y));
+        const uint32_t y = __shfl_sync(FULL, hp[K - 1], rot);
+        const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fc_prev), y, 0x5410) : y;
 #pragma unroll
         for (int k = K - 1; k >= 1; --k) hp[k] = __viaddmax_s16x2(hp[k - 1], pr[k], __vadd2(hp[k], g2));
         hp[0] = __viaddmax_s16x2(x, pr[0], __vadd2(hp[0], g2));
         fcmax = fc_prev;
       } else {
         // ---- general row: maximum over all predecessors, each from registers, the ring or memory
+        const uint32_t np = meta_npred(meta);
+        const U4 er = {e.x, e.y, e.z, e.w};
+        const bool inl = (meta & kMetaInline) != 0;
         uint32_t h[K];
         fcmax = INT32_MIN;
         const uint32_t npp = np == 0 ? 1 : np;
+#pragma unroll 1
         for (uint32_t p = 0; p < npp; ++p) {
-          const uint32_t d = p == 0 ? d0 : (inl ? rec_delta(er, p) : row - ovfm[e.w + p]);
+          // distance to predecessor p (rows are processed in rank order: distance 1 = the row in registers)
+          const uint32_t d = np == 0 ? row : (inl ? rec_delta(er, p) : row - ovfm[e.w + p]);
           uint32_t u[K];
           int32_t fcp;
           if (d == 1) {
@@ -196,22 +252,21 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
             fcp = fc_prev;
           } else if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
             const uint32_t slot = (row - d) & (kRingRows - 1);
-            row_load<K>(ring + slot * RM::kWords, lane, u);
+            lane_load<K>(ringl + slot * rw, u);
             fcp = ring_fc[slot * 32];
           } else {
             const uint32_t prow = row - d;
-            row_load<K>(Hm + static_cast<uint64_t>(prow) * rw, lane, u);
+            lane_load_global<K>(hrow - static_cast<uint64_t>(d) * rw, u);
             fcp = 0;
             if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
               if (lane == 0) fcp = static_cast<int32_t>(fcm[prow]);
-              fcp = __shfl_sync(0xFFFFFFFFu, fcp, 0);
+              fcp = __shfl_sync(FULL, fcp, 0);
             }
           }
           fcmax = fcp > fcmax ? fcp : fcmax;
           // diagonal of this lane's first cells: the previous lane's last cells
-          uint32_t x = __shfl_up_sync(0xFFFFFFFFu, u[K - 1], 1);
-          const uint32_t y = __shfl_sync(0xFFFFFFFFu, u[K - 1], 31);
-          if (lane == 0) x = pack16(fcp, lo16(y));
+          const uint32_t y = __shfl_sync(FULL, u[K - 1], rot);
+          const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fcp), y, 0x5410) : y;
           if (p == 0) {
             h[0] = __viaddmax_s16x2(x, pr[0], __vadd2(u[0], g2));
 #pragma unroll
@@ -233,27 +288,27 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         // lanes below d get their own value back from shfl_up: the max is a no-op there, no predicate needed
-        V = __vmaxs2(V, __shfl_up_sync(0xFFFFFFFFu, V, d));
+        V = __vmaxs2(V, __shfl_up_sync(FULL, V, d));
       }
-      const int32_t lowtot = lo16(__shfl_sync(0xFFFFFFFFu, V, 31));
+      const int32_t lowtot = lo16(__shfl_sync(FULL, V, 31));
       const int32_t vfc = fci + g;
       const uint32_t X = pack16(vfc, vfc > lowtot ? vfc : lowtot);
-      uint32_t E = __shfl_up_sync(0xFFFFFFFFu, V, 1);
+      uint32_t E = __shfl_up_sync(FULL, V, 1);
       E = lane == 0 ? X : __vmaxs2(E, X);
       const uint32_t base = __vadd2(E, gbase);
       if (SW) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2_relu(base, pack16(g * k, g * k), hp[k]);
+        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2_relu(base, gk[k], hp[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2(base, pack16(g * k, g * k), hp[k]);
+        for (int k = 0; k < K; ++k) hp[k] = __viaddmax_s16x2(base, gk[k], hp[k]);
       }
       // ---- write the row once (HBM) and keep it in the ring
-      row_store<K>(Hm + static_cast<uint64_t>(row) * rw, lane, hp);
+      lane_store_global<K>(hrow, hp);
       if (!SW && lane == 0) fcm[row] = static_cast<int16_t>(fci);
       if (use_ring) {
         const uint32_t slot = row & (kRingRows - 1);
-        row_store<K>(ring + slot * RM::kWords, lane, hp);
+        lane_store<K>(ringl + slot * rw, hp);
         ring_fc[slot * 32] = fci;
       }
       // ---- best cell
@@ -263,8 +318,8 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
         for (int k = 1; k < K; ++k) m = __vmaxs2(m, hp[k]);
         const uint32_t nb = __vmaxs2(bestv, m);
         const uint32_t chg = nb ^ bestv;
-        if (chg & 0xFFFFu) bestr_lo = r0 + rr;
-        if (chg >> 16) bestr_hi = r0 + rr;
+        if (chg & 0xFFFFu) bestr_lo = row - 1;
+        if (chg >> 16) bestr_hi = row - 1;
         bestv = nb;
       } else if (meta & kMetaSink) {
         uint32_t sel = hp[0];
@@ -272,7 +327,7 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
         for (int k = 1; k < K; ++k) {
           if (k == lastK) sel = hp[k];
         }
-        const uint32_t s = __shfl_sync(0xFFFFFFFFu, sel, lastL);
+        const uint32_t s = __shfl_sync(FULL, sel, lastL);
         const int32_t val = lastH ? hi16(s) : lo16(s);
         if (val > nw_best) {
           nw_best = val;
@@ -311,7 +366,7 @@ __device__ void warp_fill_t(FillIo& io, const uint8_t* codes, uint32_t len, cons
       brow = br + 1;
       uint32_t u[K];
       __syncwarp();
-      row_load<K>(Hm + static_cast<uint64_t>(brow) * rw, lane, u);
+      lane_load<K>(Hm + static_cast<uint64_t>(brow) * rw + lane * K, u);
       uint32_t bc = 0xFFFFFFFFu;
 #pragma unroll
       for (int k = K - 1; k >= 0; --k) {

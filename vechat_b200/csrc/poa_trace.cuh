@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t col_word(uint32_t c, uint32_t* hi) {
 
 // returns kWalkDone or kWalkBad; *n_out = pairs written (WEIGHTS == false) or moves taken
 template <int K, bool WEIGHTS>
-__device__ int warp_trace(const TraceIo& t, uint32_t* tile, uint32_t* n_out, uint32_t* refills_out, uint32_t* slow_out) {
+__device__ __forceinline__ int warp_trace(const TraceIo& t, uint32_t* tile, uint32_t* n_out, uint32_t* refills_out, uint32_t* slow_out) {
   constexpr uint32_t rw = 32u * K;
   constexpr uint32_t TR = kTileRows, TW = kTileWords;
   const int lane = threadIdx.x & 31;

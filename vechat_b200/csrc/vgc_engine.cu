@@ -43,6 +43,12 @@ struct Job {
 };
 constexpr uint32_t kRecRing = 32;  // row records staged in shared memory by the fill
 constexpr uint32_t kJobRound = 1u << 30, kJobSW = 1u << 31, kJobLayerMask = kJobRound - 1u;
+// Alignments are dealt to one kernel per (row width, mode) class so that every kernel holds exactly one fill and one
+// traceback variant (own register allocation, small code): class = width index * 2 + (SW ? 1 : 0)
+constexpr int kClasses = 6;
+__host__ __device__ inline uint32_t job_class(uint32_t len, bool sw) {
+  return (len <= 512u ? 0u : (len <= 640u ? 1u : 2u)) * 2u + (sw ? 1u : 0u);
+}
 
 // Arguments shared by the kernels of a lockstep pass.  `idx` below is the position of a window in the
 // pass's work list (windows ordered group by group, inside a group by decreasing number of cycles).
@@ -63,6 +69,7 @@ struct KernelArgs {
   uint8_t* pool;
   uint32_t* pool_free;     // [pool_n] ring of free buffer ids, then [pool_n] = take counter, [pool_n + 1] = give counter
   unsigned long long pool_buf_bytes;
+  unsigned long long pool_fc_off;  // byte offset of the first-column values inside a buffer
   uint32_t pool_rows;      // rows a buffer holds (at the widest row)
   uint32_t pool_n;         // buffers = CTAs of align_kernel the device can hold at once
 };
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(32 * kUpdateWins) update_kernel(const KernelAr
 // of the next alignment(s); then the pending alignments go to the group's job list for align_kernel.
 template <int K>
 __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArgs a, uint32_t base, Job* jobs,
-                                                                 uint32_t* njobs) {
+                                                                 uint32_t job_cap, uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
   WinCtx c;
   if (!win_enter(a, base + blockIdx.x, kNeedPrepare, smem, &c)) return;
@@ -274,24 +281,22 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_prepare(c.w);
   if (c.ws->pc != kPcDone && c.ws->need == kNeedFill) {
+    // hand the pending alignment(s) to the job list of their class (jobs: kClasses lists of job_cap entries)
     const int lane = threadIdx.x;
+    auto emit = [&](uint32_t layer, bool sw, uint32_t flags) {
+      const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[layer + 1] - a.bv.seq_off[layer]);
+      const uint32_t cls = job_class(len, sw);
+      Job jb;
+      jb.idx = c.idx;
+      jb.layer = layer | flags | (sw ? kJobSW : 0u);
+      jobs[static_cast<size_t>(cls) * job_cap + atomicAdd(njobs + cls, 1u)] = jb;
+    };
     if (c.ws->round) {
       const uint32_t nseq = a.bv.win_nseq[c.w];
       const uint32_t* rank = a.bv.layer_rank + a.bv.win_first[c.w];
-      uint32_t at = 0;
-      if (lane == 0) at = atomicAdd(njobs, nseq);
-      at = __shfl_sync(0xFFFFFFFFu, at, 0);
-      for (uint32_t j = lane; j < nseq; j += 32) {
-        Job jb;
-        jb.idx = c.idx;
-        jb.layer = rank[j] | kJobRound | (poa.round_mode(c.w, j) == kModeSW ? kJobSW : 0u);
-        jobs[at + j] = jb;
-      }
+      for (uint32_t j = lane; j < nseq; j += 32) emit(rank[j], poa.round_mode(c.w, j) == kModeSW, kJobRound);
     } else if (lane == 0) {
-      Job jb;
-      jb.idx = c.idx;
-      jb.layer = c.ws->fill_layer | (c.ws->fill_mode == kModeSW ? kJobSW : 0u);
-      jobs[atomicAdd(njobs, 1u)] = jb;
+      emit(c.ws->fill_layer, c.ws->fill_mode == kModeSW, 0u);
     }
   }
   win_leave(a, c);
@@ -300,42 +305,6 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
 // A: one alignment = DP fill (replaces SimdAlignmentEngine::Linear's fill) + traceback, by one warp.
 // shared memory: Slot header | codes[max_len] | recs[64 x 16 B] | fill: prof[num_codes x 32K words] | ring
 //                                                                 | trace: tile | w2[len]   (overlays prof / ring)
-// fill + traceback of one alignment with rows of KR words per lane
-struct AlignOut {
-  int st;
-  uint32_t n, refills, slow;
-  unsigned long long t_fill_end;
-};
-template <int KR>
-__device__ __forceinline__ void align_one(const KernelArgs& a, FillIo& io, TraceIo& t, const uint8_t* codes, uint32_t len,
-                                          uint32_t mode, const Scores& sc, uint32_t* prof, U4* recs, const uint8_t* smem,
-                                          bool round, bool hq, const uint8_t* quals, AlignOut* out) {
-  uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
-  const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
-  const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
-  warp_fill<KR>(io, codes, len, mode, sc, a.bv.num_codes, prof, reinterpret_cast<uint4*>(recs), ring, ring_rows);
-  out->t_fill_end = clock64();
-  // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
-  __syncwarp();
-  const int lane = threadIdx.x;
-  t.row = io.best_row;
-  t.col = io.best_col;
-  uint32_t* tile = prof;
-  uint32_t* w2 = tile + kTraceTileBytes / 4;
-  t.w2 = w2;
-  if (round) {
-    for (uint32_t i = lane; i < len; i += 32) {
-      uint32_t v = 0;
-      if (i >= 1) v = hq ? a.bv.wlut[quals[i - 1]] + a.bv.wlut[quals[i]] : 2u;
-      w2[i] = v;
-    }
-    __syncwarp();
-    out->st = warp_trace<KR, true>(t, tile, &out->n, &out->refills, &out->slow);
-  } else {
-    out->st = warp_trace<KR, false>(t, tile, &out->n, &out->refills, &out->slow);
-  }
-}
-
 __device__ __forceinline__ void win_fail(const KernelArgs& a, WinState* gws, uint32_t w, uint32_t st) {
   gws->status = st;
   gws->pc = kPcDone;
@@ -343,7 +312,7 @@ __device__ __forceinline__ void win_fail(const KernelArgs& a, WinState* gws, uin
   a.status[w] = st;
 }
 
-template <int K>
+template <int KR, bool SW>
 __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelArgs a, const Job* jobs,
                                                                    const uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -353,7 +322,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   const Job jb = jobs[blockIdx.x];
   const uint32_t idx = jb.idx, l = jb.layer & kJobLayerMask;
   const bool round = (jb.layer & kJobRound) != 0;
-  const uint32_t mode = (jb.layer & kJobSW) ? kModeSW : kModeNW;
+  constexpr uint32_t mode = SW ? kModeSW : kModeNW;
   WinState* gws = a.wstates + idx;
   if (gws->pc == kPcDone) return;  // another alignment of the round failed the window
   Slot* sl = reinterpret_cast<Slot*>(smem);
@@ -385,24 +354,29 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   sw.m = 3;  // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
   sw.x = -5;
   sw.g = -4;
-  const Scores sc = mode == kModeNW ? a.nw : sw;
-  // row width for this alignment (fill_width): narrow layers run the 512-column variant
-  const uint32_t kr = fill_width(K, len);
+  const Scores sc = SW ? sw : a.nw;
   FillIo io;
   io.H = reinterpret_cast<uint32_t*>(pb);
-  io.fc = reinterpret_cast<int16_t*>(pb + static_cast<unsigned long long>(a.pool_rows) * (RowMap<K>::kWords * 4));
+  io.fc = reinterpret_cast<int16_t*>(pb + a.pool_fc_off);
   io.rowprog = sl->rowprog;
   io.ovf = sl->ovf;
   io.nR = nR;
   io.best_row = io.best_col = 0;
   io.best_score = 0;
-  AlignOut ao;
-  ao.st = kWalkDone;
-  ao.n = ao.refills = ao.slow = 0;
-  ao.t_fill_end = t0;
-  if (nR + 1 > a.pool_rows) {
-    ao.st = kWalkBad;
+  int st = kWalkDone;
+  uint32_t n = 0, refills = 0;
+  unsigned long long t1 = t0;
+  if (nR + 1 > a.pool_rows || len > 64u * KR) {
+    st = kWalkBad;
   } else {
+    // ---- fill (rows of KR words per lane; the ring of recent rows only if the shared memory holds it)
+    uint32_t* ring = prof + a.bv.num_codes * RowMap<KR>::kWords;
+    const uint32_t used = static_cast<uint32_t>(reinterpret_cast<uint8_t*>(ring) - smem);
+    const int ring_rows = used + kRingRows * (RowMap<KR>::kWords * 4 + 128) <= a.smem_bytes ? kRingRows : 0;
+    warp_fill_t<KR, SW>(io, codes, len, sc, a.bv.num_codes, prof, reinterpret_cast<uint4*>(recs), ring, ring_rows);
+    t1 = clock64();
+    // ---- traceback (the profile and the ring are dead: the tile and the weights take their place)
+    __syncwarp();
     TraceIo t;
     t.H = io.H;
     t.fc = io.fc;
@@ -413,7 +387,9 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
     t.m = sc.m;
     t.x = sc.x;
     t.g = sc.g;
-    t.sw = mode == kModeSW;
+    t.sw = SW;
+    t.row = io.best_row;
+    t.col = io.best_col;
     t.max_steps = nR + len + 2;
     t.aln_node = sl->aln_node;
     t.aln_pos = sl->aln_pos;
@@ -422,16 +398,23 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
     t.ew = sl->g[cur].ew;
     t.ieid = sl->g[cur].ieid;
     t.in_stride = sl->in_stride;
-    const bool hq = a.bv.has_qual[l] != 0;
-    const uint8_t* quals = a.bv.quals + o;
-    if (kr == 8) align_one<8>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
-    else if (kr == 10) align_one<10>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
-    else align_one<K>(a, io, t, codes, len, mode, sc, prof, recs, smem, round, hq, quals, &ao);
+    uint32_t* tile = prof;
+    uint32_t* w2 = tile + kTraceTileBytes / 4;
+    t.w2 = w2;
+    if (round) {
+      const bool hq = a.bv.has_qual[l] != 0;
+      const uint8_t* quals = a.bv.quals + o;
+      for (uint32_t i = lane; i < len; i += 32) {
+        uint32_t v = 0;
+        if (i >= 1) v = hq ? a.bv.wlut[quals[i - 1]] + a.bv.wlut[quals[i]] : 2u;
+        w2[i] = v;
+      }
+      __syncwarp();
+      st = warp_trace<KR, true>(t, tile, &n, &refills, &slow_steps);
+    } else {
+      st = warp_trace<KR, false>(t, tile, &n, &refills, &slow_steps);
+    }
   }
-  const int st = ao.st;
-  const uint32_t n = ao.n, refills = ao.refills;
-  slow_steps = ao.slow;
-  const unsigned long long t1 = ao.t_fill_end;
   __syncwarp();
   if (lane == 0) {
     __threadfence();
@@ -648,22 +631,29 @@ BatchView make_view(vgc_engine* h) {
 
 constexpr int kMaxGroups = 64;
 
-template <int K>
-int set_kernel_attrs(const vgc_engine* h, uint32_t smem_align) {
-  auto set = [](const void* f, uint32_t smem) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  };
-  VGC_CUDA(set(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * h->smem_update));
-  VGC_CUDA(set(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
-  VGC_CUDA(set(reinterpret_cast<const void*>(align_kernel<K>), smem_align));
-  return VGC_OK;
+typedef void (*AlignFn)(const KernelArgs, const Job*, const uint32_t*);
+inline AlignFn align_fn(int cls) {
+  switch (cls) {
+    case 0: return align_kernel<8, false>;
+    case 1: return align_kernel<8, true>;
+    case 2: return align_kernel<10, false>;
+    case 3: return align_kernel<10, true>;
+    case 4: return align_kernel<16, false>;
+    default: return align_kernel<16, true>;
+  }
+}
+constexpr uint32_t kClassK[kClasses] = {8, 8, 10, 10, 16, 16};
+
+inline cudaError_t set_smem_attr(const void* f, uint32_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 }
 
 template <int K>
-int align_occupancy(uint32_t smem_align, int* per_sm) {
-  VGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, align_kernel<K>, 32, smem_align));
+int set_kernel_attrs(const vgc_engine* h) {
+  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * h->smem_update));
+  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
   return VGC_OK;
 }
 
@@ -719,9 +709,25 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
   const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
-  // ---- align kernel: shared memory, residency, pool geometry
+  // ---- align kernels (one per class): shared memory, residency, pool geometry
   const uint32_t smem_budget = static_cast<uint32_t>(((228 * 1024 - VGC_ALIGN_CTAS * 1024) / VGC_ALIGN_CTAS) & ~255);
-  uint32_t smem_align = align_smem(K, pr.num_codes, ml, smem_budget);
+  uint32_t smem_align[kClasses];
+  int rc;
+  if ((rc = set_kernel_attrs<K>(h))) return rc;
+  int occ_max = 0;
+  for (int cls = 0; cls < kClasses; ++cls) {
+    smem_align[cls] = 0;
+    if (kClassK[cls] > static_cast<uint32_t>(K)) continue;  // no layer of this batch is that wide
+    smem_align[cls] = align_smem(kClassK[cls], pr.num_codes, ml, smem_budget);
+    VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(align_fn(cls)), smem_align[cls]));
+    int occ = 0;
+    VGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_fn(cls), 32, smem_align[cls]));
+    if (occ < 1) {
+      set_err("align kernel does not fit an SM (shared memory)");
+      return VGC_ERR_CAPACITY;
+    }
+    occ_max = std::max(occ_max, occ);
+  }
   size_t pos = 0;
   while (pos < wins.size()) {
     // ---- chunk: as many windows as the budget holds (the pool of DP buffers takes its share first)
@@ -736,31 +742,16 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       pool_rows = std::max<uint32_t>(pool_rows, 64) + 1;
     }
     // a buffer = pool_rows rows of 32*K words + the first-column value (int16) of every row
-    const uint64_t buf_bytes = align_up(static_cast<uint64_t>(pool_rows) * (128ull * K) + 2ull * pool_rows + 64, 256);
-    int rc;
-    if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
-    int occ = 0;
-    if ((rc = align_occupancy<K>(smem_align, &occ))) return rc;
-    if (occ < 1) {
-      set_err("align kernel does not fit an SM (shared memory)");
-      return VGC_ERR_CAPACITY;
-    }
-    uint32_t per_sm = static_cast<uint32_t>(occ);
-    // the pool may take at most 40 % of the budget: fewer buffers per SM if rows are long (exact pass, deep windows)
+    const uint64_t pool_fc_off = static_cast<uint64_t>(pool_rows) * (128ull * K);
+    const uint64_t buf_bytes = align_up(pool_fc_off + 2ull * pool_rows + 64, 256);
+    // one buffer per CTA the device can hold; the pool may take at most 40 % of the budget: with fewer buffers (long
+    // rows: exact pass, deep windows) CTAs wait for a buffer to come back
+    uint32_t per_sm = static_cast<uint32_t>(occ_max);
     const uint64_t pool_cap = h->mem_budget * 2 / 5;
     while (per_sm > 1 && static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes > pool_cap) --per_sm;
     if (static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes > h->mem_budget) {
       set_err("a window's DP matrix needs more scratch than the device memory budget");
       return VGC_ERR_CAPACITY;
-    }
-    if (per_sm < static_cast<uint32_t>(occ)) {
-      // cap the residency at the number of buffers by asking for more shared memory per CTA
-      uint32_t want = static_cast<uint32_t>((227u * 1024u / per_sm - 1024u) & ~255u);
-      want = std::min<uint32_t>(want, 200u * 1024u);
-      smem_align = std::max(smem_align, want);
-      if ((rc = set_kernel_attrs<K>(h, smem_align))) return rc;
-      if ((rc = align_occupancy<K>(smem_align, &occ))) return rc;
-      per_sm = std::max<uint32_t>(1, std::min<uint32_t>(per_sm, static_cast<uint32_t>(occ)));
     }
     const uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
     if ((rc = h->d_pool.reserve(pool_bytes))) return rc;
@@ -856,8 +847,8 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     // job lists (one per group, reused every cycle) and their per-cycle counters
     std::vector<uint64_t> gjob_off(G + 1, 0);
     for (int g = 0; g < G; ++g) gjob_off[g + 1] = gjob_off[g] + gjobs_cap[g];
-    if ((rc = h->d_jobs.reserve(std::max<uint64_t>(gjob_off[G], 1) * sizeof(Job)))) return rc;
-    const size_t ncnt = static_cast<size_t>(G) * (max_cyc + 1);
+    if ((rc = h->d_jobs.reserve(std::max<uint64_t>(gjob_off[G], 1) * kClasses * sizeof(Job)))) return rc;
+    const size_t ncnt = static_cast<size_t>(G) * (max_cyc + 1) * kClasses;
     if ((rc = h->d_jobcnt.reserve(4ull * ncnt))) return rc;
     VGC_CUDA(cudaMemsetAsync(h->d_jobcnt.p, 0, 4ull * ncnt, h->stream));
     VGC_CUDA(cudaMemcpyAsync(h->d_work.p, work.data(), 4ull * n, cudaMemcpyHostToDevice, h->stream));
@@ -884,6 +875,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     a.pool = h->d_pool.as<uint8_t>();
     a.pool_free = h->d_pool_busy.as<uint32_t>();
     a.pool_buf_bytes = buf_bytes;
+    a.pool_fc_off = pool_fc_off;
     a.pool_rows = pool_rows;
     a.pool_n = pool_n;
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
@@ -904,10 +896,26 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         ka.smem_bytes = h->smem_update;  // per window (warp)
         update_kernel<K><<<(nlive + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * ka.smem_bytes, st>>>(ka, gbase[g], nlive);
         ++nl;
-        uint64_t njobs = 0;
+        uint32_t ncls[kClasses] = {0, 0, 0, 0, 0, 0};  // alignments this cycle hands to each class kernel (exact)
         uint32_t nprep = 0;  // windows that still have a prepare step in this cycle: all but those that just emitted
         for (uint32_t i = 0; i < nlive; ++i) {
-          njobs += win_jobs(ns[i], hap, num_prune, c);
+          const uint32_t nj = win_jobs(ns[i], hap, num_prune, c);
+          if (nj) {
+            const uint32_t w = work[gbase[g] + i];
+            const uint32_t f = win_first[w];
+            if (nj > 1) {
+              for (uint32_t j = 0; j < ns[i]; ++j) {
+                const uint32_t l = pr.layer_rank[f + j];
+                ncls[job_class(static_cast<uint32_t>(seq_off[l + 1] - seq_off[l]), pr.layer_sw[l] != 0)] += 1;
+              }
+            } else if (c + 1 < ns[i]) {  // build alignment: layer c + 1 in rank order, global
+              const uint32_t l = pr.layer_rank[f + c + 1];
+              ncls[job_class(static_cast<uint32_t>(seq_off[l + 1] - seq_off[l]), false)] += 1;
+            } else {  // final local alignment of the backbone
+              const uint32_t l = pr.layer_rank[f];
+              ncls[job_class(static_cast<uint32_t>(seq_off[l + 1] - seq_off[l]), true)] += 1;
+            }
+          }
           if (win_cycles(ns[i], hap, num_prune) > c + 1) nprep = i + 1;
         }
         if (!nprep) continue;
@@ -920,14 +928,16 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
           const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
           ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
         }
-        Job* jobs = h->d_jobs.as<Job>() + gjob_off[g];
-        uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + static_cast<size_t>(g) * (max_cyc + 1) + c;
+        Job* jobs = h->d_jobs.as<Job>() + gjob_off[g] * kClasses;
+        const uint32_t job_cap = static_cast<uint32_t>(gjobs_cap[g]);
+        uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + (static_cast<size_t>(g) * (max_cyc + 1) + c) * kClasses;
         ka.smem_bytes = ss;
-        sort_kernel<K><<<nprep, 32, ss, st>>>(ka, gbase[g], jobs, cnt);
+        sort_kernel<K><<<nprep, 32, ss, st>>>(ka, gbase[g], jobs, job_cap, cnt);
         ++nl;
-        if (njobs) {
-          ka.smem_bytes = smem_align;
-          align_kernel<K><<<static_cast<uint32_t>(njobs), 32, smem_align, st>>>(ka, jobs, cnt);
+        for (int cls = 0; cls < kClasses; ++cls) {
+          if (!ncls[cls]) continue;
+          ka.smem_bytes = smem_align[cls];
+          align_fn(cls)<<<ncls[cls], 32, smem_align[cls], st>>>(ka, jobs + static_cast<size_t>(cls) * job_cap, cnt + cls);
           ++nl;
         }
       }
