@@ -159,27 +159,31 @@ __device__ __forceinline__ int warp_trace(const TraceIo& t, uint32_t* tile, uint
     // lane k: cell (i - k, j - k), taken as a chain row.  Needs: row >= 1, column >= 2, an inline record with exactly
     // one predecessor, and the four cells (own, diagonal, vertical, horizontal) inside the tile.
     bool took = false;
-    if (i >= 1 && j >= 2) {
+    // the record of the current row decides: a chain row (one predecessor) starts a RUN step, anything else goes
+    // straight to the GENERAL step (a RUN would consume nothing)
+    const U4 rec = i == 0 ? U4{0, 0, 0, 0}
+                          : ((have && i <= ti && ti - i < TR) ? recs[ti - i] : t.rp[i - 1]);
+    if (i >= 1 && j >= 2 && (rec.x & kMetaInline) && meta_npred(rec.x) == 1) {
 #pragma unroll 1
       for (int attempt = 0; attempt < 2 && !took; ++attempt) {
         const uint32_t rk = i - lane, jk = j - lane;  // wrap for lanes beyond the border: excluded below
         const bool in_rows = static_cast<uint32_t>(lane) < i && static_cast<uint32_t>(lane) + 2 <= j && have &&
                              rk <= ti && ti - rk < TR;
-        U4 rec = {0, 0, 0, 0};
-        if (in_rows) rec = recs[ti - rk];
-        const uint32_t d0 = rec.y & 0xFFFFu;
+        U4 lrec = {0, 0, 0, 0};
+        if (in_rows) lrec = recs[ti - rk];
+        const uint32_t d0 = lrec.y & 0xFFFFu;
         const uint32_t prow = rk - d0;
         uint32_t hi1, hi0;
         const uint32_t w1 = col_word<K>(jk - 1, &hi1), w0 = col_word<K>(jk - 2, &hi0);
         const bool in_cols = w1 - wb < TW && w0 - wb < TW;
-        const bool simple = in_rows && in_cols && (rec.x & kMetaInline) && meta_npred(rec.x) == 1 && d0 <= rk &&
+        const bool simple = in_rows && in_cols && (lrec.x & kMetaInline) && meta_npred(lrec.x) == 1 && d0 <= rk &&
                             ti - prow < TR;
         uint32_t mv = 3;  // 0 diagonal, 1 vertical, 2 horizontal, 3 none / not evaluated
         bool stop = false;
         if (simple) {
           const uint32_t own = tile_cell(rk, w1, hi1);
           const uint32_t cd = tile_cell(prow, w0, hi0), cv = tile_cell(prow, w1, hi1), ch = tile_cell(rk, w0, hi0);
-          const uint32_t mc = static_cast<uint32_t>(meta_code(rec.x) == t.codes[jk - 1] ? m : x);
+          const uint32_t mc = static_cast<uint32_t>(meta_code(lrec.x) == t.codes[jk - 1] ? m : x);
           const uint32_t gu = static_cast<uint32_t>(g);
           stop = sw && own == 0;
           mv = ((cd + mc) & 0xFFFFu) == own ? 0u : (((cv + gu) & 0xFFFFu) == own ? 1u : (((ch + gu) & 0xFFFFu) == own ? 2u : 3u));
@@ -213,7 +217,7 @@ __device__ __forceinline__ int warp_trace(const TraceIo& t, uint32_t* tile, uint
             if (mv == 0 && static_cast<uint32_t>(lane) + 1 < consumed && ((dmask >> (lane + 1)) & 1u))
               atomicAdd(t.wacc + (rk - 1) * kInlinePreds, t.w2[jk - 1]);
           } else {
-            t.aln_node[n + lane] = mv == 2 ? -1 : node_of(rk, rec.x);
+            t.aln_node[n + lane] = mv == 2 ? -1 : node_of(rk, lrec.x);
             t.aln_pos[n + lane] = mv == 1 ? -1 : static_cast<int32_t>(jk - 1);
           }
         }
@@ -247,8 +251,6 @@ __device__ __forceinline__ int warp_trace(const TraceIo& t, uint32_t* tile, uint
     }
     if (took) continue;
     // =============================== GENERAL step ===========================================================
-    const U4 rec = i == 0 ? U4{0, 0, 0, 0}
-                          : ((have && i <= ti && ti - i < TR) ? recs[ti - i] : t.rp[i - 1]);
     const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
     const uint32_t code = meta_code(rec.x);
     // kind: 0 diagonal, 1 vertical, 2 horizontal; psel = predecessor (in-edge slot) of a diagonal / vertical move

@@ -35,6 +35,7 @@
 namespace vgc {
 
 constexpr int kSmemHeader = 768;  // Slot + WinState copies
+constexpr int kAlignHeader = 448; // align kernels keep only the Slot copy
 
 // One pending alignment: position of its window in the pass's work list, and layer | flags.
 struct Job {
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   }
   buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
   uint8_t* pb = a.pool + static_cast<unsigned long long>(buf) * a.pool_buf_bytes;
-  uint8_t* sm = smem + kSmemHeader;
+  uint8_t* sm = smem + kAlignHeader;
   const uint32_t max_len = sl->max_len;
   uint8_t* codes = sm;
   U4* recs = reinterpret_cast<U4*>(sm + ((max_len + 15u) & ~15u));
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
 }
 
 static_assert(sizeof(Slot) + sizeof(WinState) + 32 <= kSmemHeader, "shared-memory header too small");
+static_assert(sizeof(Slot) <= kAlignHeader, "align kernel header too small");
 
 }  // namespace vgc
 
@@ -661,7 +663,7 @@ int set_kernel_attrs(const vgc_engine* h) {
 // The ring of recent rows is dropped when it does not fit `budget` (what the CTAs-per-SM target leaves); a profile
 // that does not fit either (many codes x wide rows) takes what it needs and fewer CTAs run per SM.
 uint32_t align_smem(uint32_t K, uint32_t num_codes, uint32_t max_len, uint32_t budget) {
-  const uint32_t fixed = kSmemHeader + ((max_len + 15u) & ~15u) + 16u * kRecRing;
+  const uint32_t fixed = kAlignHeader + ((max_len + 15u) & ~15u) + 16u * kRecRing;
   const uint32_t prof = num_codes * 128u * K;
   const uint32_t ring = kRingRows * (128u * K + 128u);
   const uint32_t trace = kTraceTileBytes + 4u * max_len + 16u;
