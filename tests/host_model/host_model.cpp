@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#define VGC_CHECK_ORDER 1
+unsigned long long g_order_checks[4];  // incremental order: equal to the full sort / fell back / DIFFERENT
 #include "host_prep.h"
 #include "poa_core.h"
 #include "vgc.h"
@@ -40,6 +42,7 @@ struct HostEx {
     return o;
   }
   uint32_t bcast(uint32_t v, uint32_t /*src*/) { return v; }
+  uint32_t ballot(bool p) { return p ? 1u : 0u; }
   std::vector<U4> tile_h, tile_r;  // U4: the walker fetches 16-byte vectors
   void trace_tile(uint32_t** th, U4** tr) {
     tile_h.assign(kTR * kTW / 4, U4{0, 0, 0, 0});
@@ -161,6 +164,10 @@ struct HostEx {
 }  // namespace
 
 extern "C" {
+
+void hm_order_checks(unsigned long long* out) {
+  for (int i = 0; i < 4; ++i) out[i] = g_order_checks[i];
+}
 
 void hm_dist_hist(unsigned long long* out, unsigned long long* np) {
   for (int i = 0; i < 2 * 66; ++i) out[i] = (&g_dhist[0][0])[i];

@@ -33,6 +33,7 @@ def lib():
         _lib.hm_polish.restype = C.c_int
         _lib.hm_polish.argtypes = [C.POINTER(VgcBatch), C.POINTER(VgcParams), C.POINTER(VgcResult), C.c_int, C.c_int,
                                    C.POINTER(C.c_uint32)]
+        _lib.hm_order_checks.argtypes = [C.POINTER(C.c_ulonglong)]
     return _lib
 
 
@@ -73,6 +74,25 @@ def test_host_model_fuzz_vs_oracle(seed):
     batch = fuzz_batch(seed, **kw)
     p = make_params(**pkw)
     assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d %r %r" % (seed, kw, pkw))
+
+
+def test_incremental_order_equals_full_sort():
+    """The engine maintains the topological order incrementally after AddAlignment (poa_core.h order_update: only the
+    DFS blocks an alignment touched are re-sorted).  The host model re-runs the reference's full DFS after every
+    update and compares order, ranks, owners and block tables node for node."""
+    out = (C.c_ulonglong * 4)()
+    lib().hm_order_checks(out)
+    before = list(out)
+    for seed, kw, pkw in [(520, dict(n_windows=6, partial=0.5, depth=25, length=200), dict()),
+                          (521, dict(n_windows=6, partial=0.9, err=0.3, depth=12, length=120), dict(haplotype=0)),
+                          (522, dict(n_windows=4, depth=50, length=80), dict())]:
+        batch = fuzz_batch(seed, **kw)
+        p = make_params(**pkw)
+        assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d" % seed)
+    lib().hm_order_checks(out)
+    same, fallback, different = (out[i] - before[i] for i in range(3))
+    assert different == 0, "incremental order differs from the full sort in %d updates" % different
+    assert same > 300 and same > 20 * fallback, (same, fallback)
 
 
 def ngs_batch(seed, **kw):

@@ -316,6 +316,13 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
   t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_node
   t((static_cast<uint64_t>(d.max_len) + N + 2) * 4);     // aln_pos
   t(N * kInlinePreds * 4);                                // wacc
+  t(N * 4);                                               // owner
+  t(N * 4);                                               // bsize
+  t(N * 4);                                               // bstart
+  t(N * 4);                                               // bstart2
+  t(N * 4);                                               // r2n2
+  t((static_cast<uint64_t>(d.max_len) + 2) * 4);          // anch
+  t(N);                                                   // dirty
   return off;
 }
 
@@ -372,6 +379,13 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
   P(&s->aln_node);
   P(&s->aln_pos);
   P(&s->wacc);
+  P(&s->owner);
+  P(&s->bsize);
+  P(&s->bstart);
+  P(&s->bstart2);
+  P(&s->r2n2);
+  P(&s->anch);
+  P(&s->dirty);
   s->aln_cap = d.max_len + d.max_nodes + 2;
   s->h_words = static_cast<uint32_t>(std::min<uint64_t>(d.h_words ? d.h_words : graph_scratch_words(d), 0xFFFFFFFFu));
 }

@@ -45,6 +45,12 @@
 #define VGC_INL inline
 #endif
 
+#ifdef VGC_CHECK_ORDER
+#include <algorithm>
+#include <vector>
+extern unsigned long long g_order_checks[4];
+#endif
+
 namespace vgc {
 
 constexpr int kMaxAligned = 7;     // clique size - 1  (<= kMaxCodes - 1)
@@ -153,6 +159,14 @@ struct Slot {
                        // (index r * kInlinePreds + p) by the round's concurrent alignments; folded into ew by fold_weights()
   uint32_t h_words;    // words behind H (the device keeps only the graph passes' scratch there; DP rows live in the
                        // align kernel's per-SM pool)
+  // incremental topological order (Poa::order_update): the order is a sequence of blocks, one per DFS root
+  uint32_t* owner;     // [max_nodes] node -> root of the DFS that emits it (smallest id it can reach forwards)
+  uint32_t* bsize;     // [max_nodes] root -> nodes in its block (0: not a root)
+  uint32_t* bstart;    // [max_nodes] root -> rank of its block's first node
+  uint32_t* bstart2;   // [max_nodes] the other buffer (bstart / bstart2 and r2n / r2n2 swap on every update)
+  uint32_t* r2n2;      // [max_nodes]
+  uint32_t* anch;      // [max_len + 2] per sequence position: owner of its (old or aligned-to) node, kNone: new unaligned
+  uint8_t* dirty;      // [max_nodes] root -> its block must be re-sorted (all zero between updates)
 };
 
 // Row program record (16 B per DP row, rank order):
@@ -207,6 +221,7 @@ struct WinState {
   uint32_t fill_k;       // words per lane the fill used for the pending alignment (row layout: 32 * fill_k words per half)
   uint32_t need;         // kNeed*
   uint32_t prep;         // kPrep* flags for step_prepare
+  uint32_t order_ok;     // r2n / rank_of / owner / bsize / bstart describe the current graph (maintained by order_update)
   uint32_t round;        // the pending fill is a whole re-alignment round: one alignment per sequence of the window,
                          // all against the same frozen graph (AddWeights only adds to edge weights, so they commute)
   uint32_t jobs_total;   // alignments of the pending step handed to the align kernel / how many of them are finished
@@ -589,7 +604,7 @@ struct Poa {
   //      roots, in-edges and aligned links restricted to nodes with kFMember.  Output: dst[0..n).
   template <class IdxT, class StkT>
   VGC_HD uint32_t toposort_impl(uint8_t* flags, const IdxT* off, const IdxT* adj, StkT* stack, uint32_t stack_cap,
-                                bool member_only, uint32_t* dst, bool* overflow) {
+                                bool member_only, uint32_t* dst, bool* overflow, uint32_t* own = nullptr) {
     const uint32_t nV = G().nV;
     uint32_t n = 0, sp = 0;
     *overflow = false;
@@ -637,10 +652,12 @@ struct Poa {
         if (valid) {
           flags[curr] = (fc & ~kFMarkMask) | 2;
           if (primary) {
+            if (own) own[curr] = root;
             dst[n++] = curr;
             for (uint32_t i = in_e; i < e; ++i) {
               const uint32_t a = adj[i];
               if (member_only && !(flags[a] & kFMember)) continue;
+              if (own) own[a] = root;
               dst[n++] = a;
             }
           }
@@ -680,7 +697,7 @@ struct Poa {
 
   template <bool SUB, class StkT>
   VGC_HD uint32_t toposort_fast(uint32_t* rec, const uint16_t* adj, StkT* stack, uint32_t stack_cap, uint32_t* dst,
-                                uint32_t* rank_of, bool* overflow) {
+                                uint32_t* rank_of, bool* overflow, uint32_t* own = nullptr) {
     const uint32_t nV = G().nV;
     uint32_t n = 0;
     *overflow = false;
@@ -734,12 +751,14 @@ struct Poa {
             rec[curr] = r | kRDone;
             if (primary) {
               rank_of[curr] = n;
+              if (!SUB && own) own[curr] = root;
               dst[n++] = curr;
 #pragma unroll 1
               for (uint32_t i = 0; i < nal; ++i) {
                 const uint32_t a = adj[off + nin + i];
                 if (SUB && !(rec[a] & kRMember)) continue;
                 rank_of[a] = n;
+                if (!SUB && own) own[a] = root;
                 dst[n++] = a;
               }
             }
@@ -831,17 +850,17 @@ struct Poa {
           extract_fast(rec, adj16, gstack, sub_end, sub_begin);
           n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf);
         } else {
-          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf);
+          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf, sl.owner);
         }
         if (ovf) {
           // deep recursion: redo with the big stack in HBM (records: clear the marks, keep membership)
           for (uint32_t v = 0; v < nV; ++v) rec[v] &= ~(kRExpanded | kRDone | kRIgnored);
           if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf);
-          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf);
+          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf, sl.owner);
         }
       } else {
         if (sub) extract_impl<uint32_t>(fl, goff, gadj, gstack, sub_end, sub_begin);
-        n = toposort_impl<uint32_t, uint32_t>(fl, goff, gadj, gstack, 0xFFFFFFFFu, sub, dst, &ovf);
+        n = toposort_impl<uint32_t, uint32_t>(fl, goff, gadj, gstack, 0xFFFFFFFFu, sub, dst, &ovf, sub ? nullptr : sl.owner);
       }
       ws.scratch[0] = n;
     }
@@ -854,6 +873,25 @@ struct Poa {
     staged = fast;  // the row-program builder reads the adjacency (and the ranks the sort wrote) from here
     st_rec = rec;
     st_adj = adj16;
+    if (!sub) {
+      // block tables of the incremental order: blocks are runs of equal owner in `dst`
+      for (uint32_t v = L; v < nV; v += W) {
+        sl.bsize[v] = 0;
+        sl.dirty[v] = 0;
+      }
+      ex.sync();
+      for (uint32_t q = L; q < n; q += W) {
+        const uint32_t r = sl.owner[dst[q]];
+        if (q == 0 || sl.owner[dst[q - 1]] != r) sl.bstart[r] = q;
+      }
+      ex.sync();
+      for (uint32_t q = L; q < n; q += W) {
+        const uint32_t r = sl.owner[dst[q]];
+        if (q + 1 == n || sl.owner[dst[q + 1]] != r) sl.bsize[r] = q + 1 - sl.bstart[r];
+      }
+      if (ex.leader()) ws.order_ok = (n == nV) ? 1u : 0u;
+      ex.sync();
+    }
     if (sub) {
       // keep the membership where the row-program builder can see it
       for (uint32_t v = L; v < nV; v += W) sl.flags[v] = fast ? ((rec[v] & kRMember) ? kFMember : 0) : (fl[v] & kFMember);
@@ -1010,18 +1048,23 @@ struct Poa {
     const uint32_t n = ws.aln_len;
     uint32_t* npos = sl.tmp1;  // node id of every sequence position
     const int W = ex.width(), L = ex.lane();
+    const bool track = ws.order_ok != 0;  // keep the incremental order's inputs (anchors, dirty blocks) up to date
+    uint32_t* anch = sl.anch;
     auto new_node = [&](uint32_t v, uint32_t code) {
       g.code[v] = static_cast<uint8_t>(code);
       g.nal[v] = 0;
       g.nin[v] = 0;
       g.nout[v] = 0;
       g.cov[v] = covinc;
+      sl.flags[v] = 0;
+      sl.dirty[v] = 0;
     };
     uint32_t newV = 0;
     if (n == 0) {
       for (uint32_t pos = L; pos < len; pos += W) {
         new_node(nV0 + pos, codes[pos]);
         npos[pos] = nV0 + pos;
+        anch[pos] = kNone;
       }
       newV = len;
     } else {
@@ -1045,11 +1088,13 @@ struct Poa {
       for (uint32_t pos = L; pos < vfront; pos += W) {
         new_node(nV0 + pos, codes[pos]);
         npos[pos] = nV0 + pos;
+        anch[pos] = kNone;
       }
       for (uint32_t pos = vback + 1 + L; pos < len; pos += W) {
         const uint32_t v = nV0 + nPre + (pos - vback - 1);
         new_node(v, codes[pos]);
         npos[pos] = v;
+        anch[pos] = kNone;
       }
       const uint32_t base = nV0 + nPre + nSuf;
       uint32_t carry = 0;
@@ -1108,7 +1153,12 @@ struct Poa {
         } else if (pos != -1) {
           g.cov[curr] += covinc;
         }
-        if (pos != -1) npos[pos] = curr;
+        if (pos != -1) {
+          npos[pos] = curr;
+          // anchor of the incremental order: the block owner of the node this position joins (existing node, or the
+          // aligned group a new node enters); a new unaligned node has none
+          if (track) anch[pos] = kind == 1 ? kNone : sl.owner[kind == 2 ? static_cast<uint32_t>(nd) : curr];
+        }
         carry += tot;
       }
       newV = nPre + nSuf + carry;
@@ -1155,12 +1205,249 @@ struct Poa {
         g.ein_ord[e] = slot;
         g.eout_ord[e] = g.nout[tail];
         g.nout[tail] = g.nout[tail] + 1;
+        // a new edge inside one block changes that block's DFS
+        if (track && tail < nV0 && head < nV0 && sl.owner[tail] == sl.owner[head]) sl.dirty[sl.owner[head]] = 1;
       }
       ecarry += tot;
     }
     if (ex.leader()) {
       g.nV = nV0 + newV;
       g.nE = nE0 + ecarry;
+    }
+    ex.sync();
+    if (ws.status != kStOk) return;
+    if (nV0 == 0 && n == 0) order_init_chain(len);
+    else order_update(nV0, len, npos);
+#ifdef VGC_CHECK_ORDER
+    order_check();
+#endif
+  }
+
+#ifdef VGC_CHECK_ORDER
+  // test hook (host model): the incremental order must equal the full DFS's, node for node
+  void order_check() {
+    if (!ws.order_ok) {
+      g_order_checks[1] += 1;
+      return;
+    }
+    Graph& g = G();
+    const uint32_t nV = g.nV;
+    std::vector<uint32_t> inc(sl.r2n, sl.r2n + nV), inc_owner(sl.owner, sl.owner + nV), inc_rank(sl.rank_of, sl.rank_of + nV);
+    std::vector<uint32_t> inc_bsize(sl.bsize, sl.bsize + nV), inc_bstart(sl.bstart, sl.bstart + nV);
+    std::vector<uint32_t> full(nV);
+    const uint32_t sorts = ws.sorts, hbm = ws.sorts_hbm, nm = ws.nMain;
+    uint32_t* keep = sl.r2n;
+    sl.r2n = full.data();
+    const uint32_t n = sort_graph(false, 0, 0, full.data());
+    sl.r2n = keep;
+    ws.sorts = sorts;
+    ws.sorts_hbm = hbm;
+    ws.nMain = nm;
+    bool same = n == nV;
+    for (uint32_t i = 0; same && i < nV; ++i) same = full[i] == inc[i] && sl.owner[i] == inc_owner[i] && sl.rank_of[i] == inc_rank[i] && sl.bsize[i] == inc_bsize[i] && (inc_bsize[i] == 0 || sl.bstart[i] == inc_bstart[i]);
+    g_order_checks[same ? 0 : 2] += 1;
+    std::copy(inc.begin(), inc.end(), sl.r2n);
+  }
+#endif
+
+  // ---------------------------------------------------------------------------------------------------------
+  // Incremental Graph::TopologicalSort (graph.cpp:301-371).
+  //
+  // The reference's DFS takes the roots in node-id order and, from each root that is not finished yet, emits the
+  // root's unfinished ancestors (in-edge tails and aligned nodes, transitively) in post-order, then the root.  The
+  // order is therefore a sequence of BLOCKS, one per root r, in increasing r, and node u belongs to the block of
+  //     owner(u) = the smallest id among the nodes reachable from u along out-edges and aligned links (u included),
+  // because that is the first root whose DFS reaches u.  Inside DFS(r) every node with a smaller owner is finished
+  // and no node with a larger owner is reachable, so the internal order of block r depends only on the in-lists and
+  // aligned lists of its own members.
+  //
+  // AddAlignment adds nodes with ids above every old id, and edges / aligned links along one path.  If the owners
+  // of the old nodes on the path (for a new aligned node: of the group it joins) never decrease along the path —
+  // always true when the alignment was computed on this very order, because the DP visits rows in rank order and
+  // blocks are contiguous in rank — then no old owner changes (an old node only gains successors whose owner is
+  // not smaller than its own), a new node's owner is the owner of the next such node on the path (its own id if
+  // there is none: the unaligned tail of the read), and only blocks that gained a member or an inner edge need their
+  // DFS again.  Everything else keeps its internal order and just moves by the growth of the blocks before it.
+  // Anything else (an alignment on a Subgraph view may break the monotonicity; a block too large for a lane's stack)
+  // clears ws.order_ok and the full sort runs instead.
+  VGC_HD VGC_INL static uint32_t ctz32(uint32_t m) {
+    uint32_t c = 0;
+    while (!((m >> c) & 1u)) ++c;
+    return c;
+  }
+
+  VGC_HD void order_init_chain(uint32_t len) {
+    for (uint32_t u = ex.lane(); u < len; u += ex.width()) {
+      sl.r2n[u] = u;
+      sl.rank_of[u] = u;
+      sl.owner[u] = u;
+      sl.bsize[u] = 1;
+      sl.bstart[u] = u;
+      sl.dirty[u] = 0;
+    }
+    if (ex.leader()) {
+      ws.order_ok = 1;
+      ws.nMain = len;
+    }
+    ex.sync();
+  }
+
+  // DFS of one block (root r): graph.cpp:312-368 restricted to the nodes whose owner is r.  Lane-private.
+  VGC_HD bool block_dfs(uint32_t r, uint32_t* stk, uint32_t cap, uint32_t start, uint32_t expect, uint32_t* out) {
+    Graph& g = G();
+    const uint32_t S = sl.in_stride;
+    uint32_t sp = 0, n = 0;
+    stk[sp++] = r;
+    while (sp > 0) {
+      const uint32_t curr = stk[sp - 1];
+      const uint8_t fc = sl.flags[curr];
+      if ((fc & kFMarkMask) == 2) {
+        --sp;
+        continue;
+      }
+      const uint32_t nin = g.nin[curr], nal = g.nal[curr];
+      if (sp + nin + nal + 1 > cap) return false;
+      bool valid = true;
+      for (uint32_t i = 0; i < nin; ++i) {
+        const uint32_t t = g.itail[curr * S + i];
+        if (sl.owner[t] == r && (sl.flags[t] & kFMarkMask) != 2) {
+          stk[sp++] = t;
+          valid = false;
+        }
+      }
+      const bool primary = !(fc & kFIgnored);
+      if (primary) {
+        for (uint32_t i = 0; i < nal; ++i) {
+          const uint32_t a = g.al[curr * kAlStride + i];
+          const uint8_t fa = sl.flags[a];
+          if ((fa & kFMarkMask) != 2) {
+            stk[sp++] = a;
+            sl.flags[a] = fa | kFIgnored;
+            valid = false;
+          }
+        }
+      }
+      if (valid) {
+        sl.flags[curr] = static_cast<uint8_t>((fc & ~kFMarkMask) | 2);
+        if (primary) {
+          if (n + 1 + nal > expect) return false;
+          out[start + n] = curr;
+          sl.rank_of[curr] = start + n;
+          ++n;
+          for (uint32_t i = 0; i < nal; ++i) {
+            const uint32_t a = g.al[curr * kAlStride + i];
+            out[start + n] = a;
+            sl.rank_of[a] = start + n;
+            ++n;
+          }
+        }
+        --sp;
+      } else {
+        sl.flags[curr] = static_cast<uint8_t>((fc & ~kFMarkMask) | 1);
+      }
+    }
+    return n == expect;
+  }
+
+  VGC_HD void order_update(uint32_t nV0, uint32_t len, const uint32_t* npos) {
+    if (!ws.order_ok) return;
+    Graph& g = G();
+    const uint32_t nV = g.nV;
+    const int W = ex.width(), L = ex.lane();
+    uint32_t* anch = sl.anch;
+    bool bad = ws.nMain != nV0;
+    // 1. owner of every new unaligned node = the next anchor's along the path (kNone: its own id); anchors must not
+    //    decrease.  Chunks of W positions, last chunk first; `carry` = owner of the first anchor behind the chunk.
+    uint32_t carry = kNone;
+    for (uint32_t c0 = ((len - 1) / W) * W;; c0 -= W) {
+      const uint32_t pos = c0 + L;
+      const bool valid = pos < len;
+      const uint32_t a = valid ? anch[pos] : kNone;
+      const bool is_anchor = valid && a != kNone;
+      const uint32_t mask = ex.ballot(is_anchor);
+      const uint32_t above = L + 1 < 32 ? (mask >> (L + 1)) : 0u;
+      uint32_t nxt = ex.bcast(a, above ? L + 1 + ctz32(above) : 0u);
+      if (!above) nxt = carry;
+      if (valid) {
+        if (is_anchor) {
+          if (nxt != kNone && a > nxt) bad = true;
+        } else {
+          anch[pos] = nxt;
+        }
+      }
+      if (mask) carry = ex.bcast(a, ctz32(mask));
+      if (c0 == 0) break;
+    }
+    if (ex.reduce_max(bad ? 1u : 0u)) {
+      if (ex.leader()) ws.order_ok = 0;
+      ex.sync();
+      return;
+    }
+    // 2. new nodes: owner, block sizes, dirty blocks
+    for (uint32_t v = nV0 + L; v < nV; v += W) sl.bsize[v] = 0;
+    ex.sync();
+    for (uint32_t pos = L; pos < len; pos += W) {
+      const uint32_t v = npos[pos];
+      if (v < nV0) continue;
+      const uint32_t r = anch[pos] == kNone ? v : anch[pos];
+      sl.owner[v] = r;
+      ex.atomic_add(&sl.bsize[r], 1u);
+      sl.dirty[r] = 1;
+    }
+    ex.sync();
+    // 3. new block starts (exclusive scan of the sizes over the roots) and the list of dirty roots
+    uint32_t* list = sl.tmp0;
+    uint32_t nd = 0, total = 0;
+    for (uint32_t base = 0; base < nV; base += W) {
+      const uint32_t r = base + L;
+      const uint32_t c = r < nV ? sl.bsize[r] : 0u;
+      uint32_t tot;
+      const uint32_t q = ex.excl_scan(c, &tot);
+      if (r < nV) sl.bstart2[r] = total + q;
+      total += tot;
+      const uint32_t f = (r < nV && sl.dirty[r]) ? 1u : 0u;
+      const uint32_t k = ex.excl_scan(f, &tot);
+      if (f) list[nd + k] = r;
+      nd += tot;
+    }
+    ex.sync();
+    // 4. clean blocks keep their internal order and move; nodes of dirty blocks get fresh DFS marks
+    for (uint32_t q = L; q < nV0; q += W) {
+      const uint32_t u = sl.r2n[q];
+      const uint32_t r = sl.owner[u];
+      if (sl.dirty[r]) {
+        sl.flags[u] = 0;
+      } else {
+        const uint32_t nr = sl.bstart2[r] + (q - sl.bstart[r]);
+        sl.r2n2[nr] = u;
+        sl.rank_of[u] = nr;
+      }
+    }
+    ex.sync();
+    // 5. dirty blocks: one DFS per lane at a time, lane-private stacks in the graph scratch
+    const uint32_t seg = sl.h_words / static_cast<uint32_t>(W);
+    bool ok = total == nV;
+    if (ok) {
+      for (uint32_t b = L; b < nd; b += W) {
+        const uint32_t r = list[b];
+        ok = block_dfs(r, sl.H + static_cast<size_t>(L) * seg, seg, sl.bstart2[r], sl.bsize[r], sl.r2n2) && ok;
+      }
+    }
+    const bool all_ok = ex.reduce_max(ok ? 0u : 1u) == 0;
+    ex.sync();
+    for (uint32_t b = L; b < nd; b += W) sl.dirty[list[b]] = 0;
+    if (ex.leader()) {
+      if (all_ok) {
+        uint32_t* t0 = sl.r2n;
+        sl.r2n = sl.r2n2;
+        sl.r2n2 = t0;
+        uint32_t* t1 = sl.bstart;
+        sl.bstart = sl.bstart2;
+        sl.bstart2 = t1;
+        ws.nMain = nV;
+      } else {
+        ws.order_ok = 0;
+      }
     }
     ex.sync();
   }
@@ -1617,7 +1904,8 @@ struct Poa {
         ws.k = k;
         // an alignment against a Subgraph view sorts that view itself and the graph changes again before anything
         // could use the main order, so the main sort is skipped then (the reference sorts both, with the same result)
-        ws.prep = prep | ((changed && !(prep & kPrepSubSort)) ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
+        if (largest) ws.order_ok = 0;  // LargestSubgraph rebuilds the graph: full sort
+        ws.prep = prep | ((changed && !ws.order_ok && !(prep & kPrepSubSort)) ? kPrepMainSort : 0u) | (largest ? kPrepLargest : 0u);
         ws.fill_layer = layer;
         ws.fill_mode = mode;
         ws.round = round ? 1u : 0u;

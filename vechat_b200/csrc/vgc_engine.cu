@@ -34,8 +34,8 @@
 
 namespace vgc {
 
-constexpr int kSmemHeader = 768;  // Slot + WinState copies
-constexpr int kAlignHeader = 448; // align kernels keep only the Slot copy
+constexpr int kSmemHeader = 832;  // Slot + WinState copies
+constexpr int kAlignHeader = 512; // align kernels keep only the Slot copy
 
 // One pending alignment: position of its window in the pass's work list, and layer | flags.
 struct Job {
@@ -91,6 +91,7 @@ struct WarpEx {
   __device__ __forceinline__ void sync() { __syncwarp(mask_); }
   __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) { return __shfl_sync(mask_, v, src, G); }
+  __device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(mask_, p); }
   // never used on the device: the traceback runs in align_kernel (poa_trace.cuh)
   __device__ __forceinline__ void trace_tile(uint32_t** th, U4** tr) {
     *th = nullptr;
@@ -226,6 +227,10 @@ __device__ __forceinline__ void win_leave(const KernelArgs& a, const WinCtx& c) 
     gs->g[0].nE = c.sl->g[0].nE;
     gs->g[1].nV = c.sl->g[1].nV;
     gs->g[1].nE = c.sl->g[1].nE;
+    gs->r2n = c.sl->r2n;  // the incremental order swaps its buffers
+    gs->r2n2 = c.sl->r2n2;
+    gs->bstart = c.sl->bstart;
+    gs->bstart2 = c.sl->bstart2;
   }
   copy_words(c.gws, c.ws, sizeof(WinState), c.lane, c.width);
   if (c.lane == 0 && c.ws->pc == kPcDone) {
