@@ -29,6 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+import vechat_b200  # noqa: E402,F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before torch creates the CUDA context)
 
 WORKLOAD = "pb_clr_10k_x_10kb"
 METRIC = "poa_windows_per_sec"

@@ -85,6 +85,13 @@ struct HostEx {
     *cap = c;
     return true;
   }
+  std::vector<uint32_t> blk;
+  uint32_t block_bytes = 1u << 20;  // test hook: a small value forces order_update's fallback to the full sort
+  void block_arena(uint32_t** base, uint32_t* bytes) {
+    blk.assign(block_bytes / 4 + 4, 0);
+    *base = blk.data();
+    *bytes = block_bytes;
+  }
   uint8_t* seq_codes() {
     if (codes.size() < 70000) codes.assign(70000, 0);
     return codes.data();
@@ -174,8 +181,8 @@ void hm_dist_hist(unsigned long long* out, unsigned long long* np) {
   for (int i = 0; i < 16; ++i) np[i] = g_npred[i];
 }
 
-// Same contract as ref_polish / oracle_polish.  flags: bit0 = disable the staged (16-bit) sort path,
-// bits 8.. = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).
+// Same contract as ref_polish / oracle_polish.  flags: bit0 = disable the staged (16-bit) sort path, bit1 = tiny
+// storage for the incremental order's dirty blocks, bits 8-23 = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).
 int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags, int k_regs, uint32_t* status_out) {
   Prepared prep;
   std::string err;
@@ -215,7 +222,8 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   std::vector<uint32_t> out_len(b->n_windows, 0);
   HostEx ex;
   ex.allow_fast = !(flags & 1);
-  ex.small_stack = static_cast<uint32_t>(flags) >> 8;
+  ex.small_stack = (static_cast<uint32_t>(flags) >> 8) & 0xFFFFu;
+  if (flags & 2) ex.block_bytes = 512;  // most incremental order updates then fall back to the full sort
   Scores nw{p->match, p->mismatch, p->gap};
   for (uint32_t w = 0; w < b->n_windows; ++w) {
     if (status_out) status_out[w] = 0;

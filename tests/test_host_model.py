@@ -54,9 +54,10 @@ def test_host_model_vs_committed_reference_outputs(name):
     assert_same(got, want, name)
 
 
-@pytest.mark.parametrize("flags,k", [(1, 10), (8 << 8, 10), (0, 16)])
+@pytest.mark.parametrize("flags,k", [(1, 10), (8 << 8, 10), (0, 16), (2, 10)])
 def test_host_model_slow_paths(flags, k):
-    """flags bit0: sort without the staged 16-bit CSR; flags>>8: tiny DFS stack -> overflow redo; k=16: wide rows."""
+    """flags bit0: sort without the staged 16-bit CSR; flags>>8: tiny DFS stack -> overflow redo; k=16: wide rows;
+    bit1: the incremental order's dirty blocks do not fit their storage -> full sort."""
     for seed, kw, pkw in [(301, dict(n_windows=8), dict()), (302, dict(n_windows=8, partial=0.7), dict(haplotype=0))]:
         batch = fuzz_batch(seed, **kw)
         p = make_params(**pkw)

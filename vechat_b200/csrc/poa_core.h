@@ -555,6 +555,7 @@ struct Poa {
   using RM = RowMap<K>;
   // staged graph of the last sort_graph() of this step (executor fast storage): records + 16-bit adjacency
   bool staged = false;
+  bool ranks_ok = false;  // rank_of already holds the ranks of r2n (incremental order, no sort in this step)
   const uint32_t* st_rec = nullptr;
   const uint16_t* st_adj = nullptr;
 
@@ -801,6 +802,9 @@ struct Poa {
     Graph& g = G();
     const uint32_t nV = g.nV, nE = g.nE;
     const int W = ex.width(), L = ex.lane();
+    // ranks of a Subgraph view go to their own array (r2n2 is dead between order updates): rank_of keeps describing
+    // the main order, which order_update maintains incrementally
+    uint32_t* rk = sub ? sl.r2n2 : sl.rank_of;
     uint32_t* goff = sl.H;
     // offsets = exclusive scan of (in-degree + aligned count)
     uint32_t carry = 0;
@@ -848,15 +852,15 @@ struct Poa {
       if (fast) {
         if (sub) {
           extract_fast(rec, adj16, gstack, sub_end, sub_begin);
-          n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf);
+          n = toposort_fast<true, uint16_t>(rec, adj16, stk16, stk_cap, dst, rk, &ovf);
         } else {
-          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, sl.rank_of, &ovf, sl.owner);
+          n = toposort_fast<false, uint16_t>(rec, adj16, stk16, stk_cap, dst, rk, &ovf, sl.owner);
         }
         if (ovf) {
           // deep recursion: redo with the big stack in HBM (records: clear the marks, keep membership)
           for (uint32_t v = 0; v < nV; ++v) rec[v] &= ~(kRExpanded | kRDone | kRIgnored);
-          if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf);
-          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, sl.rank_of, &ovf, sl.owner);
+          if (sub) n = toposort_fast<true, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, rk, &ovf);
+          else n = toposort_fast<false, uint32_t>(rec, adj16, gstack, 0xFFFFFFFFu, dst, rk, &ovf, sl.owner);
         }
       } else {
         if (sub) extract_impl<uint32_t>(fl, goff, gadj, gstack, sub_end, sub_begin);
@@ -905,6 +909,7 @@ struct Poa {
   VGC_HD void build_rowprog(const uint32_t* order, uint32_t nR, bool sub) {
     Graph& g = G();
     const uint32_t S = sl.in_stride;
+    uint32_t* rk = sub ? sl.r2n2 : sl.rank_of;  // see sort_graph
     if (ex.leader()) {
       ws.ovf_n = 0;
       ws.nR = nR;
@@ -921,12 +926,74 @@ struct Poa {
         }
       }
     }
-    // with a staged sort the DFS wrote rank_of itself and the in-tails are in the staged adjacency (same order)
+    // with a staged sort the DFS wrote rank_of itself and the in-tails are in the staged adjacency (same order); an
+    // order maintained incrementally (order_update) comes with its ranks too
     const bool st = staged;
-    if (!st) {
-      for (uint32_t r = ex.lane(); r < nR; r += ex.width()) sl.rank_of[order[r]] = r;
+    if (!st && !(ranks_ok && !sub)) {
+      for (uint32_t r = ex.lane(); r < nR; r += ex.width()) rk[order[r]] = r;
     }
     ex.sync();
+    if (!st && !sub) {
+      // ---- no staged copy (the sort was skipped): everything comes from HBM through three levels of dependent loads
+      //      (rank -> node -> in-tails -> their ranks), so every lane works on four rows at a time to keep
+      //      4 x (1 + 3 + 6 + 6) loads in flight instead of one chain
+      constexpr int kB = 4;
+      const int W = ex.width(), L = ex.lane();
+      for (uint32_t r0 = 0; r0 < nR; r0 += kB * W) {
+        uint32_t v[kB], ni[kB], cd[kB], no[kB], tl[kB][kInlinePreds], tr[kB][kInlinePreds];
+#pragma unroll
+        for (int t = 0; t < kB; ++t) {
+          const uint32_t r = r0 + t * W + L;
+          v[t] = r < nR ? order[r] : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < kB; ++t) {
+          const uint32_t r = r0 + t * W + L;
+          ni[t] = r < nR ? g.nin[v[t]] : 0u;
+          cd[t] = g.code[v[t]];
+          no[t] = g.nout[v[t]];
+#pragma unroll
+          for (uint32_t i = 0; i < kInlinePreds; ++i) tl[t][i] = g.itail[v[t] * S + (i < S ? i : 0u)];
+        }
+#pragma unroll
+        for (int t = 0; t < kB; ++t) {
+#pragma unroll
+          for (uint32_t i = 0; i < kInlinePreds; ++i) tr[t][i] = i < ni[t] ? rk[tl[t][i]] : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < kB; ++t) {
+          const uint32_t r = r0 + t * W + L;
+          if (r >= nR) continue;
+          const uint32_t row = r + 1, np = ni[t];
+          uint32_t d[kInlinePreds], far = 0;
+#pragma unroll
+          for (uint32_t i = 0; i < kInlinePreds; ++i) {
+            d[i] = i < np ? row - (tr[t][i] + 1) : row;
+            far |= d[i] > 0xFFFFu ? 1u : 0u;
+          }
+          const bool inl = np <= kInlinePreds && !far && row <= 0xFFFFu;
+          U4 rec;
+          if (inl) {
+            const uint32_t fill_d = d[0];
+#pragma unroll
+            for (uint32_t i = 1; i < kInlinePreds; ++i) d[i] = i < np ? d[i] : fill_d;
+            rec.y = d[0] | (d[1] << 16);
+            rec.z = d[2] | (d[3] << 16);
+            rec.w = d[4] | (d[5] << 16);
+          } else {
+            const uint32_t o = ex.atomic_add(&ws.ovf_n, np);
+            for (uint32_t i = 0; i < np; ++i) sl.ovf[o + i] = rk[g.itail[v[t] * S + i]] + 1;
+            rec.y = rec.z = 0;
+            rec.w = o;
+          }
+          if (np > kMetaMaxPred) fail(kStDegreeOverflow);
+          rec.x = meta_pack(cd[t], np, no[t] == 0, inl, v[t], inl && np <= 1 && d[0] == 1);
+          *reinterpret_cast<U4*>(sl.rowprog + 4 * static_cast<size_t>(r)) = rec;
+        }
+      }
+      ex.sync();
+      return;
+    }
     // DP rows live in rank space: row = rank + 1 (0 = the virtual row)
     for (uint32_t r = ex.lane(); r < nR; r += ex.width()) {
       const uint32_t v = order[r];
@@ -939,7 +1006,7 @@ struct Poa {
       for (uint32_t i = b; i < e; ++i) {
         const uint32_t t = st ? static_cast<uint32_t>(st_adj[i]) : g.itail[i];
         if (sub && !(st ? (st_rec[t] & kRMember) != 0 : (sl.flags[t] & kFMember) != 0)) continue;
-        const uint32_t dist = row - (sl.rank_of[t] + 1);
+        const uint32_t dist = row - (rk[t] + 1);
         if (np < kInlinePreds) d[np] = dist;
         far |= dist > 0xFFFFu ? 1u : 0u;
         ++np;
@@ -958,7 +1025,7 @@ struct Poa {
         for (uint32_t i = v * S; i < v * S + g.nin[v]; ++i) {
           const uint32_t t = g.itail[i];
           if (sub && !(sl.flags[t] & kFMember)) continue;
-          sl.ovf[o + k++] = sl.rank_of[t] + 1;
+          sl.ovf[o + k++] = rk[t] + 1;
         }
         rec.y = rec.z = 0;
         rec.w = o;
@@ -1268,8 +1335,8 @@ struct Poa {
   // not smaller than its own), a new node's owner is the owner of the next such node on the path (its own id if
   // there is none: the unaligned tail of the read), and only blocks that gained a member or an inner edge need their
   // DFS again.  Everything else keeps its internal order and just moves by the growth of the blocks before it.
-  // Anything else (an alignment on a Subgraph view may break the monotonicity; a block too large for a lane's stack)
-  // clears ws.order_ok and the full sort runs instead.
+  // Anything else (an alignment on a Subgraph view may break the monotonicity; dirty blocks that do not fit the
+  // executor's fast storage) clears ws.order_ok and the full sort runs instead.
   VGC_HD VGC_INL static uint32_t ctz32(uint32_t m) {
     uint32_t c = 0;
     while (!((m >> c) & 1u)) ++c;
@@ -1292,62 +1359,78 @@ struct Poa {
     ex.sync();
   }
 
-  // DFS of one block (root r): graph.cpp:312-368 restricted to the nodes whose owner is r.  Lane-private.
-  VGC_HD bool block_dfs(uint32_t r, uint32_t* stk, uint32_t cap, uint32_t start, uint32_t expect, uint32_t* out) {
-    Graph& g = G();
-    const uint32_t S = sl.in_stride;
-    uint32_t sp = 0, n = 0;
-    stk[sp++] = r;
-    while (sp > 0) {
-      const uint32_t curr = stk[sp - 1];
-      const uint8_t fc = sl.flags[curr];
-      if ((fc & kFMarkMask) == 2) {
-        --sp;
-        continue;
-      }
-      const uint32_t nin = g.nin[curr], nal = g.nal[curr];
-      if (sp + nin + nal + 1 > cap) return false;
-      bool valid = true;
-      for (uint32_t i = 0; i < nin; ++i) {
-        const uint32_t t = g.itail[curr * S + i];
-        if (sl.owner[t] == r && (sl.flags[t] & kFMarkMask) != 2) {
-          stk[sp++] = t;
-          valid = false;
-        }
-      }
-      const bool primary = !(fc & kFIgnored);
-      if (primary) {
-        for (uint32_t i = 0; i < nal; ++i) {
-          const uint32_t a = g.al[curr * kAlStride + i];
-          const uint8_t fa = sl.flags[a];
-          if ((fa & kFMarkMask) != 2) {
-            stk[sp++] = a;
-            sl.flags[a] = fa | kFIgnored;
-            valid = false;
+  // DFS of one dirty block over its staged copy (order_update step 5): graph.cpp:312-368 restricted to the nodes whose
+  // owner is the block's root.  Nodes carry compact ids; one 32-bit record per node: adjacency offset (bits 0-15) |
+  // in-block in-degree (16-21) | aligned count (22-25) | expanded (26) | done (27) | ignored (28).  Same single-scan
+  // scheme as toposort_fast.  Lane-private: the stack segment holds 1 + the block's adjacency entries, which bounds
+  // the pushes (a node is expanded once).
+  static constexpr uint32_t kBExpanded = 1u << 26, kBDone = 1u << 27, kBIgnored = 1u << 28;
+  VGC_HD uint32_t block_dfs(uint32_t* rec, const uint16_t* adj, const uint16_t* node, uint16_t* stack, uint32_t cap,
+                            uint32_t root, uint32_t start, uint32_t expect, uint32_t* out) {
+    uint32_t n = 0, sp = 1, curr = root, r = rec[root];
+    stack[0] = static_cast<uint16_t>(root);
+    while (true) {
+      bool pop = (r & kBDone) != 0;
+      if (!pop) {
+        const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 15u;
+        const bool primary = !(r & kBIgnored);
+        uint32_t last = kNone, last_r = 0;
+        if (!(r & kBExpanded)) {
+          if (sp + nin + nal > cap) return kNone;
+          for (uint32_t i = 0; i < nin; ++i) {
+            const uint32_t t = adj[off + i];
+            const uint32_t rt = rec[t];
+            if (!(rt & kBDone)) {
+              stack[sp++] = static_cast<uint16_t>(t);
+              last = t;
+              last_r = rt;
+            }
+          }
+          if (primary) {
+            for (uint32_t i = 0; i < nal; ++i) {
+              const uint32_t a = adj[off + nin + i];
+              const uint32_t ra = rec[a];
+              if (!(ra & kBDone)) {
+                stack[sp++] = static_cast<uint16_t>(a);
+                rec[a] = ra | kBIgnored;
+                last = a;
+                last_r = ra | kBIgnored;
+              }
+            }
           }
         }
-      }
-      if (valid) {
-        sl.flags[curr] = static_cast<uint8_t>((fc & ~kFMarkMask) | 2);
-        if (primary) {
-          if (n + 1 + nal > expect) return false;
-          out[start + n] = curr;
-          sl.rank_of[curr] = start + n;
-          ++n;
-          for (uint32_t i = 0; i < nal; ++i) {
-            const uint32_t a = g.al[curr * kAlStride + i];
-            out[start + n] = a;
-            sl.rank_of[a] = start + n;
+        if (last == kNone) {
+          rec[curr] = r | kBDone;
+          if (primary) {
+            if (n + 1 + nal > expect) return kNone;
+            const uint32_t v = node[curr];
+            out[start + n] = v;
+            sl.rank_of[v] = start + n;
             ++n;
+            for (uint32_t i = 0; i < nal; ++i) {
+              const uint32_t va = node[adj[off + nin + i]];
+              out[start + n] = va;
+              sl.rank_of[va] = start + n;
+              ++n;
+            }
           }
+          pop = true;
+        } else {
+          rec[curr] = r | kBExpanded;
+          curr = last;
+          r = last_r;
         }
-        --sp;
-      } else {
-        sl.flags[curr] = static_cast<uint8_t>((fc & ~kFMarkMask) | 1);
+      }
+      if (pop) {
+        if (--sp == 0) break;
+        curr = stack[sp - 1];
+        r = rec[curr];
       }
     }
-    return n == expect;
+    return n;
   }
+
+  static constexpr uint32_t kBDirty = 0x80000000u;  // bstart2[r]: the block of root r is re-sorted by this update
 
   VGC_HD void order_update(uint32_t nV0, uint32_t len, const uint32_t* npos) {
     if (!ws.order_ok) return;
@@ -1355,7 +1438,7 @@ struct Poa {
     const uint32_t nV = g.nV;
     const int W = ex.width(), L = ex.lane();
     uint32_t* anch = sl.anch;
-    bool bad = ws.nMain != nV0;
+    bool bad = ws.nMain != nV0 || nV >= 65535u;
     // 1. owner of every new unaligned node = the next anchor's along the path (kNone: its own id); anchors must not
     //    decrease.  Chunks of W positions, last chunk first; `carry` = owner of the first anchor behind the chunk.
     uint32_t carry = kNone;
@@ -1395,47 +1478,147 @@ struct Poa {
       sl.dirty[r] = 1;
     }
     ex.sync();
-    // 3. new block starts (exclusive scan of the sizes over the roots) and the list of dirty roots
+    // 3. new block starts (exclusive scan of the sizes over the roots; kBDirty marks the blocks to re-sort) and the
+    //    list of dirty roots.  `need[r]` (tmp1: npos is dead by now) will count the block's staged adjacency entries.
+    //    Four roots per lane and turn so that the loads of a turn are in flight together.
     uint32_t* list = sl.tmp0;
+    uint32_t* need = sl.tmp1;
     uint32_t nd = 0, total = 0;
-    for (uint32_t base = 0; base < nV; base += W) {
-      const uint32_t r = base + L;
-      const uint32_t c = r < nV ? sl.bsize[r] : 0u;
-      uint32_t tot;
-      const uint32_t q = ex.excl_scan(c, &tot);
-      if (r < nV) sl.bstart2[r] = total + q;
-      total += tot;
-      const uint32_t f = (r < nV && sl.dirty[r]) ? 1u : 0u;
-      const uint32_t k = ex.excl_scan(f, &tot);
-      if (f) list[nd + k] = r;
-      nd += tot;
-    }
-    ex.sync();
-    // 4. clean blocks keep their internal order and move; nodes of dirty blocks get fresh DFS marks
-    for (uint32_t q = L; q < nV0; q += W) {
-      const uint32_t u = sl.r2n[q];
-      const uint32_t r = sl.owner[u];
-      if (sl.dirty[r]) {
-        sl.flags[u] = 0;
-      } else {
-        const uint32_t nr = sl.bstart2[r] + (q - sl.bstart[r]);
-        sl.r2n2[nr] = u;
-        sl.rank_of[u] = nr;
+    constexpr int kU = 4;
+    for (uint32_t base = 0; base < nV; base += kU * W) {
+      uint32_t c[kU], f[kU];
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t r = base + t * W + L;
+        c[t] = r < nV ? sl.bsize[r] : 0u;
+        f[t] = r < nV ? sl.dirty[r] : 0u;
+      }
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t r = base + t * W + L;
+        uint32_t tot;
+        const uint32_t q = ex.excl_scan(c[t], &tot);
+        if (r < nV) sl.bstart2[r] = (total + q) | (f[t] ? kBDirty : 0u);
+        total += tot;
+        const uint32_t k = ex.excl_scan(f[t] ? 1u : 0u, &tot);
+        if (f[t]) {
+          list[nd + k] = r;
+          need[r] = 1;
+          sl.dirty[r] = 0;
+        }
+        nd += tot;
       }
     }
     ex.sync();
-    // 5. dirty blocks: one DFS per lane at a time, lane-private stacks in the graph scratch
-    const uint32_t seg = sl.h_words / static_cast<uint32_t>(W);
-    bool ok = total == nV;
+    // 4. clean blocks keep their internal order and move; the members of dirty blocks (every new node is one) get
+    //    compact numbers, kept in rank_of until their DFS writes the real rank
+    uint32_t* memb = sl.order;  // compact id -> node (the Subgraph order is rebuilt before every use)
+    uint32_t M = 0;
+    for (uint32_t base = 0; base < nV; base += kU * W) {
+      uint32_t q[kU], b1[kU], b2[kU];
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t u = base + t * W + L;
+        const uint32_t r = u < nV ? sl.owner[u] : 0u;
+        q[t] = u < nV0 ? sl.rank_of[u] : 0u;
+        b2[t] = u < nV ? sl.bstart2[r] : 0u;
+        b1[t] = u < nV0 ? sl.bstart[r] : 0u;
+      }
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t u = base + t * W + L;
+        const bool is_m = u < nV && (b2[t] & kBDirty) != 0;
+        uint32_t tot;
+        const uint32_t k = ex.excl_scan(is_m ? 1u : 0u, &tot);
+        if (is_m) {
+          memb[M + k] = u;
+          sl.rank_of[u] = M + k;
+        } else if (u < nV) {
+          const uint32_t nr = b2[t] + (q[t] - b1[t]);
+          sl.r2n2[nr] = u;
+          sl.rank_of[u] = nr;
+        }
+        M += tot;
+      }
+    }
+    ex.sync();
+    // 5. dirty blocks: staged in the executor's fast storage as  rec32[M] | node16[M] | adj16[A] | stacks16[A + nd]
+    //    and re-sorted there, one block per lane at a time
+    uint32_t* ab;
+    uint32_t abytes;
+    ex.block_arena(&ab, &abytes);
+    const uint32_t S = sl.in_stride;
+    bool ok = total == nV && (static_cast<uint64_t>(M) * 6u + 8u) <= abytes;
+    uint32_t* rec = ab;
+    uint16_t* node = reinterpret_cast<uint16_t*>(ab + M);
+    uint16_t* adj = node + ((M + 1u) & ~1u);
+    uint32_t A = 0;
     if (ok) {
+      // 5a. records: in-block in-degree + aligned count, adjacency offsets
+      for (uint32_t base = 0; base < M; base += W) {
+        const uint32_t c = base + L;
+        uint32_t cin = 0, nal = 0, r = 0, u = 0;
+        if (c < M) {
+          u = memb[c];
+          r = sl.owner[u];
+          const uint32_t nin = g.nin[u];
+          nal = g.nal[u];
+          for (uint32_t i = 0; i < nin; ++i) cin += sl.owner[g.itail[u * S + i]] == r ? 1u : 0u;
+          if (cin > 63u || nal > 15u) ok = false;
+        }
+        uint32_t tot;
+        const uint32_t off = ex.excl_scan(cin + nal, &tot);
+        if (c < M) {
+          rec[c] = ((A + off) & 0xFFFFu) | ((cin & 63u) << 16) | ((nal & 15u) << 22);
+          node[c] = static_cast<uint16_t>(u);
+          ex.atomic_add(&need[r], cin + nal);
+        }
+        A += tot;
+      }
+      if (A >= 65535u || static_cast<uint64_t>(M) * 6u + 8u + 2ull * A + 2ull * (A + nd) > abytes) ok = false;
+    }
+    ok = ex.reduce_max(ok ? 0u : 1u) == 0;
+    ex.sync();
+    if (ok) {
+      // 5b. adjacency (compact ids): in-block tails in in-list order, then the aligned nodes; stack segments
+      for (uint32_t c = L; c < M; c += W) {
+        const uint32_t u = memb[c];
+        const uint32_t r = sl.owner[u];
+        const uint32_t nin = g.nin[u], nal = g.nal[u];
+        uint32_t k = rec[c] & 0xFFFFu;
+        for (uint32_t i = 0; i < nin; ++i) {
+          const uint32_t t = g.itail[u * S + i];
+          if (sl.owner[t] == r) adj[k++] = static_cast<uint16_t>(sl.rank_of[t]);
+        }
+        for (uint32_t i = 0; i < nal; ++i) adj[k++] = static_cast<uint16_t>(sl.rank_of[g.al[u * kAlStride + i]]);
+      }
+      uint16_t* stacks = adj + A;
+      uint32_t scarry = 0;
+      for (uint32_t base = 0; base < nd; base += W) {
+        const uint32_t b = base + L;
+        const uint32_t r = b < nd ? list[b] : 0u;
+        const uint32_t nb = b < nd ? need[r] : 0u;
+        uint32_t tot;
+        const uint32_t so = ex.excl_scan(nb, &tot);
+        if (b < nd) need[r] = scarry + so;
+        scarry += tot;
+      }
+      ex.sync();
+      // 5c. the DFS of each dirty block
       for (uint32_t b = L; b < nd; b += W) {
         const uint32_t r = list[b];
-        ok = block_dfs(r, sl.H + static_cast<size_t>(L) * seg, seg, sl.bstart2[r], sl.bsize[r], sl.r2n2) && ok;
+        const uint32_t so = need[r];
+        const uint32_t start = sl.bstart2[r] & ~kBDirty, expect = sl.bsize[r];
+        // (the stack segment is large enough by construction: see block_dfs)
+        const uint32_t n = block_dfs(rec, adj, node, stacks + so, 0xFFFFFFFFu, sl.rank_of[r], start, expect, sl.r2n2);
+        if (n != expect) ok = false;
+        sl.bstart2[r] = start;
       }
+    } else {
+      for (uint32_t b = L; b < nd; b += W) sl.bstart2[list[b]] &= ~kBDirty;
     }
     const bool all_ok = ex.reduce_max(ok ? 0u : 1u) == 0;
     ex.sync();
-    for (uint32_t b = L; b < nd; b += W) sl.dirty[list[b]] = 0;
     if (ex.leader()) {
       if (all_ok) {
         uint32_t* t0 = sl.r2n;
@@ -1800,6 +1983,7 @@ struct Poa {
     const uint32_t prep = ws.prep;
     uint32_t nMain = ws.nMain;
     staged = false;
+    ranks_ok = ws.order_ok != 0 && !(prep & (kPrepMainSort | kPrepLargest));  // rank_of describes r2n already
     if (prep & kPrepLargest) {
       largest_subgraph();
       tick(kPhLargest);

@@ -74,14 +74,24 @@ __device__ __forceinline__ void lane_load_global(const uint32_t* p, uint32_t (&u
   }
 }
 
-// K words of this lane from / to `p` (already offset to the lane's words): 16-byte vectors when the lane stride allows
+// K words of this lane from / to shared memory at `p` (already offset to the lane's words): 16-byte vectors when the
+// lane stride allows.  With K = 8 (16) the lane stride is 32 (64) bytes, so the eight lanes of a quarter warp that one
+// LDS.128 / STS.128 wavefront serves would fall on 4 (2) distinct bank groups: the lane's 16-byte chunks are rotated
+// by `sw` chunks (lane_swizzle: a per-lane constant) so that a wavefront covers all eight groups.  Only the owning
+// lane ever reads what it wrote, so the permutation needs no agreement with anybody else.
 template <int K>
-__device__ __forceinline__ void lane_load(const uint32_t* __restrict__ p, uint32_t (&u)[K]) {
+__device__ __forceinline__ int lane_swizzle(int lane) {
+  if constexpr (K == 8) return (lane >> 2) & 1;
+  if constexpr (K == 16) return (lane >> 1) & 3;
+  return 0;
+}
+template <int K>
+__device__ __forceinline__ void lane_load(const uint32_t* __restrict__ p, uint32_t (&u)[K], int sw = 0) {
   if constexpr (K % 4 == 0) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
     for (int k = 0; k < K; k += 4) {
-      uint4 t = q[k >> 2];
+      uint4 t = q[((k >> 2) + sw) & (K / 4 - 1)];
       u[k] = t.x;
       u[k + 1] = t.y;
       u[k + 2] = t.z;
@@ -99,11 +109,11 @@ __device__ __forceinline__ void lane_load(const uint32_t* __restrict__ p, uint32
 }
 
 template <int K>
-__device__ __forceinline__ void lane_store(uint32_t* __restrict__ p, const uint32_t (&h)[K]) {
+__device__ __forceinline__ void lane_store(uint32_t* __restrict__ p, const uint32_t (&h)[K], int sw = 0) {
   if constexpr (K % 4 == 0) {
     uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
-    for (int k = 0; k < K; k += 4) q[k >> 2] = make_uint4(h[k], h[k + 1], h[k + 2], h[k + 3]);
+    for (int k = 0; k < K; k += 4) q[((k >> 2) + sw) & (K / 4 - 1)] = make_uint4(h[k], h[k + 1], h[k + 2], h[k + 3]);
   } else {
     uint2* q = reinterpret_cast<uint2*>(p);
 #pragma unroll
@@ -152,13 +162,16 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       cl[k] = a < len ? codes[a] : 0xFFu;
       ch[k] = b < len ? codes[b] : 0xFFu;
     }
+    const int swz0 = lane_swizzle<K>(lane);
     for (uint32_t c = 0; c < num_codes; ++c) {
+      uint32_t pw[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int32_t vl = cl[k] == 0xFFu ? pad : (cl[k] == c ? sc.m : sc.x);
         const int32_t vh = ch[k] == 0xFFu ? pad : (ch[k] == c ? sc.m : sc.x);
-        prof[c * RM::kWords + RM::word(lane, k)] = pack16(vl, vh);
+        pw[k] = pack16(vl, vh);
       }
+      lane_store<K>(prof + c * RM::kWords + lane * K, pw, swz0);
     }
   }
   // ---- per-lane constants
@@ -170,6 +183,7 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
   uint32_t gk[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) gk[k] = pinned(pack16(g * k, g * k));
+  const int swz = lane_swizzle<K>(lane);
   const int rot = (lane + 31) & 31;              // the lane to my left (lane 0: lane 31, whose low half feeds my high half)
   const uint32_t* const profl = prof + lane * K;  // my words of the profile rows / ring rows / matrix rows
   uint32_t* const ringl = ring + lane * K;
@@ -190,7 +204,7 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
   //  and first columns alike, so the ring needs no warp synchronisation)
   int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * rw) + lane;
   if (use_ring) {
-    lane_store<K>(ringl, hp);
+    lane_store<K>(ringl, hp, swz);
     ring_fc[0] = 0;
   }
 
@@ -222,7 +236,7 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       ++row;
       hrow += rw;
       uint32_t pr[K];
-      lane_load<K>(profl + meta_code(meta) * rw, pr);
+      lane_load<K>(profl + meta_code(meta) * rw, pr, swz);
       int32_t fcmax;
       if (meta & kMetaChain) {
         // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
@@ -252,7 +266,7 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
             fcp = fc_prev;
           } else if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
             const uint32_t slot = (row - d) & (kRingRows - 1);
-            lane_load<K>(ringl + slot * rw, u);
+            lane_load<K>(ringl + slot * rw, u, swz);
             fcp = ring_fc[slot * 32];
           } else {
             const uint32_t prow = row - d;
@@ -308,7 +322,7 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       if (!SW && lane == 0) fcm[row] = static_cast<int16_t>(fci);
       if (use_ring) {
         const uint32_t slot = row & (kRingRows - 1);
-        lane_store<K>(ringl + slot * rw, hp);
+        lane_store<K>(ringl + slot * rw, hp, swz);
         ring_fc[slot * 32] = fci;
       }
       // ---- best cell

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -73,7 +74,24 @@ struct KernelArgs {
   unsigned long long pool_fc_off;  // byte offset of the first-column values inside a buffer
   uint32_t pool_rows;      // rows a buffer holds (at the widest row)
   uint32_t pool_n;         // buffers = CTAs of align_kernel the device can hold at once
+  // diagnostics (VGC_TIMELINE=file): one record per warp-sized unit of work {start ns, duration ns, SM | kind << 16}
+  uint4* tl;               // [1 + tl_cap]; tl[0].x = records taken
+  uint32_t tl_cap;
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_record(const KernelArgs& a, uint32_t kind, unsigned long long t0) {
+  if (!a.tl) return;
+  const unsigned long long t1 = gtime_ns();
+  uint32_t sm;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  const uint32_t i = atomicAdd(&a.tl[0].x, 1u);
+  if (i < a.tl_cap) a.tl[1 + i] = make_uint4(static_cast<uint32_t>(t0), static_cast<uint32_t>(t0 >> 32), static_cast<uint32_t>(t1 - t0), sm | (kind << 16));
+}
 
 // Executor: the device side of poa_core.h's `Ex` concept.  G lanes work on one window (G = 32: a whole warp).
 template <int K, int G = 32>
@@ -147,6 +165,11 @@ struct WarpEx {
     *s = reinterpret_cast<uint16_t*>(base + so);
     *cap = (avail - so) / 2u;
     return true;
+  }
+  // order_update's staged dirty blocks
+  __device__ __forceinline__ void block_arena(uint32_t** base, uint32_t* bytes) {
+    *base = reinterpret_cast<uint32_t*>(arena());
+    *bytes = arena_bytes();
   }
   // LargestSubgraph's staged live adjacency: off16[nV+1] | adj16[nA] | visited[nV] | stack16[>= 256]
   __device__ bool stage_lsg(uint32_t nV, uint32_t nA, uint16_t** o, uint16_t** t, uint8_t** vis, uint16_t** s,
@@ -258,21 +281,53 @@ __device__ __forceinline__ WarpEx<K> make_ex(const KernelArgs& a, uint8_t* smem,
 // U: graph update + phase transitions + choice of the next alignment (Graph::AddAlignment, the end of a
 // re-alignment round, PruneGraph, GenerateCorrectedSequence / GenerateConsensus, and Window::generate_consensus'
 // control flow).
+// hand the pending alignment(s) of a window that has just been prepared to the job list of their class
+// (jobs: kClasses lists of job_cap entries, njobs: their fill counts)
+template <class P>
+__device__ __forceinline__ void emit_jobs(const KernelArgs& a, const WinCtx& c, const P& poa, Job* jobs, uint32_t job_cap,
+                                          uint32_t* njobs) {
+  if (c.ws->pc == kPcDone || c.ws->need != kNeedFill) return;
+  auto emit = [&](uint32_t layer, bool sw, uint32_t flags) {
+    const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[layer + 1] - a.bv.seq_off[layer]);
+    const uint32_t cls = job_class(len, sw);
+    Job jb;
+    jb.idx = c.idx;
+    jb.layer = layer | flags | (sw ? kJobSW : 0u);
+    jobs[static_cast<size_t>(cls) * job_cap + atomicAdd(njobs + cls, 1u)] = jb;
+  };
+  if (c.ws->round) {
+    const uint32_t nseq = a.bv.win_nseq[c.w];
+    const uint32_t* rank = a.bv.layer_rank + a.bv.win_first[c.w];
+    for (uint32_t j = c.lane; j < nseq; j += c.width) emit(rank[j], poa.round_mode(c.w, j) == kModeSW, kJobRound);
+  } else if (c.lane == 0) {
+    emit(c.ws->fill_layer, c.ws->fill_mode == kModeSW, 0u);
+  }
+}
+
 constexpr int kUpdateWins = 4;  // windows (= warps) per CTA: the SM's 32-CTA limit must not cap the light kernel
 template <int K>
-__global__ void __launch_bounds__(32 * kUpdateWins) update_kernel(const KernelArgs a, uint32_t base, uint32_t count) {
+__global__ void __launch_bounds__(32 * kUpdateWins) update_kernel(const KernelArgs a, uint32_t base, uint32_t count,
+                                                                  Job* jobs, uint32_t job_cap, uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem_all[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t i = blockIdx.x * kUpdateWins + warp;
   if (i >= count) return;
   uint8_t* smem = smem_all + warp * a.smem_bytes;
   WinCtx c;
+  const unsigned long long tl0 = a.tl ? gtime_ns() : 0ull;
   if (!win_enter(a, base + i, kNeedUpdate, smem, &c, threadIdx.x & 31)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_update(c.w, a.haplotype != 0, a.trim != 0, a.min_confidence, a.min_support, a.num_prune,
                   a.out + a.bv.out_off[c.w], a.out_len + c.w);
+  // the common case needs no sort (the order was maintained incrementally by AddAlignment): the row program is built
+  // right here and the window skips the sort kernel
+  if (c.ws->pc != kPcDone && c.ws->need == kNeedPrepare && !(c.ws->prep & (kPrepMainSort | kPrepSubSort | kPrepLargest))) {
+    poa.step_prepare(c.w);
+    emit_jobs(a, c, poa, jobs, job_cap, njobs);
+  }
   win_leave(a, c);
+  if (c.lane == 0) tl_record(a, 0, tl0);
 }
 
 // T: Graph::TopologicalSort (+ Subgraph view of a partial layer, LargestSubgraph after a prune) and the row program
@@ -282,30 +337,14 @@ __global__ void __launch_bounds__(32, VGC_SORT_CTAS) sort_kernel(const KernelArg
                                                                  uint32_t job_cap, uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
   WinCtx c;
+  const unsigned long long tl0 = a.tl ? gtime_ns() : 0ull;
   if (!win_enter(a, base + blockIdx.x, kNeedPrepare, smem, &c)) return;
   WarpEx<K> ex = make_ex<K>(a, smem, c.sl);
   Poa<WarpEx<K>, K> poa(ex, a.bv, *c.sl, *c.ws, a.nw);
   poa.step_prepare(c.w);
-  if (c.ws->pc != kPcDone && c.ws->need == kNeedFill) {
-    // hand the pending alignment(s) to the job list of their class (jobs: kClasses lists of job_cap entries)
-    const int lane = threadIdx.x;
-    auto emit = [&](uint32_t layer, bool sw, uint32_t flags) {
-      const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[layer + 1] - a.bv.seq_off[layer]);
-      const uint32_t cls = job_class(len, sw);
-      Job jb;
-      jb.idx = c.idx;
-      jb.layer = layer | flags | (sw ? kJobSW : 0u);
-      jobs[static_cast<size_t>(cls) * job_cap + atomicAdd(njobs + cls, 1u)] = jb;
-    };
-    if (c.ws->round) {
-      const uint32_t nseq = a.bv.win_nseq[c.w];
-      const uint32_t* rank = a.bv.layer_rank + a.bv.win_first[c.w];
-      for (uint32_t j = lane; j < nseq; j += 32) emit(rank[j], poa.round_mode(c.w, j) == kModeSW, kJobRound);
-    } else if (lane == 0) {
-      emit(c.ws->fill_layer, c.ws->fill_mode == kModeSW, 0u);
-    }
-  }
+  emit_jobs(a, c, poa, jobs, job_cap, njobs);
   win_leave(a, c);
+  if (c.lane == 0) tl_record(a, 1, tl0);
 }
 
 // A: one alignment = DP fill (replaces SimdAlignmentEngine::Linear's fill) + traceback, by one warp.
@@ -323,6 +362,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
                                                                    const uint32_t* njobs) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (blockIdx.x >= *njobs) return;
+  const unsigned long long tl0 = a.tl ? gtime_ns() : 0ull;
   const unsigned long long t0 = clock64();
   const int lane = threadIdx.x;
   const Job jb = jobs[blockIdx.x];
@@ -431,6 +471,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
     atomicMax(a.totals + 5 + kPhCount, t2 - t1);
     atomicAdd(a.totals + 6 + kPhCount, static_cast<unsigned long long>(slow_steps));
     atomicAdd(a.totals + 7 + kPhCount, static_cast<unsigned long long>(pool_spins));
+    tl_record(a, 2u + (SW ? 1u : 0u) + (round ? 2u : 0u), tl0);
     if (st != kWalkDone) {
       win_fail(a, gws, w, kStInternal);
     } else if (round) {
@@ -463,6 +504,15 @@ static_assert(sizeof(Slot) <= kAlignHeader, "align kernel header too small");
 namespace {
 
 thread_local std::string g_err;
+
+// A pass runs up to 48 stream groups side by side.  The driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware
+// queues (default 8); streams that share a queue serialise on each other's dependencies (measured: 31.3 k -> 34.2 k
+// windows/s with 32 queues).  The variable is read when the CUDA context is created, so it is set when the library
+// is loaded (never overriding the user's choice); hosts that create the context first set it themselves
+// (vechat_b200/__init__.py).
+struct ConnectionsInit {
+  ConnectionsInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_init;
 
 void set_err(const std::string& s) { g_err = s; }
 
@@ -532,6 +582,7 @@ struct vgc_engine {
   DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
   DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
   DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem, d_wstates;
+  DevBuf d_tl;  // diagnostics timeline (VGC_TIMELINE)
   DevBuf d_pool, d_pool_busy, d_jobs, d_jobcnt;  // align kernel: DP-matrix pool, per-group job lists, per-cycle counters
   // host staging (pinned)
   uint8_t* h_out = nullptr;
@@ -885,6 +936,15 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     a.pool_fc_off = pool_fc_off;
     a.pool_rows = pool_rows;
     a.pool_n = pool_n;
+    a.tl = nullptr;
+    a.tl_cap = 0;
+    const char* tl_path = std::getenv("VGC_TIMELINE");
+    if (tl_path) {
+      a.tl_cap = 8u << 20;
+      if ((rc = h->d_tl.reserve(16ull * (a.tl_cap + 1)))) return rc;
+      a.tl = h->d_tl.as<uint4>();
+      VGC_CUDA(cudaMemsetAsync(a.tl, 0, 16, h->stream));
+    }
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
     // ---- lockstep: the lists are sorted by decreasing cycles, so the live windows of a cycle are a prefix
@@ -901,7 +961,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         cudaStream_t st = h->gstream[g];
         KernelArgs ka = a;
         ka.smem_bytes = h->smem_update;  // per window (warp)
-        update_kernel<K><<<(nlive + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * ka.smem_bytes, st>>>(ka, gbase[g], nlive);
+        Job* jobs = h->d_jobs.as<Job>() + gjob_off[g] * kClasses;
+        const uint32_t job_cap = static_cast<uint32_t>(gjobs_cap[g]);
+        uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + (static_cast<size_t>(g) * (max_cyc + 1) + c) * kClasses;
+        update_kernel<K><<<(nlive + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * ka.smem_bytes, st>>>(ka, gbase[g], nlive, jobs, job_cap, cnt);
         ++nl;
         uint32_t ncls[kClasses] = {0, 0, 0, 0, 0, 0};  // alignments this cycle hands to each class kernel (exact)
         uint32_t nprep = 0;  // windows that still have a prepare step in this cycle: all but those that just emitted
@@ -935,9 +998,6 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
           const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
           ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
         }
-        Job* jobs = h->d_jobs.as<Job>() + gjob_off[g] * kClasses;
-        const uint32_t job_cap = static_cast<uint32_t>(gjobs_cap[g]);
-        uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + (static_cast<size_t>(g) * (max_cyc + 1) + c) * kClasses;
         ka.smem_bytes = ss;
         sort_kernel<K><<<nprep, 32, ss, st>>>(ka, gbase[g], jobs, job_cap, cnt);
         ++nl;
@@ -961,6 +1021,17 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     float kms = 0.f;
     VGC_CUDA(cudaEventElapsedTime(&kms, h->ev[6], h->ev[7]));
     h->pass_kernel_ms += kms;
+    if (tl_path) {
+      uint4 head;
+      VGC_CUDA(cudaMemcpy(&head, a.tl, 16, cudaMemcpyDeviceToHost));
+      const uint32_t nrec = std::min(head.x, a.tl_cap);
+      std::vector<uint4> recs(nrec);
+      VGC_CUDA(cudaMemcpy(recs.data(), a.tl + 1, 16ull * nrec, cudaMemcpyDeviceToHost));
+      if (FILE* f = std::fopen(tl_path, "wb")) {  // the last pass wins
+        std::fwrite(recs.data(), 16, nrec, f);
+        std::fclose(f);
+      }
+    }
     pos = e;
   }
   return VGC_OK;
@@ -1159,7 +1230,8 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
   auto smem_for = [](int ctas) { return static_cast<uint32_t>(((228 * 1024 - ctas * 1024) / ctas) & ~255); };
   h->smem_sort = smem_for(VGC_SORT_CTAS);
-  h->smem_update = std::min<uint32_t>(smem_for(VGC_UPDATE_CTAS), 4096);
+  h->smem_update = 8192;  // header + codes + the staged dirty blocks of the incremental order (poa_core.h order_update)
+  if (const char* s = std::getenv("VGC_UPDATE_SMEM")) h->smem_update = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));
   if (const char* s = std::getenv("VGC_NODE_SHARE_DIV")) h->node_share_div = static_cast<uint32_t>(std::max(1, std::atoi(s)));
@@ -1180,7 +1252,7 @@ int vgc_destroy(vgc_handle h) {
   for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
                     &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
                     &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
-                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs,
+                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs, &h->d_tl,
                     &h->d_jobcnt})
     d->release();
   if (h->h_out) cudaFreeHost(h->h_out);
