@@ -28,7 +28,7 @@ for what in "$@"; do
       python tools/launch_summary.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt ;;
     ncuk)
       # generic: NCU_KERNEL regex, NCU_SKIP, output gpurun_out/prof_${NCU_NAME}
-      VGC_GROUPS=${NCU_GROUPS:-1} timeout 1500 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL} -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_${NCU_NAME:-k} \
+      VGC_GROUPS=${NCU_GROUPS:-1} timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base ${NCU_BASE:-function} -k regex:${NCU_KERNEL} -s ${NCU_SKIP:-100} -c 1 -f -o gpurun_out/prof_${NCU_NAME:-k} \
         python bench.py --steps 1 --warmup 1 --targets ${NCU_TARGETS:-100} --no-cpu-baseline > gpurun_out/ncuk_${NCU_NAME:-k}.log 2>&1; echo "ncuk rc=$?"
       ls -la gpurun_out/prof_${NCU_NAME:-k}.ncu-rep ;;
   esac

@@ -238,66 +238,109 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       uint32_t pr[K];
       lane_load<K>(profl + meta_code(meta) * rw, pr, swz);
       int32_t fcmax;
-      if (meta & kMetaChain) {
-        // ---- chain row: the only predecessor is the row in registers; update it in place (descending k)
+      // fetch predecessor row `row - d` (d >= 2) and its first-column value: the ring of recent rows, else L2 / HBM
+      auto fetch = [&](uint32_t d, uint32_t (&u)[K], int32_t& fcp) {
+        if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
+          const uint32_t slot = (row - d) & (kRingRows - 1);
+          lane_load<K>(ringl + slot * rw, u, swz);
+          fcp = ring_fc[slot * 32];
+        } else {
+          lane_load_global<K>(hrow - static_cast<uint64_t>(d) * rw, u);
+          fcp = 0;
+          if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
+            if (lane == 0) fcp = static_cast<int32_t>(fcm[row - d]);
+            fcp = __shfl_sync(FULL, fcp, 0);
+          }
+        }
+      };
+      if ((meta & (0x7F80u | kMetaInline)) == kMetaInline) {
+        // ---- at most one predecessor (78 % of the rows): bring it into the row registers unless it is the row just
+        //      computed (distance 1), then update in place (descending k) — no copies, no loop over predecessors
+        const uint32_t d = e.y & 0xFFFFu;
+        if (d != 1) fetch(d, hp, fc_prev);
         const uint32_t y = __shfl_sync(FULL, hp[K - 1], rot);
         const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fc_prev), y, 0x5410) : y;
 #pragma unroll
         for (int k = K - 1; k >= 1; --k) hp[k] = __viaddmax_s16x2(hp[k - 1], pr[k], __vadd2(hp[k], g2));
         hp[0] = __viaddmax_s16x2(x, pr[0], __vadd2(hp[0], g2));
         fcmax = fc_prev;
+        // horizontal, in-lane part: running max over the lane's cells
+#pragma unroll
+        for (int k = 1; k < K; ++k) hp[k] = __viaddmax_s16x2(hp[k - 1], g2, hp[k]);
       } else {
-        // ---- general row: maximum over all predecessors, each from registers, the ring or memory
+        // ---- several predecessors: maximum over all of them, each from registers, the ring or memory
         const uint32_t np = meta_npred(meta);
         const U4 er = {e.x, e.y, e.z, e.w};
-        const bool inl = (meta & kMetaInline) != 0;
-        uint32_t h[K];
-        fcmax = INT32_MIN;
-        const uint32_t npp = np == 0 ? 1 : np;
-#pragma unroll 1
-        for (uint32_t p = 0; p < npp; ++p) {
-          // distance to predecessor p (rows are processed in rank order: distance 1 = the row in registers)
-          const uint32_t d = np == 0 ? row : (inl ? rec_delta(er, p) : row - ovfm[e.w + p]);
-          uint32_t u[K];
-          int32_t fcp;
-          if (d == 1) {
+        uint32_t acc[K], u[K];
+        int32_t fcp;
+        // diagonal of this lane's first cells: the previous lane's last cells
+        auto pred_first = [&](const uint32_t (&v)[K], int32_t fcv) {
+          const uint32_t y = __shfl_sync(FULL, v[K - 1], rot);
+          const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fcv), y, 0x5410) : y;
+          acc[0] = __viaddmax_s16x2(x, pr[0], __vadd2(v[0], g2));
 #pragma unroll
-            for (int k = 0; k < K; ++k) u[k] = hp[k];
-            fcp = fc_prev;
-          } else if (use_ring && d <= static_cast<uint32_t>(kRingRows)) {
-            const uint32_t slot = (row - d) & (kRingRows - 1);
-            lane_load<K>(ringl + slot * rw, u, swz);
-            fcp = ring_fc[slot * 32];
+          for (int k = 1; k < K; ++k) acc[k] = __viaddmax_s16x2(v[k - 1], pr[k], __vadd2(v[k], g2));
+          fcmax = fcv;
+        };
+        auto pred_more = [&](const uint32_t (&v)[K], int32_t fcv) {
+          const uint32_t y = __shfl_sync(FULL, v[K - 1], rot);
+          const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fcv), y, 0x5410) : y;
+          acc[0] = __viaddmax_s16x2(v[0], g2, __viaddmax_s16x2(x, pr[0], acc[0]));
+#pragma unroll
+          for (int k = 1; k < K; ++k) acc[k] = __viaddmax_s16x2(v[k], g2, __viaddmax_s16x2(v[k - 1], pr[k], acc[k]));
+          fcmax = fcv > fcmax ? fcv : fcmax;
+        };
+        if (meta & kMetaInline) {
+          // two to six predecessors, distances in the record; the first two without any indexing
+          const uint32_t d0 = e.y & 0xFFFFu, d1 = e.y >> 16;
+          if (d0 == 1) {
+            pred_first(hp, fc_prev);
           } else {
-            const uint32_t prow = row - d;
-            lane_load_global<K>(hrow - static_cast<uint64_t>(d) * rw, u);
-            fcp = 0;
-            if (!SW) {  // lane 0 owns fc[] (it wrote it): read there, broadcast
-              if (lane == 0) fcp = static_cast<int32_t>(fcm[prow]);
-              fcp = __shfl_sync(FULL, fcp, 0);
-            }
+            fetch(d0, u, fcp);
+            pred_first(u, fcp);
           }
-          fcmax = fcp > fcmax ? fcp : fcmax;
-          // diagonal of this lane's first cells: the previous lane's last cells
-          const uint32_t y = __shfl_sync(FULL, u[K - 1], rot);
-          const uint32_t x = lane == 0 ? __byte_perm(static_cast<uint32_t>(fcp), y, 0x5410) : y;
-          if (p == 0) {
-            h[0] = __viaddmax_s16x2(x, pr[0], __vadd2(u[0], g2));
-#pragma unroll
-            for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k - 1], pr[k], __vadd2(u[k], g2));
+          if (d1 == 1) {
+            pred_more(hp, fc_prev);
           } else {
-            h[0] = __viaddmax_s16x2(u[0], g2, __viaddmax_s16x2(x, pr[0], h[0]));
+            fetch(d1, u, fcp);
+            pred_more(u, fcp);
+          }
+#pragma unroll 1
+          for (uint32_t p = 2; p < np; ++p) {
+            const uint32_t d = rec_delta(er, p);
+            if (d == 1) {
 #pragma unroll
-            for (int k = 1; k < K; ++k) h[k] = __viaddmax_s16x2(u[k], g2, __viaddmax_s16x2(u[k - 1], pr[k], h[k]));
+              for (int k = 0; k < K; ++k) u[k] = hp[k];
+              fcp = fc_prev;
+            } else {
+              fetch(d, u, fcp);
+            }
+            pred_more(u, fcp);
+          }
+        } else {
+          // rare: more than six predecessors or one further than 65535 rows up (list in ovf[]); np == 0: the virtual row
+          const uint32_t npp = np == 0 ? 1 : np;
+#pragma unroll 1
+          for (uint32_t p = 0; p < npp; ++p) {
+            const uint32_t d = np == 0 ? row : row - ovfm[e.w + p];
+            if (d == 1) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) u[k] = hp[k];
+              fcp = fc_prev;
+            } else {
+              fetch(d, u, fcp);
+            }
+            if (p == 0) pred_first(u, fcp);
+            else pred_more(u, fcp);
           }
         }
+        // horizontal, in-lane part (moves the row into the row registers on the way)
+        hp[0] = acc[0];
 #pragma unroll
-        for (int k = 0; k < K; ++k) hp[k] = h[k];
+        for (int k = 1; k < K; ++k) hp[k] = __viaddmax_s16x2(hp[k - 1], g2, acc[k]);
       }
       const int32_t fci = SW ? 0 : fcmax + g;
-      // ---- horizontal: in-lane running max, then the cross-lane max-plus scan
-#pragma unroll
-      for (int k = 1; k < K; ++k) hp[k] = __viaddmax_s16x2(hp[k - 1], g2, hp[k]);
+      // ---- horizontal, cross-lane part: the max-plus scan over the lanes' segments
       uint32_t V = __vadd2(hp[K - 1], voff);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {

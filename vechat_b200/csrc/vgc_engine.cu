@@ -1230,7 +1230,7 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   // shared memory per one-warp CTA of each kernel: what its CTAs-per-SM target leaves (1 KB reserved per CTA)
   auto smem_for = [](int ctas) { return static_cast<uint32_t>(((228 * 1024 - ctas * 1024) / ctas) & ~255); };
   h->smem_sort = smem_for(VGC_SORT_CTAS);
-  h->smem_update = 8192;  // header + codes + the staged dirty blocks of the incremental order (poa_core.h order_update)
+  h->smem_update = 6144;  // header + codes + the staged dirty blocks of the incremental order (poa_core.h order_update)
   if (const char* s = std::getenv("VGC_UPDATE_SMEM")) h->smem_update = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_SORT_SMEM")) h->smem_sort = static_cast<uint32_t>(std::atoi(s));
   if (const char* s = std::getenv("VGC_GROUP_MODE")) h->group_mode = std::max(0, std::min(2, std::atoi(s)));

@@ -12,7 +12,7 @@ from ._ffi import (VgcBatch, VgcParams, VgcResult, VgcStats, WindowBatch, Polish
                    finish_result, make_params)
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvgc.so")
+LIB_PATH = os.environ.get("VGC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvgc.so")  # VGC_LIB: experiments
 
 EXPORTS = ["vgc_create", "vgc_destroy", "vgc_result_bound", "vgc_polish", "vgc_upload", "vgc_polish_resident",
            "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile"]
