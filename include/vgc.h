@@ -40,6 +40,15 @@ extern "C" {
 #define VGC_ERR_CAPACITY       4   /* a window exceeded a hard engine limit (see vgc_limits)        */
 #define VGC_ERR_NOMEM          5
 
+/* Hard limits of the engine (the reference has none of the first two; vgc_limits() reports them at run time).
+ * Within them every window runs: layers up to VGC_FAST_LAYER_LEN bases with scores inside the int16 range go through
+ * the packed int16 kernels, anything else through the int32 "wide" kernel (the reference makes the same switch of
+ * lane width, vendor/spoa/src/simd_alignment_engine_implementation.hpp:699-706). */
+#define VGC_MAX_LAYER_LEN   16383u  /* bases of one layer (racon -w up to ~8000)                      */
+#define VGC_MAX_CODES       16u     /* distinct base bytes per batch: A C G T N + all IUPAC codes     */
+#define VGC_FAST_LAYER_LEN  1024u   /* longest layer the int16 kernels take                           */
+#define VGC_MAX_BACKBONE    65535u  /* createWindow's own limit (src/window.cpp:216,232: uint16 loops) */
+
 typedef struct vgc_engine* vgc_handle;
 
 /* Scoring / pruning parameters: racon::createPolisher arguments that reach the hot path
@@ -62,7 +71,9 @@ typedef struct {
 typedef struct {
   uint32_t        n_windows;
   uint32_t        n_layers;     /* total over all windows, backbones included                  */
-  const uint8_t*  bases;        /* concatenated layer bases (any byte < 128; upper-cased)       */
+  const uint8_t*  bases;        /* concatenated layer bases (any byte < 128 — the reference indexes
+                                   its coder with a signed char; at most VGC_MAX_CODES distinct
+                                   values per batch)                                            */
   const uint8_t*  quals;        /* concatenated qualities, same offsets as bases; bytes of a
                                    layer with has_qual == 0 are ignored; may be NULL iff no
                                    layer has a quality                                          */
@@ -104,6 +115,8 @@ typedef struct {
   uint32_t relaunched_windows; /* windows re-run with a larger scratch arena                      */
 } vgc_stats;
 
+/* Fails with VGC_ERR_INVALID on the parameters spoa::AlignmentEngine::Create rejects
+ * (vendor/spoa/src/alignment_engine.cpp:37-51: positive gap penalty), same message. */
 int vgc_create(vgc_handle* out, int device, const vgc_params* params);
 int vgc_destroy(vgc_handle h);
 
@@ -126,6 +139,22 @@ int vgc_polish_resident(vgc_handle h, vgc_result* result, vgc_stats* stats);
  * kernel launches, 12 TopologicalSort runs, 13 how many of them sorted out of HBM because the staged graph did not fit
  * the kernel's shared memory. */
 int vgc_phase_profile(vgc_handle h, double out[16]);
+
+typedef struct {
+  uint32_t max_layer_len;    /* VGC_MAX_LAYER_LEN                                                  */
+  uint32_t max_backbone_len; /* VGC_MAX_BACKBONE                                                   */
+  uint32_t max_codes;        /* VGC_MAX_CODES                                                      */
+  uint32_t fast_layer_len;   /* VGC_FAST_LAYER_LEN: longer layers run on the int32 wide kernel     */
+  uint32_t int16_score_bound;/* an alignment stays on the int16 kernels while
+                                (max(rows, cols) + cols + 2) * max|score| <= this (rows = graph nodes,
+                                cols = 512 / 640 / 1024, whichever fits the layer)                 */
+  uint32_t reserved[3];
+} vgc_limits_t;
+void vgc_limits(vgc_limits_t* out);
+
+/* Per-window status of the last vgc_polish / vgc_polish_resident call of this handle (0 = ok; otherwise the
+ * engine's kSt* code of the window that made the call fail, vechat_b200/csrc/poa_core.h).  n = windows of the batch. */
+int vgc_window_status(vgc_handle h, uint32_t* status, uint32_t n);
 
 const char* vgc_last_error(void);
 const char* vgc_version(void);

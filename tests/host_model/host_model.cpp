@@ -97,10 +97,57 @@ struct HostEx {
     return codes.data();
   }
 
+  // the wide path's matrix: int32, row-major, cols = len + 1 (poa_wide.cuh on the device)
+  bool force_wide = false;
+  void fill_wide(Slot& sl, WinState& ws, const uint8_t* codes_, uint32_t len, uint32_t mode, const Scores& sc) {
+    const uint32_t nR = ws.nR;
+    const uint64_t cols = len + 1;
+    int32_t* H = reinterpret_cast<int32_t*>(sl.H);
+    for (uint32_t j = 0; j <= len; ++j) H[j] = mode == kModeSW ? 0 : static_cast<int32_t>(j) * sc.g;
+    int32_t best = mode == kModeSW ? 0 : INT32_MIN;
+    uint32_t best_row = 0, best_col = 0;
+    for (uint32_t r = 0; r < nR; ++r) {
+      const U4 er = {sl.rowprog[4 * r], sl.rowprog[4 * r + 1], sl.rowprog[4 * r + 2], sl.rowprog[4 * r + 3]};
+      const uint32_t code = meta_code(er.x), npred = meta_npred(er.x), np = npred == 0 ? 1 : npred;
+      int32_t* out = H + (r + 1) * cols;
+      for (uint32_t j = 0; j <= len; ++j) out[j] = INT32_MIN / 2;
+      for (uint32_t p = 0; p < np; ++p) {
+        const uint32_t pr = npred == 0 ? 0 : rec_pred(er, r + 1, p, sl.ovf);
+        const int32_t* hp = H + pr * cols;
+        out[0] = std::max(out[0], hp[0] + sc.g);
+        for (uint32_t j = 1; j <= len; ++j) {
+          const int32_t s = codes_[j - 1] == code ? sc.m : sc.x;
+          out[j] = std::max(out[j], std::max(hp[j - 1] + s, hp[j] + sc.g));
+        }
+      }
+      if (mode == kModeSW) out[0] = 0;
+      for (uint32_t j = 1; j <= len; ++j) {
+        out[j] = std::max(out[j], out[j - 1] + sc.g);
+        if (mode == kModeSW) {
+          out[j] = std::max(out[j], 0);
+          if (best < out[j]) {
+            best = out[j];
+            best_row = r + 1;
+            best_col = j;
+          }
+        } else if ((er.x & kMetaSink) && j == len && best < out[j]) {
+          best = out[j];
+          best_row = r + 1;
+          best_col = j;
+        }
+      }
+    }
+    ws.best_row = best_row;
+    ws.best_col = best_col;
+    ws.best_score = best;
+  }
+
   template <int K>
   void fill(Slot& sl, WinState& ws, const uint8_t* codes_, uint32_t len, uint32_t mode, const Scores& sc,
             uint32_t /*num_codes*/) {
     const uint32_t nR = ws.nR;
+    if (force_wide) ws.wide = 1;
+    if (ws.wide) return fill_wide(sl, ws, codes_, len, mode, sc);
     const uint32_t half = 32u * fill_width(K, len);  // the device's per-alignment row width
     ws.fill_k = half / 32u;
     auto cell = [&](uint32_t row, uint32_t c) -> int16_t* {  // lane-major words: low half = column w, high = 32K + w
@@ -182,7 +229,7 @@ void hm_dist_hist(unsigned long long* out, unsigned long long* np) {
 }
 
 // Same contract as ref_polish / oracle_polish.  flags: bit0 = disable the staged (16-bit) sort path, bit1 = tiny
-// storage for the incremental order's dirty blocks, bits 8-23 = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).
+// storage for the incremental order's dirty blocks, bit2 = every alignment on the wide (int32) path, bits 8-23 = fast-stack capacity override (0 = default).  k_regs selects the row template (10 or 16).
 int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags, int k_regs, uint32_t* status_out) {
   Prepared prep;
   std::string err;
@@ -194,7 +241,9 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   d.max_edges = 2 * d.max_nodes + 64;
   d.max_len = std::max<uint32_t>(prep.max_len, 16);
   d.row_words = 32 * K;
-  d.h_words = (static_cast<uint64_t>(d.max_nodes) + 1) * d.row_words;  // the host model keeps whole DP matrices here
+  // the host model keeps whole DP matrices here (packed int16 rows, or int32 rows of len + 1 cells on the wide path)
+  d.h_words = (static_cast<uint64_t>(d.max_nodes) + 1) * std::max<uint64_t>(d.row_words, d.max_len + 1);
+  d.al_stride = prep.num_codes > 8 ? 16 : 8;
   d.in_stride = 8;
   for (uint32_t w = 0; w < b->n_windows; ++w) d.in_stride = std::max(d.in_stride, prep.win_nseq[w] + 1);
   std::vector<uint8_t> buf(slot_bytes(d));
@@ -223,7 +272,8 @@ int hm_polish(const vgc_batch* b, const vgc_params* p, vgc_result* r, int flags,
   HostEx ex;
   ex.allow_fast = !(flags & 1);
   ex.small_stack = (static_cast<uint32_t>(flags) >> 8) & 0xFFFFu;
-  if (flags & 2) ex.block_bytes = 512;  // most incremental order updates then fall back to the full sort
+  if (flags & 2) ex.block_bytes = 512;
+  ex.force_wide = (flags & 4) != 0;  // every alignment through the wide (int32) path  // most incremental order updates then fall back to the full sort
   Scores nw{p->match, p->mismatch, p->gap};
   for (uint32_t w = 0; w < b->n_windows; ++w) {
     if (status_out) status_out[w] = 0;

@@ -26,15 +26,23 @@ _engines = {}
 def eng(**pkw):
     key = tuple(sorted(pkw.items()))
     if key not in _engines:
+        if len(_engines) >= 6:  # an engine keeps its scratch (GBs after a wide-path test): do not hoard them
+            for e in _engines.values():
+                e.close()
+            _engines.clear()
         _engines[key] = Engine(0, **pkw)
     return _engines[key]
 
 
+def want_of(batch, pkw):
+    """The authority: the compiled unmodified reference when its .so travelled, else the oracle port."""
+    p = make_params(**pkw)
+    return checker.ref_polish(batch, p, threads=8) if checker.have_ref() else checker.oracle_polish(batch, p, threads=8)
+
+
 def check(batch, pkw, label):
     got, st = eng(**pkw).polish(batch)
-    p = make_params(**pkw)
-    want = checker.ref_polish(batch, p, threads=8) if checker.have_ref() else checker.oracle_polish(batch, p, threads=8)
-    assert_same(got, want, label)
+    assert_same(got, want_of(batch, pkw), label)
     return st
 
 
@@ -68,9 +76,77 @@ def test_golden(name):
     (413, dict(n_windows=8, length=560, depth=12), dict()),           # rows up to ~640 columns
     (414, dict(n_windows=4, length=800, depth=8), dict()),            # wide-row template (K = 16)
     (415, dict(n_windows=4, length=800, depth=8, partial=0.6), dict(haplotype=0)),
+    (416, dict(n_windows=3, length=120, depth=200), dict()),          # fuzz to depth 200 ...
+    (417, dict(n_windows=3, length=700, depth=40, partial=0.3), dict()),   # ... and length 700
+    (418, dict(n_windows=2, length=700, depth=200), dict(haplotype=0)),
 ])
 def test_fuzz(seed, kw, pkw):
     check(fuzz_batch(seed, **kw), pkw, "seed %d" % seed)
+
+
+# ---- no capacity cliffs: the reference takes any layer length, any byte, any int8 scores ----------
+@pytest.mark.parametrize("length,depth,pkw", [
+    (1000, 10, dict()),                 # racon -w 1000: layers of ~1000-1150 bases, beyond the int16 kernels' widest row
+    (2000, 8, dict()),                  # racon -w 2000
+    (2000, 6, dict(haplotype=0)),
+    (5000, 4, dict()),
+])
+def test_long_windows_run_on_the_wide_path(length, depth, pkw):
+    b = fuzz_batch(600 + length, n_windows=3, length=length, depth=depth, partial=0.3)
+    assert max(np.diff(b.seq_off)) > 1024
+    st = check(b, pkw, "-w %d" % length)
+    assert st["relaunched_windows"] >= 0
+
+
+@pytest.mark.parametrize("pkw", [dict(), dict(haplotype=0)])
+def test_iupac_reads_more_than_eight_codes(pkw):
+    b = fuzz_batch(610, n_windows=24, length=180, depth=14, iupac_frac=0.08)
+    assert len(set(b.bases.tobytes())) >= 12
+    check(b, pkw, "IUPAC")
+
+
+def test_bytes_above_127_are_invalid():
+    """The reference indexes spoa's coder table with a signed char (it crashes on such input): rejected up front."""
+    b = fuzz_batch(611, n_windows=6, length=100, depth=8)
+    bases = b.bases.copy()
+    bases[bases == ord("T")] = 200
+    b2 = WindowBatch(bases, b.quals, b.seq_off, b.has_qual, b.begin, b.end, b.win_first, b.win_flags)
+    with pytest.raises(VgcError) as e:
+        eng().polish(b2)
+    assert e.value.code == 1 and ">= 128" in str(e.value)
+
+
+def test_more_than_sixteen_codes_is_a_capacity_error():
+    b = fuzz_batch(612, n_windows=2, length=100, depth=4)
+    bases = b.bases.copy()
+    bases[:40] = np.arange(40, dtype=np.uint8) + 40
+    b2 = WindowBatch(bases, b.quals, b.seq_off, b.has_qual, b.begin, b.end, b.win_first, b.win_flags)
+    with pytest.raises(VgcError) as e:
+        eng().polish(b2)
+    assert "16 distinct" in str(e.value)
+
+
+@pytest.mark.parametrize("pkw,depth,length", [
+    (dict(match=5, mismatch=-10, gap=-16), 60, 300),    # VERDICT: -m 5 -x -10 -g -16 leaves int16 on ~1900 rows
+    (dict(match=5, mismatch=-4, gap=-8), 200, 400),     # scripts/vechat defaults on a deep window (ADVICE r1)
+    (dict(match=127, mismatch=-128, gap=-128), 10, 150),  # int8 extremes: wide from the first alignment
+    (dict(match=5, mismatch=-10, gap=-16, haplotype=0), 60, 300),
+])
+def test_scores_beyond_int16_switch_to_int32(pkw, depth, length):
+    b = fuzz_batch(620 + depth, n_windows=2, length=length, depth=depth)
+    check(b, pkw, "scores %r depth %d" % (pkw, depth))
+
+
+def test_positive_gap_is_rejected_like_the_reference():
+    """spoa::AlignmentEngine::Create throws on g > 0 (vendor/spoa/src/alignment_engine.cpp:44-48)."""
+    with pytest.raises(VgcError) as e:
+        Engine(0, gap=1)
+    assert "gap opening penalty must be non-positive" in str(e.value)
+
+
+def test_limits_are_reported():
+    lim = eng().limits()
+    assert lim["max_layer_len"] == 16383 and lim["max_codes"] == 16 and lim["fast_layer_len"] == 1024
 
 
 @pytest.mark.parametrize("pkw", [dict(haplotype=0, trim=1), dict()])
@@ -135,7 +211,7 @@ def test_scratch_regrow_path(monkeypatch):
     b = fuzz_batch(420, n_windows=6, depth=45, length=400)
     got, st = e.polish(b)
     p = make_params()
-    assert_same(got, checker.oracle_polish(b, p, threads=8), "regrow")
+    assert_same(got, want_of(b, {}), "regrow")
     e.close()
 
 
@@ -147,7 +223,7 @@ def test_retry_pass_with_exact_capacities(monkeypatch):
     b = fuzz_batch(421, n_windows=12, depth=30, length=300, err=0.3)
     got, st = e.polish(b)
     assert st["relaunched_windows"] > 0
-    assert_same(got, checker.oracle_polish(b, make_params(), threads=8), "retry pass")
+    assert_same(got, want_of(b, {}), "retry pass")
     e.close()
 
 
@@ -162,7 +238,7 @@ def test_sort_out_of_hbm_when_shared_memory_is_short(monkeypatch, env):
         e = Engine(0, **pkw)
         b = fuzz_batch(seed, **kw)
         got, _ = e.polish(b)
-        assert_same(got, checker.oracle_polish(b, make_params(**pkw), threads=8), "hbm sort %s" % (env,))
+        assert_same(got, want_of(b, pkw), "hbm sort %s" % (env,))
         e.close()
 
 

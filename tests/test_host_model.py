@@ -54,10 +54,11 @@ def test_host_model_vs_committed_reference_outputs(name):
     assert_same(got, want, name)
 
 
-@pytest.mark.parametrize("flags,k", [(1, 10), (8 << 8, 10), (0, 16), (2, 10)])
+@pytest.mark.parametrize("flags,k", [(1, 10), (8 << 8, 10), (0, 16), (2, 10), (4, 10)])
 def test_host_model_slow_paths(flags, k):
     """flags bit0: sort without the staged 16-bit CSR; flags>>8: tiny DFS stack -> overflow redo; k=16: wide rows;
-    bit1: the incremental order's dirty blocks do not fit their storage -> full sort."""
+    bit1: the incremental order's dirty blocks do not fit their storage -> full sort; bit2: every alignment on the
+    wide (int32, any width) path."""
     for seed, kw, pkw in [(301, dict(n_windows=8), dict()), (302, dict(n_windows=8, partial=0.7), dict(haplotype=0))]:
         batch = fuzz_batch(seed, **kw)
         p = make_params(**pkw)
@@ -75,6 +76,21 @@ def test_host_model_fuzz_vs_oracle(seed):
     batch = fuzz_batch(seed, **kw)
     p = make_params(**pkw)
     assert_same(hm_polish(batch, p), checker.oracle_polish(batch, p, threads=4), "seed %d %r %r" % (seed, kw, pkw))
+
+
+@pytest.mark.parametrize("pkw", [dict(), dict(haplotype=0)])
+def test_host_model_wide_path_and_alphabet(pkw):
+    """Layers longer than the fast rows (K = 10: 640 columns) take the int32 wide path by themselves; IUPAC reads bring
+    more than 8 distinct bytes (aligned lists of stride 16); big penalties leave the int16 range on a small graph."""
+    p = make_params(**pkw)
+    b = fuzz_batch(530, n_windows=3, length=760, depth=5)
+    assert_same(hm_polish(b, p), checker.oracle_polish(b, p, threads=4), "long layers %r" % pkw)
+    b = fuzz_batch(531, n_windows=6, length=150, depth=10, iupac_frac=0.08)
+    assert len(set(b.bases.tobytes())) >= 12
+    assert_same(hm_polish(b, p), checker.oracle_polish(b, p, threads=4), "iupac %r" % pkw)
+    p2 = make_params(match=127, mismatch=-128, gap=-128, **pkw)
+    b = fuzz_batch(532, n_windows=4, length=200, depth=8)
+    assert_same(hm_polish(b, p2), checker.oracle_polish(b, p2, threads=4), "int8-extreme scores %r" % pkw)
 
 
 def test_incremental_order_equals_full_sort():

@@ -227,12 +227,13 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
     bool seen = false;
     for (const Part& part : parts) seen = seen || part.seen[c];
     if (!seen || out->coder[c] != 0xFF) continue;
-    if (c >= 128) {
+    if (c >= 128) {  // the reference indexes spoa's 256-entry coder with a (signed) char: such input crashes it
       *err = "base byte >= 128";
       return VGC_ERR_INVALID;
     }
     if (out->num_codes >= static_cast<uint32_t>(kMaxCodes)) {
-      *err = "more than 8 distinct base bytes in one batch";
+      *err = "more than 16 distinct base bytes in one batch (engine limit, see vgc_limits; the nucleotide alphabet "
+             "with N and every IUPAC ambiguity code has 16)";
       return VGC_ERR_CAPACITY;
     }
     out->coder[c] = static_cast<uint8_t>(out->num_codes);
@@ -261,15 +262,16 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
 struct SlotDims {
   uint32_t max_nodes, max_edges, max_len, row_words;
   uint32_t in_stride = 8;  // in-list capacity per node (exact bound: the number of sequences of the window)
+  uint32_t al_stride = 8;  // aligned-list capacity per node: 8, or 16 when the batch has more than 8 distinct bytes
   uint64_t h_words = 0;    // words behind Slot::H; 0 = graph_scratch_words() (device: the DP rows live in the align pool)
 };
 
 // Scratch the graph passes carve out of Slot::H: sort_graph = offsets (nV + 1) + adjacency (nE + sum of aligned
 // counts) + DFS stack (<= adjacency + nV + 1); LargestSubgraph = offsets + live adjacency (2 nE) + stack (nV);
-// heaviest bundle = 5 nV.  Aligned lists hold at most kMaxAligned entries per node.
+// heaviest bundle = 5 nV.  Aligned lists hold at most al_stride - 1 entries per node.
 inline uint64_t graph_scratch_words(const SlotDims& d) {
   const uint64_t N = d.max_nodes, E = d.max_edges;
-  return 2 * E + (4 + 2 * static_cast<uint64_t>(kMaxAligned)) * N + 1024;
+  return 2 * E + (4 + 2 * static_cast<uint64_t>(d.al_stride - 1)) * N + 1024;
 }
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -288,7 +290,7 @@ inline uint64_t slot_walk(const SlotDims& d, F&& take) {
   for (int gi = 0; gi < 2; ++gi) {
     t(N);                      // code
     t(N);                      // nal
-    t(N * kAlStride * 4);      // al
+    t(N * d.al_stride * 4);    // al
     t(N * 4);                  // nin
     t(N * 4);                  // nout
     t(N * 4);                  // cov
@@ -346,6 +348,7 @@ inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
   s->max_len = d.max_len;
   s->row_words = d.row_words;
   s->in_stride = d.in_stride;
+  s->al_stride = d.al_stride;
   for (int gi = 0; gi < 2; ++gi) {
     Graph& g = s->g[gi];
     g.nV = g.nE = 0;

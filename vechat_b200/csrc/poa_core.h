@@ -53,12 +53,12 @@ extern unsigned long long g_order_checks[4];
 
 namespace vgc {
 
-constexpr int kMaxAligned = 7;     // clique size - 1  (<= kMaxCodes - 1)
-constexpr int kAlStride = 8;       // aligned-list stride per node (32 B: the first four ids load as one 16 B vector)
+constexpr int kMaxAligned = 15;    // clique size - 1  (<= kMaxCodes - 1)
+// aligned-list stride per node = Slot::al_stride: 8 ids (32 B) while the batch has at most 8 distinct bytes, else 16
 struct alignas(16) U4 {
   uint32_t x, y, z, w;
 };
-constexpr int kMaxCodes = 8;       // distinct bytes per batch
+constexpr int kMaxCodes = 16;      // distinct bytes per batch (A C G T N + the IUPAC ambiguity codes fit)
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 // window status codes (device -> host)
@@ -72,6 +72,7 @@ enum : uint32_t {
   kStAlignedOverflow = 6,
   kStInternal = 7,
   kStDegreeOverflow = 8, // a node's in-degree outgrew the slot's in-list stride: rerun with a larger one
+  kStWideCapacity = 9,   // the int32 matrix of a wide alignment does not fit the wide pool's buffers
 };
 
 enum : uint32_t { kModeNW = 0, kModeSW = 1 };
@@ -87,7 +88,6 @@ enum : uint8_t {
   kFIgnored = 4,
   kFHasAligned = 8,
   kFMember = 16,
-  kFNalShift = 5,   // bits 5..7: number of aligned nodes (<= kMaxAligned)
 };
 
 struct Scores {
@@ -121,7 +121,7 @@ struct Graph {
   uint32_t nV, nE;
   uint8_t* code;
   uint8_t* nal;
-  uint32_t* al;        // [max_nodes * kAlStride]
+  uint32_t* al;        // [max_nodes * al_stride]
   uint32_t* nin;
   uint32_t* nout;
   uint32_t* cov;       // sequences through the node (linear mode coverage)
@@ -139,6 +139,7 @@ struct Graph {
 struct Slot {
   uint32_t max_nodes, max_edges, max_len, row_words;
   uint32_t in_stride;  // capacity of a node's in-list
+  uint32_t al_stride;  // capacity of a node's aligned list (8 or 16)
   Graph g[2];
   uint32_t* out_off;   // [max_nodes + 1]
   uint32_t* out_eid;   // [max_edges]
@@ -221,6 +222,8 @@ struct WinState {
   uint32_t fill_k;       // words per lane the fill used for the pending alignment (row layout: 32 * fill_k words per half)
   uint32_t need;         // kNeed*
   uint32_t prep;         // kPrep* flags for step_prepare
+  uint32_t wide;         // the pending alignment(s) run in the int32 / any-width kernel (wide_* below): a layer longer
+                         // than the fast rows, or scores beyond the int16 range for this graph
   uint32_t order_ok;     // r2n / rank_of / owner / bsize / bstart describe the current graph (maintained by order_update)
   uint32_t round;        // the pending fill is a whole re-alignment round: one alignment per sequence of the window,
                          // all against the same frozen graph (AddWeights only adds to edge weights, so they commute)
@@ -286,7 +289,7 @@ struct TraceWalker {
   const uint32_t* ovf;
   const uint32_t* nodes;   // rank -> node id; nullptr: the id is in the row record (slots below 65536 nodes)
   const uint8_t* seq;      // the sequence's bases
-  uint64_t dec64;          // code -> base byte, 8 codes packed (byte c = decoder[c])
+  const uint8_t* dec;      // code -> base byte
   int32_t* aln_node;
   int32_t* aln_pos;
   uint32_t aln_cap, rw, half_words;
@@ -303,12 +306,7 @@ struct TraceWalker {
   uint32_t ti, wb, rec_base;  // tile anchor row, first word, row of tr[0]
   bool have, fresh, started;
 
-  VGC_HD VGC_INL static uint64_t pack_decoder(const uint8_t* decoder) {
-    uint64_t d = 0;
-    for (int c = 0; c < kMaxCodes; ++c) d |= static_cast<uint64_t>(decoder[c]) << (8 * c);
-    return d;
-  }
-  VGC_HD VGC_INL uint32_t base_of(uint32_t code) const { return static_cast<uint32_t>(dec64 >> (8 * code)) & 0xFFu; }
+  VGC_HD VGC_INL uint32_t base_of(uint32_t code) const { return dec[code]; }
   VGC_HD VGC_INL static int32_t half_of(uint32_t v, uint32_t hi) {
     return static_cast<int16_t>(hi ? (v >> 16) : (v & 0xFFFFu));
   }
@@ -544,6 +542,102 @@ struct TraceWalker {
 // ---------------------------------------------------------------------------------------------------
 // The algorithm.  Ex (executor) provides: lane(), width(), leader(), sync(), atomic_add(u32*,u32),
 // excl_scan(v, &total), fill<K>(...) and the flag/CSR staging storage.
+// ---------------------------------------------------------------------------------------------------
+// Wide path: alignments the packed int16 kernels cannot take (a layer longer than their widest row, or scores that
+// may leave the int16 range on this graph) run on an int32 matrix of any width.  Replaces the same reference code as
+// the fast path (simd_alignment_engine_implementation.hpp:760-1105 with the int32 lanes the reference selects at
+// :699-706).  The matrix is row-major: H[row * cols + j], cols = len + 1, column 0 = the first column, row 0 = the
+// virtual row; rows in rank space like everywhere else.  The fill is in poa_wide.cuh (device) and in the host model;
+// the traceback below is shared by both: every lane computes the same walk, the leader writes.
+struct WideIo {
+  const int32_t* H;
+  uint32_t cols;
+  const U4* rp;            // row program (rank order)
+  const uint32_t* ovf;
+  const uint32_t* nodes;   // rank -> node id; nullptr: the id is in the row record
+  const uint8_t* codes;    // codes of the sequence
+  int32_t m, x, g;
+  bool sw;
+  uint32_t row, col;       // start cell; 0,0 = empty alignment
+  uint32_t max_steps;
+  int32_t* aln_node;       // WEIGHTS == false: the alignment, reversed
+  int32_t* aln_pos;
+  uint32_t aln_cap;
+  uint32_t* ew;            // WEIGHTS == true: Graph::AddWeights fused into the walk (see poa_trace.cuh)
+  const uint32_t* ieid;
+  uint32_t in_stride;
+  const uint8_t* quals;    // qualities of the sequence (nullptr: every base weighs 1)
+  const uint32_t* wlut;    // quality byte -> weight
+};
+
+template <bool WEIGHTS, class Ex>
+VGC_HD int wide_trace(Ex& ex, const WideIo& t, uint32_t* n_out) {
+  uint32_t i = t.row, j = t.col, n = 0;
+  *n_out = 0;
+  if (i == 0 && j == 0) return kWalkDone;
+  const int32_t m = t.m, x = t.x, g = t.g;
+  const uint64_t cols = t.cols;
+  uint32_t pend = kNone, pend_w = 0;  // WEIGHTS: edge of the matched pair emitted last
+  while (true) {
+    if (!t.sw && i == 0 && j == 0) break;
+    if (n >= t.max_steps) return kWalkBad;
+    const int32_t h = t.H[i * cols + j];
+    if (t.sw && h == 0) break;
+    U4 rec = {0, 0, 0, 0};
+    if (i != 0) rec = t.rp[i - 1];
+    const uint32_t np = i != 0 ? meta_npred(rec.x) : 0u;
+    const uint32_t npp = i != 0 ? (np == 0 ? 1u : np) : 0u;
+    int32_t mc = 0;
+    if (i != 0 && j != 0) mc = meta_code(rec.x) == t.codes[j - 1] ? m : x;
+    uint32_t kind = 3, psel = 0, pi = i;
+    if (j != 0) {
+      for (uint32_t p = 0; p < npp && kind == 3; ++p) {
+        const uint32_t pr = np == 0 ? 0u : rec_pred(rec, i, p, t.ovf);
+        if (h == t.H[pr * cols + j - 1] + mc) {
+          kind = 0;
+          psel = p;
+          pi = pr;
+        }
+      }
+    }
+    for (uint32_t p = 0; p < npp && kind == 3; ++p) {
+      const uint32_t pr = np == 0 ? 0u : rec_pred(rec, i, p, t.ovf);
+      if (h == t.H[pr * cols + j] + g) {
+        kind = 1;
+        psel = p;
+        pi = pr;
+      }
+    }
+    if (kind == 3 && j != 0 && h == t.H[i * cols + j - 1] + g) {
+      kind = 2;
+      pi = i;
+    }
+    if (kind == 3) return kWalkBad;
+    const uint32_t nd = i != 0 ? (t.nodes ? t.nodes[i - 1] : meta_node(rec.x)) : 0u;
+    if (WEIGHTS) {
+      if (kind == 0) {
+        if (pend != kNone && ex.leader()) ex.atomic_add(t.ew + pend, pend_w);
+        pend = np == 0 ? kNone : t.ieid[static_cast<uint64_t>(nd) * t.in_stride + psel];
+        // weight(pos - 1) + weight(pos) for pos = j - 1 (a pair at pos 0 is never followed by a matched pair)
+        pend_w = j >= 2 ? (t.quals ? t.wlut[t.quals[j - 2]] + t.wlut[t.quals[j - 1]] : 2u) : 0u;
+      } else {
+        pend = kNone;
+      }
+    } else {
+      if (n >= t.aln_cap) return kWalkBad;
+      if (ex.leader()) {
+        t.aln_node[n] = kind == 2 ? -1 : static_cast<int32_t>(nd);
+        t.aln_pos[n] = kind == 1 ? -1 : static_cast<int32_t>(j - 1);
+      }
+    }
+    ++n;
+    i = pi;
+    if (kind != 1) j = j - 1;
+  }
+  *n_out = n;
+  return kWalkDone;
+}
+
 template <class Ex, int K>
 struct Poa {
   Ex& ex;
@@ -622,7 +716,7 @@ struct Poa {
           continue;
         }
         const uint32_t b = off[curr], e = off[curr + 1];
-        const uint32_t in_e = e - (fc >> kFNalShift);
+        const uint32_t in_e = b + G().nin[curr];  // adjacency = in-tails, then the aligned nodes
         if (sp + (e - b) + 1 > stack_cap) {
           *overflow = true;
           return 0;
@@ -689,11 +783,11 @@ struct Poa {
   }
 
   // ---- the same sort over the staged graph of the executor's fast storage.  One 32-bit record per node:
-  //      adjacency offset (bits 0-15) | in-degree (16-21) | aligned count (22-24) | expanded (25) | done (26) |
-  //      ignored (27) | member (28).  A node is scanned once: the first visit pushes what is not done yet and
+  //      adjacency offset (bits 0-15) | in-degree (16-21) | aligned count (22-25) | expanded (26) | done (27) |
+  //      ignored (28) | member (29).  A node is scanned once: the first visit pushes what is not done yet and
   //      marks it expanded; when it surfaces again everything it pushed is done (the graph is a DAG), so the second
   //      visit only emits — the reference re-scans and finds exactly that (graph.cpp:318-352).
-  static constexpr uint32_t kRExpanded = 1u << 25, kRDone = 1u << 26, kRIgnored = 1u << 27, kRMember = 1u << 28;
+  static constexpr uint32_t kRExpanded = 1u << 26, kRDone = 1u << 27, kRIgnored = 1u << 28, kRMember = 1u << 29;
   VGC_HD VGC_INL static uint32_t rec_pack(uint32_t off, uint32_t nin, uint32_t nal) { return off | (nin << 16) | (nal << 22); }
 
   template <bool SUB, class StkT>
@@ -713,7 +807,7 @@ struct Poa {
       while (true) {
         bool pop = (r & kRDone) != 0;
         if (!pop) {
-          const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 7u;
+          const uint32_t off = r & 0xFFFFu, nin = (r >> 16) & 63u, nal = (r >> 22) & 15u;
           const bool primary = !(r & kRIgnored);
           uint32_t last = kNone, last_r = 0;
           if (!(r & kRExpanded)) {
@@ -787,7 +881,7 @@ struct Poa {
       const uint32_t curr = stack[--sp];
       const uint32_t r = rec[curr];
       if (!(r & kRMember) && curr >= floor_id) {
-        const uint32_t off = r & 0xFFFFu, cnt = ((r >> 16) & 63u) + ((r >> 22) & 7u);
+        const uint32_t off = r & 0xFFFFu, cnt = ((r >> 16) & 63u) + ((r >> 22) & 15u);
 #pragma unroll 1
         for (uint32_t i = 0; i < cnt; ++i) stack[sp++] = adj[off + i];
         rec[curr] = r | kRMember;
@@ -833,12 +927,12 @@ struct Poa {
       const uint32_t na = g.nal[v];
       const uint32_t o = goff[v] + g.nin[v];
       for (uint32_t i = 0; i < na; ++i) {
-        const uint32_t a = g.al[v * kAlStride + i];
+        const uint32_t a = g.al[v * sl.al_stride + i];
         if (fast) adj16[o + i] = static_cast<uint16_t>(a);
         else gadj[o + i] = a;
       }
       if (fast) rec[v] = rec_pack(goff[v], g.nin[v], na);
-      else fl[v] = static_cast<uint8_t>((na ? kFHasAligned : 0) | (na << kFNalShift));
+      else fl[v] = static_cast<uint8_t>(na ? kFHasAligned : 0);
     }
     for (uint32_t e = L; e < nE; e += W) {
       const uint32_t pos = goff[g.ehead[e]] + g.ein_ord[e];
@@ -1048,7 +1142,7 @@ struct Poa {
     t.ovf = sl.ovf;
     t.nodes = sl.max_nodes < 65536u ? nullptr : (ws.sub ? sl.order : sl.r2n);
     t.seq = bv.bases + bv.seq_off[layer];
-    t.dec64 = TraceWalker::pack_decoder(bv.decoder);
+    t.dec = bv.decoder;
     t.aln_node = sl.aln_node;
     t.aln_pos = sl.aln_pos;
     t.aln_cap = sl.aln_cap;
@@ -1064,6 +1158,36 @@ struct Poa {
   }
 
   VGC_HD void traceback(uint32_t layer, uint32_t mode) {
+    if (ws.wide) {
+      const Scores& sc = mode == kModeNW ? nw : sw;
+      WideIo t;
+      t.H = reinterpret_cast<const int32_t*>(sl.H);
+      t.cols = layer_len(layer) + 1;
+      t.rp = reinterpret_cast<const U4*>(sl.rowprog);
+      t.ovf = sl.ovf;
+      t.nodes = sl.max_nodes < 65536u ? nullptr : (ws.sub ? sl.order : sl.r2n);
+      t.codes = ex.seq_codes();
+      t.m = sc.m;
+      t.x = sc.x;
+      t.g = sc.g;
+      t.sw = mode == kModeSW;
+      t.row = ws.best_row;
+      t.col = ws.best_col;
+      t.max_steps = ws.nR + layer_len(layer) + 2;
+      t.aln_node = sl.aln_node;
+      t.aln_pos = sl.aln_pos;
+      t.aln_cap = sl.aln_cap;
+      t.ew = nullptr;
+      t.ieid = nullptr;
+      t.in_stride = 0;
+      t.quals = nullptr;
+      t.wlut = nullptr;
+      uint32_t n = 0;
+      if (wide_trace<false>(ex, t, &n) != kWalkDone) fail(kStInternal);
+      if (ex.leader()) ws.aln_len = n;
+      ex.sync();
+      return;
+    }
     if (ex.leader()) {
       if (ws.best_row == 0 && ws.best_col == 0) {
         ws.aln_len = 0;
@@ -1184,7 +1308,7 @@ struct Poa {
             } else {
               const uint32_t na = g.nal[jt];
               for (uint32_t i = 0; i < na; ++i) {
-                const uint32_t kt = g.al[jt * kAlStride + i];
+                const uint32_t kt = g.al[jt * sl.al_stride + i];
                 if (g.code[kt] == code) {
                   curr = kt;
                   break;
@@ -1202,18 +1326,18 @@ struct Poa {
           if (kind == 2) {
             const uint32_t jt = static_cast<uint32_t>(nd);
             const uint32_t na = g.nal[jt];
-            if (na + 1 > static_cast<uint32_t>(kMaxAligned)) {
+            if (na + 1 > sl.al_stride - 1u) {  // cannot happen: a clique holds distinct codes, al_stride > num_codes - 1
               fail(kStAlignedOverflow);
             } else {
               for (uint32_t i = 0; i < na; ++i) {
-                const uint32_t kt = g.al[jt * kAlStride + i];
-                g.al[kt * kAlStride + g.nal[kt]] = curr;
+                const uint32_t kt = g.al[jt * sl.al_stride + i];
+                g.al[kt * sl.al_stride + g.nal[kt]] = curr;
                 g.nal[kt] = g.nal[kt] + 1;
-                g.al[curr * kAlStride + i] = kt;
+                g.al[curr * sl.al_stride + i] = kt;
               }
-              g.al[jt * kAlStride + na] = curr;
+              g.al[jt * sl.al_stride + na] = curr;
               g.nal[jt] = static_cast<uint8_t>(na + 1);
-              g.al[curr * kAlStride + na] = jt;
+              g.al[curr * sl.al_stride + na] = jt;
               g.nal[curr] = static_cast<uint8_t>(na + 1);
             }
           }
@@ -1590,7 +1714,7 @@ struct Poa {
           const uint32_t t = g.itail[u * S + i];
           if (sl.owner[t] == r) adj[k++] = static_cast<uint16_t>(sl.rank_of[t]);
         }
-        for (uint32_t i = 0; i < nal; ++i) adj[k++] = static_cast<uint16_t>(sl.rank_of[g.al[u * kAlStride + i]]);
+        for (uint32_t i = 0; i < nal; ++i) adj[k++] = static_cast<uint16_t>(sl.rank_of[g.al[u * sl.al_stride + i]]);
       }
       uint16_t* stacks = adj + A;
       uint32_t scarry = 0;
@@ -1937,7 +2061,7 @@ struct Poa {
       const uint32_t v = path[n - 1 - i];
       out[i] = bv.decoder[g.code[v]];
       uint32_t c = g.cov[v];
-      for (uint32_t a = 0; a < g.nal[v]; ++a) c += g.cov[g.al[v * kAlStride + a]];
+      for (uint32_t a = 0; a < g.nal[v]; ++a) c += g.cov[g.al[v * sl.al_stride + a]];
       cov_out[i] = c;
     }
     return n;
@@ -2044,7 +2168,11 @@ struct Poa {
         //  -rows * max|score| from below)
         const int64_t cols = 64ll * fill_width(K, maxlen);
         const int64_t rows = static_cast<int64_t>(ws.nR);
-        if (((rows > cols ? rows : cols) + cols + 2) * a > 32000) fail(kStScoreRange);
+        // beyond the int16 range, or a layer longer than the widest fast row: the int32 kernel takes the step (the
+        // reference switches its SIMD lanes to int32 by a bound of the same kind, simd_..._implementation.hpp:699-706)
+        ws.wide = (maxlen > static_cast<uint32_t>(RM::kCols) || ((rows > cols ? rows : cols) + cols + 2) * a > 32000) ? 1u : 0u;
+        // int32 itself: |score| <= 127 (int8 in the reference), rows + columns < 2^24
+        if ((rows + static_cast<int64_t>(maxlen) + 2) * a > 2000000000ll) fail(kStScoreRange);
         ws.alignments += naln;
         ws.cells += cells;
         ws.jobs_total = naln;
@@ -2113,10 +2241,10 @@ struct Poa {
         for (int i = 0; i < kPhCount; ++i) ws.phase[i] = 0;
       }
       ex.sync();
-      // every layer must fit one row of the H matrix
+      // every layer must fit the staging buffers (rows wider than the fast kernels' go to the wide kernel)
       for (uint32_t t = 0; t < nseq; ++t) {
         const uint32_t len = layer_len(rank[t]);
-        if (len > static_cast<uint32_t>(RM::kCols) || len > sl.max_len) {
+        if (len > sl.max_len) {
           if (ex.leader()) fail(kStTooLong);
         }
       }

@@ -31,6 +31,7 @@
 #include "poa_core.h"
 #include "poa_fill.cuh"
 #include "poa_trace.cuh"
+#include "poa_wide.cuh"
 #include "vgc.h"
 
 namespace vgc {
@@ -47,7 +48,8 @@ constexpr uint32_t kRecRing = 32;  // row records staged in shared memory by the
 constexpr uint32_t kJobRound = 1u << 30, kJobSW = 1u << 31, kJobLayerMask = kJobRound - 1u;
 // Alignments are dealt to one kernel per (row width, mode) class so that every kernel holds exactly one fill and one
 // traceback variant (own register allocation, small code): class = width index * 2 + (SW ? 1 : 0)
-constexpr int kClasses = 6;
+// plus one list for the wide path (poa_wide.cuh: int32 cells, any width), served by a persistent kernel
+constexpr int kFastClasses = 6, kClassWide = 6, kClasses = 7;
 __host__ __device__ inline uint32_t job_class(uint32_t len, bool sw) {
   return (len <= 512u ? 0u : (len <= 640u ? 1u : 2u)) * 2u + (sw ? 1u : 0u);
 }
@@ -74,6 +76,11 @@ struct KernelArgs {
   unsigned long long pool_fc_off;  // byte offset of the first-column values inside a buffer
   uint32_t pool_rows;      // rows a buffer holds (at the widest row)
   uint32_t pool_n;         // buffers = CTAs of align_kernel the device can hold at once
+  // wide path: its own pool of int32 matrices (same ticket ring), wide_n buffers of wide_buf_bytes
+  uint8_t* wide_pool;
+  uint32_t* wide_free;
+  unsigned long long wide_buf_bytes;
+  uint32_t wide_n;
   // diagnostics (VGC_TIMELINE=file): one record per warp-sized unit of work {start ns, duration ns, SM | kind << 16}
   uint4* tl;               // [1 + tl_cap]; tl[0].x = records taken
   uint32_t tl_cap;
@@ -289,7 +296,7 @@ __device__ __forceinline__ void emit_jobs(const KernelArgs& a, const WinCtx& c, 
   if (c.ws->pc == kPcDone || c.ws->need != kNeedFill) return;
   auto emit = [&](uint32_t layer, bool sw, uint32_t flags) {
     const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[layer + 1] - a.bv.seq_off[layer]);
-    const uint32_t cls = job_class(len, sw);
+    const uint32_t cls = c.ws->wide ? static_cast<uint32_t>(kClassWide) : job_class(len, sw);
     Job jb;
     jb.idx = c.idx;
     jb.layer = layer | flags | (sw ? kJobSW : 0u);
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
   uint8_t* pb = a.pool + static_cast<unsigned long long>(buf) * a.pool_buf_bytes;
   uint8_t* sm = smem + kAlignHeader;
-  const uint32_t max_len = sl->max_len;
+  const uint32_t max_len = min(sl->max_len, 64u * KR);  // this class takes no longer layer
   uint8_t* codes = sm;
   U4* recs = reinterpret_cast<U4*>(sm + ((max_len + 15u) & ~15u));
   uint32_t* prof = reinterpret_cast<uint32_t*>(recs + kRecRing);
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   int st = kWalkDone;
   uint32_t n = 0, refills = 0;
   unsigned long long t1 = t0;
-  if (nR + 1 > a.pool_rows || len > 64u * KR) {
+  if (nR + 1 > a.pool_rows || len > max_len) {
     st = kWalkBad;
   } else {
     // ---- fill (rows of KR words per lane; the ring of recent rows only if the shared memory holds it)
@@ -489,6 +496,120 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
       gws->phase[kPhTrace] += t2 - t1;
       gws->phase[kPhOther] += refills;
       gws->need = kNeedUpdate;
+    }
+  }
+}
+
+// W: the wide path — same contract as align_kernel for the alignments of the wide list (int32 matrix of any width in
+// the wide pool, poa_wide.cuh + wide_trace).  Persistent: the host does not know how many wide alignments a cycle has
+// (the score-range test depends on the graph), so a fixed grid strides over the list.
+// shared memory: Slot header | codes[max_len]
+__global__ void __launch_bounds__(32) align_wide_kernel(const KernelArgs a, const Job* jobs, const uint32_t* njobs) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x;
+  const uint32_t nj = *njobs;
+  for (uint32_t jn = blockIdx.x; jn < nj; jn += gridDim.x) {
+    __syncwarp();
+    const unsigned long long tl0 = a.tl ? gtime_ns() : 0ull;
+    const unsigned long long t0 = clock64();
+    const Job jb = jobs[jn];
+    const uint32_t idx = jb.idx, l = jb.layer & kJobLayerMask;
+    const bool round = (jb.layer & kJobRound) != 0, swm = (jb.layer & kJobSW) != 0;
+    WinState* gws = a.wstates + idx;
+    if (gws->pc == kPcDone) continue;
+    Slot* sl = reinterpret_cast<Slot*>(smem);
+    copy_words(sl, a.slots + idx, sizeof(Slot), lane);
+    const uint32_t nR = gws->nR, sub = gws->sub, cur = gws->cur;
+    const uint32_t w = a.work[idx];
+    __syncwarp();
+    uint32_t buf = 0;
+    if (lane == 0) {
+      const uint32_t ticket = atomicAdd(a.wide_free + a.wide_n, 1u);
+      uint32_t* slot = a.wide_free + ticket % a.wide_n;
+      while ((buf = atomicExch(slot, kNone)) == kNone) __nanosleep(200);
+    }
+    buf = __shfl_sync(0xFFFFFFFFu, buf, 0);
+    int32_t* H = reinterpret_cast<int32_t*>(a.wide_pool + static_cast<unsigned long long>(buf) * a.wide_buf_bytes);
+    uint8_t* codes = smem + kAlignHeader;
+    const uint64_t o = a.bv.seq_off[l];
+    const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
+    for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
+    __syncwarp();
+    Scores sw;
+    sw.m = 3;  // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
+    sw.x = -5;
+    sw.g = -4;
+    const Scores sc = swm ? sw : a.nw;
+    int st = kWalkDone;
+    uint32_t n = 0;
+    unsigned long long t1 = t0;
+    WideFillIo io;
+    io.best_row = io.best_col = 0;
+    io.best_score = 0;
+    uint32_t fail_st = kStInternal;
+    if ((static_cast<unsigned long long>(nR) + 1) * (len + 1ull) * 4ull > a.wide_buf_bytes) {
+      st = kWalkBad;
+      fail_st = kStWideCapacity;
+    } else {
+      io.H = H;
+      io.cols = len + 1;
+      io.rp = reinterpret_cast<const U4*>(sl->rowprog);
+      io.ovf = sl->ovf;
+      io.nR = nR;
+      if (swm) warp_fill_wide<true>(io, codes, len, sc);
+      else warp_fill_wide<false>(io, codes, len, sc);
+      t1 = clock64();
+      WideIo t;
+      t.H = H;
+      t.cols = len + 1;
+      t.rp = io.rp;
+      t.ovf = sl->ovf;
+      t.nodes = sl->max_nodes < 65536u ? nullptr : (sub ? sl->order : sl->r2n);
+      t.codes = codes;
+      t.m = sc.m;
+      t.x = sc.x;
+      t.g = sc.g;
+      t.sw = swm;
+      t.row = io.best_row;
+      t.col = io.best_col;
+      t.max_steps = nR + len + 2;
+      t.aln_node = sl->aln_node;
+      t.aln_pos = sl->aln_pos;
+      t.aln_cap = sl->aln_cap;
+      t.ew = sl->g[cur].ew;
+      t.ieid = sl->g[cur].ieid;
+      t.in_stride = sl->in_stride;
+      t.quals = a.bv.has_qual[l] ? a.bv.quals + o : nullptr;
+      t.wlut = a.bv.wlut;
+      struct {
+        int lane;
+        __device__ bool leader() const { return lane == 0; }
+        __device__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+      } wex{lane};
+      st = round ? wide_trace<true>(wex, t, &n) : wide_trace<false>(wex, t, &n);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(a.wide_free + atomicAdd(a.wide_free + a.wide_n + 1, 1u) % a.wide_n, buf);
+      const unsigned long long t2 = clock64();
+      tl_record(a, 6u, tl0);
+      if (st != kWalkDone) {
+        win_fail(a, gws, w, fail_st);
+      } else if (round) {
+        atomicAdd(&gws->phase[kPhFill], t1 - t0);
+        atomicAdd(&gws->phase[kPhTrace], t2 - t1);
+        __threadfence();
+        if (atomicAdd(&gws->jobs_done, 1u) + 1u == gws->jobs_total) gws->need = kNeedUpdate;
+      } else {
+        gws->aln_len = n;
+        gws->best_row = io.best_row;
+        gws->best_col = io.best_col;
+        gws->best_score = io.best_score;
+        gws->phase[kPhFill] += t1 - t0;
+        gws->phase[kPhTrace] += t2 - t1;
+        gws->need = kNeedUpdate;
+      }
     }
   }
 }
@@ -578,11 +699,13 @@ struct vgc_engine {
   cudaEvent_t gev[64] = {};
   uint32_t smem_update = 0, smem_sort = 0;
   size_t mem_budget = 0;
+  bool mem_budget_fixed = false;  // VGC_MEM_BUDGET_MB given
   // device copies of the batch
   DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
   DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
   DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem, d_wstates;
   DevBuf d_tl;  // diagnostics timeline (VGC_TIMELINE)
+  DevBuf d_wide, d_wide_free;  // wide path: pool of int32 DP matrices + its ring of free ids
   DevBuf d_pool, d_pool_busy, d_jobs, d_jobcnt;  // align kernel: DP-matrix pool, per-group job lists, per-cycle counters
   // host staging (pinned)
   uint8_t* h_out = nullptr;
@@ -700,7 +823,7 @@ inline AlignFn align_fn(int cls) {
     default: return align_kernel<16, true>;
   }
 }
-constexpr uint32_t kClassK[kClasses] = {8, 8, 10, 10, 16, 16};
+constexpr uint32_t kClassK[kFastClasses] = {8, 8, 10, 10, 16, 16};
 
 inline cudaError_t set_smem_attr(const void* f, uint32_t smem) {
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -709,9 +832,9 @@ inline cudaError_t set_smem_attr(const void* f, uint32_t smem) {
 }
 
 template <int K>
-int set_kernel_attrs(const vgc_engine* h) {
-  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * h->smem_update));
-  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(sort_kernel<K>), h->smem_sort));
+int set_kernel_attrs(uint32_t smem_update, uint32_t smem_sort) {
+  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(update_kernel<K>), kUpdateWins * smem_update));
+  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(sort_kernel<K>), smem_sort));
   return VGC_OK;
 }
 
@@ -767,16 +890,34 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
   const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
+  // scratch budget of this pass: a share of what is free now plus what this engine already holds for scratch (other
+  // engines of the process may have taken memory since vgc_create)
+  if (!h->mem_budget_fixed) {
+    size_t free_b = 0, total_b = 0;
+    VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    h->mem_budget = static_cast<size_t>((free_b + h->d_slot_mem.cap + h->d_pool.cap + h->d_wide.cap) * 0.70);
+  }
   // ---- align kernels (one per class): shared memory, residency, pool geometry
   const uint32_t smem_budget = static_cast<uint32_t>(((228 * 1024 - VGC_ALIGN_CTAS * 1024) / VGC_ALIGN_CTAS) & ~255);
-  uint32_t smem_align[kClasses];
+  uint32_t smem_align[kFastClasses];
   int rc;
-  if ((rc = set_kernel_attrs<K>(h))) return rc;
+  // every kernel stages the codes of a layer (up to ml bytes) behind its header: long layers (wide path) need room
+  const uint32_t ml16 = (ml + 15u) & ~15u;
+  const uint32_t smem_update = std::max<uint32_t>(h->smem_update, (kSmemHeader + ml16 + 3072u + 255u) & ~255u);
+  const uint32_t smem_sort_cap = std::max<uint32_t>(h->smem_sort, (kSmemHeader + ml16 + 8192u + 255u) & ~255u);
+  const uint32_t smem_wide = (kAlignHeader + ml16 + 255u) & ~255u;
+  if ((rc = set_kernel_attrs<K>(smem_update, smem_sort_cap))) return rc;
+  VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(align_wide_kernel), smem_wide));
+  const int32_t max_abs_score = [&]() {
+    int32_t a = 5;  // the SW engine's 3/-5/-4
+    for (int32_t v : {h->params.match, h->params.mismatch, h->params.gap}) a = std::max(a, v < 0 ? -v : v);
+    return a;
+  }();
   int occ_max = 0;
-  for (int cls = 0; cls < kClasses; ++cls) {
+  for (int cls = 0; cls < kFastClasses; ++cls) {
     smem_align[cls] = 0;
     if (kClassK[cls] > static_cast<uint32_t>(K)) continue;  // no layer of this batch is that wide
-    smem_align[cls] = align_smem(kClassK[cls], pr.num_codes, ml, smem_budget);
+    smem_align[cls] = align_smem(kClassK[cls], pr.num_codes, std::min<uint32_t>(ml, 64u * kClassK[cls]), smem_budget);
     VGC_CUDA(set_smem_attr(reinterpret_cast<const void*>(align_fn(cls)), smem_align[cls]));
     int occ = 0;
     VGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_fn(cls), 32, smem_align[cls]));
@@ -811,8 +952,45 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       set_err("a window's DP matrix needs more scratch than the device memory budget");
       return VGC_ERR_CAPACITY;
     }
-    const uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
+    uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
     if ((rc = h->d_pool.reserve(pool_bytes))) return rc;
+    // ---- wide path (poa_wide.cuh): can any alignment of the rest of the pass leave the fast kernels?  A layer beyond
+    // their widest row, or the device's int16 score bound (poa_core.h step_prepare) evaluated with the slot's node
+    // capacity as the number of rows.  Its int32 matrices live in their own pool, sized for the largest such window.
+    uint32_t wide_n = 0;
+    uint64_t wide_buf = 0;
+    {
+      uint64_t need = 0;
+      for (size_t e = pos; e < wins.size(); ++e) {
+        const uint32_t w = wins[e];
+        const uint32_t f = win_first[w];
+        const int64_t rows = estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div) + 1;
+        const uint32_t mlw = pr.win_max_len[w];
+        const int64_t cols = 64ll * fill_width(K, mlw);
+        if (mlw > 64u * K || (std::max(rows, cols) + cols + 2) * max_abs_score > 32000)
+          need = std::max<uint64_t>(need, static_cast<uint64_t>(rows + 1) * (mlw + 1ull) * 4ull);
+      }
+      if (need) {
+        wide_buf = align_up(need, 256);
+        const uint64_t cap = h->mem_budget * 3 / 10;
+        wide_n = static_cast<uint32_t>(std::min<uint64_t>(2ull * h->sm_count, cap / wide_buf));
+        if (wide_n == 0) {
+          if (wide_buf > h->mem_budget - pool_bytes) {
+            set_err("the int32 DP matrix of a wide alignment needs more scratch than the device memory budget");
+            return VGC_ERR_CAPACITY;
+          }
+          wide_n = 1;
+        }
+        if ((rc = h->d_wide.reserve(wide_buf * wide_n))) return rc;
+        if ((rc = h->d_wide_free.reserve(4ull * (wide_n + 2)))) return rc;
+        std::vector<uint32_t> init(wide_n + 2);
+        for (uint32_t i = 0; i < wide_n; ++i) init[i] = i;
+        init[wide_n] = 0;
+        init[wide_n + 1] = wide_n;
+        VGC_CUDA(cudaMemcpy(h->d_wide_free.p, init.data(), 4ull * (wide_n + 2), cudaMemcpyHostToDevice));
+        pool_bytes += wide_buf * wide_n;
+      }
+    }
     const uint32_t pool_n = per_sm * static_cast<uint32_t>(h->sm_count);
     if ((rc = h->d_pool_busy.reserve(4ull * (pool_n + 2)))) return rc;
     std::vector<uint32_t> pool_init(pool_n + 2);
@@ -835,6 +1013,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       d.max_len = ml;
       d.row_words = 32 * K;
       // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
+      d.al_stride = pr.num_codes > 8 ? 16 : 8;
       d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : std::min<uint32_t>(16, std::max<uint32_t>(8, pr.win_nseq[w] + 1));
       const uint64_t sb = slot_bytes(d);
       if (bytes + sb > slot_budget && e > pos) break;
@@ -936,6 +1115,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     a.pool_fc_off = pool_fc_off;
     a.pool_rows = pool_rows;
     a.pool_n = pool_n;
+    a.wide_pool = h->d_wide.as<uint8_t>();
+    a.wide_free = h->d_wide_free.as<uint32_t>();
+    a.wide_buf_bytes = wide_buf;
+    a.wide_n = wide_n;
     a.tl = nullptr;
     a.tl_cap = 0;
     const char* tl_path = std::getenv("VGC_TIMELINE");
@@ -960,13 +1143,13 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         if (!nlive) continue;
         cudaStream_t st = h->gstream[g];
         KernelArgs ka = a;
-        ka.smem_bytes = h->smem_update;  // per window (warp)
+        ka.smem_bytes = smem_update;  // per window (warp)
         Job* jobs = h->d_jobs.as<Job>() + gjob_off[g] * kClasses;
         const uint32_t job_cap = static_cast<uint32_t>(gjobs_cap[g]);
         uint32_t* cnt = h->d_jobcnt.as<uint32_t>() + (static_cast<size_t>(g) * (max_cyc + 1) + c) * kClasses;
         update_kernel<K><<<(nlive + kUpdateWins - 1) / kUpdateWins, 32 * kUpdateWins, kUpdateWins * ka.smem_bytes, st>>>(ka, gbase[g], nlive, jobs, job_cap, cnt);
         ++nl;
-        uint32_t ncls[kClasses] = {0, 0, 0, 0, 0, 0};  // alignments this cycle hands to each class kernel (exact)
+        uint32_t ncls[kFastClasses] = {0, 0, 0, 0, 0, 0};  // alignments this cycle hands to each class kernel (exact)
         uint32_t nprep = 0;  // windows that still have a prepare step in this cycle: all but those that just emitted
         for (uint32_t i = 0; i < nlive; ++i) {
           const uint32_t nj = win_jobs(ns[i], hap, num_prune, c);
@@ -992,19 +1175,26 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         // shared memory of the sort kernel: sized for the graph this cycle can have reached (build phase: the
         // backbone + a share of the bases added so far), so early cycles run more CTAs per SM; a graph that
         // outgrows it sorts out of HBM instead (slower, same result)
-        uint32_t ss = h->smem_sort;
+        uint32_t ss = smem_sort_cap;
         if (c + 1 < gmin_nseq[g]) {
           const double nvb = gblen[g] + h->sort_growth * c * gavglen[g] + 64.0;
           const double need = kSmemHeader + ((ml + 15u) & ~15u) + 9.2 * nvb + 1024.0;
-          ss = std::min<uint32_t>(h->smem_sort, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
+          ss = std::min<uint32_t>(smem_sort_cap, std::max<uint32_t>(4096u, (static_cast<uint32_t>(need) + 255u) & ~255u));
         }
         ka.smem_bytes = ss;
         sort_kernel<K><<<nprep, 32, ss, st>>>(ka, gbase[g], jobs, job_cap, cnt);
         ++nl;
-        for (int cls = 0; cls < kClasses; ++cls) {
-          if (!ncls[cls]) continue;
+        uint32_t njobs_cycle = 0;
+        for (int cls = 0; cls < kFastClasses; ++cls) {
+          njobs_cycle += ncls[cls];
+          if (!ncls[cls] || !smem_align[cls]) continue;
           ka.smem_bytes = smem_align[cls];
           align_fn(cls)<<<ncls[cls], 32, smem_align[cls], st>>>(ka, jobs + static_cast<size_t>(cls) * job_cap, cnt + cls);
+          ++nl;
+        }
+        if (wide_n && njobs_cycle) {
+          ka.smem_bytes = smem_wide;
+          align_wide_kernel<<<std::min(njobs_cycle, wide_n), 32, smem_wide, st>>>(ka, jobs + static_cast<size_t>(kClassWide) * job_cap, cnt + kClassWide);
           ++nl;
         }
       }
@@ -1074,8 +1264,9 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   if (n_dev) {
     const int K = pr.max_len <= 640 ? 10 : 16;
-    if (pr.max_len > 1024) {
-      set_err("layer longer than 1024 bases: beyond the engine's row capacity");
+    if (pr.max_len > VGC_MAX_LAYER_LEN) {
+      set_err("a layer is longer than 16383 bases (engine limit, see vgc_limits): use a window length (racon -w) "
+              "below ~8000");
       return VGC_ERR_CAPACITY;
     }
     VGC_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -1085,7 +1276,8 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     // second pass, exact capacities, for windows whose graph outgrew the estimate
     std::vector<uint32_t> retry;
     for (uint32_t w : pr.device_windows) {
-      if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow || h->h_status[w] == kStDegreeOverflow)
+      if (h->h_status[w] == kStNodeOverflow || h->h_status[w] == kStEdgeOverflow || h->h_status[w] == kStDegreeOverflow ||
+          h->h_status[w] == kStWideCapacity)
         retry.push_back(w);
     }
     if (!retry.empty()) {
@@ -1178,6 +1370,8 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
 
 }  // namespace
 
+static int engine_init(vgc_engine* h);
+
 extern "C" {
 
 const char* vgc_last_error(void) { return g_err.c_str(); }
@@ -1191,12 +1385,36 @@ const char* vgc_version(void) { return "vechat_b200 0.1 (sm_100a)"; }
 
 void vgc_weight_lut(uint32_t lut[256]) { vgc::weight_lut(lut); }
 
+void vgc_limits(vgc_limits_t* out) {
+  if (!out) return;
+  std::memset(out, 0, sizeof(*out));
+  out->max_layer_len = VGC_MAX_LAYER_LEN;
+  out->max_backbone_len = VGC_MAX_BACKBONE;
+  out->max_codes = VGC_MAX_CODES;
+  out->fast_layer_len = VGC_FAST_LAYER_LEN;
+  out->int16_score_bound = 32000;
+}
+
+int vgc_window_status(vgc_handle h, uint32_t* status, uint32_t n) {
+  if (!h || !status) return VGC_ERR_INVALID;
+  for (uint32_t w = 0; w < n; ++w) status[w] = (h->h_status && w < h->h_win_cap) ? h->h_status[w] : 0u;
+  return VGC_OK;
+}
+
 int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   if (!out || !params) {
     set_err("null argument");
     return VGC_ERR_INVALID;
   }
   *out = nullptr;
+  if (params->gap > 0) {  // vendor/spoa/src/alignment_engine.cpp:37-51 (linear gaps: g == e == q == c)
+    set_err("[spoa::AlignmentEngine::Create] error: gap opening penalty must be non-positive!");
+    return VGC_ERR_INVALID;
+  }
+  if (params->haplotype && params->num_prune == 0) {
+    set_err("invalid params: num_prune must be >= 1 in haplotype mode");
+    return VGC_ERR_INVALID;
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
@@ -1216,6 +1434,18 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   h->device = device;
   h->params = *params;
   h->sm_count = prop.multiProcessorCount;
+  const int rc_init = engine_init(h);
+  if (rc_init != VGC_OK) {
+    vgc_destroy(h);  // frees whatever was created
+    return rc_init;
+  }
+  *out = h;
+  return VGC_OK;
+}
+
+}  // extern "C"
+
+static int engine_init(vgc_engine* h) {
   VGC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) VGC_CUDA(cudaEventCreate(&ev));
   // groups are ordered deepest windows first: their chain of cycles is the critical path of a pass, so their
@@ -1241,10 +1471,14 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
   h->mem_budget = static_cast<size_t>(free_b * 0.70);
-  if (const char* s = std::getenv("VGC_MEM_BUDGET_MB")) h->mem_budget = static_cast<size_t>(std::atoll(s)) << 20;
-  *out = h;
+  if (const char* s = std::getenv("VGC_MEM_BUDGET_MB")) {
+    h->mem_budget = static_cast<size_t>(std::atoll(s)) << 20;
+    h->mem_budget_fixed = true;
+  }
   return VGC_OK;
 }
+
+extern "C" {
 
 int vgc_destroy(vgc_handle h) {
   if (!h) return VGC_OK;
@@ -1252,7 +1486,7 @@ int vgc_destroy(vgc_handle h) {
   for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
                     &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
                     &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
-                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs, &h->d_tl,
+                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs, &h->d_tl, &h->d_wide, &h->d_wide_free,
                     &h->d_jobcnt})
     d->release();
   if (h->h_out) cudaFreeHost(h->h_out);

@@ -15,7 +15,7 @@ _LIB = None
 LIB_PATH = os.environ.get("VGC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvgc.so")  # VGC_LIB: experiments
 
 EXPORTS = ["vgc_create", "vgc_destroy", "vgc_result_bound", "vgc_polish", "vgc_upload", "vgc_polish_resident",
-           "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile"]
+           "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile", "vgc_limits", "vgc_window_status"]
 
 
 class VgcError(RuntimeError):
@@ -48,6 +48,10 @@ def load_library():
         lib.vgc_last_error.restype = C.c_char_p
         lib.vgc_version.restype = C.c_char_p
         lib.vgc_weight_lut.argtypes = [C.POINTER(C.c_uint32)]
+        lib.vgc_limits.restype = None
+        lib.vgc_limits.argtypes = [C.POINTER(C.c_uint32)]
+        lib.vgc_window_status.restype = C.c_int
+        lib.vgc_window_status.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32]
         _LIB = lib
     return _LIB
 
@@ -86,6 +90,19 @@ class Engine:
         st = VgcStats()
         self._check(self.lib.vgc_polish(self._h, C.byref(b), C.byref(r), C.byref(st)))
         return finish_result(batch, arrays), _stats(st)
+
+    def limits(self):
+        """vgc_limits(): the engine's hard limits (include/vgc.h)."""
+        out = (C.c_uint32 * 8)()
+        self.lib.vgc_limits(out)
+        names = ["max_layer_len", "max_backbone_len", "max_codes", "fast_layer_len", "int16_score_bound"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
+
+    def window_status(self, n_windows):
+        """Per-window status codes of the last polish call (0 = ok)."""
+        out = (C.c_uint32 * max(1, n_windows))()
+        self._check(self.lib.vgc_window_status(self._h, out, n_windows))
+        return list(out)[:n_windows]
 
     def upload(self, batch: WindowBatch):
         b = batch.c_struct()

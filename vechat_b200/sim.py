@@ -147,7 +147,7 @@ def _mutate(rng, truth, e_ins, e_del, e_sub, alphabet):
 
 
 def fuzz_window(rng, length=120, depth=8, err=0.15, partial=0.3, fastq=True, null_qual=0.0, n_frac=0.0,
-                n_hap=2, dummy_backbone=False, window_length=None):
+                n_hap=2, dummy_backbone=False, window_length=None, iupac_frac=0.0):
     """One random window: two haplotypes of a random truth, backbone + `depth` noisy layers, a fraction of
     which are partial spans.  Returns (layers, flags) in WindowBatch.from_windows form."""
     alphabet = [65, 67, 71, 84]
@@ -165,6 +165,9 @@ def fuzz_window(rng, length=120, depth=8, err=0.15, partial=0.3, fastq=True, nul
         if n_frac > 0:
             m = rng.random(len(s)) < n_frac
             s[m] = ord("N")
+        if iupac_frac > 0:  # ambiguity codes: up to 15 distinct bytes with A C G T
+            m = rng.random(len(s)) < iupac_frac
+            s[m] = rng.choice(np.frombuffer(b"NRYKMSWBDHV", dtype=np.uint8), size=int(m.sum()))
         return s
 
     def qual(n):
