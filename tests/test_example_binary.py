@@ -314,7 +314,7 @@ def _b200(opts, **kw):
                                      "(python -m vechat_b200.build) so that it travels with the snapshot"
     r = run(B200_BIN, opts, devices="0", **kw)
     assert r.returncode == 0, r.stderr[-600:]
-    assert b"[racon::B200Polisher::polish] generated consensus" in r.stderr  # the GPU polisher ran, not the CPU one
+    assert b"[racon::createPolisherB200] consensus on B200 device(s)" in r.stderr  # the GPU polisher ran, not the CPU one
     return r.stdout
 
 
@@ -333,7 +333,7 @@ def test_gpu_binary_with_gpu_overlap_alignment(opts, want, mode):
     reproduces the host aligner's alignments exactly."""
     r = run(B200_BIN, opts, devices="0", gpu_align=mode)
     assert r.returncode == 0, r.stderr[-600:]
-    assert b"aligned overlaps on the GPU" in r.stderr and b"[racon::B200Polisher::polish] generated consensus" in r.stderr
+    assert b"aligned overlaps on the GPU" in r.stderr and b"[racon::createPolisherB200] consensus on B200 device(s)" in r.stderr
     assert r.stdout == golden(want)
 
 

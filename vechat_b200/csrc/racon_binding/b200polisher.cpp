@@ -359,6 +359,12 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
 
   // In-order stitch per target with the reference's header tags (polisher.cpp:520-546): a target ends where the
   // next window has rank 0.
+  // (the progress bar is the reference's own, polisher.cpp:524,549-558: one step per 1/20 of the windows stitched)
+  const uint64_t logger_step = n / 20;
+  auto bar_after = [&](size_t k) {  // k = index of the window just stitched
+    if (logger_step != 0 && (k + 1) % logger_step == 0 && (k + 1) / logger_step < 20)
+      logger_->bar("[racon::Polisher::polish] generating consensus");
+  };
   size_t i = 0;
   while (i < n) {
     std::string data;
@@ -367,6 +373,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     do {
       good += polished[j] ? 1 : 0;
       data += windows_[j]->consensus();
+      bar_after(j);
       ++j;
     } while (j < n && windows_[j]->rank() != 0);
     const Window& tail = *windows_[j - 1];
@@ -381,7 +388,11 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     }
     for (; i < j; ++i) windows_[i].reset();
   }
-  logger_->log("[racon::B200Polisher::polish] generated consensus");
+  if (logger_step != 0) {
+    logger_->bar("[racon::Polisher::polish] generating consensus");
+  } else {
+    logger_->log("[racon::Polisher::polish] generated consensus");
+  }
 
   std::vector<std::shared_ptr<Window>>().swap(windows_);
   std::vector<std::unique_ptr<Sequence>>().swap(sequences_);
@@ -443,6 +454,18 @@ std::unique_ptr<Polisher> createPolisherB200(const std::string& sequences_path, 
 
   if (type != PolisherType::kC && type != PolisherType::kF) die("createPolisher", "invalid polisher type!");
   if (window_length == 0) die("createPolisher", "invalid window length!");
+  // engine limits, checked before initialize() is paid for (include/vgc.h: a layer may hold VGC_MAX_LAYER_LEN bases;
+  // layers are about as long as the window, insertions included)
+  if (window_length > VGC_MAX_LAYER_LEN / 2)
+    die("createPolisher", "window length (-w) above 8191 is beyond the B200 engine's layer limit (16383 bases); "
+                          "lower -w or run the CPU path (unset VECHAT_B200_DEVICES)!");
+  if (gap > 0) die("createPolisher", "gap penalty (-g) must be non-positive!");
+  {
+    std::string list;
+    for (int d : devices) list += (list.empty() ? "" : ",") + std::to_string(d);
+    std::fprintf(stderr, "[racon::createPolisherB200] consensus on B200 device(s) %s (libvgc %s)\n", list.c_str(),
+                 vgc_version());
+  }
   auto sparser = sequence_parser(sequences_path);
   auto oparser = overlap_parser(overlaps_path);
   auto tparser = sequence_parser(target_path);

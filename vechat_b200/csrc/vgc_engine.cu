@@ -16,6 +16,7 @@
 // No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
 
 #include <algorithm>
 #include <chrono>
@@ -626,6 +627,12 @@ namespace {
 
 thread_local std::string g_err;
 
+// NVTX range for the phases of a call (pack / H2D / pass / D2H + stitch), SURVEY.md §5
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 // A pass runs up to 48 stream groups side by side.  The driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware
 // queues (default 8); streams that share a queue serialise on each other's dependencies (measured: 31.3 k -> 34.2 k
 // windows/s with 32 queues).  The variable is read when the CUDA context is created, so it is set when the library
@@ -730,6 +737,7 @@ using namespace vgc;
 // Host -> device copies of a batch, in two parts so that the bulk (bases, qualities, layer tables: everything the
 // caller owns) is already in flight on the copy stream while the host prepares the rest (prepare_batch).
 int upload_part(vgc_engine* h, const vgc_batch* b, bool raw, uint64_t* bytes_io) {
+  NvtxRange nvtx(raw ? "vgc: H2D batch" : "vgc: H2D prepared tables");
   const uint32_t nw = b->n_windows, nl = b->n_layers;
   const uint64_t nb = nl ? b->seq_off[nl] : 0;
   Prepared& pr = h->prep;
@@ -886,6 +894,7 @@ uint32_t estimate_nodes(const Prepared& pr, uint32_t w, uint32_t blen, bool exac
 template <int K>
 int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, const uint64_t* seq_off,
                const uint32_t* win_first, uint32_t* launches) {
+  NvtxRange nvtx(exact ? "vgc: POA pass (exact capacities)" : "vgc: POA pass");
   const Prepared& pr = h->prep;
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
@@ -1286,6 +1295,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     }
     VGC_CUDA(cudaEventRecord(h->ev[1], h->stream));
   }
+  NvtxRange nvtx_out("vgc: D2H + stitch");
   VGC_CUDA(cudaEventRecord(h->ev[2], h->stream));
   VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
   VGC_CUDA(cudaMemcpyAsync(h->h_out_len, h->d_out_len.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
@@ -1525,7 +1535,9 @@ int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_sta
   const bool early = batch_shape_ok(batch);
   if (early && (rc = upload_part(h, batch, true, &in_bytes))) return rc;
   const auto t0 = std::chrono::steady_clock::now();
+  nvtxRangePushA("vgc: host prepare (rank sort, weights)");
   rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
+  nvtxRangePop();
   const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (rc != VGC_OK) {
     cudaStreamSynchronize(h->stream);  // the caller may free its buffers as soon as we return
