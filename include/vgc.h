@@ -113,6 +113,7 @@ typedef struct {
   double   host_prep_ms;   /* host-side batch preparation (rank sort, average weights), wall clock          */
   uint32_t kernel_launches;
   uint32_t relaunched_windows; /* windows re-run with a larger scratch arena                      */
+  double   host_pack_ms;   /* host-side packing of the bases (2 or 4 bits each), overlapped with host_prep_ms    */
 } vgc_stats;
 
 /* Fails with VGC_ERR_INVALID on the parameters spoa::AlignmentEngine::Create rejects
@@ -125,6 +126,15 @@ uint64_t vgc_result_bound(const vgc_batch* batch);
 
 /* Host buffers in, host buffers out (H2D + kernels + D2H inside the call). */
 int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_stats* stats);
+
+/* The same call in two halves, for callers with more than one batch: vgc_submit stages a batch —
+ * host preparation, packing of the bases (2 bits each while the batch holds A C G T only, else 4), H2D on a copy
+ * stream — on a worker thread and returns at once; vgc_collect waits for the oldest submitted batch and runs its
+ * kernels + D2H.  Submitting batch i + 1 before collecting batch i overlaps its staging with the kernels of batch i
+ * (device inputs are double-buffered; at most two batches may be in flight).  The arrays of a submitted batch must
+ * stay valid until its vgc_collect returns.  vgc_polish(b) == vgc_submit(b) + vgc_collect(). */
+int vgc_submit(vgc_handle h, const vgc_batch* batch);
+int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats);
 
 /* Device-resident variant used by bench.py's `value` leg: vgc_upload copies the batch to HBM
  * once; vgc_polish_resident runs only the kernels (+ the D2H of the corrected bytes when

@@ -7,6 +7,8 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +34,8 @@ struct vgc_engine {
   vgc_params params;
   int device;
   int id;
+  std::mutex mu;
+  std::deque<vgc_batch> queue;  // vgc_submit'ed, not yet collected
 };
 
 extern "C" {
@@ -63,6 +67,31 @@ int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_sta
   const int rc = ref_polish()(batch, &h->params, result, 4);
   if (rc != 0) g_err = "mock: ref_polish failed";
   return rc;
+}
+
+// the two-halves form the binding uses: the mock "stages" by remembering the caller's arrays
+int vgc_submit(vgc_handle h, const vgc_batch* batch) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (h->queue.size() >= 2) {
+    g_err = "mock: two batches are already staged";
+    return VGC_ERR_INVALID;
+  }
+  h->queue.push_back(*batch);
+  return VGC_OK;
+}
+
+int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
+  vgc_batch b;
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (h->queue.empty()) {
+      g_err = "mock: nothing submitted";
+      return VGC_ERR_INVALID;
+    }
+    b = h->queue.front();
+    h->queue.pop_front();
+  }
+  return vgc_polish(h, &b, result, stats);
 }
 
 }  // extern "C"

@@ -32,7 +32,7 @@ def test_struct_sizes():
     assert C.sizeof(VgcParams) == 32
     assert C.sizeof(VgcBatch) == 8 + 8 * 8
     assert C.sizeof(VgcResult) == 32
-    assert C.sizeof(VgcStats) == 4 * 8 + 5 * 8 + 8
+    assert C.sizeof(VgcStats) == 4 * 8 + 5 * 8 + 8 + 8  # + host_pack_ms
 
 
 def test_weight_lut_formula():

@@ -59,6 +59,7 @@ class VgcStats(C.Structure):
         ("host_prep_ms", C.c_double),
         ("kernel_launches", C.c_uint32),
         ("relaunched_windows", C.c_uint32),
+        ("host_pack_ms", C.c_double),
     ]
 
 

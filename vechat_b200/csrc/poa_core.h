@@ -96,7 +96,8 @@ struct Scores {
 
 // Read-only batch, device-resident copy of vgc_batch + host-prepared per-window metadata.
 struct BatchView {
-  const uint8_t* bases;
+  const uint8_t* bases;        // base_bits == 8: the caller's bytes; 2 / 4: codes packed by the engine's staging
+  uint32_t base_bits = 8;      // (vgc_engine.cu stage_batch: 2 bits while the batch holds A C G T only, else 4)
   const uint8_t* quals;
   const uint64_t* seq_off;
   const uint8_t* has_qual;
@@ -116,6 +117,13 @@ struct BatchView {
   const uint32_t* wlut;        // [256] quality byte -> weight
   uint32_t num_codes;
 };
+
+// code of base `idx` of the batch (global base offset)
+VGC_HD VGC_INL uint32_t base_code(const BatchView& bv, uint64_t idx) {
+  if (bv.base_bits == 2) return (bv.bases[idx >> 2] >> ((idx & 3u) * 2u)) & 3u;
+  if (bv.base_bits == 4) return (bv.bases[idx >> 1] >> ((idx & 1u) * 4u)) & 15u;
+  return bv.coder[bv.bases[idx]];
+}
 
 struct Graph {
   uint32_t nV, nE;
@@ -1994,7 +2002,7 @@ struct Poa {
   VGC_HD uint8_t* stage_codes(uint32_t layer) {
     const uint32_t len = static_cast<uint32_t>(bv.seq_off[layer + 1] - bv.seq_off[layer]);
     uint8_t* codes = ex.seq_codes();
-    for (uint32_t i = ex.lane(); i < len; i += ex.width()) codes[i] = bv.coder[bv.bases[bv.seq_off[layer] + i]];
+    for (uint32_t i = ex.lane(); i < len; i += ex.width()) codes[i] = static_cast<uint8_t>(base_code(bv, bv.seq_off[layer] + i));
     ex.sync();
     return codes;
   }

@@ -320,8 +320,21 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
       first = last;
     }
     const unsigned pack_threads = std::max<unsigned>(1, num_threads_ / nd);
+    // two-deep pipeline over vgc_submit / vgc_collect: while the device works on batch x, a helper thread packs batch
+    // x + 1 (the windows only borrow their bytes, so packing is a pure read of Polisher::sequences_) and submits it —
+    // its host preparation and H2D overlap the kernels of batch x
     Packed cur, next;
-    if (!batches.empty()) CUDABatchProcessor::pack(windows_, batches[0].first, batches[0].second, &cur, pack_threads);
+    int rc_submit = VGC_OK;
+    std::string submit_err;
+    if (!batches.empty()) {
+      CUDABatchProcessor::pack(windows_, batches[0].first, batches[0].second, &cur, pack_threads);
+      const vgc_batch b0 = cur.view();
+      if (vgc_submit(h, &b0) != VGC_OK) {
+        errors[d] = vgc_last_error();
+        vgc_destroy(h);
+        return;
+      }
+    }
     for (size_t x = 0; x < batches.size(); ++x) {
       const size_t first = batches[x].first, last = batches[x].second;
       std::thread packer;
@@ -329,16 +342,20 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
         next = Packed();
         packer = std::thread([&, x] {
           CUDABatchProcessor::pack(windows_, batches[x + 1].first, batches[x + 1].second, &next, pack_threads);
+          const vgc_batch bn = next.view();
+          rc_submit = vgc_submit(h, &bn);
+          if (rc_submit != VGC_OK) submit_err = vgc_last_error();
         });
       }
       const vgc_batch batch = cur.view();
       std::vector<uint8_t> cons(vgc_result_bound(&batch));
       std::vector<uint64_t> off(batch.n_windows + 1);
       vgc_result r = {cons.data(), cons.size(), off.data(), polished.data() + first};
-      const int rc = vgc_polish(h, &batch, &r, nullptr);  // no CPU fallback
+      const int rc = vgc_collect(h, &r, nullptr);  // no CPU fallback
       if (rc != VGC_OK) errors[d] = vgc_last_error();
       if (packer.joinable()) packer.join();
-      if (rc != VGC_OK) break;
+      if (rc == VGC_OK && rc_submit != VGC_OK) errors[d] = submit_err;
+      if (rc != VGC_OK || rc_submit != VGC_OK) break;
       // consensus_ of batch x is written only after the packer of batch x + 1 is done: pack reads sequences_ of
       // other windows only, but this keeps the two phases trivially disjoint
       for (size_t i = first; i < last; ++i)

@@ -19,6 +19,7 @@
 #include <nvtx3/nvToolsExt.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(32, VGC_ALIGN_CTAS) align_kernel(const KernelA
   uint32_t* prof = reinterpret_cast<uint32_t*>(recs + kRecRing);
   const uint64_t o = a.bv.seq_off[l];
   const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
-  for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
+  for (uint32_t i = lane; i < len; i += 32) codes[i] = static_cast<uint8_t>(base_code(a.bv, o + i));
   __syncwarp();
   Scores sw;
   sw.m = 3;  // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(32) align_wide_kernel(const KernelArgs a, cons
     uint8_t* codes = smem + kAlignHeader;
     const uint64_t o = a.bv.seq_off[l];
     const uint32_t len = static_cast<uint32_t>(a.bv.seq_off[l + 1] - o);
-    for (uint32_t i = lane; i < len; i += 32) codes[i] = a.bv.coder[a.bv.bases[o + i]];
+    for (uint32_t i = lane; i < len; i += 32) codes[i] = static_cast<uint8_t>(base_code(a.bv, o + i));
     __syncwarp();
     Scores sw;
     sw.m = 3;  // the SW engine is hard-wired to 3/-5/-4 (window.cpp:326)
@@ -687,6 +688,24 @@ struct DevBuf {
 
 }  // namespace
 
+// One staged batch: device copies of the caller's arrays + what the host prepared (host_prep.h).
+struct InputSet {
+  DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
+  DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables;
+  vgc::Prepared prep;
+  uint32_t base_bits = 8;        // bases in HBM: 2 bits each (A C G T only), 4 bits (up to 16 codes)
+  uint8_t* h_packed = nullptr;   // pinned staging of the packed bases
+  size_t h_packed_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // first / last H2D of the staging, copy stream
+  // staging in flight (vgc_submit)
+  std::thread worker;
+  vgc_batch batch;               // the caller's arrays (must stay valid until vgc_collect returns)
+  int rc = VGC_OK;
+  std::string err;
+  uint64_t in_bytes = 0;
+  double prep_ms = 0.0, pack_ms = 0.0;
+};
+
 struct vgc_engine {
   int device = 0;
   vgc_params params;
@@ -707,9 +726,16 @@ struct vgc_engine {
   uint32_t smem_update = 0, smem_sort = 0;
   size_t mem_budget = 0;
   bool mem_budget_fixed = false;  // VGC_MEM_BUDGET_MB given
-  // device copies of the batch
-  DevBuf d_bases, d_quals, d_seq_off, d_has_qual, d_begin, d_end, d_win_first, d_win_flags;
-  DevBuf d_rank, d_nseq, d_avgw, d_out_off, d_out_cap, d_tables, d_work;
+  // device copies of a batch: two sets, so that vgc_submit can stage batch i + 1 (host prepare, packing, H2D on the
+  // copy stream) while vgc_collect runs the kernels of batch i out of the other set
+  InputSet in[2];
+  InputSet* I = &in[0];          // the set the running / last pass reads
+  int queued[2] = {-1, -1};      // submitted, not yet collected (oldest first)
+  int n_queued = 0;
+  std::mutex qmu;                // guards queued / n_queued / running / I: vgc_submit may come from another thread
+  bool running = false;          // vgc_collect is inside its pass (another thread may call vgc_submit meanwhile)
+  cudaStream_t copy_stream = nullptr;
+  DevBuf d_work;
   DevBuf d_out, d_out_len, d_status, d_misc, d_slots, d_slot_mem, d_wstates;
   DevBuf d_tl;  // diagnostics timeline (VGC_TIMELINE)
   DevBuf d_wide, d_wide_free;  // wide path: pool of int32 DP matrices + its ring of free ids
@@ -722,7 +748,6 @@ struct vgc_engine {
   size_t h_win_cap = 0;
   // resident batch (vgc_upload)
   bool resident = false;
-  vgc::Prepared prep;
   std::vector<uint8_t> backbone_copy;  // backbones of < 3-sequence windows (resident mode)
   std::vector<uint64_t> r_seq_off;
   std::vector<uint32_t> r_win_first;
@@ -734,19 +759,91 @@ namespace {
 
 using namespace vgc;
 
-// Host -> device copies of a batch, in two parts so that the bulk (bases, qualities, layer tables: everything the
-// caller owns) is already in flight on the copy stream while the host prepares the rest (prepare_batch).
-int upload_part(vgc_engine* h, const vgc_batch* b, bool raw, uint64_t* bytes_io) {
-  NvtxRange nvtx(raw ? "vgc: H2D batch" : "vgc: H2D prepared tables");
+// basic shape checks needed before anything is read from the batch's arrays (prepare_batch repeats them)
+bool batch_shape_ok(const vgc_batch* b) {
+  const uint32_t nw = b->n_windows;
+  if (!nw) return true;
+  return b->win_first && b->seq_off && b->bases && b->begin && b->end && b->has_qual && b->win_flags &&
+         b->win_first[nw] == b->n_layers;
+}
+
+// Bases travel packed: 2 bits per base while the batch holds A C G T only (their codes are 0-3 by construction,
+// host_prep.h), 4 bits otherwise (up to 16 codes).  `coder` == nullptr: the speculative 2-bit pass (the alphabet
+// prepare_batch finds decides whether it stands).  Bytes of the output are written by exactly one thread.
+bool pack_bases(const uint8_t* bases, uint64_t nb, const uint8_t* coder, uint8_t* out, unsigned threads) {
+  static const std::array<uint8_t, 256> acgt = [] {
+    std::array<uint8_t, 256> t;
+    t.fill(0xFF);
+    t['A'] = 0;
+    t['C'] = 1;
+    t['G'] = 2;
+    t['T'] = 3;
+    return t;
+  }();
+  const uint64_t per = coder ? 2 : 4;  // bases per output byte
+  const uint64_t nbytes = (nb + per - 1) / per;
+  std::vector<uint8_t> bad(threads, 0);
+  auto work = [&](unsigned t) {
+    const uint64_t b0 = (nbytes * t / threads) & ~1ull, b1 = t + 1 == threads ? nbytes : ((nbytes * (t + 1) / threads) & ~1ull);
+    uint8_t other = 0;
+    for (uint64_t q = b0; q < b1; ++q) {
+      const uint64_t i = q * per;
+      uint32_t v = 0;
+      if (!coder) {
+        if ((q & 1u) == 0 && q + 1 < b1 && i + 8 <= nb) {
+          // eight bases at once: (c >> 1) & 3 maps A C G T to 0 1 3 2, x ^ (x >> 1) puts them in code order 0 1 2 3;
+          // then the eight 2-bit fields are squeezed together.  Whether the batch really holds A C G T only is
+          // decided by the alphabet prepare_batch finds (the caller re-packs with 4 bits otherwise).
+          uint64_t w8;
+          std::memcpy(&w8, bases + i, 8);
+          uint64_t x = (w8 >> 1) & 0x0303030303030303ull;
+          x ^= (x >> 1) & 0x0101010101010101ull;
+          x = (x | (x >> 6)) & 0x000F000F000F000Full;
+          x = (x | (x >> 12)) & 0x000000FF000000FFull;
+          x = (x | (x >> 24)) & 0xFFFFull;
+          out[q] = static_cast<uint8_t>(x);
+          out[q + 1] = static_cast<uint8_t>(x >> 8);
+          ++q;
+          continue;
+        }
+        for (uint64_t k = 0; k < 4 && i + k < nb; ++k) {
+          const uint8_t c = acgt[bases[i + k]];
+          other |= c;
+          v |= static_cast<uint32_t>(c & 3u) << (2 * k);
+        }
+      } else {
+        v = coder[bases[i]] & 15u;
+        if (i + 1 < nb) v |= static_cast<uint32_t>(coder[bases[i + 1]] & 15u) << 4;
+      }
+      out[q] = static_cast<uint8_t>(v);
+    }
+    bad[t] = other & 0x80u;
+  };
+  if (threads <= 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < threads; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (uint8_t x : bad)
+    if (x) return false;
+  return true;
+}
+
+// Stage one batch into an input set: H2D of the caller's arrays (qualities and layer tables as they are, bases
+// packed), host preparation (rank sort, average weights, alphabet), H2D of the prepared tables — everything on the
+// copy stream, finished (synchronised) on return.  Runs on the caller's thread (vgc_polish, vgc_upload) or on the
+// set's worker thread (vgc_submit).
+int stage_batch(vgc_engine* h, InputSet* in, const vgc_batch* b) {
+  cudaSetDevice(h->device);
   const uint32_t nw = b->n_windows, nl = b->n_layers;
-  const uint64_t nb = nl ? b->seq_off[nl] : 0;
-  Prepared& pr = h->prep;
   uint64_t bytes = 0;
   auto put = [&](DevBuf& d, const void* src, size_t n) -> int {
     int rc = d.reserve(std::max<size_t>(n, 16));
     if (rc != VGC_OK) return rc;
     if (n) {
-      cudaError_t e = cudaMemcpyAsync(d.p, src, n, cudaMemcpyHostToDevice, h->stream);
+      cudaError_t e = cudaMemcpyAsync(d.p, src, n, cudaMemcpyHostToDevice, h->copy_stream);
       if (e != cudaSuccess) {
         set_err(std::string("H2D copy failed: ") + cudaGetErrorString(e));
         return VGC_ERR_CUDA;
@@ -756,65 +853,106 @@ int upload_part(vgc_engine* h, const vgc_batch* b, bool raw, uint64_t* bytes_io)
     return VGC_OK;
   };
   int rc;
-  if (raw) {
-    if ((rc = put(h->d_bases, b->bases, nb))) return rc;
-    if ((rc = put(h->d_quals, b->quals, b->quals ? nb : 0))) return rc;
-    if ((rc = put(h->d_seq_off, b->seq_off, (nl + 1) * sizeof(uint64_t)))) return rc;
-    if ((rc = put(h->d_has_qual, b->has_qual, nl))) return rc;
-    if ((rc = put(h->d_begin, b->begin, nl * 4ull))) return rc;
-    if ((rc = put(h->d_end, b->end, nl * 4ull))) return rc;
-    if ((rc = put(h->d_win_first, b->win_first, (nw + 1) * 4ull))) return rc;
-    if ((rc = put(h->d_win_flags, b->win_flags, nw))) return rc;
-    *bytes_io += bytes;
-    return VGC_OK;
+  in->in_bytes = 0;
+  in->prep_ms = in->pack_ms = 0.0;
+  VGC_CUDA(cudaEventRecord(in->ev0, h->copy_stream));
+  const bool shape_ok = batch_shape_ok(b);
+  const uint64_t nb = (shape_ok && nl) ? b->seq_off[nl] : 0;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned pack_threads = nb >= (1u << 22) ? std::min(8u, hw) : 1u;
+  std::thread packer;
+  bool acgt_only = false;
+  double pack_ms = 0.0;
+  if (shape_ok) {
+    NvtxRange nvtx("vgc: H2D batch");
+    // the bulk the caller owns goes first and overlaps the host-side preparation; the bases are packed meanwhile
+    if ((rc = put(in->d_quals, b->quals, b->quals ? nb : 0))) return rc;
+    if ((rc = put(in->d_seq_off, b->seq_off, (nl + 1) * sizeof(uint64_t)))) return rc;
+    if ((rc = put(in->d_has_qual, b->has_qual, nl))) return rc;
+    if ((rc = put(in->d_begin, b->begin, nl * 4ull))) return rc;
+    if ((rc = put(in->d_end, b->end, nl * 4ull))) return rc;
+    if ((rc = put(in->d_win_first, b->win_first, (nw + 1) * 4ull))) return rc;
+    if ((rc = put(in->d_win_flags, b->win_flags, nw))) return rc;
+    const size_t want = nb / 2 + 64;  // the 4-bit form is the larger one
+    if (in->h_packed_cap < want) {
+      if (in->h_packed) cudaFreeHost(in->h_packed);
+      in->h_packed = nullptr;
+      in->h_packed_cap = 0;
+      VGC_CUDA(cudaMallocHost(&in->h_packed, want + want / 8));
+      in->h_packed_cap = want + want / 8;
+    }
+    packer = std::thread([&, nb] {
+      const auto t0 = std::chrono::steady_clock::now();
+      acgt_only = pack_bases(b->bases, nb, nullptr, in->h_packed, pack_threads);
+      pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    });
   }
-  if ((rc = put(h->d_rank, pr.layer_rank.data(), nl * 4ull))) return rc;
-  if ((rc = put(h->d_nseq, pr.win_nseq.data(), nw * 4ull))) return rc;
-  if ((rc = put(h->d_avgw, pr.win_avgw.data(), nw * 8ull))) return rc;
-  if ((rc = put(h->d_out_off, pr.out_off.data(), nw * 8ull))) return rc;
-  if ((rc = put(h->d_out_cap, pr.out_cap.data(), nw * 4ull))) return rc;
-  // tables: coder[256] | decoder[8] | pad | wlut[256]
+  std::string err;
+  const auto t0 = std::chrono::steady_clock::now();
+  nvtxRangePushA("vgc: host prepare (rank sort, weights)");
+  rc = vgc::prepare_batch(b, &h->params, &in->prep, &err);
+  nvtxRangePop();
+  in->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (packer.joinable()) packer.join();
+  if (rc != VGC_OK) {
+    cudaStreamSynchronize(h->copy_stream);  // the caller may free its buffers as soon as we return
+    set_err(err);
+    return rc;
+  }
+  Prepared& pr = in->prep;
+  NvtxRange nvtx("vgc: H2D packed bases + prepared tables");
+  if (acgt_only && pr.num_codes == 4) {
+    in->base_bits = 2;
+  } else {
+    const auto t1 = std::chrono::steady_clock::now();
+    pack_bases(b->bases, nb, pr.coder, in->h_packed, pack_threads);
+    pack_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    in->base_bits = 4;
+  }
+  in->pack_ms = pack_ms;
+  if ((rc = put(in->d_bases, in->h_packed, (nb * in->base_bits + 7) / 8))) return rc;
+  if ((rc = put(in->d_rank, pr.layer_rank.data(), nl * 4ull))) return rc;
+  if ((rc = put(in->d_nseq, pr.win_nseq.data(), nw * 4ull))) return rc;
+  if ((rc = put(in->d_avgw, pr.win_avgw.data(), nw * 8ull))) return rc;
+  if ((rc = put(in->d_out_off, pr.out_off.data(), nw * 8ull))) return rc;
+  if ((rc = put(in->d_out_cap, pr.out_cap.data(), nw * 4ull))) return rc;
+  // tables: coder[256] | decoder[16] | wlut[256]
   std::vector<uint8_t> tab(256 + 16 + 1024);
   std::memcpy(tab.data(), pr.coder, 256);
   std::memcpy(tab.data() + 256, pr.decoder, kMaxCodes);
   std::memcpy(tab.data() + 272, pr.wlut, 1024);
-  if ((rc = put(h->d_tables, tab.data(), tab.size()))) return rc;
-  cudaError_t e = cudaStreamSynchronize(h->stream);  // `tab` and prep vectors must outlive the copies
+  if ((rc = put(in->d_tables, tab.data(), tab.size()))) return rc;
+  VGC_CUDA(cudaEventRecord(in->ev1, h->copy_stream));
+  cudaError_t e = cudaStreamSynchronize(h->copy_stream);  // `tab` and the prepared vectors must outlive the copies
   if (e != cudaSuccess) {
     set_err(std::string("H2D sync failed: ") + cudaGetErrorString(e));
     return VGC_ERR_CUDA;
   }
-  *bytes_io += bytes;
+  in->in_bytes = bytes;
   return VGC_OK;
 }
 
-// basic shape checks needed before anything is read from the batch's arrays (prepare_batch repeats them)
-bool batch_shape_ok(const vgc_batch* b) {
-  const uint32_t nw = b->n_windows;
-  if (!nw) return true;
-  return b->win_first && b->seq_off && b->bases && b->begin && b->end && b->has_qual && b->win_flags &&
-         b->win_first[nw] == b->n_layers;
-}
-
 BatchView make_view(vgc_engine* h) {
+  const InputSet& in = *h->I;
   BatchView v;
-  v.bases = h->d_bases.as<uint8_t>();
-  v.quals = h->d_quals.as<uint8_t>();
-  v.seq_off = h->d_seq_off.as<uint64_t>();
-  v.has_qual = h->d_has_qual.as<uint8_t>();
-  v.begin = h->d_begin.as<uint32_t>();
-  v.end = h->d_end.as<uint32_t>();
-  v.win_first = h->d_win_first.as<uint32_t>();
-  v.win_flags = h->d_win_flags.as<uint8_t>();
-  v.layer_rank = h->d_rank.as<uint32_t>();
-  v.win_nseq = h->d_nseq.as<uint32_t>();
-  v.win_avgw = h->d_avgw.as<double>();
-  v.out_off = h->d_out_off.as<uint64_t>();
-  v.out_cap = h->d_out_cap.as<uint32_t>();
-  v.coder = h->d_tables.as<uint8_t>();
-  v.decoder = h->d_tables.as<uint8_t>() + 256;
-  v.wlut = reinterpret_cast<const uint32_t*>(h->d_tables.as<uint8_t>() + 272);
-  v.num_codes = h->prep.num_codes;
+  v.bases = in.d_bases.as<uint8_t>();
+  v.base_bits = in.base_bits;
+  v.quals = in.d_quals.as<uint8_t>();
+  v.seq_off = in.d_seq_off.as<uint64_t>();
+  v.has_qual = in.d_has_qual.as<uint8_t>();
+  v.begin = in.d_begin.as<uint32_t>();
+  v.end = in.d_end.as<uint32_t>();
+  v.win_first = in.d_win_first.as<uint32_t>();
+  v.win_flags = in.d_win_flags.as<uint8_t>();
+  v.layer_rank = in.d_rank.as<uint32_t>();
+  v.win_nseq = in.d_nseq.as<uint32_t>();
+  v.win_avgw = in.d_avgw.as<double>();
+  v.out_off = in.d_out_off.as<uint64_t>();
+  v.out_cap = in.d_out_cap.as<uint32_t>();
+  v.coder = in.d_tables.as<uint8_t>();
+  v.decoder = in.d_tables.as<uint8_t>() + 256;
+  v.wlut = reinterpret_cast<const uint32_t*>(in.d_tables.as<uint8_t>() + 272);
+  v.num_codes = in.prep.num_codes;
   return v;
 }
 
@@ -895,7 +1033,7 @@ template <int K>
 int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, const uint64_t* seq_off,
                const uint32_t* win_first, uint32_t* launches) {
   NvtxRange nvtx(exact ? "vgc: POA pass (exact capacities)" : "vgc: POA pass");
-  const Prepared& pr = h->prep;
+  const Prepared& pr = h->I->prep;
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
   const uint32_t ml = std::max<uint32_t>(pr.max_len, 16);
@@ -1244,7 +1382,7 @@ int run_pass(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, int K
 
 int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t input_bytes,
                   const uint8_t* host_bases, const uint64_t* seq_off, const uint32_t* win_first, uint32_t nw) {
-  Prepared& pr = h->prep;
+  Prepared& pr = h->I->prep;
   int rc;
   if ((rc = h->d_out.reserve(std::max<uint64_t>(pr.out_total, 16)))) return rc;
   if ((rc = h->d_out_len.reserve(std::max<size_t>(nw, 4) * 4))) return rc;
@@ -1457,7 +1595,12 @@ int vgc_create(vgc_handle* out, int device, const vgc_params* params) {
 
 static int engine_init(vgc_engine* h) {
   VGC_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  VGC_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) VGC_CUDA(cudaEventCreate(&ev));
+  for (InputSet& in : h->in) {
+    VGC_CUDA(cudaEventCreate(&in.ev0));
+    VGC_CUDA(cudaEventCreate(&in.ev1));
+  }
   // groups are ordered deepest windows first: their chain of cycles is the critical path of a pass, so their
   // streams get the higher priorities
   int prio_least = 0, prio_greatest = 0;
@@ -1490,13 +1633,25 @@ static int engine_init(vgc_engine* h) {
 
 extern "C" {
 
+// wait for a staging in flight on `in` (its worker thread), if any
+static void join_set(InputSet* in) {
+  if (in->worker.joinable()) in->worker.join();
+}
+
 int vgc_destroy(vgc_handle h) {
   if (!h) return VGC_OK;
   cudaSetDevice(h->device);
-  for (DevBuf* d : {&h->d_bases, &h->d_quals, &h->d_seq_off, &h->d_has_qual, &h->d_begin, &h->d_end,
-                    &h->d_win_first, &h->d_win_flags, &h->d_rank, &h->d_nseq, &h->d_avgw, &h->d_out_off,
-                    &h->d_out_cap, &h->d_tables, &h->d_work, &h->d_out, &h->d_out_len, &h->d_status,
-                    &h->d_misc, &h->d_slots, &h->d_slot_mem, &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs, &h->d_tl, &h->d_wide, &h->d_wide_free,
+  for (InputSet& in : h->in) {
+    join_set(&in);
+    for (DevBuf* d : {&in.d_bases, &in.d_quals, &in.d_seq_off, &in.d_has_qual, &in.d_begin, &in.d_end, &in.d_win_first,
+                      &in.d_win_flags, &in.d_rank, &in.d_nseq, &in.d_avgw, &in.d_out_off, &in.d_out_cap, &in.d_tables})
+      d->release();
+    if (in.h_packed) cudaFreeHost(in.h_packed);
+    if (in.ev0) cudaEventDestroy(in.ev0);
+    if (in.ev1) cudaEventDestroy(in.ev1);
+  }
+  for (DevBuf* d : {&h->d_work, &h->d_out, &h->d_out_len, &h->d_status, &h->d_misc, &h->d_slots, &h->d_slot_mem,
+                    &h->d_wstates, &h->d_pool, &h->d_pool_busy, &h->d_jobs, &h->d_tl, &h->d_wide, &h->d_wide_free,
                     &h->d_jobcnt})
     d->release();
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -1510,6 +1665,7 @@ int vgc_destroy(vgc_handle h) {
     if (h->gev[g]) cudaEventDestroy(h->gev[g]);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return VGC_OK;
 }
@@ -1519,43 +1675,110 @@ uint64_t vgc_result_bound(const vgc_batch* batch) {
   return batch->seq_off[batch->n_layers] + 16;
 }
 
+int vgc_submit(vgc_handle h, const vgc_batch* batch) {
+  if (!h || !batch) {
+    set_err("null argument");
+    return VGC_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(h->qmu);
+  if (h->n_queued >= 2) {
+    set_err("two batches are already staged: call vgc_collect first");
+    return VGC_ERR_INVALID;
+  }
+  // a set is queued, or being read by the running pass (h->I while vgc_collect is inside polish_device), or free
+  int idx = -1;
+  for (int i = 0; i < 2 && idx < 0; ++i) {
+    bool busy = h->running && &h->in[i] == h->I;
+    for (int q = 0; q < h->n_queued; ++q) busy = busy || h->queued[q] == i;
+    if (!busy) idx = i;
+  }
+  if (idx < 0) {
+    set_err("no free input set: call vgc_collect first");
+    return VGC_ERR_INVALID;
+  }
+  InputSet* in = &h->in[idx];
+  join_set(in);
+  h->resident = h->resident && in != h->I;  // staging over the resident batch's set ends its residency
+  in->batch = *batch;
+  in->rc = VGC_OK;
+  in->err.clear();
+  h->queued[h->n_queued++] = idx;
+  in->worker = std::thread([h, in] {
+    in->rc = stage_batch(h, in, &in->batch);
+    if (in->rc != VGC_OK) in->err = vgc_last_error();  // thread-local: carry it to the collecting thread
+  });
+  return VGC_OK;
+}
+
+int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
+  if (!h || !result) {
+    set_err("null argument");
+    return VGC_ERR_INVALID;
+  }
+  VGC_CUDA(cudaSetDevice(h->device));
+  InputSet* in;
+  {
+    std::lock_guard<std::mutex> lock(h->qmu);
+    if (h->n_queued == 0) {
+      set_err("nothing submitted: call vgc_submit first");
+      return VGC_ERR_INVALID;
+    }
+    in = &h->in[h->queued[0]];
+    h->queued[0] = h->queued[1];
+    --h->n_queued;
+    h->I = in;  // from here on the set counts as busy for vgc_submit
+    h->running = true;
+  }
+  join_set(in);
+  if (in->rc != VGC_OK) {
+    set_err(in->err);
+    std::lock_guard<std::mutex> lock(h->qmu);
+    h->running = false;
+    return in->rc;
+  }
+  h->resident = false;
+  const vgc_batch* b = &in->batch;
+  const int rc = polish_device(h, result, stats, in->in_bytes, b->bases, b->seq_off, b->win_first, b->n_windows);
+  {
+    std::lock_guard<std::mutex> lock(h->qmu);
+    h->running = false;
+  }
+  if (rc != VGC_OK) return rc;
+  if (stats) {
+    float h2d_ms = 0.f;
+    VGC_CUDA(cudaEventElapsedTime(&h2d_ms, in->ev0, in->ev1));
+    stats->h2d_ms = h2d_ms;
+    stats->host_prep_ms = in->prep_ms;
+    stats->host_pack_ms = in->pack_ms;
+  }
+  return VGC_OK;
+}
+
 int vgc_polish(vgc_handle h, const vgc_batch* batch, vgc_result* result, vgc_stats* stats) {
   if (!h || !batch || !result) {
     set_err("null argument");
     return VGC_ERR_INVALID;
   }
-  VGC_CUDA(cudaSetDevice(h->device));
-  h->resident = false;
-  std::string err;
-  uint64_t in_bytes = 0;
-  float h2d_ms = 0.f;
-  int rc;
-  // the bulk copies start first and overlap the host-side preparation
-  VGC_CUDA(cudaEventRecord(h->ev[4], h->stream));
-  const bool early = batch_shape_ok(batch);
-  if (early && (rc = upload_part(h, batch, true, &in_bytes))) return rc;
-  const auto t0 = std::chrono::steady_clock::now();
-  nvtxRangePushA("vgc: host prepare (rank sort, weights)");
-  rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
-  nvtxRangePop();
-  const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (rc != VGC_OK) {
-    cudaStreamSynchronize(h->stream);  // the caller may free its buffers as soon as we return
-    set_err(err);
-    return rc;
+  if (h->n_queued) {
+    set_err("vgc_polish with batches still queued: collect them first");
+    return VGC_ERR_INVALID;
   }
-  if (!early && (rc = upload_part(h, batch, true, &in_bytes))) return rc;
-  if ((rc = upload_part(h, batch, false, &in_bytes))) return rc;
-  VGC_CUDA(cudaEventRecord(h->ev[5], h->stream));
-  rc = polish_device(h, result, stats, in_bytes, batch->bases, batch->seq_off, batch->win_first, batch->n_windows);
+  VGC_CUDA(cudaSetDevice(h->device));
+  // the same two steps as vgc_submit + vgc_collect, on this thread
+  InputSet* in = h->I;
+  join_set(in);
+  h->resident = false;
+  int rc = stage_batch(h, in, batch);
+  if (rc != VGC_OK) return rc;
+  rc = polish_device(h, result, stats, in->in_bytes, batch->bases, batch->seq_off, batch->win_first, batch->n_windows);
   if (rc != VGC_OK) return rc;
   if (stats) {
-    VGC_CUDA(cudaEventElapsedTime(&h2d_ms, h->ev[4], h->ev[5]));
+    float h2d_ms = 0.f;
+    VGC_CUDA(cudaEventElapsedTime(&h2d_ms, in->ev0, in->ev1));
     stats->h2d_ms = h2d_ms;
-    float dev_ms = 0.f;
-    VGC_CUDA(cudaEventElapsedTime(&dev_ms, h->ev[4], h->ev[3]));
-    stats->device_ms = dev_ms;
-    stats->host_prep_ms = prep_ms;
+    stats->device_ms += h2d_ms;
+    stats->host_prep_ms = in->prep_ms;
+    stats->host_pack_ms = in->pack_ms;
   }
   return VGC_OK;
 }
@@ -1565,17 +1788,17 @@ int vgc_upload(vgc_handle h, const vgc_batch* batch) {
     set_err("null argument");
     return VGC_ERR_INVALID;
   }
+  if (h->n_queued) {
+    set_err("vgc_upload with batches still queued: collect them first");
+    return VGC_ERR_INVALID;
+  }
   VGC_CUDA(cudaSetDevice(h->device));
   h->resident = false;
-  std::string err;
-  int rc = vgc::prepare_batch(batch, &h->params, &h->prep, &err);
-  if (rc != VGC_OK) {
-    set_err(err);
-    return rc;
-  }
-  h->r_input_bytes = 0;
-  if ((rc = upload_part(h, batch, true, &h->r_input_bytes))) return rc;
-  if ((rc = upload_part(h, batch, false, &h->r_input_bytes))) return rc;
+  InputSet* in = h->I;
+  join_set(in);
+  int rc = stage_batch(h, in, batch);
+  if (rc != VGC_OK) return rc;
+  h->r_input_bytes = in->in_bytes;
   // keep what the stitcher needs from the host batch
   h->r_n_windows = batch->n_windows;
   h->r_n_layers = batch->n_layers;

@@ -15,7 +15,8 @@ _LIB = None
 LIB_PATH = os.environ.get("VGC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvgc.so")  # VGC_LIB: experiments
 
 EXPORTS = ["vgc_create", "vgc_destroy", "vgc_result_bound", "vgc_polish", "vgc_upload", "vgc_polish_resident",
-           "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile", "vgc_limits", "vgc_window_status"]
+           "vgc_last_error", "vgc_version", "vgc_weight_lut", "vgc_phase_profile", "vgc_limits", "vgc_window_status", "vgc_submit",
+           "vgc_collect"]
 
 
 class VgcError(RuntimeError):
@@ -39,6 +40,10 @@ def load_library():
         lib.vgc_result_bound.argtypes = [C.POINTER(VgcBatch)]
         lib.vgc_polish.restype = C.c_int
         lib.vgc_polish.argtypes = [C.c_void_p, C.POINTER(VgcBatch), C.POINTER(VgcResult), C.POINTER(VgcStats)]
+        lib.vgc_submit.restype = C.c_int
+        lib.vgc_submit.argtypes = [C.c_void_p, C.POINTER(VgcBatch)]
+        lib.vgc_collect.restype = C.c_int
+        lib.vgc_collect.argtypes = [C.c_void_p, C.POINTER(VgcResult), C.POINTER(VgcStats)]
         lib.vgc_upload.restype = C.c_int
         lib.vgc_upload.argtypes = [C.c_void_p, C.POINTER(VgcBatch)]
         lib.vgc_polish_resident.restype = C.c_int
@@ -89,6 +94,25 @@ class Engine:
         r, arrays = alloc_result(batch)
         st = VgcStats()
         self._check(self.lib.vgc_polish(self._h, C.byref(b), C.byref(r), C.byref(st)))
+        return finish_result(batch, arrays), _stats(st)
+
+    def submit(self, batch: WindowBatch):
+        """vgc_submit: stage a batch (host prepare, packing, H2D) on the engine's worker thread; returns at once.
+        Submit batch i + 1 before collect() of batch i to overlap its staging with the kernels of batch i."""
+        b = batch.c_struct()
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._inflight.append((batch, b))  # the arrays must outlive the collect
+        self._check(self.lib.vgc_submit(self._h, C.byref(b)))
+
+    def collect(self):
+        """vgc_collect: kernels + D2H of the oldest submitted batch.  Returns (PolishResult, stats dict)."""
+        batch, _b = self._inflight[0]
+        r, arrays = alloc_result(batch)
+        st = VgcStats()
+        rc = self.lib.vgc_collect(self._h, C.byref(r), C.byref(st))
+        self._inflight.pop(0)
+        self._check(rc)
         return finish_result(batch, arrays), _stats(st)
 
     def limits(self):

@@ -129,6 +129,18 @@ class Polisher:
         self.last_stats = stats
         return result
 
+    def submit_shard(self, shard_batch):
+        """First half of polish_shard for callers with several batches (vgc_submit): host prepare, packing of the
+        bases and H2D of `shard_batch` start on the engine's worker thread.  Submit batch i + 1 before collecting
+        batch i and its staging overlaps the kernels of batch i."""
+        self.engine.submit(shard_batch)
+
+    def collect_shard(self):
+        """Second half (vgc_collect): kernels + D2H of the oldest submitted batch."""
+        result, stats = self.engine.collect()
+        self.last_stats = stats
+        return result
+
     def polish(self, batch, names, coverages=None, fragment_correction=True, drop_unpolished=False,
                shard_batch=None, gather_device=None):
         """batch: WindowBatch of ALL windows with .win_target/.win_rank (every rank holds the tiling, as every
