@@ -247,9 +247,9 @@ def main():
         with ThreadPoolExecutor(1) as ex:
             prev = None
             for k in range(steps):
+                fut = ex.submit(pol.collect_shard)
                 if k + 1 < steps:
                     pol.submit_shard(batch)
-                fut = ex.submit(pol.collect_shard)
                 if prev is not None:
                     recs = finish(prev)
                 prev = fut.result()

@@ -333,9 +333,10 @@ inline uint64_t slot_bytes(const SlotDims& d) {
 }
 
 inline void slot_carve(const SlotDims& d, uint8_t* base, Slot* s) {
-  std::vector<uint64_t> offs;
+  uint64_t offs[96];  // (a pass carves tens of thousands of slots: no heap traffic here)
+  size_t n_offs = 0;
   slot_walk(d, [&](uint64_t o) {
-    offs.push_back(o);
+    offs[n_offs++] = o;
     return 0;
   });
   size_t i = 0;

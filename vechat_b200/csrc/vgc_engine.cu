@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -714,6 +715,7 @@ struct vgc_engine {
   double phase_cycles[16] = {0};  // last call: leader-lane cycles per kPh* phase, summed over windows
   double pool_spins = 0.0;      // last call: failed attempts to take a DP buffer (0 unless the residency bound is off)
   double launch_ms = 0.0;       // host wall time spent enqueueing the kernel launches of the current call
+  double setup_ms = 0.0;        // host wall time from the start of a pass to its first launch (slots, groups, pools)
   double pass_kernel_ms = 0.0;  // device time of the POA kernel launches of the current call (events 6/7)
   int sm_count = 0;
   int groups = 48;                // streams of a lockstep pass (upper bound)
@@ -732,6 +734,7 @@ struct vgc_engine {
   InputSet* I = &in[0];          // the set the running / last pass reads
   int queued[2] = {-1, -1};      // submitted, not yet collected (oldest first)
   int n_queued = 0;
+  std::atomic<bool> in_setup{false};  // a pass is between its start and its first launches: staging workers hold back
   std::mutex qmu;                // guards queued / n_queued / running / I: vgc_submit may come from another thread
   bool running = false;          // vgc_collect is inside its pass (another thread may call vgc_submit meanwhile)
   cudaStream_t copy_stream = nullptr;
@@ -1033,6 +1036,7 @@ template <int K>
 int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, const uint64_t* seq_off,
                const uint32_t* win_first, uint32_t* launches) {
   NvtxRange nvtx(exact ? "vgc: POA pass (exact capacities)" : "vgc: POA pass");
+  const auto t_entry = std::chrono::steady_clock::now();
   const Prepared& pr = h->I->prep;
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
@@ -1276,6 +1280,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       VGC_CUDA(cudaMemsetAsync(a.tl, 0, 16, h->stream));
     }
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    h->setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count();
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
     // ---- lockstep: the lists are sorted by decreasing cycles, so the live windows of a cycle are a prefix
     std::vector<uint32_t> live(G);
@@ -1283,6 +1288,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     const auto tl0 = std::chrono::steady_clock::now();
     uint32_t nl = 0;
     for (uint32_t c = 0; c < max_cyc; ++c) {
+      if (c == 3) h->in_setup.store(false, std::memory_order_release);  // the device has work queued: staging may start
       for (int g = 0; g < G; ++g) {
         const std::vector<uint32_t>& ns = gnseq[g];
         while (live[g] > 0 && win_cycles(ns[live[g] - 1], hap, num_prune) <= c) --live[g];
@@ -1406,6 +1412,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
   float kernel_ms = 0.f, d2h_ms = 0.f;
   h->pass_kernel_ms = 0.0;
   h->launch_ms = 0.0;
+  h->setup_ms = 0.0;
   VGC_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 256, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_out_len.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
   VGC_CUDA(cudaMemsetAsync(h->d_status.p, 0, std::max<size_t>(nw, 4) * 4, h->stream));
@@ -1498,8 +1505,8 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     h->phase_cycles[0] = static_cast<double>(totals[6 + vgc::kPhCount]);
     h->pool_spins = static_cast<double>(totals[7 + vgc::kPhCount]);
     if (std::getenv("VGC_VERBOSE"))
-      std::fprintf(stderr, "[vgc] pass: %.1f ms kernels, %u launches, pool waits %.0f, slow trace steps %.0f, max fill %.0f / trace %.0f cycles\n",
-                   h->pass_kernel_ms, launches, h->pool_spins, h->phase_cycles[0], h->phase_cycles[14], h->phase_cycles[15]);
+      std::fprintf(stderr, "[vgc] pass: %.1f ms kernels, %.1f ms host setup before the first launch, %.1f ms enqueueing, %u launches, pool waits %.0f, slow trace steps %.0f, max fill %.0f / trace %.0f cycles\n",
+                   h->pass_kernel_ms, h->setup_ms, h->launch_ms, launches, h->pool_spins, h->phase_cycles[0], h->phase_cycles[14], h->phase_cycles[15]);
     stats->cells = totals[0];
     stats->alignments = totals[1];
     stats->input_bytes = input_bytes;
@@ -1704,6 +1711,10 @@ int vgc_submit(vgc_handle h, const vgc_batch* batch) {
   in->err.clear();
   h->queued[h->n_queued++] = idx;
   in->worker = std::thread([h, in] {
+    // the serial host work at the start of a pass (slots, groups, first launches) is on the device's critical path:
+    // let it finish before two dozen staging threads compete with it for the cores
+    for (int spin = 0; spin < 400 && h->in_setup.load(std::memory_order_acquire); ++spin)
+      std::this_thread::sleep_for(std::chrono::microseconds(500));
     in->rc = stage_batch(h, in, &in->batch);
     if (in->rc != VGC_OK) in->err = vgc_last_error();  // thread-local: carry it to the collecting thread
   });
@@ -1728,12 +1739,14 @@ int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
     --h->n_queued;
     h->I = in;  // from here on the set counts as busy for vgc_submit
     h->running = true;
+    h->in_setup.store(true, std::memory_order_release);
   }
   join_set(in);
   if (in->rc != VGC_OK) {
     set_err(in->err);
     std::lock_guard<std::mutex> lock(h->qmu);
     h->running = false;
+    h->in_setup.store(false, std::memory_order_release);
     return in->rc;
   }
   h->resident = false;
@@ -1742,6 +1755,7 @@ int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
   {
     std::lock_guard<std::mutex> lock(h->qmu);
     h->running = false;
+    h->in_setup.store(false, std::memory_order_release);
   }
   if (rc != VGC_OK) return rc;
   if (stats) {
