@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--workload", default="pb", choices=["pb", "ont", "hap2"],
                     help="pb = BASELINE configs[1] (the benchmark); ont / hap2 = configs[2] / configs[3], extra evidence only")
+    ap.add_argument("--hap2-leg", action="store_true", help="also run the hap2 (configs[3] shape) leg at N = 1 (always run at N > 1)")
     ap.add_argument("--num-prune", type=int, default=3, help="diagnostics only: -k of the haplotype path (3 = the benchmark)")
     return ap.parse_args()
 
@@ -188,7 +189,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": workload_config(args, 1), "corrected_bases_per_sec": bases / dt,
+            "config": workload_config(args, args.gpus), "corrected_bases_per_sec": bases / dt,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -196,22 +197,8 @@ def run_reference(args):
     return 0
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+def measure(args, torch, dist, world, rank, local, cpu_seconds):
+    """One workload through both legs on every rank; returns the JSON line (rank 0) or None."""
     from vechat_b200._ffi import make_params
     from vechat_b200.engine import Engine
     from vechat_b200.polisher import Polisher, stitch, _gather_records
@@ -361,8 +348,8 @@ def main():
         line["phase_raw"] = {k: float(v) for k, v in ph.items()}
         line["alignments"] = int(res_stats[-1]["alignments"])
         line["relaunched_windows"] = int(res_stats[-1]["relaunched_windows"])
-        if world == 1 and not args.no_cpu_baseline:
-            kind, cores, sb, fn = cpu_leg(batch, params, args.cpu_seconds)
+        if cpu_seconds > 0:
+            kind, cores, sb, fn = cpu_leg(batch, params, cpu_seconds)
             t0 = time.perf_counter()
             r = fn(sb, params, threads=cores)
             dt = time.perf_counter() - t0
@@ -376,6 +363,45 @@ def main():
                       if result.window(int(w)) != r.window(i) or int(result.polished[int(w)]) != int(r.polished[i]))
             line["parity"] = {"windows_checked": int(sb.n_windows), "mismatches": int(bad),
                               "against": "compiled reference" if kind == "reference" else "oracle port"}
+        eng.close()
+        return line
+    eng.close()
+    return None
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    line = measure(args, torch, dist, world, rank, local,
+                   args.cpu_seconds if (world == 1 and not args.no_cpu_baseline) else 0.0)
+    if (world > 1 or args.hap2_leg) and args.workload == "pb":
+        # the shape the 8-GPU target is quoted on (BASELINE configs[3]: 2-haplotype mix, depth ~60), on disjoint
+        # target ranges (50k reads): same legs, fewer steps, with a parity sample against the CPU reference on rank 0
+        import copy
+        a2 = copy.copy(args)
+        a2.workload = "hap2"
+        a2.steps = max(2, min(args.steps, 3))
+        a2.warmup = 3
+        a2.targets = min(args.targets, 800)
+        h = measure(a2, torch, dist, world, rank, local, 0.0 if args.no_cpu_baseline else 8.0)
+        if rank == 0:
+            keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "windows_per_step", "e2e",
+                    "roofline", "cpu_baseline", "parity", "alignments", "relaunched_windows")
+            line["hap2"] = {k: h[k] for k in keep if k in h}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
