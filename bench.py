@@ -363,6 +363,25 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
                       if result.window(int(w)) != r.window(i) or int(result.polished[int(w)]) != int(r.polished[i]))
             line["parity"] = {"windows_checked": int(sb.n_windows), "mismatches": int(bad),
                               "against": "compiled reference" if kind == "reference" else "oracle port"}
+            # two more CPU figures on a smaller sample: the same reference on ONE core, and its
+            # -mavx2 build (spoa's 16-lane engine) on all cores
+            if kind == "reference" and args.workload == "pb":
+                from oracle import checker
+                variants = {}
+                small = batch.select(sb.sample_index[:: max(1, len(sb.sample_index) // max(8, sb.n_windows // 40))])
+                t0 = time.perf_counter()
+                fn(small, params, threads=1)
+                variants["sse41_1_core"] = {"value": small.n_windows / (time.perf_counter() - t0), "unit": UNIT,
+                                            "cores": 1, "windows": int(small.n_windows)}
+                if checker.have_ref_avx2():
+                    mid = batch.select(sb.sample_index[::3])
+                    t0 = time.perf_counter()
+                    r2 = checker.ref_avx2_polish(mid, params, threads=cores)
+                    variants["avx2_all_cores"] = {"value": mid.n_windows / (time.perf_counter() - t0), "unit": UNIT,
+                                                  "cores": cores, "windows": int(mid.n_windows),
+                                                  "same_output_as_sse41": all(
+                                                      r2.window(i) == r.window(3 * i) for i in range(mid.n_windows))}
+                line["cpu_baseline"]["variants"] = variants
         eng.close()
         return line
     eng.close()

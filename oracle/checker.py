@@ -65,6 +65,30 @@ def ref_polish(batch, params, threads=1):
     return _polish(_load_ref().ref_polish, batch, params, threads)
 
 
+REF_AVX2_SO = os.path.join(HERE, "_ref", "libvechat_ref_avx2.so")
+_ref_avx2 = None
+
+
+def have_ref_avx2():
+    """The -mavx2 build of the reference (second CPU baseline) is there and this CPU can run it."""
+    if not os.path.exists(REF_AVX2_SO):
+        return False
+    try:
+        return " avx2 " in open("/proc/cpuinfo").read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def ref_avx2_polish(batch, params, threads=1):
+    global _ref_avx2
+    if _ref_avx2 is None:
+        lib = C.CDLL(REF_AVX2_SO)
+        lib.ref_polish.restype = C.c_int
+        lib.ref_polish.argtypes = [C.POINTER(VgcBatch), C.POINTER(VgcParams), C.POINTER(VgcResult), C.c_int]
+        _ref_avx2 = lib
+    return _polish(_ref_avx2.ref_polish, batch, params, threads)
+
+
 def oracle_polish(batch, params, threads=1):
     return _polish(_load_oracle().oracle_polish, batch, params, threads)
 

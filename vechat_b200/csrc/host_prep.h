@@ -69,7 +69,8 @@ struct Prepared {
 
 // Returns VGC_OK or VGC_ERR_INVALID / VGC_ERR_CAPACITY with a message.  Windows are independent, so the
 // per-window part runs on a few host threads (the reference does the same work inside its per-window tasks).
-inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out, std::string* err) {
+inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out, std::string* err,
+                         unsigned max_threads = 16) {
   const uint32_t nw = b->n_windows, nl = b->n_layers;
   if (p->gap > 0 || (p->num_prune == 0 && p->haplotype)) {
     *err = "invalid params: gap must be non-positive, num_prune >= 1";
@@ -194,7 +195,7 @@ inline int prepare_batch(const vgc_batch* b, const vgc_params* p, Prepared* out,
       }
     }
   };
-  unsigned nt = nw >= 1024 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  unsigned nt = nw >= 1024 ? std::min(std::max(1u, max_threads), std::max(1u, std::thread::hardware_concurrency())) : 1u;
   std::vector<Part> parts(nt);
   if (nt == 1) {
     run_range(0, nw, &parts[0]);

@@ -16,7 +16,10 @@
 // No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
 
 #include <cuda_runtime.h>
-#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
+#include <nvtx3/nvToolsExt.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
 
 #include <algorithm>
 #include <array>
@@ -721,6 +724,8 @@ struct vgc_engine {
   int groups = 48;                // streams of a lockstep pass (upper bound)
   uint32_t node_share_div = 6;    // first-pass node capacity = backbone + (sum of layer lengths) / this + one layer
   double sort_growth = 0.055;     // new graph nodes per base added, upper estimate (sizes the sort kernel's shared memory)
+  unsigned host_threads = 16;     // host threads of a staging (prepare + packing): VGC_HOST_THREADS, else the cores
+                                  // divided by the processes sharing the host (LOCAL_WORLD_SIZE), at most 16
   int launch_threads = 1;         // host threads enqueueing the launches of a pass (measured: the enqueue is not the limit)
   int group_mode = 2;             // 2: one group per number of fills, 1: equal contiguous blocks of the depth-sorted list, 0: round-robin
   cudaStream_t gstream[64] = {};
@@ -861,8 +866,7 @@ int stage_batch(vgc_engine* h, InputSet* in, const vgc_batch* b) {
   VGC_CUDA(cudaEventRecord(in->ev0, h->copy_stream));
   const bool shape_ok = batch_shape_ok(b);
   const uint64_t nb = (shape_ok && nl) ? b->seq_off[nl] : 0;
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const unsigned pack_threads = nb >= (1u << 22) ? std::min(8u, hw) : 1u;
+  const unsigned pack_threads = nb >= (1u << 22) ? std::max(1u, std::min(8u, h->host_threads / 2)) : 1u;
   std::thread packer;
   bool acgt_only = false;
   double pack_ms = 0.0;
@@ -893,7 +897,7 @@ int stage_batch(vgc_engine* h, InputSet* in, const vgc_batch* b) {
   std::string err;
   const auto t0 = std::chrono::steady_clock::now();
   nvtxRangePushA("vgc: host prepare (rank sort, weights)");
-  rc = vgc::prepare_batch(b, &h->params, &in->prep, &err);
+  rc = vgc::prepare_batch(b, &h->params, &in->prep, &err, h->host_threads);
   nvtxRangePop();
   in->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (packer.joinable()) packer.join();
@@ -1628,6 +1632,12 @@ static int engine_init(vgc_engine* h) {
   if (const char* s = std::getenv("VGC_SORT_GROWTH")) h->sort_growth = std::atof(s);
   if (const char* s = std::getenv("VGC_LAUNCH_THREADS")) h->launch_threads = std::max(1, std::min(16, std::atoi(s)));
   if (const char* s = std::getenv("VGC_GROUPS")) h->groups = std::max(1, std::min(kMaxGroups, std::atoi(s)));
+  {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency()), procs = 1;
+    if (const char* s = std::getenv("LOCAL_WORLD_SIZE")) procs = static_cast<unsigned>(std::max(1, std::atoi(s)));
+    h->host_threads = std::max(1u, std::min(16u, hw / procs));
+    if (const char* s = std::getenv("VGC_HOST_THREADS")) h->host_threads = static_cast<unsigned>(std::max(1, std::min(64, std::atoi(s))));
+  }
   size_t free_b = 0, total_b = 0;
   VGC_CUDA(cudaMemGetInfo(&free_b, &total_b));
   h->mem_budget = static_cast<size_t>(free_b * 0.70);
@@ -1713,6 +1723,9 @@ int vgc_submit(vgc_handle h, const vgc_batch* batch) {
   in->worker = std::thread([h, in] {
     // the serial host work at the start of a pass (slots, groups, first launches) is on the device's critical path:
     // let it finish before two dozen staging threads compete with it for the cores
+    // ... and it runs at a lower priority than the thread that enqueues the kernel launches of the running pass (the
+    // threads prepare_batch and the packer start inherit it)
+    setpriority(PRIO_PROCESS, static_cast<id_t>(syscall(SYS_gettid)), 10);
     for (int spin = 0; spin < 400 && h->in_setup.load(std::memory_order_acquire); ++spin)
       std::this_thread::sleep_for(std::chrono::microseconds(500));
     in->rc = stage_batch(h, in, &in->batch);
