@@ -230,16 +230,23 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
         prepare + packing + H2D), runs the kernels, copies the corrected windows back and stitches them; the
         staging of step k + 1 and the stitch of step k - 1 overlap the kernels of step k."""
         stats, result, recs = [], None, None
+        trace = os.environ.get("BENCH_TRACE") and rank == 0
         pol.submit_shard(batch)
         with ThreadPoolExecutor(1) as ex:
             prev = None
             for k in range(steps):
+                ta = time.perf_counter()
                 fut = ex.submit(pol.collect_shard)
                 if k + 1 < steps:
                     pol.submit_shard(batch)
+                tb = time.perf_counter()
                 if prev is not None:
                     recs = finish(prev)
+                tc = time.perf_counter()
                 prev = fut.result()
+                if trace:
+                    print("[bench] step %d: submit %.1f ms, finish(prev) %.1f ms, waited %.1f ms more for collect" % (
+                        k, (tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
                 stats.append(pol.last_stats)
             result = prev
             recs = finish(prev)
@@ -302,14 +309,14 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
         alg_bytes_per_launch = 2.0 * cells
         k_avg_s = kern_ms / 1e3 / max(k_launches, 1)
         achieved = alg_bytes_per_launch / k_avg_s / 1e9
-        # DRAM traffic of the fill kernel per pass: bytes per DP cell measured once with `ncu --set full`
-        # (dram__bytes_read.sum + dram__bytes_write.sum of one fill_kernel launch / the cells that launch filled,
-        # profiles/traffic.json) x the cells of this pass
+        # DRAM traffic of the align kernels per pass: bytes per DP cell measured with ncu over every align_kernel
+        # launch of whole passes of this workload on the final binary (dram__bytes_read.sum + dram__bytes_write.sum,
+        # profiles/traffic.json says how) x the cells of this pass
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = float(json.load(open(tpath))["fill_dram_bytes_per_cell"]) * cells
+                traffic = float(json.load(open(tpath))["align_dram_bytes_per_cell"]) * cells
             except Exception:
                 traffic = None
         line = {
@@ -332,7 +339,7 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fill_kernel, charged with the whole lockstep pass (trace/update/sort/fill)",
+                         "kernel": "align_kernel (DP fill + traceback), charged with the whole lockstep pass (update / sort / align)",
                          "launch_unit": "one pass = one step (all kernel launches of a vgc_polish_resident call)",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "dp_cells_per_launch": cells, "kernel_ms_per_launch": k_avg_s * 1e3,

@@ -6,6 +6,7 @@
 #include "b200polisher.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -277,71 +278,68 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
   const size_t n = windows_.size();
   std::vector<uint8_t> polished(n, 0);
 
-  // One contiguous range of WHOLE targets per device (a target's windows are consecutive and start at rank 0,
-  // polisher.cpp:389-404), balanced by layer bytes.
+  // The windows are cut into batches (<= 64 k windows / 1 GB of bases per vgc call) that form ONE queue for all
+  // devices: every device has its own host thread + vgc_handle (the model of the legacy path,
+  // cudapolisher.cpp:229-241,255-277, whose threads pull windows under a mutex) and pulls the next batch when it
+  // starts working on the one it holds — the multi-GPU form of scripts/vechat's --split chunk loop (:300-361), without
+  // a process launch and a FASTA round trip per chunk.  Windows are independent, so a batch may end anywhere; with
+  // several devices the batches are made small enough that every device gets at least four (load balance: the DP
+  // work of a window varies with its depth).
   const size_t nd = devices_.size();
-  std::vector<size_t> cut(nd + 1, n);
-  cut[0] = 0;
-  if (nd > 1) {
-    std::vector<uint64_t> acc(n + 1, 0);
-    for (size_t i = 0; i < n; ++i) acc[i + 1] = acc[i] + CUDABatchProcessor::bytes(*windows_[i]);
-    size_t i = 0;
-    for (size_t d = 1; d < nd; ++d) {
-      const uint64_t want = acc[n] / nd * d;
-      while (i < n && (acc[i] < want || windows_[i]->rank() != 0)) ++i;
-      cut[d] = i;
-    }
-  }
-
-  // vgc_polish is re-entrant per handle and keeps no global state (vgc_last_error is thread-local): one host
-  // thread + one handle per device, the model of the legacy path (cudapolisher.cpp:229-241,255-277).
-  uint64_t kBatchBytes = 1ull << 30;  // bases per vgc_polish call
-  size_t kBatchWindows = 1u << 16;    // windows per vgc_polish call (VECHAT_B200_BATCH_WINDOWS: smaller batches)
+  uint64_t kBatchBytes = 1ull << 30;  // bases per vgc call
+  size_t kBatchWindows = 1u << 16;    // windows per vgc call (VECHAT_B200_BATCH_WINDOWS: smaller batches)
+  if (nd > 1) kBatchWindows = std::min<size_t>(kBatchWindows, std::max<size_t>(4096, (n + 4 * nd - 1) / (4 * nd)));
   if (const char* env = std::getenv("VECHAT_B200_BATCH_WINDOWS")) {
     const long v = std::strtol(env, nullptr, 10);
     if (v > 0) kBatchWindows = static_cast<size_t>(v);
   }
+  std::vector<std::pair<size_t, size_t>> batches;
+  for (size_t first = 0; first < n;) {
+    size_t last = first;
+    uint64_t b = 0;
+    while (last < n && last - first < kBatchWindows && (last == first || b < kBatchBytes))
+      b += CUDABatchProcessor::bytes(*windows_[last++]);
+    batches.emplace_back(first, last);
+    first = last;
+  }
+  std::atomic<size_t> queue_head(0);
+  std::vector<size_t> taken(nd, 0);
   std::vector<std::string> errors(nd);
+  std::atomic<bool> failed(false);
   auto run_device = [&](size_t d) {
     vgc_handle h = nullptr;
     if (vgc_create(&h, devices_[d], &prm) != VGC_OK) {
       errors[d] = vgc_last_error();
+      failed.store(true);
       return;
     }
-    // batches of this device's range, then a two-deep pipeline: while vgc_polish works on batch i, a helper thread
-    // packs batch i + 1 (the windows only borrow their bytes, so packing is a pure read of Polisher::sequences_)
-    std::vector<std::pair<size_t, size_t>> batches;
-    for (size_t first = cut[d]; first < cut[d + 1];) {
-      size_t last = first;
-      uint64_t b = 0;
-      while (last < cut[d + 1] && last - first < kBatchWindows && (last == first || b < kBatchBytes))
-        b += CUDABatchProcessor::bytes(*windows_[last++]);
-      batches.emplace_back(first, last);
-      first = last;
-    }
     const unsigned pack_threads = std::max<unsigned>(1, num_threads_ / nd);
-    // two-deep pipeline over vgc_submit / vgc_collect: while the device works on batch x, a helper thread packs batch
-    // x + 1 (the windows only borrow their bytes, so packing is a pure read of Polisher::sequences_) and submits it —
-    // its host preparation and H2D overlap the kernels of batch x
+    // two-deep pipeline over vgc_submit / vgc_collect: while the device works on batch x, a helper thread packs the
+    // batch this device pulled next (the windows only borrow their bytes, so packing is a pure read of
+    // Polisher::sequences_) and submits it — its host preparation and H2D overlap the kernels of batch x
     Packed cur, next;
     int rc_submit = VGC_OK;
     std::string submit_err;
-    if (!batches.empty()) {
-      CUDABatchProcessor::pack(windows_, batches[0].first, batches[0].second, &cur, pack_threads);
+    size_t x = queue_head.fetch_add(1);
+    if (x < batches.size()) {
+      CUDABatchProcessor::pack(windows_, batches[x].first, batches[x].second, &cur, pack_threads);
       const vgc_batch b0 = cur.view();
       if (vgc_submit(h, &b0) != VGC_OK) {
         errors[d] = vgc_last_error();
+        failed.store(true);
         vgc_destroy(h);
         return;
       }
     }
-    for (size_t x = 0; x < batches.size(); ++x) {
+    while (x < batches.size() && !failed.load()) {
       const size_t first = batches[x].first, last = batches[x].second;
+      ++taken[d];
+      const size_t xn = queue_head.fetch_add(1);
       std::thread packer;
-      if (x + 1 < batches.size()) {
+      if (xn < batches.size()) {
         next = Packed();
-        packer = std::thread([&, x] {
-          CUDABatchProcessor::pack(windows_, batches[x + 1].first, batches[x + 1].second, &next, pack_threads);
+        packer = std::thread([&, xn] {
+          CUDABatchProcessor::pack(windows_, batches[xn].first, batches[xn].second, &next, pack_threads);
           const vgc_batch bn = next.view();
           rc_submit = vgc_submit(h, &bn);
           if (rc_submit != VGC_OK) submit_err = vgc_last_error();
@@ -355,12 +353,16 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
       if (rc != VGC_OK) errors[d] = vgc_last_error();
       if (packer.joinable()) packer.join();
       if (rc == VGC_OK && rc_submit != VGC_OK) errors[d] = submit_err;
-      if (rc != VGC_OK || rc_submit != VGC_OK) break;
-      // consensus_ of batch x is written only after the packer of batch x + 1 is done: pack reads sequences_ of
+      if (rc != VGC_OK || rc_submit != VGC_OK) {
+        failed.store(true);
+        break;
+      }
+      // consensus_ of batch x is written only after the packer of the next batch is done: pack reads sequences_ of
       // other windows only, but this keeps the two phases trivially disjoint
       for (size_t i = first; i < last; ++i)
         CUDABatchProcessor::store(*windows_[i], cons.data() + off[i - first], off[i - first + 1] - off[i - first]);
       std::swap(cur, next);
+      x = xn;
     }
     vgc_destroy(h);
   };
@@ -373,6 +375,11 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
   }
   for (size_t d = 0; d < nd; ++d)
     if (!errors[d].empty()) die("B200Polisher::polish", errors[d].c_str());
+  if (nd > 1) {
+    std::string msg = "[racon::B200Polisher::polish] " + std::to_string(batches.size()) + " batches from one queue:";
+    for (size_t d = 0; d < nd; ++d) msg += " device " + std::to_string(devices_[d]) + " took " + std::to_string(taken[d]);
+    fprintf(stderr, "%s\n", msg.c_str());
+  }
 
   // In-order stitch per target with the reference's header tags (polisher.cpp:520-546): a target ends where the
   // next window has rank 0.

@@ -16,10 +16,10 @@
 // No CPU fallback: without a usable device every entry point fails with VGC_ERR_NO_DEVICE.
 
 #include <cuda_runtime.h>
-#include <nvtx3/nvToolsExt.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
 #include <sys/resource.h>
 #include <sys/syscall.h>
-#include <unistd.h>  // header-only: ranges show up under nsys / ncu --nvtx, and cost nothing otherwise
+#include <unistd.h>
 
 #include <algorithm>
 #include <array>
@@ -1041,6 +1041,13 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
                const uint32_t* win_first, uint32_t* launches) {
   NvtxRange nvtx(exact ? "vgc: POA pass (exact capacities)" : "vgc: POA pass");
   const auto t_entry = std::chrono::steady_clock::now();
+  auto t_lap = t_entry;
+  double laps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto lap = [&](int i) {
+    const auto now = std::chrono::steady_clock::now();
+    laps[i] += std::chrono::duration<double, std::milli>(now - t_lap).count();
+    t_lap = now;
+  };
   const Prepared& pr = h->I->prep;
   const bool hap = h->params.haplotype != 0;
   const uint32_t num_prune = h->params.num_prune;
@@ -1082,6 +1089,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     }
     occ_max = std::max(occ_max, occ);
   }
+  lap(0);
   size_t pos = 0;
   while (pos < wins.size()) {
     // ---- chunk: as many windows as the budget holds (the pool of DP buffers takes its share first)
@@ -1108,6 +1116,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       return VGC_ERR_CAPACITY;
     }
     uint64_t pool_bytes = static_cast<uint64_t>(per_sm) * h->sm_count * buf_bytes;
+    lap(1);
     if ((rc = h->d_pool.reserve(pool_bytes))) return rc;
     // ---- wide path (poa_wide.cuh): can any alignment of the rest of the pass leave the fast kernels?  A layer beyond
     // their widest row, or the device's int16 score bound (poa_core.h step_prepare) evaluated with the slot's node
@@ -1146,6 +1155,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
         pool_bytes += wide_buf * wide_n;
       }
     }
+    lap(2);
     const uint32_t pool_n = per_sm * static_cast<uint32_t>(h->sm_count);
     if ((rc = h->d_pool_busy.reserve(4ull * (pool_n + 2)))) return rc;
     std::vector<uint32_t> pool_init(pool_n + 2);
@@ -1181,6 +1191,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       bytes += sb;
       ++e;
     }
+    lap(3);
     const uint32_t n = static_cast<uint32_t>(e - pos);
     if ((rc = h->d_slot_mem.reserve(bytes))) return rc;
     if ((rc = h->d_slots.reserve(sizeof(Slot) * n))) return rc;
@@ -1190,6 +1201,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     // run the very same program, so the heavy serial steps — PruneGraph + LargestSubgraph — coincide instead of
     // stalling some cycle of every group); sparse values at the tails are merged until a group has >= 64 windows.
     // VGC_GROUP_MODE=1: equal contiguous blocks of the sorted list.
+    lap(4);
     std::vector<uint32_t> gstart;  // positions in the chunk (sorted by decreasing cycles) where a group starts
     if (h->group_mode == 2) {
       uint32_t min_group = 64;
@@ -1236,6 +1248,7 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       }
     }
     gbase[G] = k;
+    lap(5);
     // job lists (one per group, reused every cycle) and their per-cycle counters
     std::vector<uint64_t> gjob_off(G + 1, 0);
     for (int g = 0; g < G; ++g) gjob_off[g + 1] = gjob_off[g] + gjobs_cap[g];
@@ -1284,6 +1297,10 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       VGC_CUDA(cudaMemsetAsync(a.tl, 0, 16, h->stream));
     }
     VGC_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    lap(6);
+    if (std::getenv("VGC_VERBOSE"))
+      std::fprintf(stderr, "[vgc] pass setup: attrs %.2f, pool rows %.2f, pool reserve + wide %.2f, dims %.2f, reserves %.2f, "
+                   "groups + carve %.2f, copies %.2f ms\n", laps[0], laps[1], laps[2], laps[3], laps[4], laps[5], laps[6]);
     h->setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count();
     for (int g = 0; g < G; ++g) VGC_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev[6], 0));
     // ---- lockstep: the lists are sorted by decreasing cycles, so the live windows of a cycle are a prefix
@@ -1445,6 +1462,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
     VGC_CUDA(cudaEventRecord(h->ev[1], h->stream));
   }
   NvtxRange nvtx_out("vgc: D2H + stitch");
+  const auto t_out0 = std::chrono::steady_clock::now();
   VGC_CUDA(cudaEventRecord(h->ev[2], h->stream));
   VGC_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
   VGC_CUDA(cudaMemcpyAsync(h->h_out_len, h->d_out_len.p, nw * 4ull, cudaMemcpyDeviceToHost, h->stream));
@@ -1466,6 +1484,7 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
       return h->h_status[w] == kStInternal ? VGC_ERR_CUDA : VGC_ERR_CAPACITY;
     }
   }
+  const auto t_out1 = std::chrono::steady_clock::now();
   if (result) {
     // stitch: windows in order; < 3 sequences -> backbone, polished = false (window.cpp:188-192)
     uint64_t off = 0;
@@ -1491,6 +1510,12 @@ int polish_device(vgc_engine* h, vgc_result* result, vgc_stats* stats, uint64_t 
       off += n;
     }
     result->cons_off[nw] = off;
+  }
+  if (std::getenv("VGC_VERBOSE")) {
+    const auto t_out2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[vgc] after the pass: D2H + status check %.2f ms, stitch copy %.2f ms\n",
+                 std::chrono::duration<double, std::milli>(t_out1 - t_out0).count(),
+                 std::chrono::duration<double, std::milli>(t_out2 - t_out1).count());
   }
   // feedback for the next call: if more than 2 % of the sorts did not fit the shared memory the growth bound gave
   // them, the data grows its graphs faster than assumed — raise the bound (sticky per engine)
@@ -1754,7 +1779,9 @@ int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
     h->running = true;
     h->in_setup.store(true, std::memory_order_release);
   }
+  const auto tc0 = std::chrono::steady_clock::now();
   join_set(in);
+  const auto tc1 = std::chrono::steady_clock::now();
   if (in->rc != VGC_OK) {
     set_err(in->err);
     std::lock_guard<std::mutex> lock(h->qmu);
@@ -1765,6 +1792,15 @@ int vgc_collect(vgc_handle h, vgc_result* result, vgc_stats* stats) {
   h->resident = false;
   const vgc_batch* b = &in->batch;
   const int rc = polish_device(h, result, stats, in->in_bytes, b->bases, b->seq_off, b->win_first, b->n_windows);
+  if (std::getenv("VGC_VERBOSE")) {
+    const auto tc2 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b2) {
+      return std::chrono::duration<double, std::milli>(b2 - a).count();
+    };
+    std::fprintf(stderr, "[vgc] collect: waited %.1f ms for the staging, pass + D2H + stitch %.1f ms (kernels %.1f, setup %.1f, "
+                 "enqueue %.1f); staging: prepare %.1f ms, pack %.1f ms\n",
+                 ms(tc0, tc1), ms(tc1, tc2), h->pass_kernel_ms, h->setup_ms, h->launch_ms, in->prep_ms, in->pack_ms);
+  }
   {
     std::lock_guard<std::mutex> lock(h->qmu);
     h->running = false;
