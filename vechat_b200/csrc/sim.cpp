@@ -348,4 +348,81 @@ uint32_t sim_batch_num_targets(const sim_batch* sb) { return static_cast<uint32_
 uint64_t sim_batch_overlaps(const sim_batch* sb) { return sb->n_overlaps; }
 void sim_free_batch(sim_batch* sb) { delete sb; }
 
+// Reads [0, n_reads) as a FASTQ (or FASTA) file and their ground-truth all-vs-all overlaps as PAF, the inputs of the
+// whole program (`vechat_racon <reads> <overlaps> <targets>`, src/main.cpp): one PAF line per ordered pair (query,
+// target) whose genome intervals share >= min_overlap bases, grouped by query, coordinates on the strands as
+// sequenced.  Only where the reads lie is taken from the truth — the alignment itself is left to the program
+// (Overlap::find_breaking_points).  Returns the number of overlaps written, or -1.
+long long sim_export(const sim_state* st, const char* reads_path, const char* paf_path) {
+  const sim_config& cfg = st->cfg;
+  FILE* fr = std::fopen(reads_path, "wb");
+  FILE* fp = std::fopen(paf_path, "wb");
+  if (!fr || !fp) {
+    if (fr) std::fclose(fr);
+    if (fp) std::fclose(fp);
+    return -1;
+  }
+  std::vector<char> seq, qual;
+  for (uint32_t r = 0; r < cfg.n_reads; ++r) {
+    const uint32_t n = static_cast<uint32_t>(st->reads[r].seq.size());
+    seq.resize(n + 1);
+    qual.resize(n + 1);
+    sim_get_read(st, r, seq.data(), qual.data(), n + 1);
+    if (cfg.fasta) {
+      std::fprintf(fr, ">read%u\n%.*s\n", r, static_cast<int>(n), seq.data());
+    } else {
+      std::fprintf(fr, "@read%u\n%.*s\n+\n%.*s\n", r, static_cast<int>(n), seq.data(), static_cast<int>(n), qual.data());
+    }
+  }
+  std::fclose(fr);
+  // [begin, end) of read `rd` (as sequenced) covering genome interval [lo, hi)
+  auto span = [](const Read& rd, int32_t lo, int32_t hi, uint32_t* b, uint32_t* e) {
+    const uint32_t n = static_cast<uint32_t>(rd.seq.size());
+    uint32_t fb = 0, fe = n;
+    while (fb < n && (rd.gpos[fb] < 0 || rd.gpos[fb] < lo)) ++fb;
+    while (fe > fb && (rd.gpos[fe - 1] < 0 || rd.gpos[fe - 1] >= hi)) --fe;
+    if (rd.strand) {
+      *b = n - fe;
+      *e = n - fb;
+    } else {
+      *b = fb;
+      *e = fe;
+    }
+  };
+  long long written = 0;
+  const uint32_t nr = cfg.n_reads;
+  int32_t max_span = 0;
+  for (const Read& rd : st->reads) max_span = std::max(max_span, rd.g_end - rd.g_begin);
+  for (uint32_t q = 0; q < nr; ++q) {
+    const Read& qr = st->reads[q];
+    // candidates start before my end and end after my begin: walk by_start around my interval
+    auto it = std::lower_bound(st->by_start.begin(), st->by_start.end(), qr.g_begin - max_span,
+                               [&](uint32_t a, int32_t v) { return st->reads[a].g_begin < v; });
+    std::vector<uint32_t> ts;
+    for (; it != st->by_start.end() && st->reads[*it].g_begin < qr.g_end; ++it) {
+      const uint32_t t = *it;
+      if (t == q) continue;
+      const Read& tr = st->reads[t];
+      const int32_t lo = std::max(qr.g_begin, tr.g_begin), hi = std::min(qr.g_end, tr.g_end);
+      if (hi - lo < static_cast<int32_t>(cfg.min_overlap)) continue;
+      ts.push_back(t);
+    }
+    std::sort(ts.begin(), ts.end());
+    for (uint32_t t : ts) {
+      const Read& tr = st->reads[t];
+      const int32_t lo = std::max(qr.g_begin, tr.g_begin), hi = std::min(qr.g_end, tr.g_end);
+      uint32_t qb, qe, tb, te;
+      span(qr, lo, hi, &qb, &qe);
+      span(tr, lo, hi, &tb, &te);
+      if (qe <= qb || te <= tb) continue;
+      const uint32_t alen = std::max(qe - qb, te - tb);
+      std::fprintf(fp, "read%u\t%zu\t%u\t%u\t%c\tread%u\t%zu\t%u\t%u\t%u\t%u\t255\n", q, qr.seq.size(), qb, qe,
+                   qr.strand == tr.strand ? '+' : '-', t, tr.seq.size(), tb, te, alen * 7 / 10, alen);
+      ++written;
+    }
+  }
+  std::fclose(fp);
+  return written;
+}
+
 }  // extern "C"

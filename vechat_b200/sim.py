@@ -75,6 +75,8 @@ def _lib():
         lib.sim_batch_overlaps.restype = C.c_uint64
         lib.sim_batch_overlaps.argtypes = [C.c_void_p]
         lib.sim_free_batch.argtypes = [C.c_void_p]
+        lib.sim_export.restype = C.c_longlong
+        lib.sim_export.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         lib.sim_get_read.restype = C.c_uint32
         lib.sim_get_read.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32]
         _LIB = lib
@@ -107,6 +109,14 @@ class Simulator:
         q = C.create_string_buffer(cap)
         n = _lib().sim_get_read(self._h, r, s, q, cap)
         return s.raw[:n], q.raw[:n]
+
+    def export(self, reads_path, paf_path):
+        """Write the reads (FASTQ / FASTA) and their ground-truth all-vs-all overlaps (PAF) — the input files of the
+        whole program (vechat_racon <reads> <overlaps> <targets>).  Returns the number of overlaps."""
+        n = _lib().sim_export(self._h, os.fsencode(reads_path), os.fsencode(paf_path))
+        if n < 0:
+            raise OSError("sim_export could not write %s / %s" % (reads_path, paf_path))
+        return int(n)
 
     def windows(self, t0, t1, quality_threshold=10.0):
         """Windows of target reads [t0, t1).  The returned batch also carries win_target / win_rank (read id and
