@@ -18,6 +18,7 @@ import ctypes as C
 import gzip
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -404,3 +405,24 @@ def test_gpu_binary_whole_example():
     assert got.returncode == 0, got.stderr[-400:]
     with open(want, "rb") as f:
         assert got.stdout == f.read()
+
+
+# ---------------------------------------------------------------- the streaming job tool (config 5's shape, tiny)
+
+@need_b200
+@need_ref
+def test_stream_job_tool_behind_mock_engine(tmp_path):
+    """tools/stream_job.py end to end on the CPU box: simulator export (FASTQ + ground-truth PAF) -> the real
+    vechat_racon_b200 binary (two 'devices' pulling batches from one queue, mock engine) -> parity sample against the
+    reference program on the same files."""
+    import json
+    out = tmp_path / "stream.json"
+    env = dict(os.environ, VECHAT_B200_BATCH_WINDOWS="60", **_mock_env())
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stream_job.py"), "--reads", "48", "--read-len", "3000",
+                        "--devices", "0,1", "--check", "5", "--threads", "8", "--dir", str(tmp_path), "--out", str(out)],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert r.returncode == 0, (r.stdout[-600:], r.stderr[-600:])
+    s = json.loads(out.read_text())
+    assert s["corrected_reads"] == 48 and s["windows"] == 48 * 6
+    assert s["parity"]["targets_checked"] == 5 and s["parity"]["mismatches"] == 0
+    assert "batches from one queue" in s["queue"] and "device 1 took" in s["queue"]
