@@ -110,6 +110,10 @@ def main():
         "stages": [{"stage": k, "seconds": s} for k, s in st],
         "queue": queue[0].strip() if queue else None,
     }
+    # VGC_VERBOSE=1 / VECHAT_B200_VERBOSE=1: per-batch engine and binding timing
+    trace = [l.strip() for l in err.split("\n") if l.startswith("[vgc]") or l.startswith("[racon::B200Polisher::polish] ")]
+    if trace:
+        summary["engine_trace"] = trace[:64]
     print(json.dumps(summary, indent=1), flush=True)
 
     if args.check and os.path.exists(REF_BIN):

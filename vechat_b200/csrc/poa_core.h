@@ -1311,16 +1311,25 @@ struct Poa {
             kind = 1;
           } else {
             const uint32_t jt = static_cast<uint32_t>(nd);
-            if (g.code[jt] == code) {
+            // code, clique size and the first clique members are asked for together (DRAM latency, see the edge loop)
+            const uint32_t cj = g.code[jt];
+            const uint32_t na = g.nal[jt];
+            uint32_t kt4[4];
+#pragma unroll
+            for (uint32_t i = 0; i < 4; ++i) kt4[i] = g.al[jt * sl.al_stride + i];
+            if (cj == code) {
               curr = jt;
             } else {
-              const uint32_t na = g.nal[jt];
-              for (uint32_t i = 0; i < na; ++i) {
+              uint32_t ck[4];
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) ck[i] = i < na ? g.code[kt4[i]] : 0xFFFFFFFFu;
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) {
+                if (curr == kNone && ck[i] == code) curr = kt4[i];
+              }
+              for (uint32_t i = 4; i < na && curr == kNone; ++i) {
                 const uint32_t kt = g.al[jt * sl.al_stride + i];
-                if (g.code[kt] == code) {
-                  curr = kt;
-                  break;
-                }
+                if (g.code[kt] == code) curr = kt;
               }
               if (curr == kNone) kind = 2;
             }
@@ -1350,7 +1359,7 @@ struct Poa {
             }
           }
         } else if (pos != -1) {
-          g.cov[curr] += covinc;
+          if (covinc) ex.atomic_add(&g.cov[curr], covinc);  // one position per node along an alignment: nobody waits
         }
         if (pos != -1) {
           npos[pos] = curr;
@@ -1375,13 +1384,25 @@ struct Poa {
         head = npos[pos];
         w = weight_at(layer, pos - 1) + weight_at(layer, pos);
         if (tail < nV0 && head < nV0) {
+          // is there an edge tail -> head already?  The in-list entries are loaded together with the in-degree (the
+          // row has room for in_stride >= 8 entries, initialised or not) instead of one dependent load after the
+          // other: this loop is DRAM-latency bound.  Positions of one alignment touch distinct edges, so the
+          // weight goes in with a plain atomic add that nobody waits for.
           const uint32_t ni = g.nin[head];
-          for (uint32_t i = 0; i < ni; ++i) {
-            if (g.itail[head * S + i] == tail) {
-              g.ew[g.ieid[head * S + i]] += w;
-              need = false;
-              break;
-            }
+          uint32_t tl[8];
+#pragma unroll
+          for (uint32_t i = 0; i < 8; ++i) tl[i] = g.itail[head * S + i];
+          uint32_t hit = kNone;
+#pragma unroll
+          for (uint32_t i = 0; i < 8; ++i) {
+            if (hit == kNone && i < ni && tl[i] == tail) hit = i;
+          }
+          for (uint32_t i = 8; i < ni && hit == kNone; ++i) {
+            if (g.itail[head * S + i] == tail) hit = i;
+          }
+          if (hit != kNone) {
+            ex.atomic_add(&g.ew[g.ieid[head * S + hit]], w);
+            need = false;
           }
         }
       }

@@ -7,9 +7,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "bioparser/fasta_parser.hpp"
@@ -36,10 +38,34 @@ namespace {
 }
 
 // structure-of-arrays image of a run of windows (what vgc_batch points into)
+// Bytes that are always overwritten before they are read: no zero-filling, capacity kept from batch to batch (a fresh
+// 2 GB of zeroed vectors per batch cost more host time than the copy itself: page faults + memset on one thread;
+// here the first touch of a new buffer happens in the copy threads).
+struct RawBuf {
+  std::unique_ptr<uint8_t[]> p;
+  size_t cap = 0;
+  void need(size_t n) {
+    if (cap < n) {
+      cap = n + n / 8 + 64;
+      p.reset(new uint8_t[cap]);
+    }
+  }
+  uint8_t* data() const { return p.get(); }
+};
+
 struct Packed {
-  std::vector<uint8_t> bases, quals, has_qual, win_flags;
+  RawBuf bases, quals;
+  std::vector<uint8_t> has_qual, win_flags;
   std::vector<uint64_t> seq_off;
   std::vector<uint32_t> begin, end, win_first;
+  void clear() {  // keeps every capacity
+    has_qual.clear();
+    win_flags.clear();
+    seq_off.clear();
+    begin.clear();
+    end.clear();
+    win_first.clear();
+  }
   vgc_batch view() const {
     vgc_batch b;
     b.n_windows = static_cast<uint32_t>(win_flags.size());
@@ -69,6 +95,7 @@ class CUDABatchProcessor {
   // Pass 1 (serial, metadata only) lays out the layer table and the byte offsets; pass 2 copies the bytes with
   // `threads` host threads over window ranges.
   static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p, unsigned threads) {
+    p->clear();
     size_t layers = 0;
     for (size_t i = first; i < last; ++i) layers += w[i]->sequences_.size();
     p->seq_off.reserve(layers + 1);
@@ -95,8 +122,8 @@ class CUDABatchProcessor {
     }
     p->win_first.push_back(static_cast<uint32_t>(p->begin.size()));
     p->seq_off.push_back(total);
-    p->bases.resize(total);
-    p->quals.resize(total);
+    p->bases.need(total);
+    p->quals.need(total);
     const size_t nw = last - first;
     auto copy_range = [&](size_t a, size_t b) {
       for (size_t i = a; i < b; ++i) {
@@ -293,16 +320,25 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     const long v = std::strtol(env, nullptr, 10);
     if (v > 0) kBatchWindows = static_cast<size_t>(v);
   }
+  // (batches of one size: growing batches were tried to shorten the packing of the first one, but every growth of
+  //  the engine's scratch frees tens of GB of device memory, which costs more than it saves — 2.2 s measured)
   std::vector<std::pair<size_t, size_t>> batches;
   for (size_t first = 0; first < n;) {
+    const size_t cap = kBatchWindows;
     size_t last = first;
     uint64_t b = 0;
-    while (last < n && last - first < kBatchWindows && (last == first || b < kBatchBytes))
+    while (last < n && last - first < cap && (last == first || b < kBatchBytes))
       b += CUDABatchProcessor::bytes(*windows_[last++]);
     batches.emplace_back(first, last);
     first = last;
   }
+  const bool verbose = std::getenv("VECHAT_B200_VERBOSE") != nullptr;
+  const auto t_polish0 = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   std::atomic<size_t> queue_head(0);
+  std::vector<vgc_handle> handles(nd, nullptr);
   std::vector<size_t> taken(nd, 0);
   std::vector<std::string> errors(nd);
   std::atomic<bool> failed(false);
@@ -318,6 +354,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     // batch this device pulled next (the windows only borrow their bytes, so packing is a pure read of
     // Polisher::sequences_) and submits it — its host preparation and H2D overlap the kernels of batch x
     Packed cur, next;
+    double pack_ms = 0.0;
     int rc_submit = VGC_OK;
     std::string submit_err;
     size_t x = queue_head.fetch_add(1);
@@ -331,40 +368,65 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
         return;
       }
     }
+    // result buffers of two batches (no zero-filling: the engine writes every byte it reports): while the device
+    // works on batch x + 1, a helper thread stores the consensuses of batch x into their windows
+    struct Out {
+      std::unique_ptr<uint8_t[]> cons;
+      size_t cap = 0;
+      std::vector<uint64_t> off;
+    } outs[2];
+    int cur_out = 0;
+    std::thread storer;
     while (x < batches.size() && !failed.load()) {
       const size_t first = batches[x].first, last = batches[x].second;
       ++taken[d];
       const size_t xn = queue_head.fetch_add(1);
       std::thread packer;
       if (xn < batches.size()) {
-        next = Packed();
         packer = std::thread([&, xn] {
+          const auto t_p = std::chrono::steady_clock::now();
           CUDABatchProcessor::pack(windows_, batches[xn].first, batches[xn].second, &next, pack_threads);
+          pack_ms = since(t_p);
           const vgc_batch bn = next.view();
           rc_submit = vgc_submit(h, &bn);
           if (rc_submit != VGC_OK) submit_err = vgc_last_error();
         });
       }
       const vgc_batch batch = cur.view();
-      std::vector<uint8_t> cons(vgc_result_bound(&batch));
-      std::vector<uint64_t> off(batch.n_windows + 1);
-      vgc_result r = {cons.data(), cons.size(), off.data(), polished.data() + first};
+      Out& o = outs[cur_out];
+      const size_t bound = vgc_result_bound(&batch);
+      if (o.cap < bound) {
+        o.cons.reset(new uint8_t[bound]);
+        o.cap = bound;
+      }
+      o.off.resize(batch.n_windows + 1);
+      vgc_result r = {o.cons.get(), bound, o.off.data(), polished.data() + first};
+      const auto t_c = std::chrono::steady_clock::now();
       const int rc = vgc_collect(h, &r, nullptr);  // no CPU fallback
+      const double collect_ms = since(t_c);
       if (rc != VGC_OK) errors[d] = vgc_last_error();
       if (packer.joinable()) packer.join();
+      if (storer.joinable()) storer.join();
       if (rc == VGC_OK && rc_submit != VGC_OK) errors[d] = submit_err;
       if (rc != VGC_OK || rc_submit != VGC_OK) {
         failed.store(true);
         break;
       }
-      // consensus_ of batch x is written only after the packer of the next batch is done: pack reads sequences_ of
-      // other windows only, but this keeps the two phases trivially disjoint
-      for (size_t i = first; i < last; ++i)
-        CUDABatchProcessor::store(*windows_[i], cons.data() + off[i - first], off[i - first + 1] - off[i - first]);
+      if (verbose)
+        fprintf(stderr, "[racon::B200Polisher::polish] device %d batch %zu (%zu windows): collect %.1f ms, packing of the next batch %.1f ms, joined at %.1f ms\n",
+                devices_[d], x, last - first, collect_ms, pack_ms, since(t_polish0));
+      // pack only reads sequences_ of the windows of ITS batch, store only writes consensus_ of the windows of batch
+      // x: disjoint by construction
+      storer = std::thread([this, &o, first, last] {
+        for (size_t i = first; i < last; ++i)
+          CUDABatchProcessor::store(*windows_[i], o.cons.get() + o.off[i - first], o.off[i - first + 1] - o.off[i - first]);
+      });
+      cur_out ^= 1;
       std::swap(cur, next);
       x = xn;
     }
-    vgc_destroy(h);
+    if (storer.joinable()) storer.join();
+    handles[d] = h;  // destroyed behind the stitch: freeing ~100 GB of device scratch takes half a second
   };
   if (nd == 1) {
     run_device(0);
@@ -375,6 +437,11 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
   }
   for (size_t d = 0; d < nd; ++d)
     if (!errors[d].empty()) die("B200Polisher::polish", errors[d].c_str());
+  if (verbose) fprintf(stderr, "[racon::B200Polisher::polish] all batches collected at %.1f ms\n", since(t_polish0));
+  std::thread closer([&handles] {
+    for (vgc_handle h : handles)
+      if (h) vgc_destroy(h);
+  });
   if (nd > 1) {
     std::string msg = "[racon::B200Polisher::polish] " + std::to_string(batches.size()) + " batches from one queue:";
     for (size_t d = 0; d < nd; ++d) msg += " device " + std::to_string(devices_[d]) + " took " + std::to_string(taken[d]);
@@ -412,6 +479,8 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     }
     for (; i < j; ++i) windows_[i].reset();
   }
+  closer.join();
+  if (verbose) fprintf(stderr, "[racon::B200Polisher::polish] stitched at %.1f ms\n", since(t_polish0));
   if (logger_step != 0) {
     logger_->bar("[racon::Polisher::polish] generating consensus");
   } else {
