@@ -277,7 +277,10 @@ B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
   cut_on_gpu_ = align_on_gpu_ && std::strcmp(env, "cigar") != 0;
 }
 
-B200Polisher::~B200Polisher() {}
+B200Polisher::~B200Polisher() {
+  for (auto& t : closers_)
+    if (t.joinable()) t.join();
+}
 
 void B200Polisher::find_overlap_breaking_points(std::vector<std::unique_ptr<Overlap>>& overlaps) {
   if (align_on_gpu_) {
@@ -438,10 +441,8 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
   for (size_t d = 0; d < nd; ++d)
     if (!errors[d].empty()) die("B200Polisher::polish", errors[d].c_str());
   if (verbose) fprintf(stderr, "[racon::B200Polisher::polish] all batches collected at %.1f ms\n", since(t_polish0));
-  std::thread closer([&handles] {
-    for (vgc_handle h : handles)
-      if (h) vgc_destroy(h);
-  });
+  for (vgc_handle h : handles)
+    if (h) closers_.emplace_back([h] { vgc_destroy(h); });
   if (nd > 1) {
     std::string msg = "[racon::B200Polisher::polish] " + std::to_string(batches.size()) + " batches from one queue:";
     for (size_t d = 0; d < nd; ++d) msg += " device " + std::to_string(devices_[d]) + " took " + std::to_string(taken[d]);
@@ -500,7 +501,6 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     if (records[t]) dst.emplace_back(std::move(records[t]));
     for (size_t k = tstart[t]; k < tstart[t + 1]; ++k) bar_after(k);
   }
-  closer.join();
   if (verbose) fprintf(stderr, "[racon::B200Polisher::polish] stitched at %.1f ms\n", since(t_polish0));
   if (logger_step != 0) {
     logger_->bar("[racon::Polisher::polish] generating consensus");

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "polisher.hpp"  // reference: src/polisher.hpp
@@ -43,6 +44,7 @@ class B200Polisher : public Polisher {
   uint32_t num_threads_;
   std::vector<int> devices_;
   bool align_on_gpu_, cut_on_gpu_;
+  std::vector<std::thread> closers_;  // free the engines' device scratch behind the stitch and the output (joined in the destructor)
 };
 
 // Drop-in for racon::createPolisher (same signature, src/polisher.hpp:42-49).  Returns a B200Polisher when the
