@@ -42,6 +42,7 @@
 
 namespace vgc {
 
+constexpr unsigned kSetupThreads = 4;  // host threads of the per-window work at the start of a pass
 constexpr int kSmemHeader = 832;  // Slot + WinState copies
 constexpr int kAlignHeader = 512; // align kernels keep only the Slot copy
 
@@ -1018,6 +1019,20 @@ inline uint32_t win_jobs(uint32_t nseq, bool haplotype, uint32_t num_prune, uint
   return c + 2 == nseq + num_prune ? 1u : 0u;
 }
 
+// f(begin, end) over [0, n) on a few host threads (the per-window host work at the start of a pass is on the
+// device's critical path: the GPU idles until the first launch)
+template <class F>
+void parallel_ranges(size_t n, unsigned nt, F f) {
+  if (nt <= 1 || n < 4096) {
+    f(static_cast<size_t>(0), n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(f, n * t / nt, n * (t + 1) / nt);
+  f(static_cast<size_t>(0), n / nt);
+  for (auto& x : th) x.join();
+}
+
 // Node capacity of a window's slot on the first pass: backbone + a share of the layer bases (a read adds a node
 // only where it disagrees with the graph) + one layer of head-room for AddAlignment's conservative check.  Windows
 // that outgrow it are re-run with the exact upper bound (sum of layer lengths).
@@ -1164,30 +1179,37 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
     pool_init[pool_n + 1] = pool_n;  // give tickets: the initial ids count as given back
     VGC_CUDA(cudaMemcpyAsync(h->d_pool_busy.p, pool_init.data(), 4ull * (pool_n + 2), cudaMemcpyHostToDevice, h->stream));
 
-    std::vector<SlotDims> dims;
-    std::vector<uint64_t> offs;
+    // slot geometry of every remaining window (host threads), then the chunk = the prefix the budget holds
+    const size_t n_rest = wins.size() - pos;
+    std::vector<SlotDims> dims(n_rest);
+    std::vector<uint64_t> offs(n_rest);
+    parallel_ranges(n_rest, kSetupThreads, [&](size_t a, size_t b) {
+      for (size_t x = a; x < b; ++x) {
+        const uint32_t w = wins[pos + x];
+        const uint32_t f = win_first[w];
+        SlotDims d;
+        d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div), 64);
+        d.max_edges = 2 * d.max_nodes + 64;  // ~2 edges per node in practice; AddAlignment wants room for a whole layer
+        d.max_len = ml;
+        d.row_words = 32 * K;
+        // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
+        d.al_stride = pr.num_codes > 8 ? 16 : 8;
+        d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : std::min<uint32_t>(16, std::max<uint32_t>(8, pr.win_nseq[w] + 1));
+        dims[x] = d;
+        offs[x] = slot_bytes(d);  // size for now, offset below
+      }
+    });
     uint64_t bytes = 0;
     const uint64_t slot_budget = h->mem_budget - pool_bytes;
     size_t e = pos;
     while (e < wins.size()) {
-      const uint32_t w = wins[e];
-      const uint32_t f = win_first[w];
-      SlotDims d;
-      d.max_nodes = std::max<uint32_t>(estimate_nodes(pr, w, static_cast<uint32_t>(seq_off[f + 1] - seq_off[f]), exact, h->node_share_div), 64);
-      d.max_edges = 2 * d.max_nodes + 64;  // ~2 edges per node in practice; AddAlignment wants room for a whole layer
-      d.max_len = ml;
-      d.row_words = 32 * K;
-      // in-degree <= number of sequences; 16 is ample in practice, the exact pass takes the bound itself
-      d.al_stride = pr.num_codes > 8 ? 16 : 8;
-      d.in_stride = exact ? std::max<uint32_t>(8, pr.win_nseq[w] + 1) : std::min<uint32_t>(16, std::max<uint32_t>(8, pr.win_nseq[w] + 1));
-      const uint64_t sb = slot_bytes(d);
+      const uint64_t sb = offs[e - pos];
       if (bytes + sb > slot_budget && e > pos) break;
       if (sb > slot_budget) {
         set_err("a window needs more scratch than the device memory budget");
         return VGC_ERR_CAPACITY;
       }
-      dims.push_back(d);
-      offs.push_back(bytes);
+      offs[e - pos] = bytes;
       bytes += sb;
       ++e;
     }
@@ -1232,10 +1254,9 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       gbase[g] = k;
       const uint32_t b0 = gstart[g];
       const uint32_t b1 = g + 1 < G ? gstart[g + 1] : n;
+      gnseq[g].reserve(b1 - b0);
       for (uint32_t i = b0; i < b1; ++i) {
-        const uint32_t w = wins[pos + i];
-        work[k] = w;
-        slot_carve(dims[i], h->d_slot_mem.as<uint8_t>() + offs[i], &slots[k]);
+        const uint32_t w = wins[pos + i];  // (k == i: the groups are consecutive ranges of the chunk)
         gnseq[g].push_back(pr.win_nseq[w]);
         gjobs_cap[g] += pr.win_nseq[w];
         max_cyc = std::max(max_cyc, win_cycles(pr.win_nseq[w], hap, num_prune));
@@ -1248,6 +1269,15 @@ int run_pass_k(vgc_engine* h, const std::vector<uint32_t>& wins, bool exact, con
       }
     }
     gbase[G] = k;
+    {
+      uint8_t* const slot_base = h->d_slot_mem.as<uint8_t>();
+      parallel_ranges(n, kSetupThreads, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+          work[i] = wins[pos + i];
+          slot_carve(dims[i], slot_base + offs[i], &slots[i]);
+        }
+      });
+    }
     lap(5);
     // job lists (one per group, reused every cycle) and their per-cycle counters
     std::vector<uint64_t> gjob_off(G + 1, 0);
