@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--workload", default="pb", choices=["pb", "ont", "hap2"],
                     help="pb = BASELINE configs[1] (the benchmark); ont / hap2 = configs[2] / configs[3], extra evidence only")
     ap.add_argument("--hap2-leg", action="store_true", help="also run the hap2 (configs[3] shape) leg at N = 1 (always run at N > 1)")
+    ap.add_argument("--no-hap2-leg", action="store_true", help="experiments: skip the hap2 leg at N > 1")
     ap.add_argument("--num-prune", type=int, default=3, help="diagnostics only: -k of the haplotype path (3 = the benchmark)")
     return ap.parse_args()
 
@@ -284,12 +285,17 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
     kern_ms = sum(s["kernel_ms"] for s in res_stats)
     launches = sum(s["kernel_launches"] for s in res_stats) + sum(s["kernel_launches"] for s in e2e_stats)
     cells = res_stats[-1]["cells"]
-    agg = torch.tensor([dev_ms, e2e_dt * 1e3, res_wall * 1e3, kern_ms], dtype=torch.float64, device=dev)
+    # e2e diagnostics: device time of the passes inside the e2e leg (mean over the steps; max over ranks below) — a gap
+    # to the resident leg's kernel time means something shared the GPU or starved the launches, not the copies
+    e2e_kern_mean = sum(s["kernel_ms"] for s in e2e_stats) / max(1, len(e2e_stats))
+    e2e_wait_mean = sum(s.get("host_prep_ms", 0.0) + s.get("host_pack_ms", 0.0) for s in e2e_stats) / max(1, len(e2e_stats))
+    agg = torch.tensor([dev_ms, e2e_dt * 1e3, res_wall * 1e3, kern_ms, e2e_kern_mean, e2e_wait_mean],
+                       dtype=torch.float64, device=dev)
     tot = torch.tensor([batch.n_windows, corrected, launches, cells], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, res_wall_max, kern_ms_max = [float(x) for x in agg.tolist()]
+    dev_ms_max, e2e_ms_max, res_wall_max, kern_ms_max, e2e_kern_max, e2e_stage_max = [float(x) for x in agg.tolist()]
     n_windows, n_bases, n_launch, n_cells = [float(x) for x in tot.tolist()]
 
     if rank == 0:
@@ -333,6 +339,7 @@ def measure(args, torch, dist, world, rank, local, cpu_seconds):
                     "corrected_bases_per_sec": n_bases * args.steps / (e2e_ms_max / 1e3),
                     "pipeline": "vgc_submit / vgc_collect: staging of step k+1 (host prepare, 2-bit packing, H2D) and "
                                 "stitch of step k-1 overlap the kernels of step k; every step copies its own inputs",
+                    "kernel_ms_mean_max_over_ranks": e2e_kern_max, "staging_host_ms_mean_max_over_ranks": e2e_stage_max,
                     "host_prep_ms": e2e_stats[-1]["host_prep_ms"], "host_pack_ms": e2e_stats[-1]["host_pack_ms"],
                     "h2d_ms": e2e_stats[-1]["h2d_ms"],
                     "kernel_ms": e2e_stats[-1]["kernel_ms"], "d2h_ms": e2e_stats[-1]["d2h_ms"]},
@@ -409,11 +416,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL only carries the per-step gather of the corrected reads to rank 0 (and the timing reductions); it runs
+        # while the next pass owns the GPU.  Its kernels take one CTA per channel and spin there until the peers
+        # arrive, and at 8 ranks the default channel count cost the root's pass 8 % (987 vs 911 ms, round-2 run):
+        # two channels move the 0.5 GB in ~15 ms and occupy two SMs.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     line = measure(args, torch, dist, world, rank, local,
                    args.cpu_seconds if (world == 1 and not args.no_cpu_baseline) else 0.0)
-    if (world > 1 or args.hap2_leg) and args.workload == "pb":
+    if (world > 1 or args.hap2_leg) and args.workload == "pb" and not args.no_hap2_leg:
         # the shape the 8-GPU target is quoted on (BASELINE configs[3]: 2-haplotype mix, depth ~60), on disjoint
         # target ranges (50k reads): same legs, fewer steps, with a parity sample against the CPU reference on rank 0
         import copy
