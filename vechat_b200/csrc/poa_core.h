@@ -2210,6 +2210,7 @@ struct Poa {
       ex.sync();
       if (ws.status != kStOk) return finish();
     }
+    ex.sync();  // every lane has read ws.nMain / ws.prep (racecheck: the short path above has no other barrier)
     if (ex.leader()) {
       ws.nMain = nMain;
       ws.need = (prep & kPrepFill) ? kNeedFill : kNeedUpdate;
