@@ -48,21 +48,6 @@ __device__ __forceinline__ uint32_t pinned(uint32_t v) {
   return v;
 }
 
-#ifndef VGC_FAR_PREFETCH
-#define VGC_FAR_PREFETCH 0
-#endif
-// does the row of record `e` read an inline predecessor from beyond the ring of recent rows?
-__device__ __forceinline__ bool far_preds(const uint4& e, bool use_ring) {
-  if (!(e.x & kMetaInline)) return false;
-  const uint32_t reach = use_ring ? static_cast<uint32_t>(kRingRows) : 1u;
-  const uint32_t np = meta_npred(e.x);
-  const U4 er = {e.x, e.y, e.z, e.w};
-  bool far = false;
-#pragma unroll
-  for (uint32_t p = 0; p < kInlinePreds; ++p) far |= p < np && rec_delta(er, p) > reach;
-  return far;
-}
-
 // K words of this lane to global memory (`p` already offset to the lane's words), as st.global vectors
 template <int K>
 __device__ __forceinline__ void lane_store_global(uint32_t* p, const uint32_t (&h)[K]) {
@@ -215,9 +200,6 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
   // ring of the most recent rows in shared memory: row r lives in slot r % kRingRows (with its first-column value
   // in ring_fc), so "is predecessor row - d in the ring" is just d <= kRingRows — no tags to search or maintain
   const bool use_ring = ring_rows == kRingRows;
-#if VGC_FAR_PREFETCH
-  const uint32_t ring_reach = use_ring ? static_cast<uint32_t>(kRingRows) : 1u;
-#endif
   // (every lane keeps its own copy of the first-column values: a lane only ever reads what it wrote itself, rows
   //  and first columns alike, so the ring needs no warp synchronisation)
   int32_t* ring_fc = reinterpret_cast<int32_t*>(ring + kRingRows * rw) + lane;
@@ -242,12 +224,6 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
   for (uint32_t r0 = 0; r0 < nR; r0 += 32) {
     __syncwarp();
     stage[lane] = nxt;
-#if VGC_FAR_PREFETCH
-    // rows of this block with an inline predecessor beyond the ring: their predecessor rows come from L2 / HBM, and
-    // the row cannot start before they arrive.  One ballot per 32 rows marks them; the row before such a row asks
-    // for the lines (prefetch.global.L1) so that the loads find them on the SM.
-    const uint32_t farmask = __ballot_sync(FULL, far_preds(nxt, use_ring));
-#endif
     if (r0 + 32 + lane < nR) nxt = rp[r0 + 32 + lane];
     __syncwarp();
     const uint32_t rn = nR - r0 < 32 ? nR - r0 : 32;
@@ -259,20 +235,6 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       const uint32_t meta = e.x;
       ++row;
       hrow += rw;
-#if VGC_FAR_PREFETCH
-      if ((farmask >> rr) & 2u) {  // the next row (rr + 1 < 32: bit 32 does not exist) has far predecessors
-        const uint4 e2 = stage[rr + 1];
-        const U4 er2 = {e2.x, e2.y, e2.z, e2.w};
-        const uint32_t np2 = meta_npred(e2.x);
-#pragma unroll
-        for (uint32_t p = 0; p < kInlinePreds; ++p) {
-          const uint32_t d = rec_delta(er2, p);
-          // row + 1 - d <= row - 1 for d >= 2: written already (by this very lane, earlier in program order)
-          if (p < np2 && d > ring_reach)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(hrow + rw - static_cast<uint64_t>(d) * rw));
-        }
-      }
-#endif
       uint32_t pr[K];
       lane_load<K>(profl + meta_code(meta) * rw, pr, swz);
       int32_t fcmax;

@@ -34,10 +34,6 @@
 
 #include "poa_core.h"
 
-#ifndef VGC_TRACE_PREFETCH
-#define VGC_TRACE_PREFETCH 0
-#endif
-
 namespace vgc {
 
 constexpr int kTileRows = 32;    // rows ti, ti-1, .. ti-31 (rank space)
@@ -138,17 +134,6 @@ __device__ __forceinline__ int warp_trace(const TraceIo& t, uint32_t* tile, uint
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rdst), "l"(t.rp + (row - 1)) : "memory");
       }
     }
-#if VGC_TRACE_PREFETCH
-    // the tile after this one: the walk leaves through the top (32 rows further up, at most 32 columns to the left),
-    // so ask L2 for those rows now — the next refill then costs an L2 round trip instead of a DRAM one.  Two lines
-    // per row around the current left edge, and the rows' records.
-    if (ti >= TR + static_cast<uint32_t>(lane)) {
-      const uint32_t* nrow = t.H + static_cast<uint64_t>(ti - TR - lane) * rw;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (wb >= 16u ? wb - 16u : 0u)));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (wb + 16u < rw ? wb + 16u : rw - 1u)));
-    }
-    if (lane < 4 && ti >= 2 * TR + 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.rp + (ti - 2 * TR) + 8 * lane));
-#endif
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     have = true;
