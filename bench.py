@@ -431,7 +431,7 @@ def main():
         import copy
         a2 = copy.copy(args)
         a2.workload = "hap2"
-        a2.steps = max(2, min(args.steps, 3))
+        a2.steps = max(2, min(args.steps, 8))  # enough steps to amortise the pipeline fill of the e2e leg
         a2.warmup = 3
         a2.targets = min(args.targets, 800)
         h = measure(a2, torch, dist, world, rank, local, 0.0 if args.no_cpu_baseline else 8.0)
