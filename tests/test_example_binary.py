@@ -426,3 +426,29 @@ def test_stream_job_tool_behind_mock_engine(tmp_path):
     assert s["corrected_reads"] == 48 and s["windows"] == 48 * 6
     assert s["parity"]["targets_checked"] == 5 and s["parity"]["mismatches"] == 0
     assert "batches from one queue" in s["queue"] and "device 1 took" in s["queue"]
+
+
+# ---------------------------------------------------------------- f-2: the binding's own tiling (host threads)
+
+@need_b200
+@need_ref
+@pytest.mark.parametrize("opts", [HAP, LIN, HAP + ["-q", "12"], HAP + ["-w", "300"], HAP + ["-q", "11.5", "-w", "777"],
+                                  LIN + ["--no-trimming"]])
+def test_binding_tiling_equals_the_reference_tiling(opts):
+    """B200Polisher::build_tiles (layers per window built on host threads inside find_overlap_breaking_points, the
+    reference's serial loop of polisher.cpp:408-462 left with nothing to add) against the reference's own tiling
+    (VECHAT_B200_TILING=0: layers read from Window::sequences_): same FASTA, byte for byte, also where the length and
+    mean-quality filters bite (-q, -w); and both equal the reference program."""
+    outs = {}
+    for tiling in ("1", "0"):
+        env = dict(os.environ, VECHAT_B200_DEVICES="0,1", VECHAT_B200_BATCH_WINDOWS="50", VECHAT_B200_TILING=tiling,
+                   **_mock_env())
+        env.pop("VECHAT_B200_ALIGN", None)
+        r = subprocess.run([B200_BIN] + opts + ["-t", "8", "reads.fq.gz", "overlaps.paf", "targets.fq.gz"], cwd=EX, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+        assert r.returncode == 0, r.stderr[-400:]
+        assert (b"tiled the windows on host threads" in r.stderr) == (tiling == "1")
+        outs[tiling] = r.stdout
+    assert outs["1"] == outs["0"] and len(outs["1"]) > 1000
+    ref = run(REF_BIN, opts)
+    assert ref.returncode == 0 and ref.stdout == outs["1"]

@@ -86,15 +86,34 @@ struct Packed {
 
 class CUDABatchProcessor {
  public:
-  static uint64_t bytes(const Window& w) {
+  // the layers of window `idx` beyond its backbone: the binding's tiles when it tiled (else nullptr, 0 and the
+  // Window's own vectors are used)
+  struct Tiles {
+    const std::vector<B200TileLayer>* layers = nullptr;
+    const std::vector<uint64_t>* first = nullptr;
+    bool on() const { return first != nullptr && !first->empty(); }
+    const B200TileLayer* begin(size_t idx) const {
+      return idx + 1 < first->size() ? layers->data() + (*first)[idx] : nullptr;
+    }
+    size_t count(size_t idx) const { return idx + 1 < first->size() ? (*first)[idx + 1] - (*first)[idx] : 0; }
+  };
+  static uint64_t bytes(const Window& w, size_t idx, const Tiles& t) {
     uint64_t n = 0;
-    for (const auto& s : w.sequences_) n += s.second;
+    if (!t.on()) {
+      for (const auto& s : w.sequences_) n += s.second;
+      return n;
+    }
+    n = w.sequences_.front().second;
+    const B200TileLayer* l = t.begin(idx);
+    for (size_t k = 0, c = t.count(idx); k < c; ++k) n += l[k].length;
     return n;
   }
   // Window only borrows pointers into Polisher::sequences_ (freed at polisher.cpp:560-561): copy the bytes once.
   // Pass 1 (serial, metadata only) lays out the layer table and the byte offsets; pass 2 copies the bytes with
   // `threads` host threads over window ranges.
-  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p, unsigned threads) {
+  static void pack(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p, unsigned threads,
+                   const Tiles& tiles) {
+    if (tiles.on()) return pack_tiled(w, first, last, p, threads, tiles);
     p->clear();
     size_t layers = 0;
     for (size_t i = first; i < last; ++i) layers += w[i]->sequences_.size();
@@ -148,6 +167,75 @@ class CUDABatchProcessor {
       for (auto& x : th) x.join();
     }
   }
+  // the same image from the binding's tiles: layer 0 = the window's backbone (the Window holds it), then the tiles
+  static void pack_tiled(const std::vector<std::shared_ptr<Window>>& w, size_t first, size_t last, Packed* p,
+                         unsigned threads, const Tiles& tiles) {
+    p->clear();
+    const size_t nw = last - first;
+    size_t layers = nw;
+    for (size_t i = first; i < last; ++i) layers += tiles.count(i);
+    p->seq_off.resize(layers + 1);
+    p->has_qual.resize(layers);
+    p->begin.resize(layers);
+    p->end.resize(layers);
+    p->win_first.resize(nw + 1);
+    p->win_flags.resize(nw);
+    uint64_t total = 0;
+    size_t layer = 0;
+    for (size_t i = first; i < last; ++i) {  // offsets: serial prefix over the windows (metadata only)
+      const Window& win = *w[i];
+      p->win_first[i - first] = static_cast<uint32_t>(layer);
+      p->seq_off[layer++] = total;
+      total += win.sequences_.front().second;
+      const B200TileLayer* l = tiles.begin(i);
+      for (size_t k = 0, c = tiles.count(i); k < c; ++k) {
+        p->seq_off[layer++] = total;
+        total += l[k].length;
+      }
+    }
+    p->win_first[nw] = static_cast<uint32_t>(layer);
+    p->seq_off[layer] = total;
+    p->bases.need(total);
+    p->quals.need(total);
+    auto copy_range = [&](size_t a, size_t b) {
+      for (size_t i = a; i < b; ++i) {
+        const Window& win = *w[first + i];
+        size_t lay = p->win_first[i];
+        const uint32_t blen = win.sequences_.front().second;
+        // window.cpp:223 compares the backbone quality POINTER, as a C string, with a run of '!' of backbone length
+        const bool dummy = std::string(blen, '!') == win.qualities_.front().first;
+        p->win_flags[i] = static_cast<uint8_t>((win.type_ == WindowType::kTGS ? VGC_WIN_TGS : 0u) |
+                                               (dummy ? VGC_WIN_DUMMY_QUAL : 0u));
+        uint64_t o = p->seq_off[lay];
+        std::memcpy(p->bases.data() + o, win.sequences_.front().first, blen);
+        const char* bq = win.qualities_.front().first;
+        if (bq != nullptr) std::memcpy(p->quals.data() + o, bq, blen);
+        else std::memset(p->quals.data() + o, '!', blen);
+        p->has_qual[lay] = bq != nullptr ? 1 : 0;
+        p->begin[lay] = win.positions_.front().first;
+        p->end[lay] = win.positions_.front().second;
+        ++lay;
+        const B200TileLayer* l = tiles.begin(first + i);
+        for (size_t k = 0, c = tiles.count(first + i); k < c; ++k, ++lay) {
+          o = p->seq_off[lay];
+          std::memcpy(p->bases.data() + o, l[k].data, l[k].length);
+          if (l[k].quality != nullptr) std::memcpy(p->quals.data() + o, l[k].quality, l[k].length);
+          else std::memset(p->quals.data() + o, '!', l[k].length);
+          p->has_qual[lay] = l[k].quality != nullptr ? 1 : 0;
+          p->begin[lay] = l[k].begin;
+          p->end[lay] = l[k].end;
+        }
+      }
+    };
+    const unsigned nt = nw < 64 ? 1u : std::max(1u, std::min(threads, 16u));
+    if (nt == 1) {
+      copy_range(0, nw);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(copy_range, nw * t / nt, nw * (t + 1) / nt);
+      for (auto& x : th) x.join();
+    }
+  }
   static void store(Window& win, const uint8_t* s, uint64_t n) { win.consensus_.assign(reinterpret_cast<const char*>(s), n); }
 };
 
@@ -155,6 +243,7 @@ class CUDABatchProcessor {
 // coordinates, writes Overlap::cigar_.
 class CUDABatchAligner {
  public:
+  static void clear_breaking_points(Overlap& o) { std::vector<std::pair<uint32_t, uint32_t>>().swap(o.breaking_points_); }
   // cut_on_device: vga_break fills breaking_points_ directly (no CIGAR text crosses PCIe); otherwise vga_align fills
   // cigar_ and the reference's find_breaking_points_from_cigar cuts it on the host.
   // One host thread + one vga_handle per device, each over a contiguous range of the overlaps (they are independent;
@@ -270,8 +359,9 @@ B200Polisher::B200Polisher(std::unique_ptr<bioparser::Parser<Sequence>> sparser,
     : Polisher(std::move(sparser), std::move(oparser), std::move(tparser), type, haplotype, min_confidence, min_support,
                num_prune, window_length, quality_threshold, error_threshold, trim, match, mismatch, gap, num_threads),
       match_(match), mismatch_(mismatch), gap_(gap), num_threads_(num_threads), devices_(std::move(devices)),
-      align_on_gpu_(false), cut_on_gpu_(false) {
+      align_on_gpu_(false), cut_on_gpu_(false), tile_in_binding_(true) {
   if (devices_.empty()) devices_.push_back(0);
+  if (const char* t = std::getenv("VECHAT_B200_TILING")) tile_in_binding_ = t[0] != '0';
   const char* env = std::getenv("VECHAT_B200_ALIGN");
   align_on_gpu_ = env != nullptr && env[0] != '\0' && env[0] != '0';
   cut_on_gpu_ = align_on_gpu_ && std::strcmp(env, "cigar") != 0;
@@ -289,6 +379,82 @@ void B200Polisher::find_overlap_breaking_points(std::vector<std::unique_ptr<Over
     logger_->log("[racon::B200Polisher::find_overlap_breaking_points] aligned overlaps on the GPU");
   }
   Polisher::find_overlap_breaking_points(overlaps);  // cuts the breaking points; edlib only where cigar_ is empty
+  if (tile_in_binding_) build_tiles(overlaps);
+}
+
+// Polisher::initialize's last loop (src/polisher.cpp:408-462) walks every overlap serially and sums the qualities of
+// every layer on one thread — 13 s of the 10^6-window job.  Here the same decisions are taken per overlap on host
+// threads (length filter :414-417, mean-quality filter :419-433 — a sum of small integers, exact in a double in any
+// order — window and positions :435-461), the layers are grouped per window in overlap order (what the serial loop's
+// add_layer calls produce), and the overlaps' breaking points are cleared, so that the reference's loop only counts
+// targets_coverages_ and creates the (layer-less) windows.  polish() packs from these tiles.
+void B200Polisher::build_tiles(std::vector<std::unique_ptr<Overlap>>& overlaps) {
+  logger_->log();
+  const uint32_t wl = window_length_;
+  uint64_t max_t = 0;
+  for (const auto& o : overlaps) max_t = std::max<uint64_t>(max_t, o->t_id());
+  // first window of every target up to the last one an overlap names (targets are the first sequences_, :389-404)
+  std::vector<uint64_t> first_window(max_t + 2, 0);
+  for (uint64_t i = 0; i <= max_t && i < sequences_.size(); ++i)
+    first_window[i + 1] = first_window[i] + (sequences_[i]->data().size() + wl - 1) / wl;
+  const uint64_t n_win = first_window[max_t + 1];
+  struct Rec {
+    uint64_t window;
+    B200TileLayer layer;
+  };
+  const size_t no = overlaps.size();
+  const unsigned nt = no < 256 ? 1u : std::max(1u, std::min<unsigned>(num_threads_, 32));
+  std::vector<std::vector<Rec>> part(nt);
+  auto run = [&](unsigned t) {
+    std::vector<Rec>& out = part[t];
+    for (size_t i = no * t / nt; i < no * (t + 1) / nt; ++i) {
+      const Overlap& o = *overlaps[i];
+      const auto& sequence = sequences_[o.q_id()];
+      const auto& bp = o.breaking_points();
+      for (uint32_t j = 0; j + 1 < bp.size(); j += 2) {
+        const uint32_t qb = bp[j].second, qe = bp[j + 1].second;
+        if (qe - qb < 0.02 * wl) continue;
+        const bool has_q = !sequence->quality().empty() || !sequence->reverse_quality().empty();
+        if (has_q) {
+          const auto& quality = o.strand() ? sequence->reverse_quality() : sequence->quality();
+          double average_quality = 0;
+          for (uint32_t k = qb; k < qe; ++k) average_quality += static_cast<uint32_t>(quality[k]) - 33;
+          average_quality /= qe - qb;
+          if (average_quality < quality_threshold_) continue;
+        }
+        const uint32_t window_start = (bp[j].first / wl) * wl;
+        Rec r;
+        r.window = first_window[o.t_id()] + bp[j].first / wl;
+        r.layer.data = o.strand() ? &(sequence->reverse_complement()[qb]) : &(sequence->data()[qb]);
+        r.layer.length = qe - qb;
+        r.layer.quality = o.strand() ? (sequence->reverse_quality().empty() ? nullptr : &(sequence->reverse_quality()[qb]))
+                                     : (sequence->quality().empty() ? nullptr : &(sequence->quality()[qb]));
+        r.layer.begin = bp[j].first - window_start;
+        r.layer.end = bp[j + 1].first - window_start - 1;
+        out.push_back(r);
+      }
+    }
+  };
+  if (nt == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(run, t);
+    for (auto& x : th) x.join();
+  }
+  // group per window, keeping the overlap order (the parts are consecutive ranges of the overlaps)
+  tile_first_.assign(n_win + 1, 0);
+  for (const auto& p : part)
+    for (const Rec& r : p) ++tile_first_[r.window + 1];
+  for (uint64_t w = 0; w < n_win; ++w) tile_first_[w + 1] += tile_first_[w];
+  tile_layers_.resize(tile_first_[n_win]);
+  {
+    std::vector<uint64_t> cursor(tile_first_.begin(), tile_first_.end() - 1);
+    for (const auto& p : part)
+      for (const Rec& r : p) tile_layers_[cursor[r.window]++] = r.layer;
+  }
+  for (auto& o : overlaps) CUDABatchAligner::clear_breaking_points(*o);
+  logger_->log("[racon::B200Polisher::find_overlap_breaking_points] tiled the windows on host threads");
 }
 
 void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop_unpolished_sequences) {
@@ -307,6 +473,9 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
 
   const size_t n = windows_.size();
   std::vector<uint8_t> polished(n, 0);
+  CUDABatchProcessor::Tiles tiles;
+  tiles.layers = &tile_layers_;
+  tiles.first = &tile_first_;
 
   // The windows are cut into batches (<= 64 k windows / 1 GB of bases per vgc call) that form ONE queue for all
   // devices: every device has its own host thread + vgc_handle (the model of the legacy path,
@@ -331,7 +500,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     size_t last = first;
     uint64_t b = 0;
     while (last < n && last - first < cap && (last == first || b < kBatchBytes))
-      b += CUDABatchProcessor::bytes(*windows_[last++]);
+      b += CUDABatchProcessor::bytes(*windows_[last], last, tiles), ++last;
     batches.emplace_back(first, last);
     first = last;
   }
@@ -362,7 +531,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
     std::string submit_err;
     size_t x = queue_head.fetch_add(1);
     if (x < batches.size()) {
-      CUDABatchProcessor::pack(windows_, batches[x].first, batches[x].second, &cur, pack_threads);
+      CUDABatchProcessor::pack(windows_, batches[x].first, batches[x].second, &cur, pack_threads, tiles);
       const vgc_batch b0 = cur.view();
       if (vgc_submit(h, &b0) != VGC_OK) {
         errors[d] = vgc_last_error();
@@ -388,7 +557,7 @@ void B200Polisher::polish(std::vector<std::unique_ptr<Sequence>>& dst, bool drop
       if (xn < batches.size()) {
         packer = std::thread([&, xn] {
           const auto t_p = std::chrono::steady_clock::now();
-          CUDABatchProcessor::pack(windows_, batches[xn].first, batches[xn].second, &next, pack_threads);
+          CUDABatchProcessor::pack(windows_, batches[xn].first, batches[xn].second, &next, pack_threads, tiles);
           pack_ms = since(t_p);
           const vgc_batch bn = next.view();
           rc_submit = vgc_submit(h, &bn);

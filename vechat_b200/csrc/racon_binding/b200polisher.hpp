@@ -19,6 +19,15 @@
 
 namespace racon {
 
+// One layer of a window as the binding's own tiling records it: what Window::add_layer would have
+// been given (src/polisher.cpp:437-461) — bytes borrowed from Polisher::sequences_, positions inside the window.
+struct B200TileLayer {
+  const char* data;
+  const char* quality;  // nullptr: the read has no qualities
+  uint32_t length;
+  uint32_t begin, end;
+};
+
 class B200Polisher : public Polisher {
  public:
   // same argument list as the protected Polisher constructor (src/polisher.hpp:72-79) + the devices to use
@@ -44,6 +53,13 @@ class B200Polisher : public Polisher {
   uint32_t num_threads_;
   std::vector<int> devices_;
   bool align_on_gpu_, cut_on_gpu_;
+  // Tiling taken over from Polisher::initialize's serial loop (src/polisher.cpp:408-462; VECHAT_B200_TILING=0 leaves
+  // it to the reference): the layers of every window, window by window in overlap order, built on host threads
+  // inside find_overlap_breaking_points; polish() packs from here instead of from Window::sequences_.
+  void build_tiles(std::vector<std::unique_ptr<Overlap>>& overlaps);
+  bool tile_in_binding_;
+  std::vector<B200TileLayer> tile_layers_;
+  std::vector<uint64_t> tile_first_;  // [windows with layers + 1]; empty: the reference tiled
   std::vector<std::thread> closers_;  // free the engines' device scratch behind the stitch and the output (joined in the destructor)
 };
 
