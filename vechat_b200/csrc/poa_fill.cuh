@@ -227,11 +227,13 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
     if (r0 + 32 + lane < nR) nxt = rp[r0 + 32 + lane];
     __syncwarp();
     const uint32_t rn = nR - r0 < 32 ? nR - r0 : 32;
+    uint4 e_ahead = stage[0];
 #pragma unroll 1
     for (uint32_t rr = 0; rr < rn; ++rr) {
       // rows live in rank space: this is row r0 + rr + 1; e = {meta, p0p1, p2p3, p4p5 | ovf offset}, predecessors as
       // row distances
-      const uint4 e = stage[rr];
+      const uint4 e = e_ahead;
+      e_ahead = stage[(rr + 1) & 31];  // the next row's record, asked for a whole row early (rr = 31: reloaded below)
       const uint32_t meta = e.x;
       ++row;
       hrow += rw;
@@ -342,24 +344,34 @@ __device__ __forceinline__ void warp_fill_t(FillIo& io, const uint8_t* codes, ui
       const int32_t fci = SW ? 0 : fcmax + g;
       // ---- horizontal, cross-lane part: the max-plus scan over the lanes' segments
       uint32_t V = __vadd2(hp[K - 1], voff);
-      // inclusive max-scan over the lanes in three dependent levels (windows of 4, 16, 32 lanes) instead of the five
-      // of a doubling scan: seven shuffles instead of five, but the row's critical path is two shuffle latencies
-      // shorter (measured: fill cycles -2.8 %, pass -1.0 %, profiles/r02_sweep_scan_radix4.txt).  Lanes below the shift
-      // get their own value back from shfl_up: the max is a no-op there, no predicate needed.
+      // (round 2: a doubling inclusive scan, 5 levels + 2 shuffles behind it, was the longest dependent chain of a row;
+      //  radix-4 inclusive: fill cycles -2.8 %; this exclusive form + REDUX + the record fetched a row ahead: a further
+      //  -7.5 %, pass 902 -> 883 ms — profiles/r02_sweep_scan_radix4.txt, r02_sweep_scan_exclusive.txt)
+      // EXCLUSIVE max-scan over the lanes in three dependent levels (windows of 4, 16, 32 lanes to the left): the
+      // carry-in of a lane is ready right after the scan, without the extra shuffle an inclusive scan needs, and the
+      // total of the low halves (the carry into the high half) comes from one REDUX beside the scan instead of a
+      // shuffle behind it.  Level 1 masks the lanes that do not exist (shfl_up hands a lane its own value back);
+      // at levels 2 and 3 getting the own partial result back is harmless (max is idempotent).
+      const int32_t lowtot = __reduce_max_sync(FULL, lo16(V));
+      uint32_t E;
       {
-        const uint32_t a = __shfl_up_sync(FULL, V, 1), b = __shfl_up_sync(FULL, V, 2), c = __shfl_up_sync(FULL, V, 3);
-        V = __vmaxs2(__vimax3_s16x2(V, a, b), c);
+        constexpr uint32_t kNeg = 0x80008000u;
+        uint32_t a = __shfl_up_sync(FULL, V, 1), b = __shfl_up_sync(FULL, V, 2), c = __shfl_up_sync(FULL, V, 3),
+                 d = __shfl_up_sync(FULL, V, 4);
+        a = lane >= 1 ? a : kNeg;
+        b = lane >= 2 ? b : kNeg;
+        c = lane >= 3 ? c : kNeg;
+        d = lane >= 4 ? d : kNeg;
+        E = __vmaxs2(__vimax3_s16x2(a, b, c), d);
       }
       {
-        const uint32_t a = __shfl_up_sync(FULL, V, 4), b = __shfl_up_sync(FULL, V, 8), c = __shfl_up_sync(FULL, V, 12);
-        V = __vmaxs2(__vimax3_s16x2(V, a, b), c);
+        const uint32_t a = __shfl_up_sync(FULL, E, 4), b = __shfl_up_sync(FULL, E, 8), c = __shfl_up_sync(FULL, E, 12);
+        E = __vmaxs2(__vimax3_s16x2(E, a, b), c);
       }
-      V = __vmaxs2(V, __shfl_up_sync(FULL, V, 16));
-      const int32_t lowtot = lo16(__shfl_sync(FULL, V, 31));
+      E = __vmaxs2(E, __shfl_up_sync(FULL, E, 16));
       const int32_t vfc = fci + g;
       const uint32_t X = pack16(vfc, vfc > lowtot ? vfc : lowtot);
-      uint32_t E = __shfl_up_sync(FULL, V, 1);
-      E = lane == 0 ? X : __vmaxs2(E, X);
+      E = __vmaxs2(E, X);  // lane 0: max(kNeg, X) = X
       const uint32_t base = __vadd2(E, gbase);
       if (SW) {
 #pragma unroll
