@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B of library variants under exp_libs/ (built with -D switches): tools/sweep5.sh base F T FT
-# first argument "parity:<tag>" runs the GPU parity tests against that variant first
-mkdir -p gpurun_out
+# A/B of library variants (run under gpurun): build variants of libvgc.so with -D switches into exp_libs/libvgc_<tag>.so
+# (nvcc line of vechat_b200/build.py + the switch), then `tools/sweep5.sh [parity:<tag>] default <tag> default <tag> ...`:
+# "parity:<tag>" runs the GPU parity tests against that variant, every other word is one short bench run (VGC_LIB).
+# Same box, alternating order: box-to-box variation is ~1 %, run-to-run on one box ~0.1 %.
 run() {
   local tag="$1"; shift
   env "$@" timeout 600 python bench.py --steps ${STEPS:-3} --warmup 3 --no-cpu-baseline > gpurun_out/sw_$tag.json 2> gpurun_out/sw_$tag.err
