@@ -3,6 +3,7 @@
 # (nvcc line of vechat_b200/build.py + the switch), then `tools/sweep5.sh [parity:<tag>] default <tag> default <tag> ...`:
 # "parity:<tag>" runs the GPU parity tests against that variant, every other word is one short bench run (VGC_LIB).
 # Same box, alternating order: box-to-box variation is ~1 %, run-to-run on one box ~0.1 %.
+mkdir -p gpurun_out
 run() {
   local tag="$1"; shift
   env "$@" timeout 600 python bench.py --steps ${STEPS:-3} --warmup 3 --no-cpu-baseline > gpurun_out/sw_$tag.json 2> gpurun_out/sw_$tag.err
