@@ -452,3 +452,30 @@ def test_binding_tiling_equals_the_reference_tiling(opts):
     assert outs["1"] == outs["0"] and len(outs["1"]) > 1000
     ref = run(REF_BIN, opts)
     assert ref.returncode == 0 and ref.stdout == outs["1"]
+
+
+@need_b200
+@need_ref
+def test_binding_tiling_fasta_and_contig_mode(tmp_path):
+    """The tiles on inputs without qualities (FASTA reads: the mean-quality filter is skipped, layers carry no quality
+    pointer, window.cpp:223's dummy-quality branch) and in contig mode (no -f: PolisherType::kC keeps one overlap per
+    read, polisher.cpp:292-316) — binding tiles == reference tiling == reference program."""
+    for src, dst in (("reads.fq.gz", "reads.fa"), ("targets.fq.gz", "targets.fa")):
+        with gzip.open(os.path.join(EX, src), "rt") as f, open(tmp_path / dst, "w") as g:
+            lines = f.read().split("\n")
+            for i in range(0, len(lines) - 3, 4):
+                g.write(">" + lines[i][1:] + "\n" + lines[i + 1] + "\n")
+    paf = os.path.join(EX, "overlaps.paf")
+    cases = [(HAP, "reads.fa", "targets.fa", str(tmp_path)), (LIN, "reads.fa", "targets.fa", str(tmp_path)),
+             (["-p", "-d", "0.2", "-s", "0.2"], "reads.fq.gz", "targets.fq.gz", EX), ([], "reads.fq.gz", "targets.fq.gz", EX)]
+    for opts, reads, targets, cwd in cases:
+        want = run(REF_BIN, opts, reads, paf, targets, cwd=cwd)
+        assert want.returncode == 0, want.stderr[-400:]
+        for tiling in ("1", "0"):
+            env = dict(os.environ, VECHAT_B200_DEVICES="0", VECHAT_B200_BATCH_WINDOWS="70", VECHAT_B200_TILING=tiling,
+                       **_mock_env())
+            env.pop("VECHAT_B200_ALIGN", None)
+            r = subprocess.run([B200_BIN] + opts + ["-t", "8", reads, paf, targets], cwd=cwd, env=env,
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+            assert r.returncode == 0, r.stderr[-400:]
+            assert r.stdout == want.stdout, (opts, reads, tiling)
